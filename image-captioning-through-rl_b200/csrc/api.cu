@@ -1,0 +1,268 @@
+// extern "C" surface of libicrl_b200.so (declared in include/icrl_b200.h) and the per-phase drivers
+// that sequence the kernels of the policy rollout and the parameter-gradient contractions.
+#include <stdarg.h>
+#include <string.h>
+#include "../../include/icrl_b200.h"
+#include "internal.h"
+
+static thread_local char g_err[512] = "";
+
+void icrl_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+#define TRY(x)                     \
+  do {                             \
+    int rc__ = (x);                \
+    if (rc__ != ICRL_OK) return rc__; \
+  } while (0)
+
+static inline cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline void bump(int* l, int n) { if (l) *l += n; }
+constexpr int H = ICRL_H;
+
+extern "C" {
+
+const char* icrl_last_error(void) { return g_err; }
+int icrl_version(void) { return 100; }
+
+int icrl_device_info(int* out4) {
+  int dev = 0;
+  ICRL_CUDA(cudaGetDevice(&dev));
+  ICRL_CUDA(cudaDeviceGetAttribute(&out4[0], cudaDevAttrMultiProcessorCount, dev));
+  ICRL_CUDA(cudaDeviceGetAttribute(&out4[1], cudaDevAttrComputeCapabilityMajor, dev));
+  ICRL_CUDA(cudaDeviceGetAttribute(&out4[2], cudaDevAttrComputeCapabilityMinor, dev));
+  ICRL_CUDA(cudaDeviceGetAttribute(&out4[3], cudaDevAttrCooperativeLaunch, dev));
+  return ICRL_OK;
+}
+
+int icrl_gemm_f32(void* stream, int transA, int transB, int M, int N, int K, const float* A, int lda,
+                  const float* B, int ldb, float* C, int ldc, const float* bias, float beta, float* ws,
+                  size_t ws_bytes, int* launches) {
+  return icrl_gemm_f32_impl(S_(stream), transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, beta, ws, ws_bytes,
+                            launches);
+}
+
+int icrl_pack_gate_table(void* stream, int V, int G, int fold, const float* E, const float* W_ih,
+                         const float* b_ih, const float* b_hh, float* table, int* launches) {
+  // table = E [V][512] * W_ih^T ([G][512], K contiguous)
+  TRY(icrl_gemm_f32_impl(S_(stream), 0, 1, V, G, H, E, H, W_ih, H, table, G, nullptr, 0.f, nullptr, 0, launches));
+  TRY(icrl_add_gate_bias_impl(S_(stream), V, G, fold, b_ih, b_hh, table));
+  bump(launches, 1);
+  return ICRL_OK;
+}
+
+int icrl_pack_value_head(void* stream, const float* W1, const float* b1, const float* W2, const float* b2,
+                         float* w_eff, float* b_eff, int* launches) {
+  TRY(icrl_pack_value_head_impl(S_(stream), W1, b1, W2, b2, w_eff, b_eff));
+  bump(launches, 1);
+  return ICRL_OK;
+}
+
+int icrl_policy_rollout_fwd(void* stream, int B, int V, int p0, int S, int greedy, const float* features,
+                            const float* W_cnn, const float* b_cnn, const float* table, const float* W_hh,
+                            const float* W_v, const float* b_v, const double* uniforms, const long long* forced,
+                            int* tokcm, long long* tokens_out, float* logp, float* Hs, float* Cs, float* Gs, float* logits,
+                            float* gpre, int* launches) {
+  ICRL_REQUIRE(B > 0 && V > 0 && p0 >= 1 && S >= 1, "bad rollout shape");
+  ICRL_REQUIRE(greedy || uniforms || forced, "sampling needs uniforms");
+  cudaStream_t st = S_(stream);
+  const int n_cell = p0 - 1 + S;
+  const size_t BH = (size_t)B * H;
+  // h0 = cnn2linear(features), c0 = 0   (models.py:75-78)
+  TRY(icrl_gemm_f32_impl(st, 0, 1, B, H, H, features, H, W_cnn, H, Hs, H, b_cnn, 0.f, nullptr, 0, launches));
+  ICRL_CUDA(cudaMemsetAsync(Cs, 0, BH * sizeof(float), st));
+  for (int j = 0; j < n_cell; ++j) {
+    // recurrent half of the gates: h_{j-1} W_hh^T ; input half comes from the gate table
+    TRY(icrl_gemm_f32_impl(st, 0, 1, B, 4 * H, H, Hs + j * BH, H, W_hh, H, gpre, 4 * H, nullptr, 0.f, nullptr, 0,
+                           launches));
+    TRY(icrl_lstm_pointwise_fwd(st, B, gpre, table, tokcm + (size_t)j * B, Cs + j * BH, Gs + (size_t)j * B * 4 * H,
+                                Cs + (j + 1) * BH, Hs + (j + 1) * BH));
+    bump(launches, 1);
+    const int s = j - (p0 - 1);
+    if (s >= 0) {
+      float* lg = logits + (size_t)s * B * V;
+      TRY(icrl_gemm_f32_impl(st, 0, 1, B, V, H, Hs + (j + 1) * BH, H, W_v, H, lg, V, b_v, 0.f, nullptr, 0, launches));
+      TRY(icrl_softmax_sample(st, B, V, lg, V, (greedy || !uniforms) ? nullptr : uniforms + (size_t)s * B, greedy, forced,
+                              tokcm + (size_t)(p0 + s) * B, tokens_out, logp, S, s, nullptr));
+      bump(launches, 1);
+    }
+  }
+  return ICRL_OK;
+}
+
+size_t icrl_colsum_ws_floats(long long rows, int cols) { return (size_t)icrl_wcolsum_chunks(rows) * cols; }
+
+int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, const float* features, const float* E,
+                            const float* W_ih, const float* W_hh, const float* W_v, const int* tokcm,
+                            const long long* tokens_out, const float* dlogp, const float* Hs, const float* Cs,
+                            const float* Gs, float* logits, float* dHv, float* DG, float* dh, float* dc,
+                            float* dtable, float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE,
+                            float* dW_cnn, float* db_cnn, float* dW_ih, float* dW_hh, float* db_ih, float* db_hh,
+                            float* dW_v, float* db_v, int* launches) {
+  cudaStream_t st = S_(stream);
+  const int n_cell = p0 - 1 + S;
+  const size_t BH = (size_t)B * H;
+  const int SB = S * B;
+  // 1. dL/dlogits in place (log(softmax(z))[a] backward)
+  TRY(icrl_softmax_bwd(st, B, S, V, logits, V, tokens_out, dlogp));
+  bump(launches, 1);
+  const float* dZ = logits;
+  const float* Hsel = Hs + (size_t)p0 * BH;          // h after cell step p0-1+s, s = 0..S-1
+  // 2. vocab projection gradients
+  TRY(icrl_gemm_f32_impl(st, 1, 0, V, H, SB, dZ, V, Hsel, H, dW_v, H, nullptr, 0.f, gemm_ws, gemm_ws_bytes, launches));
+  TRY(icrl_wcolsum(st, SB, V, dZ, nullptr, 0, colsum_ws, db_v));
+  bump(launches, 2);
+  // 3. dL/dh from the vocab path, all steps at once
+  TRY(icrl_gemm_f32_impl(st, 0, 0, SB, H, V, dZ, V, W_v, H, dHv, H, nullptr, 0.f, nullptr, 0, launches));
+  // 4. BPTT
+  float* dh_cur = dh;
+  float* dh_nxt = dh + BH;
+  ICRL_CUDA(cudaMemsetAsync(dh_cur, 0, BH * sizeof(float), st));
+  ICRL_CUDA(cudaMemsetAsync(dc, 0, BH * sizeof(float), st));
+  for (int j = n_cell - 1; j >= 0; --j) {
+    const int s = j - (p0 - 1);
+    float* dg = DG + (size_t)j * B * 4 * H;
+    TRY(icrl_lstm_pointwise_bwd(st, B, dh_cur, s >= 0 ? dHv + (size_t)s * BH : nullptr, dc,
+                                Gs + (size_t)j * B * 4 * H, Cs + j * BH, Cs + (j + 1) * BH, dg));
+    bump(launches, 1);
+    TRY(icrl_gemm_f32_impl(st, 0, 0, B, H, 4 * H, dg, 4 * H, W_hh, H, dh_nxt, H, nullptr, 0.f, nullptr, 0, launches));
+    float* t = dh_cur; dh_cur = dh_nxt; dh_nxt = t;
+  }
+  // dh_cur = dL/dh0
+  // 5. recurrent weight gradient: DG^T [2048 x nB] * H_prev [nB x 512]
+  const long long nB = (long long)n_cell * B;
+  TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, H, (int)nB, DG, 4 * H, Hs, H, dW_hh, H, nullptr, 0.f, gemm_ws, gemm_ws_bytes,
+                         launches));
+  // 6. gate-table gradient, then its factors
+  ICRL_CUDA(cudaMemsetAsync(dtable, 0, (size_t)V * 4 * H * sizeof(float), st));
+  TRY(icrl_scatter_add_rows(st, nB, 4 * H, DG, tokcm, dtable));
+  bump(launches, 1);
+  TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, H, V, dtable, 4 * H, E, H, dW_ih, H, nullptr, 0.f, nullptr, 0, launches));
+  TRY(icrl_gemm_f32_impl(st, 0, 0, V, H, 4 * H, dtable, 4 * H, W_ih, H, dE, H, nullptr, 0.f, nullptr, 0, launches));
+  TRY(icrl_wcolsum(st, V, 4 * H, dtable, nullptr, 0, colsum_ws, db_ih));
+  bump(launches, 2);
+  ICRL_CUDA(cudaMemcpyAsync(db_hh, db_ih, 4 * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // 7. cnn2linear
+  TRY(icrl_gemm_f32_impl(st, 1, 0, H, H, B, dh_cur, H, features, H, dW_cnn, H, nullptr, 0.f, nullptr, 0, launches));
+  TRY(icrl_wcolsum(st, B, H, dh_cur, nullptr, 0, colsum_ws, db_cnn));
+  bump(launches, 2);
+  return ICRL_OK;
+}
+
+long long icrl_stream_len(int B, int p0, int S, int extra) {
+  return (long long)B * ((long long)S * (p0 + extra) + (long long)S * (S - 1) / 2);
+}
+
+int icrl_build_stream(void* stream, int B, int p0, int S, int extra, const int* tokcm, int* stream_out, int* take,
+                      int* take_pos, int* launches) {
+  ICRL_REQUIRE(icrl_stream_len(B, p0, S, extra) < (1ll << 31), "token stream longer than 2^31");
+  TRY(icrl_build_stream_impl(S_(stream), B, p0, S, extra, tokcm, stream_out, take, take_pos));
+  bump(launches, 1);
+  return ICRL_OK;
+}
+
+size_t icrl_chain_sync_bytes(void) { return icrl_chain_sync_bytes_impl(); }
+
+int icrl_chain_lstm_fwd(void* stream, const int* tok_stream, int T, const float* table, const float* W_hh,
+                        const float* h0, const float* c0, float* stash_h, float* stash_c, float* stash_gates,
+                        float* h_out, float* c_out, void* sync_state, int* launches) {
+  TRY(icrl_chain_lstm_fwd_impl(S_(stream), tok_stream, T, table, W_hh, h0, c0, stash_h, stash_c, stash_gates, h_out,
+                               c_out, sync_state));
+  bump(launches, 1);
+  return ICRL_OK;
+}
+
+int icrl_chain_gru_fwd(void* stream, const int* tok_stream, int T, const float* table, const float* W_hh,
+                       const float* b_hn, const float* h0, float* stash_h, float* h_out, void* sync_state,
+                       int* launches) {
+  TRY(icrl_chain_gru_fwd_impl(S_(stream), tok_stream, T, table, W_hh, b_hn, h0, stash_h, h_out, sync_state));
+  bump(launches, 1);
+  return ICRL_OK;
+}
+
+int icrl_chains_fwd_fused(void* stream, const int* v_stream, int v_T, const float* v_table, const float* v_W_hh,
+                          float* v_stash_h, float* v_stash_c, float* v_stash_gates, const int* r_stream, int r_T,
+                          const float* r_table, const float* r_W_hh, const float* r_b_hn, float* r_stash_h,
+                          void* sync_state, int* launches) {
+  TRY(icrl_chains_fwd_fused_impl(S_(stream), v_stream, v_T, v_table, v_W_hh, v_stash_h, v_stash_c, v_stash_gates,
+                                 r_stream, r_T, r_table, r_W_hh, r_b_hn, r_stash_h, sync_state));
+  bump(launches, 1);
+  return ICRL_OK;
+}
+
+int icrl_chain_lstm_bwd(void* stream, int T, const float* W_hh, const float* stash_gates, const float* stash_c,
+                        const int* take, const float* dh_take, float* dgates, void* sync_state, int* launches) {
+  TRY(icrl_chain_lstm_bwd_impl(S_(stream), T, W_hh, stash_gates, stash_c, take, dh_take, dgates, sync_state));
+  bump(launches, 1);
+  return ICRL_OK;
+}
+
+int icrl_chain_check(void* stream, void* sync_state) { return icrl_chain_check_impl(S_(stream), sync_state); }
+
+int icrl_gather_rows(void* stream, long long R, const float* src, const int* idx, long long row_offset, float* dst,
+                     int* launches) {
+  TRY(icrl_gather_rows_impl(S_(stream), R, src, idx, row_offset, dst));
+  bump(launches, 1);
+  return ICRL_OK;
+}
+
+int icrl_value_head_fwd(void* stream, int B, int S, const float* features, const float* h_take, const float* w_eff,
+                        const float* b_eff, float* values, int* launches) {
+  TRY(icrl_value_head_fwd_impl(S_(stream), B, S, features, h_take, w_eff, b_eff, values));
+  bump(launches, 1);
+  return ICRL_OK;
+}
+
+int icrl_value_head_bwd(void* stream, int B, int S, const float* features, const float* h_take, const float* dv_sb,
+                        const float* sum_dv, const float* W1, const float* b1, const float* W2, const float* w_eff,
+                        float* dh_take, float* dW1, float* db1, float* dW2, float* db2, float* ws, int* launches) {
+  cudaStream_t st = S_(stream);
+  const long long SB = (long long)S * B;
+  float* g = ws;                  // [1024] = sum dv * [f, h]
+  float* part = ws + 2 * H;
+  TRY(icrl_wcolsum(st, SB, H, features, dv_sb, B, part, g));          // row r = s*B+b -> features[b]
+  TRY(icrl_wcolsum(st, SB, H, h_take, dv_sb, 0, part, g + H));
+  TRY(icrl_value_head_grads_impl(st, g, sum_dv, W1, b1, W2, dW1, db1, dW2, db2));
+  TRY(icrl_value_head_dh_impl(st, SB, dv_sb, w_eff, dh_take));
+  bump(launches, 6);
+  return ICRL_OK;
+}
+
+int icrl_value_chain_param_grads(void* stream, int T, int V, const int* tok_stream, const float* dgates,
+                                 const float* stash_h, const float* E, const float* W_ih, float* dtable,
+                                 float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE, float* dW_ih,
+                                 float* dW_hh, float* db_ih, float* db_hh, int* launches) {
+  cudaStream_t st = S_(stream);
+  // dW_hh = sum_t dgates_t (x) h_{t-1};  stash_h row t = h_{t-1}
+  TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, H, T, dgates, 4 * H, stash_h, H, dW_hh, H, nullptr, 0.f, gemm_ws,
+                         gemm_ws_bytes, launches));
+  ICRL_CUDA(cudaMemsetAsync(dtable, 0, (size_t)V * 4 * H * sizeof(float), st));
+  TRY(icrl_scatter_add_rows(st, T, 4 * H, dgates, tok_stream, dtable));
+  bump(launches, 1);
+  TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, H, V, dtable, 4 * H, E, H, dW_ih, H, nullptr, 0.f, nullptr, 0, launches));
+  TRY(icrl_gemm_f32_impl(st, 0, 0, V, H, 4 * H, dtable, 4 * H, W_ih, H, dE, H, nullptr, 0.f, nullptr, 0, launches));
+  TRY(icrl_wcolsum(st, V, 4 * H, dtable, nullptr, 0, colsum_ws, db_ih));
+  bump(launches, 2);
+  ICRL_CUDA(cudaMemcpyAsync(db_hh, db_ih, 4 * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return ICRL_OK;
+}
+
+int icrl_reward_cosine_fwd(void* stream, int B, int S, const float* ve, const float* se, float* rewards,
+                           int* launches) {
+  TRY(icrl_reward_cosine_impl(S_(stream), B, S, ve, se, rewards));
+  bump(launches, 1);
+  return ICRL_OK;
+}
+
+int icrl_a2c_loss_fwd_bwd(void* stream, int B, int S, const float* values, const float* rewards, const float* logp,
+                          float inv_denom, float* out3, float* dv_sb, float* dlogp, float* sum_dv, int* launches) {
+  TRY(icrl_a2c_loss_impl(S_(stream), B, S, values, rewards, logp, inv_denom, out3, dv_sb, dlogp, sum_dv));
+  bump(launches, 1);
+  return ICRL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,363 @@
+// Serial-chain kernels for the reference's batch-as-time value (LSTM) and reward (GRU) RNNs.
+//
+// The reference feeds each caption COLUMN of B rows to a non-batch_first RNN, i.e. seq_len = B,
+// batch = 1, and carries the hidden state between calls (models.py:133, 226; reset once per
+// minibatch, trainers.py:495-496).  A minibatch is therefore ONE strictly serial recurrence over
+// T = B * sum_s (p0 + s [+1]) tokens.  It is latency bound: each step is a batch-1 GEMV against
+// W_hh followed by the cell update, and step t+1 cannot start before all of h_t exists.
+//
+// Design (grid-persistent, cooperative launch, one chain = 64 CTAs x 8 warps):
+//   * warp w of CTA c owns hidden unit u = 8c + w: its NG gate rows of W_hh (NG x 512 floats) live
+//     in REGISTERS for the whole kernel (64 regs/lane for the LSTM, 48 for the GRU); the input half
+//     W_ih E[tok] + b is a precomputed gate table gathered by token id (prefetched one step ahead).
+//   * per step every CTA needs all 512 h values.  They are exchanged through L2 as 64-bit
+//     {float value, uint32 step tag} words (single-copy atomic, no fences, no flags): the producer
+//     lane stores one word, consumers poll the words themselves.  Double buffered by step parity.
+//   * the backward kernel runs the same scheme on the 2048 pre-activation gate gradients: warp u
+//     holds column u of W_hh (2048 floats, 64 regs/lane) and computes dh_{t-1}[u].
+//   * every spin is bounded (watchdog) and checks a global abort word, so a scheduling failure
+//     returns ICRL_ERR_WATCHDOG instead of hanging the GPU.
+#include <cooperative_groups.h>
+#include "common.cuh"
+
+namespace {
+
+constexpr int H = ICRL_H;
+constexpr int UNITS = 8;              // hidden units (= warps) per CTA
+constexpr int CHAIN_CTAS = H / UNITS; // 64 CTAs per chain
+constexpr int THREADS = UNITS * 32;
+constexpr unsigned SPIN_LIMIT = 1u << 22;
+
+__device__ __forceinline__ void ld_tagged2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+}
+__device__ __forceinline__ void st_tagged(unsigned long long* p, float v, unsigned tag) {
+  const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+
+struct ChainFwdArgs {
+  const int* stream;          // [T] token ids
+  int T;
+  const float* table;         // [V][NG*H]  W_ih E[v] + b_ih (+ b_hh where it folds)
+  const float* w_hh;          // [NG*H][H]
+  const float* b_hn;          // GRU: [H] hidden bias of the n gate (kept inside r*(.)); LSTM: unused
+  const float* h0;            // [H] or null (zeros)
+  const float* c0;            // [H] or null (LSTM)
+  float* stash_h;             // [(T+1)][H]; row 0 = initial h, row t+1 = h_t
+  float* stash_c;             // LSTM: [(T+1)][H] or null
+  float* stash_gates;         // LSTM: [T][4H] activated i,f,g,o, or null
+  float* h_out;               // [H] final h or null
+  float* c_out;               // [H] final c or null
+  unsigned long long* xchg;   // [2][H] tagged exchange words, zeroed before launch
+  int* abort_flag;            // global abort word, zeroed before launch
+};
+
+// Fetch the full exchanged vector of step `tag` (N floats, N = NV * THREADS * 2) into smem.
+template <int NV>
+__device__ __forceinline__ bool fetch_exchange(const unsigned long long* buf, unsigned tag, float* sm,
+                                               volatile int* abort_flag) {
+  bool ok = true;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int e = (v * THREADS + threadIdx.x) * 2;
+    unsigned long long a, b;
+    unsigned spins = 0;
+    while (true) {
+      ld_tagged2(buf + e, a, b);
+      if ((unsigned)(a >> 32) == tag && (unsigned)(b >> 32) == tag) break;
+      if (++spins >= SPIN_LIMIT || ((spins & 1023u) == 0 && *abort_flag != 0)) { ok = false; break; }
+    }
+    reinterpret_cast<float2*>(sm)[v * THREADS + threadIdx.x] =
+        make_float2(__uint_as_float((unsigned)a), __uint_as_float((unsigned)b));
+  }
+  return ok;
+}
+
+template <int NG>   // 4 = LSTM (i,f,g,o), 3 = GRU (r,z,n)
+__device__ void chain_fwd_body(const ChainFwdArgs& p, int cta) {
+  __shared__ __align__(16) float sh_h[2][H];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = cta * UNITS + warp;
+
+  float w[NG][16];
+#pragma unroll
+  for (int g = 0; g < NG; ++g)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 t = *reinterpret_cast<const float4*>(p.w_hh + (size_t)(g * H + unit) * H + 128 * j + 4 * lane);
+      w[g][4 * j + 0] = t.x; w[g][4 * j + 1] = t.y; w[g][4 * j + 2] = t.z; w[g][4 * j + 3] = t.w;
+    }
+  const float bhn = (NG == 3) ? p.b_hn[unit] : 0.f;
+  float c = (NG == 4 && p.c0) ? p.c0[unit] : 0.f;
+  float hprev = p.h0 ? p.h0[unit] : 0.f;
+  if (lane == 0) {
+    p.stash_h[unit] = hprev;
+    if (NG == 4 && p.stash_c) p.stash_c[unit] = c;
+  }
+  // step-0 vector straight from h0
+  for (int i = threadIdx.x; i < H; i += THREADS) sh_h[0][i] = p.h0 ? p.h0[i] : 0.f;
+
+  // token / gate-table prefetch pipeline (tokens are known up front)
+  int tok_next = p.T > 1 ? p.stream[1] : 0;
+  float xg[NG];
+  {
+    const int tok0 = p.stream[0];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) xg[g] = p.table[(size_t)tok0 * (NG * H) + g * H + unit];
+  }
+
+  for (int t = 0; t < p.T; ++t) {
+    const int buf = t & 1;
+    bool ok = true;
+    if (t > 0) ok = fetch_exchange<1>(p.xchg + (size_t)((t - 1) & 1) * H, (unsigned)t, sh_h[buf], p.abort_flag);
+    if (__syncthreads_or(!ok)) {
+      if (threadIdx.x == 0) atomicExch(p.abort_flag, 1);
+      return;
+    }
+    // prefetch next step's gate-table entries and the token after it
+    float xg_n[NG];
+    {
+      const int tk = tok_next;
+      if (t + 1 < p.T) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) xg_n[g] = p.table[(size_t)tk * (NG * H) + g * H + unit];
+      } else {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) xg_n[g] = 0.f;
+      }
+      tok_next = (t + 2 < p.T) ? p.stream[t + 2] : 0;
+    }
+    // batch-1 GEMV: NG rows x 512, weights in registers, h from smem
+    float acc[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) acc[g] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 hv = *reinterpret_cast<const float4*>(&sh_h[buf][128 * j + 4 * lane]);
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        acc[g] = fmaf(w[g][4 * j + 0], hv.x, acc[g]);
+        acc[g] = fmaf(w[g][4 * j + 1], hv.y, acc[g]);
+        acc[g] = fmaf(w[g][4 * j + 2], hv.z, acc[g]);
+        acc[g] = fmaf(w[g][4 * j + 3], hv.w, acc[g]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int g = 0; g < NG; ++g) acc[g] += __shfl_xor_sync(0xffffffffu, acc[g], o);
+
+    float hnew;
+    if constexpr (NG == 4) {
+      const float i = sigmoidf_acc(acc[0] + xg[0]);
+      const float f = sigmoidf_acc(acc[1] + xg[1]);
+      const float g = tanhf(acc[2] + xg[2]);
+      const float o = sigmoidf_acc(acc[3 % NG] + xg[3 % NG]);
+      c = f * c + i * g;
+      hnew = o * tanhf(c);
+      if (p.stash_gates) {
+        const float sel = lane == 0 ? i : (lane == 1 ? f : (lane == 2 ? g : o));
+        if (lane < 4) p.stash_gates[(size_t)t * 4 * H + lane * H + unit] = sel;
+      }
+      if (p.stash_c && lane == 4) p.stash_c[(size_t)(t + 1) * H + unit] = c;
+    } else {
+      const float r = sigmoidf_acc(acc[0] + xg[0]);
+      const float z = sigmoidf_acc(acc[1] + xg[1]);
+      const float n = tanhf(xg[2] + r * (acc[2] + bhn));
+      hnew = (1.f - z) * n + z * hprev;
+    }
+    hprev = hnew;
+    if (lane == 0) st_tagged(p.xchg + (size_t)buf * H + unit, hnew, (unsigned)(t + 1));
+    if (lane == 5) p.stash_h[(size_t)(t + 1) * H + unit] = hnew;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) xg[g] = xg_n[g];
+  }
+  if (lane == 0) {
+    if (p.h_out) p.h_out[unit] = hprev;
+    if (NG == 4 && p.c_out) p.c_out[unit] = c;
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) chain_lstm_fwd_kernel(ChainFwdArgs a) { chain_fwd_body<4>(a, blockIdx.x); }
+__global__ void __launch_bounds__(THREADS, 1) chain_gru_fwd_kernel(ChainFwdArgs a) { chain_fwd_body<3>(a, blockIdx.x); }
+// value LSTM chain on CTAs 0..63 and reward GRU chain on CTAs 64..127 of one cooperative launch
+__global__ void __launch_bounds__(THREADS, 1) chains_fwd_fused_kernel(ChainFwdArgs lstm, ChainFwdArgs gru) {
+  if (blockIdx.x < CHAIN_CTAS) chain_fwd_body<4>(lstm, blockIdx.x);
+  else chain_fwd_body<3>(gru, blockIdx.x - CHAIN_CTAS);
+}
+
+struct ChainBwdArgs {
+  int T;
+  const float* w_hh;          // [4H][H]
+  const float* stash_gates;   // [T][4H] activated i,f,g,o
+  const float* stash_c;       // [(T+1)][H]
+  const int* take;            // [T]  row of dh_take injected at step t, or -1
+  const float* dh_take;       // [S*B][H] dL/dh at the take positions (from the value head)
+  float* dgates;              // [T][4H] pre-activation gate gradients (output, feeds dW_hh / table grads)
+  unsigned long long* xchg;   // [2][4H]
+  int* abort_flag;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_kernel(ChainBwdArgs p) {
+  __shared__ __align__(16) float sh_dg[2][4 * H];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * UNITS + warp;
+
+  // column `unit` of W_hh: element j = 128*jj + 4*lane + q  ->  w[4*jj + q]
+  float w[64];
+#pragma unroll
+  for (int jj = 0; jj < 16; ++jj)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[4 * jj + q] = p.w_hh[(size_t)(128 * jj + 4 * lane + q) * H + unit];
+
+  float dc = 0.f;
+  // prefetch pipeline for the stashed activations of step t and the injected head gradient
+  auto load_step = [&](int t, float& gi, float& gf, float& gg, float& go, float& cc, float& cp, float& inj) {
+    const float* ga = p.stash_gates + (size_t)t * 4 * H;
+    gi = ga[unit]; gf = ga[H + unit]; gg = ga[2 * H + unit]; go = ga[3 * H + unit];
+    cc = p.stash_c[(size_t)(t + 1) * H + unit];
+    cp = p.stash_c[(size_t)t * H + unit];
+    const int tk = p.take[t];
+    inj = tk >= 0 ? p.dh_take[(size_t)tk * H + unit] : 0.f;
+  };
+  float gi, gf, gg, go, cc, cp, inj;
+  load_step(p.T - 1, gi, gf, gg, go, cc, cp, inj);
+
+  for (int it = 0; it < p.T; ++it) {
+    const int t = p.T - 1 - it;
+    const int buf = it & 1;
+    bool ok = true;
+    if (it > 0) ok = fetch_exchange<4>(p.xchg + (size_t)((it - 1) & 1) * 4 * H, (unsigned)it, sh_dg[buf], p.abort_flag);
+    if (__syncthreads_or(!ok)) {
+      if (threadIdx.x == 0) atomicExch(p.abort_flag, 1);
+      return;
+    }
+    float ngi = 0.f, ngf = 0.f, ngg = 0.f, ngo = 0.f, ncc = 0.f, ncp = 0.f, ninj = 0.f;
+    if (t > 0) load_step(t - 1, ngi, ngf, ngg, ngo, ncc, ncp, ninj);
+
+    float dh = 0.f;
+    if (it > 0) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        const float4 v = *reinterpret_cast<const float4*>(&sh_dg[buf][128 * jj + 4 * lane]);
+        a0 = fmaf(w[4 * jj + 0], v.x, a0);
+        a1 = fmaf(w[4 * jj + 1], v.y, a1);
+        a2 = fmaf(w[4 * jj + 2], v.z, a2);
+        a3 = fmaf(w[4 * jj + 3], v.w, a3);
+      }
+      dh = warp_sum((a0 + a1) + (a2 + a3));
+    }
+    dh += inj;
+    const float tc = tanhf(cc);
+    const float dct = dc + dh * go * (1.f - tc * tc);
+    const float di = dct * gg * gi * (1.f - gi);
+    const float df = dct * cp * gf * (1.f - gf);
+    const float dg = dct * gi * (1.f - gg * gg);
+    const float dob = dh * tc * go * (1.f - go);
+    dc = dct * gf;
+    if (lane < 4) {
+      const float sel = lane == 0 ? di : (lane == 1 ? df : (lane == 2 ? dg : dob));
+      st_tagged(p.xchg + (size_t)buf * 4 * H + lane * H + unit, sel, (unsigned)(it + 1));
+      p.dgates[(size_t)t * 4 * H + lane * H + unit] = sel;
+    }
+    gi = ngi; gf = ngf; gg = ngg; go = ngo; cc = ncc; cp = ncp; inj = ninj;
+  }
+}
+
+int coop_launch(const void* fn, int grid, void** args, cudaStream_t st) {
+  int dev = 0, coop = 0, sms = 0, per_sm = 0;
+  ICRL_CUDA(cudaGetDevice(&dev));
+  ICRL_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  ICRL_REQUIRE(coop, "device lacks cooperative launch");
+  ICRL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  ICRL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, THREADS, 0));
+  ICRL_REQUIRE(per_sm * sms >= grid, "chain grid is not co-resident on this device");
+  ICRL_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(THREADS), args, 0, st));
+  return ICRL_OK;
+}
+
+}  // namespace
+
+int icrl_chain_ctas() { return CHAIN_CTAS; }
+
+static ChainFwdArgs make_fwd(const int* stream, int T, const float* table, const float* w_hh, const float* b_hn,
+                             const float* h0, const float* c0, float* stash_h, float* stash_c, float* stash_gates,
+                             float* h_out, float* c_out, unsigned long long* xchg, int* abort_flag) {
+  ChainFwdArgs a;
+  a.stream = stream; a.T = T; a.table = table; a.w_hh = w_hh; a.b_hn = b_hn; a.h0 = h0; a.c0 = c0;
+  a.stash_h = stash_h; a.stash_c = stash_c; a.stash_gates = stash_gates; a.h_out = h_out; a.c_out = c_out;
+  a.xchg = xchg; a.abort_flag = abort_flag;
+  return a;
+}
+
+// sync_state layout (device, caller-owned, >= icrl_chain_sync_bytes(), zeroed once by the caller):
+// [0,64) sticky abort word (+pad; cleared only by icrl_chain_check), then exchange buffers
+// (re-zeroed before every launch): lstm fwd 2*H, gru fwd 2*H, lstm bwd 2*4H  64-bit words.
+size_t icrl_chain_sync_bytes_impl() { return 64 + sizeof(unsigned long long) * (2 * H + 2 * H + 2 * 4 * H); }
+
+static int* sync_abort(void* s) { return reinterpret_cast<int*>(s); }
+static unsigned long long* sync_xchg(void* s, int which) {
+  unsigned long long* base = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(s) + 64);
+  return base + (which == 0 ? 0 : (which == 1 ? 2 * H : 4 * H));
+}
+
+int icrl_chain_lstm_fwd_impl(cudaStream_t st, const int* stream, int T, const float* table, const float* w_hh,
+                             const float* h0, const float* c0, float* stash_h, float* stash_c, float* stash_gates,
+                             float* h_out, float* c_out, void* sync_state) {
+  ICRL_REQUIRE(T > 0 && stash_h, "empty chain");
+  ICRL_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(sync_state) + 64, 0, icrl_chain_sync_bytes_impl() - 64, st));
+  ChainFwdArgs a = make_fwd(stream, T, table, w_hh, nullptr, h0, c0, stash_h, stash_c, stash_gates, h_out, c_out,
+                            sync_xchg(sync_state, 0), sync_abort(sync_state));
+  void* args[] = {&a};
+  return coop_launch((const void*)chain_lstm_fwd_kernel, CHAIN_CTAS, args, st);
+}
+
+int icrl_chain_gru_fwd_impl(cudaStream_t st, const int* stream, int T, const float* table, const float* w_hh,
+                            const float* b_hn, const float* h0, float* stash_h, float* h_out, void* sync_state) {
+  ICRL_REQUIRE(T > 0 && stash_h, "empty chain");
+  ICRL_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(sync_state) + 64, 0, icrl_chain_sync_bytes_impl() - 64, st));
+  ChainFwdArgs a = make_fwd(stream, T, table, w_hh, b_hn, h0, nullptr, stash_h, nullptr, nullptr, h_out, nullptr,
+                            sync_xchg(sync_state, 1), sync_abort(sync_state));
+  void* args[] = {&a};
+  return coop_launch((const void*)chain_gru_fwd_kernel, CHAIN_CTAS, args, st);
+}
+
+int icrl_chains_fwd_fused_impl(cudaStream_t st, const int* v_stream, int v_T, const float* v_table,
+                               const float* v_w_hh, float* v_stash_h, float* v_stash_c, float* v_stash_gates,
+                               const int* r_stream, int r_T, const float* r_table, const float* r_w_hh,
+                               const float* r_b_hn, float* r_stash_h, void* sync_state) {
+  ICRL_REQUIRE(v_T > 0 && r_T > 0, "empty chain");
+  ICRL_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(sync_state) + 64, 0, icrl_chain_sync_bytes_impl() - 64, st));
+  ChainFwdArgs a = make_fwd(v_stream, v_T, v_table, v_w_hh, nullptr, nullptr, nullptr, v_stash_h, v_stash_c,
+                            v_stash_gates, nullptr, nullptr, sync_xchg(sync_state, 0), sync_abort(sync_state));
+  ChainFwdArgs b = make_fwd(r_stream, r_T, r_table, r_w_hh, r_b_hn, nullptr, nullptr, r_stash_h, nullptr, nullptr,
+                            nullptr, nullptr, sync_xchg(sync_state, 1), sync_abort(sync_state));
+  void* args[] = {&a, &b};
+  return coop_launch((const void*)chains_fwd_fused_kernel, 2 * CHAIN_CTAS, args, st);
+}
+
+int icrl_chain_lstm_bwd_impl(cudaStream_t st, int T, const float* w_hh, const float* stash_gates, const float* stash_c,
+                             const int* take, const float* dh_take, float* dgates, void* sync_state) {
+  ICRL_REQUIRE(T > 0, "empty chain");
+  ICRL_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(sync_state) + 64, 0, icrl_chain_sync_bytes_impl() - 64, st));
+  ChainBwdArgs a;
+  a.T = T; a.w_hh = w_hh; a.stash_gates = stash_gates; a.stash_c = stash_c; a.take = take; a.dh_take = dh_take;
+  a.dgates = dgates; a.xchg = sync_xchg(sync_state, 2); a.abort_flag = sync_abort(sync_state);
+  void* args[] = {&a};
+  return coop_launch((const void*)chain_lstm_bwd_kernel, CHAIN_CTAS, args, st);
+}
+
+// Reads the abort word (synchronises the stream).  Returns ICRL_ERR_WATCHDOG if a chain gave up.
+int icrl_chain_check_impl(cudaStream_t st, void* sync_state) {
+  int flag = 0;
+  ICRL_CUDA(cudaMemcpyAsync(&flag, sync_state, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ICRL_CUDA(cudaStreamSynchronize(st));
+  if (flag != 0) {
+    ICRL_CUDA(cudaMemsetAsync(sync_state, 0, 64, st));
+    icrl_set_error("serial-chain watchdog tripped: a CTA waited > %u polls for its peers", SPIN_LIMIT);
+    return ICRL_ERR_WATCHDOG;
+  }
+  return ICRL_OK;
+}

@@ -1,0 +1,50 @@
+// Internal (non-exported) entry points shared between the translation units.
+#pragma once
+#include "common.cuh"
+
+int icrl_gemm_f32_impl(cudaStream_t st, int transA, int transB, int M, int N, int K, const float* A, int lda,
+                       const float* B, int ldb, float* C, int ldc, const float* bias, float beta, float* ws,
+                       size_t ws_bytes, int* launches);
+int icrl_lstm_pointwise_fwd(cudaStream_t st, int B, const float* gpre, const float* table, const int* tok,
+                            const float* c_prev, float* gates_act, float* c_out, float* h_out);
+int icrl_lstm_pointwise_bwd(cudaStream_t st, int B, const float* dh_rec, const float* dh_add, float* dc,
+                            const float* gates_act, const float* c_prev, const float* c_cur, float* dgpre);
+int icrl_softmax_sample(cudaStream_t st, int B, int V, const float* logits, int ldl, const double* uniforms, int greedy,
+                        const long long* forced, int* tok_next, long long* tokens_out, float* logp_out, int S, int s, float* probs_out);
+int icrl_softmax_bwd(cudaStream_t st, int B, int S, int V, float* z, int ldl, const long long* tokens_out,
+                     const float* dlogp);
+int icrl_scatter_add_rows(cudaStream_t st, long long R, int C, const float* src, const int* idx, float* dst);
+int icrl_wcolsum_chunks(long long R);
+int icrl_wcolsum(cudaStream_t st, long long R, int C, const float* X, const float* w, long long row_mod,
+                 float* partial, float* out);
+
+int icrl_pack_value_head_impl(cudaStream_t st, const float* W1, const float* b1, const float* W2, const float* b2,
+                              float* w_eff, float* b_eff);
+int icrl_value_head_fwd_impl(cudaStream_t st, int B, int S, const float* features, const float* h_take,
+                             const float* w_eff, const float* b_eff, float* values);
+int icrl_value_head_dh_impl(cudaStream_t st, long long rows, const float* dv_sb, const float* w_eff, float* dh_take);
+int icrl_value_head_grads_impl(cudaStream_t st, const float* g, const float* sdv, const float* W1, const float* b1,
+                               const float* W2, float* dW1, float* db1, float* dW2, float* db2);
+int icrl_reward_cosine_impl(cudaStream_t st, int B, int S, const float* ve, const float* se, float* rewards);
+int icrl_a2c_loss_impl(cudaStream_t st, int B, int S, const float* values, const float* rewards, const float* logp,
+                       float inv_denom, float* out3, float* dv_sb, float* dlogp, float* sum_dv);
+int icrl_build_stream_impl(cudaStream_t st, int B, int p0, int S, int extra, const int* tokcm, int* stream, int* take,
+                           int* take_pos);
+int icrl_gather_rows_impl(cudaStream_t st, long long R, const float* src, const int* idx, long long row_offset,
+                          float* dst);
+int icrl_add_gate_bias_impl(cudaStream_t st, int V, int G, int fold, const float* b_ih, const float* b_hh,
+                            float* table);
+
+size_t icrl_chain_sync_bytes_impl();
+int icrl_chain_lstm_fwd_impl(cudaStream_t st, const int* stream, int T, const float* table, const float* w_hh,
+                             const float* h0, const float* c0, float* stash_h, float* stash_c, float* stash_gates,
+                             float* h_out, float* c_out, void* sync_state);
+int icrl_chain_gru_fwd_impl(cudaStream_t st, const int* stream, int T, const float* table, const float* w_hh,
+                            const float* b_hn, const float* h0, float* stash_h, float* h_out, void* sync_state);
+int icrl_chains_fwd_fused_impl(cudaStream_t st, const int* v_stream, int v_T, const float* v_table,
+                               const float* v_w_hh, float* v_stash_h, float* v_stash_c, float* v_stash_gates,
+                               const int* r_stream, int r_T, const float* r_table, const float* r_w_hh,
+                               const float* r_b_hn, float* r_stash_h, void* sync_state);
+int icrl_chain_lstm_bwd_impl(cudaStream_t st, int T, const float* w_hh, const float* stash_gates, const float* stash_c,
+                             const int* take, const float* dh_take, float* dgates, void* sync_state);
+int icrl_chain_check_impl(cudaStream_t st, void* sync_state);

@@ -1,0 +1,395 @@
+"""Fused A2C minibatch on the GPU: one call replaces the body of the reference's training loop
+(``trainers.py:432-480`` / ``:544-594``): rollout -> rewards -> values -> loss -> backward.
+
+Host code is PyTorch plumbing only (device memory, streams); all arithmetic runs in the CUDA
+kernels behind ``include/icrl_b200.h``.  There is no CPU fallback.
+
+Single-pass formulation (verified against the unmodified reference):
+  policy   one incremental LSTM pass with sampling (instead of re-running the prefix every step)
+  value    ONE serial LSTM chain over the column-major token stream, h taken at the last B
+           positions of each step block; head evaluated in collapsed form
+  reward   ONE serial GRU chain, semantic/visual embeds batched over all steps, fused cosine
+  loss     advantage = values - rewards, gradient seeds for both networks
+  backward policy BPTT (batched GEMMs + S serial cell steps), value-chain BPTT kernel, weight
+           gradients as contractions over all steps; gradients land in one flat bucket that the
+           parameters' ``.grad`` tensors alias (ready for a single all-reduce).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+H = 512
+END_TOKEN = 2       # trainers.py:436
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class StepResult(dict):
+    """Device tensors of one minibatch; ``loss`` / ``mean_reward`` / ``mean_adv`` sync lazily."""
+
+    def _stat(self, i):
+        return float(self["stats"][i].item())
+
+    @property
+    def loss(self):
+        return self._stat(0)
+
+    @property
+    def mean_reward(self):
+        return self._stat(1)
+
+    @property
+    def mean_adv(self):
+        return self._stat(2)
+
+
+class Prepared:
+    """A minibatch already resident in HBM (A2CEngine.prepare): features (B,512) f32, the prefix
+    columns int32 [p0][B], uniforms (S,B) f64 or None, and the rollout plan."""
+
+    def __init__(self, f, prefix_cm, u, B, p0, S):
+        self.f, self.prefix_cm, self.u, self.B, self.p0, self.S = f, prefix_cm, u, B, p0, S
+
+
+def plan_rollout(captions, level=None):
+    """(p0, S) as the reference derives them: caplen = max <END> column + 1 (trainers.py:436);
+    non-curriculum p0 = 1, S = caplen - 1 (:438-441); curriculum p0 = caplen - level, S = level
+    (:548-554).  Raises like the reference when no row holds <END>."""
+    caps = np.asarray(captions)
+    cols = np.nonzero(caps == END_TOKEN)[1]
+    if cols.size == 0:
+        raise ValueError("no <END> (=2) token in the caption batch (trainers.py:436 would fail on max())")
+    caplen = int(cols.max()) + 1
+    if level is None:
+        return 1, caplen - 1
+    return caplen - int(level), int(level)
+
+
+class A2CEngine:
+    def __init__(self, a2c_network, reward_network):
+        self.policy = a2c_network.policy_network
+        self.value = a2c_network.value_network
+        self.reward = reward_network
+        self.a2c = a2c_network
+        dev = self.policy.linear2vocab.weight.device
+        if dev.type != "cuda":
+            raise _lib.IcrlError("A2CEngine needs the networks on a CUDA device (no CPU fallback)")
+        _lib.load()
+        self.device = dev
+        self.V = self.policy.linear2vocab.weight.shape[0]
+        self._bufs = {}
+        self.launches = _lib.Launches()
+        self.phase_events = None          # set to [] to record (name, start, end) CUDA events per phase
+        with torch.cuda.device(dev):
+            self.sync_state = torch.zeros(int(_lib.call("icrl_chain_sync_bytes")), dtype=torch.uint8, device=dev)
+        self._check_params()
+        self._bind_flat_grads()
+
+    # ------------------------------------------------------------------ parameters / gradients
+    def _params(self):
+        return list(self.a2c.parameters())
+
+    def _check_params(self):
+        for p in list(self.a2c.parameters()) + list(self.reward.parameters()):
+            if p.dtype != torch.float32 or not p.is_contiguous() or p.device != self.device:
+                raise _lib.IcrlError("parameters must be contiguous float32 on %s" % self.device)
+
+    def _bind_flat_grads(self):
+        """One flat fp32 bucket in a2c.parameters() order; every .grad is a view into it."""
+        ps = [p for p in self._params() if p.requires_grad]
+        n = sum(p.numel() for p in ps)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self._grad_views = []
+        off = 0
+        for p in ps:
+            v = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+            self._grad_views.append((p, v))
+        self._attach_grads()
+
+    def _attach_grads(self):
+        for p, v in self._grad_views:
+            if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                p.grad = v
+
+    def _g(self, p):
+        """Gradient destination for parameter p (a scratch buffer if p is frozen)."""
+        for q, v in self._grad_views:
+            if q is p:
+                return v
+        return self._buf("frozen_grad_%d" % id(p), p.numel())
+
+    def _buf(self, name, numel, dtype=torch.float32):
+        numel = int(max(numel, 1))
+        t = self._bufs.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            t = torch.empty(numel, dtype=dtype, device=self.device)
+            self._bufs[name] = t
+        return t
+
+    class _Phase:
+        def __init__(self, eng, name):
+            self.eng, self.name = eng, name
+
+        def __enter__(self):
+            if self.eng.phase_events is not None:
+                self.t0 = torch.cuda.Event(enable_timing=True)
+                self.t0.record(torch.cuda.current_stream(self.eng.device))
+
+        def __exit__(self, *a):
+            if self.eng.phase_events is not None:
+                t1 = torch.cuda.Event(enable_timing=True)
+                t1.record(torch.cuda.current_stream(self.eng.device))
+                self.eng.phase_events.append((self.name, self.t0, t1))
+
+    def _phase(self, name):
+        return A2CEngine._Phase(self, name)
+
+    def phase_times_ms(self):
+        """Sum of CUDA-event durations per phase since phase_events was last reset (syncs)."""
+        torch.cuda.synchronize(self.device)
+        out = {}
+        for name, a, b in self.phase_events or []:
+            out.setdefault(name, []).append(a.elapsed_time(b))
+        return out
+
+    @property
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ packing
+    def pack_weights(self, reward=True):
+        """Rebuild the derived operands from the current parameters (after every optimizer step):
+        the three gate tables W_ih E + b and the collapsed value head."""
+        st, L, V = self._stream, self.launches.ref, self.V
+        P, Vn, R = self.policy, self.value, self.reward
+        c = _lib.call
+        c("icrl_pack_gate_table", st, V, 4 * H, 4 * H, _p(P.caption_embedding.weight), _p(P.lstm.weight_ih_l0),
+          _p(P.lstm.bias_ih_l0), _p(P.lstm.bias_hh_l0), _p(self._buf("p_table", V * 4 * H)), L)
+        c("icrl_pack_gate_table", st, V, 4 * H, 4 * H, _p(Vn.valrnn.caption_embedding.weight),
+          _p(Vn.valrnn.lstm.weight_ih_l0), _p(Vn.valrnn.lstm.bias_ih_l0), _p(Vn.valrnn.lstm.bias_hh_l0),
+          _p(self._buf("v_table", V * 4 * H)), L)
+        c("icrl_pack_value_head", st, _p(Vn.linear1.weight), _p(Vn.linear1.bias), _p(Vn.linear2.weight),
+          _p(Vn.linear2.bias), _p(self._buf("v_weff", 2 * H)), _p(self._buf("v_beff", 1)), L)
+        if reward:
+            self.pack_reward()
+
+    def pack_reward(self):
+        R, V = self.reward, self.V
+        _lib.call("icrl_pack_gate_table", self._stream, V, 3 * H, 2 * H, _p(R.rewrnn.caption_embedding.weight),
+                  _p(R.rewrnn.gru.weight_ih_l0), _p(R.rewrnn.gru.bias_ih_l0), _p(R.rewrnn.gru.bias_hh_l0),
+                  _p(self._buf("r_table", V * 3 * H)), self.launches.ref)
+
+    def _gemm(self, ta, tb, M, N, K, A, lda, B, ldb, C, ldc, bias=None, beta=0.0):
+        _lib.call("icrl_gemm_f32", self._stream, ta, tb, M, N, K, _p(A), lda, _p(B), ldb, _p(C), ldc, _p(bias),
+                  beta, None, 0, self.launches.ref)
+
+    # ------------------------------------------------------------------ inputs
+    def prepare(self, features, captions, uniforms=None, level=None, plan=None):
+        """Host -> HBM staging of one minibatch (the copies the end-to-end timing includes)."""
+        p0, S = plan if plan is not None else plan_rollout(captions, level)
+        if p0 < 1:
+            return None
+        dev = self.device
+        caps = captions.cpu().numpy() if isinstance(captions, torch.Tensor) else np.asarray(captions)
+        B = caps.shape[0]
+        f = torch.as_tensor(features)
+        if f.dtype != torch.float32:
+            f = f.float()
+        f = f.to(dev, non_blocking=True).contiguous()
+        pre = torch.from_numpy(np.ascontiguousarray(caps[:, :p0].T).astype(np.int32))
+        prefix_cm = pre.to(dev, non_blocking=True)
+        u = None
+        if uniforms is not None:
+            u = torch.as_tensor(uniforms, dtype=torch.float64).to(dev, non_blocking=True).contiguous()
+            assert tuple(u.shape) == (S, B), "uniforms must be (S,B) float64"
+        return Prepared(f, prefix_cm, u, B, p0, S)
+
+    def _stage_inputs(self, prep, forced):
+        B, p0, S = prep.B, prep.p0, prep.S
+        tokcm = self._buf("tokcm", (p0 + S) * B, torch.int32)
+        tokcm[:p0 * B].copy_(prep.prefix_cm.reshape(-1), non_blocking=True)
+        fo = None
+        if forced is not None:
+            fo = torch.as_tensor(np.asarray(forced), dtype=torch.int64).to(self.device).contiguous()
+            assert tuple(fo.shape) == (B, S)
+        return prep.f, tokcm, prep.u, fo, B
+
+    # ------------------------------------------------------------------ phases
+    def _policy_forward(self, f, tokcm, u, fo, B, p0, S, greedy):
+        V, P = self.V, self.policy
+        n_cell = p0 - 1 + S
+        tokens = torch.empty((B, S), dtype=torch.int64, device=self.device)
+        logp = torch.empty((B, S), dtype=torch.float32, device=self.device)
+        Hs = self._buf("p_Hs", (n_cell + 1) * B * H)
+        Cs = self._buf("p_Cs", (n_cell + 1) * B * H)
+        Gs = self._buf("p_Gs", n_cell * B * 4 * H)
+        logits = self._buf("p_logits", S * B * V)
+        gpre = self._buf("p_gpre", B * 4 * H)
+        with self._phase("policy_fwd"):
+          _lib.call("icrl_policy_rollout_fwd", self._stream, B, V, p0, S, int(bool(greedy)), _p(f),
+                  _p(P.cnn2linear.weight), _p(P.cnn2linear.bias), _p(self._bufs["p_table"]),
+                  _p(P.lstm.weight_hh_l0), _p(P.linear2vocab.weight), _p(P.linear2vocab.bias), _p(u), _p(fo),
+                  _p(tokcm), _p(tokens), _p(logp), _p(Hs), _p(Cs), _p(Gs), _p(logits), _p(gpre), self.launches.ref)
+        return tokens, logp
+
+    def _streams(self, tokcm, B, p0, S):
+        st, L = self._stream, self.launches.ref
+        Tv = int(_lib.call("icrl_stream_len", B, p0, S, 0))
+        Tr = int(_lib.call("icrl_stream_len", B, p0, S, 1))
+        i32 = torch.int32
+        v_stream, v_take, v_pos = self._buf("v_stream", Tv, i32), self._buf("v_take", Tv, i32), self._buf("v_pos", S * B, i32)
+        r_stream, r_pos = self._buf("r_stream", Tr, i32), self._buf("r_pos", S * B, i32)
+        _lib.call("icrl_build_stream", st, B, p0, S, 0, _p(tokcm), _p(v_stream), _p(v_take), _p(v_pos), L)
+        _lib.call("icrl_build_stream", st, B, p0, S, 1, _p(tokcm), _p(r_stream), None, _p(r_pos), L)
+        return Tv, Tr
+
+    def _chains_forward(self, f, B, S, Tv, Tr, train):
+        st, L, b = self._stream, self.launches.ref, self._bufs
+        Vn, R = self.value, self.reward
+        v_h = self._buf("v_stash_h", (Tv + 1) * H)
+        v_c = self._buf("v_stash_c", (Tv + 1) * H)
+        v_g = self._buf("v_stash_g", Tv * 4 * H)
+        r_h = self._buf("r_stash_h", (Tr + 1) * H)
+        with self._phase("chains_fwd_fused"):
+          _lib.call("icrl_chains_fwd_fused", st, _p(b["v_stream"]), Tv, _p(b["v_table"]), _p(Vn.valrnn.lstm.weight_hh_l0),
+                  _p(v_h), _p(v_c), _p(v_g), _p(b["r_stream"]), Tr, _p(b["r_table"]), _p(R.rewrnn.gru.weight_hh_l0),
+                  _p(R.rewrnn.gru.bias_hh_l0[2 * H:]), _p(r_h), _p(self.sync_state), L)
+        SB = S * B
+        v_take_h = self._buf("v_take_h", SB * H)
+        r_take_h = self._buf("r_take_h", SB * H)
+        _lib.call("icrl_gather_rows", st, SB, _p(v_h), _p(b["v_pos"]), 1, _p(v_take_h), L)
+        _lib.call("icrl_gather_rows", st, SB, _p(r_h), _p(b["r_pos"]), 1, _p(r_take_h), L)
+        values = torch.empty((B, S), dtype=torch.float32, device=self.device)
+        rewards = torch.empty((B, S), dtype=torch.float32, device=self.device)
+        _lib.call("icrl_value_head_fwd", st, B, S, _p(f), _p(v_take_h), _p(b["v_weff"]), _p(b["v_beff"]), _p(values), L)
+        se = self._buf("r_se", SB * H)
+        ve = self._buf("r_ve", B * H)
+        self._gemm(0, 1, SB, H, H, r_take_h, H, R.semantic_embed.weight, H, se, H, R.semantic_embed.bias)
+        self._gemm(0, 1, B, H, H, f, H, R.visual_embed.weight, H, ve, H, R.visual_embed.bias)
+        _lib.call("icrl_reward_cosine_fwd", st, B, S, _p(ve), _p(se), _p(rewards), L)
+        return values, rewards
+
+    def _backward(self, f, tokcm, tokens, B, p0, S, Tv):
+        st, L, b, V = self._stream, self.launches.ref, self._bufs, self.V
+        P, Vn = self.policy, self.value
+        SB = S * B
+        n_cell = p0 - 1 + S
+        g = self._g
+        cs_rows = max(SB, V, B)
+        colsum_ws = self._buf("colsum_ws", int(_lib.call("icrl_colsum_ws_floats", cs_rows, 4 * H)) + 2 * H + 4 * H * 8)
+        gemm_ws_floats = 24 * 4 * H * H
+        gemm_ws = self._buf("gemm_ws", gemm_ws_floats)
+        # value head -> dh at the take positions + head gradients
+        dh_take = self._buf("v_dh_take", SB * H)
+        _lib.call("icrl_value_head_bwd", st, B, S, _p(f), _p(b["v_take_h"]), _p(b["dv_sb"]), _p(b["sum_dv"]),
+                  _p(Vn.linear1.weight), _p(Vn.linear1.bias), _p(Vn.linear2.weight), _p(b["v_weff"]), _p(dh_take),
+                  _p(g(Vn.linear1.weight)), _p(g(Vn.linear1.bias)), _p(g(Vn.linear2.weight)), _p(g(Vn.linear2.bias)),
+                  _p(colsum_ws), L)
+        # value chain BPTT (serial) and its parameter gradients (contractions over all T steps)
+        dgates = self._buf("v_dgates", Tv * 4 * H)
+        with self._phase("chain_lstm_bwd"):
+          _lib.call("icrl_chain_lstm_bwd", st, Tv, _p(Vn.valrnn.lstm.weight_hh_l0), _p(b["v_stash_g"]), _p(b["v_stash_c"]),
+                  _p(b["v_take"]), _p(dh_take), _p(dgates), _p(self.sync_state), L)
+        dtable = self._buf("dtable", V * 4 * H)
+        lstm = Vn.valrnn.lstm
+        with self._phase("value_param_grads"):
+          _lib.call("icrl_value_chain_param_grads", st, Tv, V, _p(b["v_stream"]), _p(dgates), _p(b["v_stash_h"]),
+                  _p(Vn.valrnn.caption_embedding.weight), _p(lstm.weight_ih_l0), _p(dtable), _p(colsum_ws), _p(gemm_ws),
+                  gemm_ws_floats * 4, _p(g(Vn.valrnn.caption_embedding.weight)), _p(g(lstm.weight_ih_l0)),
+                  _p(g(lstm.weight_hh_l0)), _p(g(lstm.bias_ih_l0)), _p(g(lstm.bias_hh_l0)), L)
+        # policy BPTT
+        pl = P.lstm
+        with self._phase("policy_bwd"):
+          _lib.call("icrl_policy_rollout_bwd", st, B, V, p0, S, _p(f), _p(P.caption_embedding.weight), _p(pl.weight_ih_l0),
+                  _p(pl.weight_hh_l0), _p(P.linear2vocab.weight), _p(tokcm), _p(tokens), _p(b["dlogp"]), _p(b["p_Hs"]),
+                  _p(b["p_Cs"]), _p(b["p_Gs"]), _p(b["p_logits"]), _p(self._buf("p_dHv", SB * H)),
+                  _p(self._buf("p_DG", n_cell * B * 4 * H)), _p(self._buf("p_dh", 2 * B * H)), _p(self._buf("p_dc", B * H)),
+                  _p(dtable), _p(colsum_ws), _p(gemm_ws), gemm_ws_floats * 4, _p(g(P.caption_embedding.weight)),
+                  _p(g(P.cnn2linear.weight)), _p(g(P.cnn2linear.bias)), _p(g(pl.weight_ih_l0)), _p(g(pl.weight_hh_l0)),
+                  _p(g(pl.bias_ih_l0)), _p(g(pl.bias_hh_l0)), _p(g(P.linear2vocab.weight)), _p(g(P.linear2vocab.bias)), L)
+
+    # ------------------------------------------------------------------ public API
+    def step(self, features, captions=None, uniforms=None, level=None, greedy=False, backward=True,
+             global_rows=None, forced_tokens=None, repack=True, check=True, plan=None):
+        """One A2C minibatch.  `features` may be a Prepared batch (already in HBM) or host/device data:
+        features (B,512) f32, captions (B,L) int (host), uniforms (S,B) f64 or None
+        (None draws them from numpy's global MT19937 stream exactly as np.random.choice would,
+        trainers.py:447-450).  Returns StepResult or None when the curriculum level does not fit
+        (trainers.py:550).  Gradients are written to the parameters' .grad (flat bucket)."""
+        with torch.cuda.device(self.device):
+            if isinstance(features, Prepared):
+                prep = features
+            else:
+                p0, S = plan if plan is not None else plan_rollout(captions, level)
+                if p0 < 1:
+                    return None
+                if S < 1:
+                    raise ValueError("rollout needs at least one sampled step")
+                B = int(captions.shape[0])
+                if uniforms is None and not greedy and forced_tokens is None:
+                    uniforms = np.random.random_sample(S * B).reshape(S, B)
+                prep = self.prepare(features, captions, uniforms, plan=(p0, S))
+            p0, S = prep.p0, prep.S
+            self._attach_grads()
+            if repack:
+                self.pack_weights(reward="r_table" not in self._bufs)
+            f, tokcm, u, fo, B = self._stage_inputs(prep, forced_tokens)
+            tokens, logp = self._policy_forward(f, tokcm, u, fo, B, p0, S, greedy)
+            Tv, Tr = self._streams(tokcm, B, p0, S)
+            values, rewards = self._chains_forward(f, B, S, Tv, Tr, backward)
+            stats = torch.empty(3, dtype=torch.float32, device=self.device)
+            dv_sb = self._buf("dv_sb", S * B)
+            dlogp = self._buf("dlogp", S * B)
+            sum_dv = self._buf("sum_dv", 1)
+            inv = 1.0 / float((global_rows or B) * S)
+            _lib.call("icrl_a2c_loss_fwd_bwd", self._stream, B, S, _p(values), _p(rewards), _p(logp), inv, _p(stats),
+                      _p(dv_sb), _p(dlogp), _p(sum_dv), self.launches.ref)
+            if backward:
+                self._backward(f, tokcm, tokens, B, p0, S, Tv)
+            if check:
+                _lib.call("icrl_chain_check", self._stream, _p(self.sync_state))
+        return StepResult(tokens=tokens, logp=logp, values=values, rewards=rewards, stats=stats, p0=p0, S=S, B=B,
+                          Tv=Tv, Tr=Tr)
+
+    def get_rewards(self, features, captions):
+        """GetRewards on whole captions from zero state (trainers.py:108-121): (B,1) tensor."""
+        caps = np.asarray(captions)
+        B, Lc = caps.shape
+        with torch.cuda.device(self.device):
+            if "r_table" not in self._bufs:
+                self.pack_reward()
+            f, tokcm, _, _, _ = self._stage_inputs(self.prepare(features, caps, plan=(Lc, 0)), None)
+            st, L, b, R = self._stream, self.launches.ref, self._bufs, self.reward
+            T = int(_lib.call("icrl_stream_len", B, Lc, 1, 0))
+            r_stream, r_pos = self._buf("r_stream", T, torch.int32), self._buf("r_pos", B, torch.int32)
+            _lib.call("icrl_build_stream", st, B, Lc, 1, 0, _p(tokcm), _p(r_stream), None, _p(r_pos), L)
+            r_h = self._buf("r_stash_h", (T + 1) * H)
+            _lib.call("icrl_chain_gru_fwd", st, _p(r_stream), T, _p(b["r_table"]), _p(R.rewrnn.gru.weight_hh_l0),
+                      _p(R.rewrnn.gru.bias_hh_l0[2 * H:]), None, _p(r_h), None, _p(self.sync_state), L)
+            r_take_h = self._buf("r_take_h", B * H)
+            _lib.call("icrl_gather_rows", st, B, _p(r_h), _p(r_pos), 1, _p(r_take_h), L)
+            se, ve = self._buf("r_se", B * H), self._buf("r_ve", B * H)
+            self._gemm(0, 1, B, H, H, r_take_h, H, R.semantic_embed.weight, H, se, H, R.semantic_embed.bias)
+            self._gemm(0, 1, B, H, H, f, H, R.visual_embed.weight, H, ve, H, R.visual_embed.bias)
+            rewards = torch.empty((B, 1), dtype=torch.float32, device=self.device)
+            _lib.call("icrl_reward_cosine_fwd", st, B, 1, _p(ve), _p(se), _p(rewards), L)
+            _lib.call("icrl_chain_check", st, _p(self.sync_state))
+        return rewards
+
+    def greedy_decode(self, features, first_col, steps=16):
+        """GenerateCaptionsGreedy (trainers.py:57-70): (B, steps+1) int64 tokens and last-step logits."""
+        first = np.asarray(first_col, dtype=np.int64).reshape(-1, 1)
+        B = first.shape[0]
+        with torch.cuda.device(self.device):
+            self.pack_weights(reward=False)
+            f, tokcm, _, _, _ = self._stage_inputs(self.prepare(features, first, plan=(1, steps)), None)
+            tokens, _ = self._policy_forward(f, tokcm, None, None, B, 1, steps, True)
+            last = self._bufs["p_logits"][(steps - 1) * B * self.V: steps * B * self.V].view(B, self.V).clone()
+            out = torch.cat((torch.from_numpy(first).to(self.device), tokens), dim=1)
+        return out, last

@@ -1,0 +1,188 @@
+"""The reference's A2C call sites (``trainers.py``) on the fused B200 engine.
+
+Same function names, argument order and return values as the reference
+(``GetRewards :108``, ``GenerateCaptionsGreedy :57``, ``a2c_training :402``,
+``a2c_curriculum_training :503``, ``train_a2c_network :312``); the per-step Python loop
+(``:441-480``) is replaced by one ``A2CEngine.step`` per minibatch.  Sampling consumes numpy's
+global MT19937 stream exactly like the reference's ``np.random.choice`` calls (one double per row
+per step, step-major), so ``np.random.seed(s)`` reproduces the reference's token ids.
+
+Supervised pretraining (``train_policy_network`` etc.) is outside the hot path: when a
+pretrained file is missing ``train_a2c_network`` raises instead of pretraining from scratch.
+"""
+import math
+import os
+
+import numpy as np
+import torch
+import torch.optim as optim
+
+from .engine import A2CEngine
+from .models import *          # noqa: F401,F403  (torch, nn, F, np, device, MAX_SEQ_LEN, classes)
+from .models import AdvantageActorCriticNetwork, PolicyNetwork, RewardNetwork, ValueNetwork, device, MAX_SEQ_LEN
+
+try:                            # tensorboard is optional plumbing (trainers.py:19)
+    from torch.utils.tensorboard import SummaryWriter
+except Exception:               # pragma: no cover
+    class SummaryWriter:        # type: ignore
+        def __init__(self, *a, **k):
+            pass
+
+        def add_scalar(self, *a, **k):
+            pass
+
+
+def _engine_for(a2c_network, reward_network):
+    eng = getattr(a2c_network, "_icrl_engine", None)
+    if eng is None or eng.reward is not reward_network:
+        eng = A2CEngine(a2c_network, reward_network)
+        object.__setattr__(a2c_network, "_icrl_engine", eng)
+    return eng
+
+
+def get_coco_minibatches(data, batch_size=100, split="train"):
+    """Random-permutation minibatch generator with the reference's tuple contract
+    (captions (B,L) int, features (B,512) f32, urls), utilities.py:160-178."""
+    n = data["%s_captions" % split].shape[0]
+    perm = torch.randperm(n)
+    for i in range(0, n, batch_size):
+        mask = perm[i:i + batch_size].numpy()
+        idxs = data["%s_image_idxs" % split][mask]
+        yield data["%s_captions" % split][mask], data["%s_features" % split][idxs], data["%s_urls" % split][idxs]
+
+
+def global_minibatch_number(epoch, batch_id, batch_size):
+    return epoch * batch_size + batch_id            # utilities.py:204-212 (sic)
+
+
+def save_a2c_model(model, save_paths):
+    """Plain state_dict files, one per path (utilities.py:286-296)."""
+    for path in ([save_paths] if isinstance(save_paths, str) else list(save_paths)):
+        torch.save(model.state_dict(), path)
+
+
+def GetRewards(features, captions, reward_network):
+    """Cosine similarity of the visual and semantic embeddings, (B,1) (trainers.py:108-121).
+    Uses and advances ``reward_network.rewrnn.hidden_cell`` like the reference."""
+    ve, se = reward_network(features, captions)
+    dev = ve.device
+    out = torch.empty((ve.shape[0], 1), dtype=torch.float32, device=dev)
+    from . import _lib
+    import ctypes
+    with torch.cuda.device(dev):
+        _lib.call("icrl_reward_cosine_fwd", ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream), ve.shape[0], 1,
+                  ctypes.c_void_p(ve.data_ptr()), ctypes.c_void_p(se.data_ptr()), ctypes.c_void_p(out.data_ptr()), None)
+    return out
+
+
+def GenerateCaptionsGreedy(features, captions, policy_network):
+    """MAX_SEQ_LEN-1 greedy steps from column 0, no early stop: (B,17) int64 (trainers.py:57-70)."""
+    eng = getattr(policy_network, "_icrl_greedy", None)
+    if eng is None:
+        eng = _PolicyOnlyEngine(policy_network)
+        object.__setattr__(policy_network, "_icrl_greedy", eng)
+    tokens, _ = eng.greedy_decode(np.asarray(features, dtype=np.float32), np.asarray(captions)[:, 0], MAX_SEQ_LEN - 1)
+    return tokens
+
+
+class _PolicyOnlyEngine(A2CEngine):
+    """A2CEngine restricted to the policy (greedy decode needs no value / reward network)."""
+
+    def __init__(self, policy_network):
+        self.policy, self.value, self.reward, self.a2c = policy_network, None, None, policy_network
+        dev = policy_network.linear2vocab.weight.device
+        if dev.type != "cuda":
+            from . import _lib
+            raise _lib.IcrlError("GenerateCaptionsGreedy needs the policy on a CUDA device (no CPU fallback)")
+        from . import _lib
+        _lib.load()
+        self.device, self.V = dev, policy_network.linear2vocab.weight.shape[0]
+        self._bufs, self.launches = {}, _lib.Launches()
+
+    def pack_weights(self, reward=False):
+        from . import _lib
+        from .engine import _p, H
+        P = self.policy
+        _lib.call("icrl_pack_gate_table", self._stream, self.V, 4 * H, 4 * H, _p(P.caption_embedding.weight),
+                  _p(P.lstm.weight_ih_l0), _p(P.lstm.bias_ih_l0), _p(P.lstm.bias_hh_l0),
+                  _p(self._buf("p_table", self.V * 4 * H)), self.launches.ref)
+
+
+def _run_minibatches(train_data, a2c_network, reward_network, optimizer, writer, batch_size, epoch, level, tag, best):
+    eng = _engine_for(a2c_network, reward_network)
+    for minibatch_id, (captions, features, _) in enumerate(get_coco_minibatches(train_data, batch_size=batch_size)):
+        res = eng.step(features, captions, level=level)
+        if res is not None:                           # curriculum: prefix shorter than 1 => skipped (trainers.py:550)
+            optimizer.step()                          # gradients already sit in .grad (flat bucket)
+            loss = res.loss
+            best = min(best, loss)
+            n = global_minibatch_number(epoch, minibatch_id, batch_size)
+            writer.add_scalar(tag + "loss", loss, n)
+            writer.add_scalar(tag + "mean-rewards", res.mean_reward, n)
+            writer.add_scalar(tag + "mean-advantage", res.mean_adv, n)
+        # trainers.py:495-496 / :611-612 -- the engine always starts its chains from zero state;
+        # the module-level carried state is reset too so mixed use stays consistent
+        reward_network.rewrnn.init_hidden()
+        a2c_network.value_network.valrnn.init_hidden()
+    return best
+
+
+def a2c_training(train_data, a2c_network, reward_network, optimizer, plot_dir, save_paths, batch_size, epochs):
+    """trainers.py:402-500."""
+    writer = SummaryWriter(log_dir=os.path.join(plot_dir, "runs"))
+    best = float("inf")
+    for epoch in range(epochs):
+        best = _run_minibatches(train_data, a2c_network, reward_network, optimizer, writer, batch_size, epoch, None,
+                                "A2C Network-episodic-", best)
+        save_a2c_model(a2c_network, save_paths)
+    return a2c_network
+
+
+def a2c_curriculum_training(train_data, a2c_network, reward_network, optimizer, plot_dir, save_paths, batch_size,
+                            epochs, curriculum):
+    """trainers.py:503-616: for each level, rollouts start from the ground-truth prefix
+    captions[:, :caplen-level] and sample `level` tokens."""
+    writer = SummaryWriter(log_dir=os.path.join(plot_dir, "runs"))
+    for level in curriculum:
+        best = float("inf")
+        for epoch in range(epochs):
+            best = _run_minibatches(train_data, a2c_network, reward_network, optimizer, writer, batch_size, epoch,
+                                    level, "A2C Curriculum Level-%s-" % level, best)
+            save_a2c_model(a2c_network, save_paths)
+    return a2c_network
+
+
+def train_a2c_network(train_data, save_paths, network_paths, plot_dir, bidirectional, epochs, batch_size,
+                      retrain_all=False, curriculum=None):
+    """trainers.py:312-399: build the three networks, load the pretrained state dicts
+    (``torch.load(path, map_location=device)`` + ``load_state_dict(strict=False)``), freeze the
+    reward network, wrap, Adam(lr=1e-4), dispatch."""
+    if retrain_all:
+        raise NotImplementedError("supervised pretraining is outside the B200 hot path (SURVEY.md 8f row 2)")
+    w2i, emb = train_data["word_to_idx"], train_data.get("embeddings")
+    nets = {}
+    for key, cls in (("reward_network", RewardNetwork), ("policy_network", PolicyNetwork), ("value_network", ValueNetwork)):
+        net = cls(w2i, pretrained_embeddings=emb, bidirectional=bidirectional).to(device)
+        if not os.path.exists(network_paths[key]):
+            raise FileNotFoundError("%s not found at %s; the reference would pretrain it from scratch "
+                                    "(trainers.py:345-370), which is outside the hot path" % (key, network_paths[key]))
+        net.load_state_dict(torch.load(network_paths[key], map_location=device), strict=False)
+        nets[key] = net
+    reward_network = nets["reward_network"]
+    reward_network.requires_grad_(False)
+    reward_network.train(False)
+    a2c_network = AdvantageActorCriticNetwork(nets["value_network"], nets["policy_network"]).to(device)
+    a2c_network.train(True)
+    optimizer = optim.Adam(a2c_network.parameters(), lr=0.0001)
+    paths = [save_paths["model_path"], network_paths["a2c_network"]]
+    if curriculum is None:
+        a2c_network = a2c_training(train_data, a2c_network, reward_network, optimizer, plot_dir, paths, batch_size, epochs)
+    else:
+        if 16 not in curriculum:
+            curriculum.append(16)                    # trainers.py:389-390
+        a2c_network = a2c_curriculum_training(train_data, a2c_network, reward_network, optimizer, plot_dir, paths,
+                                              batch_size, epochs, curriculum)
+    with open(save_paths["results_path"], "a") as fh:
+        fh.write("\n" + "-" * 10 + " network " + "-" * 10 + "\n" + str(a2c_network) + "\n" + "-" * 10 + " network "
+                 + "-" * 10 + "\n")
+    return a2c_network

@@ -1,0 +1,145 @@
+/* icrl_b200 -- C ABI of the B200-native A2C caption-training hot path.
+ *
+ * The reference (pratikpv/image-captioning-through-rl) has no FFI layer: its operator API is the
+ * Python surface of models.py plus five trainers.py call sites.  This header
+ * is the boundary the drop-in Python modules (image-captioning-through-rl_b200/models.py,
+ * trainers.py, engine.py) bind with ctypes.  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++ or torch types.
+ *   - every function returns 0 on success or an ICRL_ERR_* code; icrl_last_error() gives the text.
+ *   - all buffers are caller-owned DEVICE pointers (fp32 unless stated); the library never allocates
+ *     persistent memory.  Row-major everywhere.  H = 512 is fixed (models.py:41,160,250).
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous on it.  The only calls
+ *     that synchronise are icrl_chain_check and icrl_device_info.
+ *   - `launches` (nullable) is incremented by the number of kernels the call launched.
+ *   - token matrices: `tokcm` is int32 [n_cols][B] (column-major captions: the order in which the
+ *     reference feeds columns to its RNNs); `tokens_out` is int64 [B][S] like the reference's actions.
+ */
+#ifndef ICRL_B200_H
+#define ICRL_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICRL_OK 0
+#define ICRL_ERR_ARG 1
+#define ICRL_ERR_CUDA 2
+#define ICRL_ERR_WATCHDOG 3
+
+const char* icrl_last_error(void);
+int icrl_version(void);
+/* out[0]=SM count, out[1]=cc major, out[2]=cc minor, out[3]=cooperative launch supported */
+int icrl_device_info(int* out4);
+
+/* ---- dense contraction (replaces the cuBLAS sgemm calls behind nn.Linear / nn.LSTM input projections,
+ *      models.py:75, 82, 177-178, 259-260).  C = beta*C + bias + op(A) op(B); see gemm_simt.cu for op().
+ *      ws/ws_bytes: optional split-K workspace. */
+int icrl_gemm_f32(void* stream, int transA, int transB, int M, int N, int K, const float* A, int lda,
+                  const float* B, int ldb, float* C, int ldc, const float* bias, float beta, float* ws,
+                  size_t ws_bytes, int* launches);
+
+/* ---- weight packing, once per optimizer step (new; the reference recomputes these products at every
+ *      RNN step).  table[v][:] = W_ih E[v] + b_ih + (b_hh for the first `fold` gate rows).
+ *      LSTM: G = 2048, fold = 2048.  GRU: G = 1536, fold = 1024 (b_hn stays inside r*(.), models.py:215). */
+int icrl_pack_gate_table(void* stream, int V, int G, int fold, const float* E, const float* W_ih,
+                         const float* b_ih, const float* b_hh, float* table, int* launches);
+/* value head linear2(linear1(.)) has no activation (models.py:177-178): w_eff = W2 W1 (1024), b_eff (1). */
+int icrl_pack_value_head(void* stream, const float* W1, const float* b1, const float* W2, const float* b2,
+                         float* w_eff, float* b_eff, int* launches);
+
+/* ---- policy rollout (replaces PolicyNetwork.forward re-run per step + softmax + np.random.choice +
+ *      log-prob gather: models.py:71-84, 286; trainers.py:441-458; greedy: trainers.py:57-70).
+ *      n_cell = p0 - 1 + S LSTM cell steps; the last S are followed by vocab projection + sampling.
+ *      uniforms: float64 [S][B] (the doubles np.random.choice would draw), ignored when greedy != 0.
+ *      forced: nullable int64 [B][S]; when given, these actions are taken instead (teacher forcing for
+ *      parity checks) while log-probs / stash are still computed.
+ *      tokcm: in: columns 0..p0-1 hold the prefix; out: columns p0..p0+S-1 hold the sampled tokens.
+ *      Stash (for backward): Hs,Cs [(n_cell+1)][B][512], Gs [n_cell][B][2048], logits [S][B][V].
+ *      gpre: workspace [B][2048]. */
+int icrl_policy_rollout_fwd(void* stream, int B, int V, int p0, int S, int greedy, const float* features,
+                            const float* W_cnn, const float* b_cnn, const float* table, const float* W_hh,
+                            const float* W_v, const float* b_v, const double* uniforms, const long long* forced,
+                            int* tokcm, long long* tokens_out, float* logp, float* Hs, float* Cs, float* Gs, float* logits,
+                            float* gpre, int* launches);
+
+/* ---- policy backward through time (replaces autograd over the S prefix re-runs, trainers.py:479).
+ *      dlogp [B][S].  logits is overwritten with dL/dlogits.  Workspaces: dHv [S*B][512],
+ *      DG [n_cell*B][2048], dh [2][B][512], dc [B][512], dtable [V][2048], colsum_ws
+ *      [icrl_colsum_ws_floats(max(S*B, V), 2048)], gemm_ws/gemm_ws_bytes.  Gradients are OVERWRITTEN. */
+int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, const float* features, const float* E,
+                            const float* W_ih, const float* W_hh, const float* W_v, const int* tokcm,
+                            const long long* tokens_out, const float* dlogp, const float* Hs, const float* Cs,
+                            const float* Gs, float* logits, float* dHv, float* DG, float* dh, float* dc,
+                            float* dtable, float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE,
+                            float* dW_cnn, float* db_cnn, float* dW_ih, float* dW_hh, float* db_ih, float* db_hh,
+                            float* dW_v, float* db_v, int* launches);
+size_t icrl_colsum_ws_floats(long long rows, int cols);
+
+/* ---- token streams of the batch-as-time chains (models.py:166-169, 253-255).  Block s = columns
+ *      0..p0+s-1+extra (extra = 0 value net, 1 reward net; for GetRewards on whole captions use
+ *      p0 = L, S = 1, extra = 0).  T = icrl_stream_len(B,p0,S,extra).  stream int32 [T];
+ *      take int32 [T] (row s*B+b or -1); take_pos int32 [S*B] (stream position of each output). */
+long long icrl_stream_len(int B, int p0, int S, int extra);
+int icrl_build_stream(void* stream, int B, int p0, int S, int extra, const int* tokcm, int* stream_out, int* take,
+                      int* take_pos, int* launches);
+
+/* ---- serial chains (replace the seq=B,batch=1 nn.LSTM / nn.GRU calls with carried hidden_cell,
+ *      models.py:130-135, 223-228).  Cooperative launches of 64 (single) or 128 (fused) CTAs.
+ *      sync_state: icrl_chain_sync_bytes() device bytes, zeroed once by the caller.
+ *      h0/c0 [512] nullable (= init_hidden zeros, models.py:122-128); h_out/c_out [512] nullable
+ *      (the carried hidden_cell after the call).  stash_h [(T+1)][512] (row 0 = h0, row t+1 = h_t);
+ *      LSTM training stash: stash_c [(T+1)][512], stash_gates [T][2048] (nullable for inference). */
+size_t icrl_chain_sync_bytes(void);
+int icrl_chain_lstm_fwd(void* stream, const int* tok_stream, int T, const float* table, const float* W_hh,
+                        const float* h0, const float* c0, float* stash_h, float* stash_c, float* stash_gates,
+                        float* h_out, float* c_out, void* sync_state, int* launches);
+int icrl_chain_gru_fwd(void* stream, const int* tok_stream, int T, const float* table, const float* W_hh,
+                       const float* b_hn, const float* h0, float* stash_h, float* h_out, void* sync_state,
+                       int* launches);
+/* value LSTM chain and reward GRU chain side by side in one launch (both from zero state) */
+int icrl_chains_fwd_fused(void* stream, const int* v_stream, int v_T, const float* v_table, const float* v_W_hh,
+                          float* v_stash_h, float* v_stash_c, float* v_stash_gates, const int* r_stream, int r_T,
+                          const float* r_table, const float* r_W_hh, const float* r_b_hn, float* r_stash_h,
+                          void* sync_state, int* launches);
+/* BPTT through the value chain (replaces autograd through the carried-state LSTM, trainers.py:479):
+ * dgates [T][2048] = dL/d(pre-activation gates); dh_take [S*B][512] injected at take[t] >= 0. */
+int icrl_chain_lstm_bwd(void* stream, int T, const float* W_hh, const float* stash_gates, const float* stash_c,
+                        const int* take, const float* dh_take, float* dgates, void* sync_state, int* launches);
+/* synchronises `stream`; ICRL_ERR_WATCHDOG if any chain launch since the last check gave up waiting */
+int icrl_chain_check(void* stream, void* sync_state);
+/* dst[r][:] = src[idx[r] + row_offset][:]  (rows of 512 floats; h at the take positions) */
+int icrl_gather_rows(void* stream, long long R, const float* src, const int* idx, long long row_offset, float* dst,
+                     int* launches);
+
+/* ---- heads and loss.
+ *      value head (models.py:175-178): values [B][S] from h_take [S][B][512]. */
+int icrl_value_head_fwd(void* stream, int B, int S, const float* features, const float* h_take, const float* w_eff,
+                        const float* b_eff, float* values, int* launches);
+/*      value head backward: dv_sb [S][B], sum_dv [1] -> dh_take [S*B][512] and the four head gradients
+ *      (overwritten).  ws: >= 1024 + icrl_colsum_ws_floats(S*B, 512) floats. */
+int icrl_value_head_bwd(void* stream, int B, int S, const float* features, const float* h_take, const float* dv_sb,
+                        const float* sum_dv, const float* W1, const float* b1, const float* W2, const float* w_eff,
+                        float* dh_take, float* dW1, float* db1, float* dW2, float* db2, float* ws, int* launches);
+/*      value-chain parameter gradients from the chain backward's dgates (overwritten):
+ *      dW_hh = dgates^T h_prev, gate-table scatter, dW_ih = dtable^T E, dE = dtable W_ih, db = colsum. */
+int icrl_value_chain_param_grads(void* stream, int T, int V, const int* tok_stream, const float* dgates,
+                                 const float* stash_h, const float* E, const float* W_ih, float* dtable,
+                                 float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE, float* dW_ih,
+                                 float* dW_hh, float* db_ih, float* db_hh, int* launches);
+/*      reward (models.py:259-260 + GetRewards trainers.py:117-120): rewards [B][S] = cos(ve[b], se[s][b]). */
+int icrl_reward_cosine_fwd(void* stream, int B, int S, const float* ve, const float* se, float* rewards,
+                           int* launches);
+/*      A2C loss (trainers.py:471-475) and its gradient seeds.  inv_denom = 1/(B_global*S).
+ *      out3 = {loss, mean reward, mean advantage} (partial sums for a data-parallel shard);
+ *      dv_sb [S][B] = dL/dvalues, dlogp [B][S] = dL/dlogp, sum_dv [1]  (all nullable). */
+int icrl_a2c_loss_fwd_bwd(void* stream, int B, int S, const float* values, const float* rewards, const float* logp,
+                          float inv_denom, float* out3, float* dv_sb, float* dlogp, float* sum_dv, int* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICRL_B200_H */

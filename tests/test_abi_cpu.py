@@ -1,0 +1,99 @@
+"""CPU-side checks of the boundary: the shared library builds, loads, and exports every symbol the
+header declares with the argument count the ctypes binding uses; the product path refuses to run
+without CUDA (no CPU fallback); the host-side planning logic matches the reference's rules."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from icrl_b200 import _lib
+    return _lib
+
+
+def _header_decls():
+    txt = open(os.path.join(ROOT, "include", "icrl_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    decls = {}
+    for m in re.finditer(r"\b(icrl_\w+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S):
+        args = m.group(2).strip()
+        n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+        decls[m.group(1)] = n
+    return decls
+
+
+def test_library_exports_every_declared_symbol(lib):
+    handle = lib.load()
+    decls = _header_decls()
+    assert len(decls) >= 20
+    for name, nargs in decls.items():
+        assert hasattr(handle, name), "missing export " + name
+        assert name in lib.SIGNATURES, "no ctypes signature for " + name
+        assert len(lib.SIGNATURES[name]) == nargs, "%s: header has %d args, binding %d" % (name, nargs, len(lib.SIGNATURES[name]))
+    assert handle.icrl_version() >= 100
+
+
+def test_host_helpers_without_gpu(lib):
+    # pure host arithmetic of the ABI (no device work)
+    assert lib.call("icrl_stream_len", 256, 1, 19, 0) == 256 * 190          # value chain, config 2
+    assert lib.call("icrl_stream_len", 256, 1, 19, 1) == 256 * 209          # reward chain
+    assert lib.call("icrl_stream_len", 8192, 20, 1, 0) == 8192 * 20         # GetRewards config 3
+    assert lib.call("icrl_chain_sync_bytes") >= 64 + 8 * 2 * 512
+
+
+def test_no_cpu_fallback(lib):
+    import icrl_b200.models as M
+    from icrl_b200.engine import A2CEngine
+    from oracle import synth
+    w2i = synth.word_to_idx(64)
+    P, V, R = M.PolicyNetwork(w2i), M.ValueNetwork(w2i), M.RewardNetwork(w2i)
+    A = M.AdvantageActorCriticNetwork(V, P)
+    with pytest.raises(lib.IcrlError):
+        A2CEngine(A, R)
+    with pytest.raises(lib.IcrlError):
+        P(torch.zeros(1, 2, 512), torch.ones(2, 3, dtype=torch.long))
+    with pytest.raises(lib.IcrlError):
+        R(torch.zeros(2, 512), torch.ones(2, 3, dtype=torch.long))
+
+
+def test_state_dict_layout_matches_reference_keys():
+    """key names / shapes of policyNetwork.pt, valueNetwork.pt, rewardNetwork.pt, a2cNetwork.pt."""
+    import icrl_b200.models as M
+    from oracle import synth
+    w = synth.make_weights(0)
+    w2i = synth.word_to_idx()
+    P, V, R = M.PolicyNetwork(w2i), M.ValueNetwork(w2i), M.RewardNetwork(w2i)
+    for mod, sd in ((P, w["policy"]), (V, w["value"]), (R, w["reward"])):
+        own = mod.state_dict()
+        assert set(own) == set(sd)
+        for k in sd:
+            assert tuple(own[k].shape) == tuple(sd[k].shape), k
+        mod.load_state_dict(sd)                       # strict
+    A = M.AdvantageActorCriticNetwork(V, P)
+    assert list(A.state_dict().keys()) == list(synth.a2c_state_dict(w).keys())
+    assert sum(p.numel() for p in A.parameters()) == 6533613
+    assert V.valrnn.hidden_cell[0].shape == (1, 1, 512) and R.rewrnn.hidden_cell.shape == (1, 1, 512)
+    with pytest.raises(NotImplementedError):
+        M.PolicyNetwork(w2i, bidirectional=True)
+
+
+def test_plan_rollout_rules():
+    from icrl_b200.engine import plan_rollout
+    caps = np.full((4, 20), 7, dtype=np.int64)
+    caps[:, 0] = 1
+    caps[:, 19] = 2
+    caps[2, 11] = 2
+    assert plan_rollout(caps) == (1, 19)              # trainers.py:436-441
+    assert plan_rollout(caps, 6) == (14, 6)           # trainers.py:548-554
+    assert plan_rollout(caps, 16) == (4, 16)
+    assert plan_rollout(caps, 20)[0] < 1              # skipped by the caller (trainers.py:550)
+    with pytest.raises(ValueError):
+        plan_rollout(np.ones((2, 5), dtype=np.int64))
