@@ -97,7 +97,7 @@ class _PolicyOnlyEngine(A2CEngine):
         from . import _lib
         _lib.load()
         self.device, self.V = dev, policy_network.linear2vocab.weight.shape[0]
-        self._bufs, self.launches = {}, _lib.Launches()
+        self._bufs, self.launches, self.phase_events = {}, _lib.Launches(), None
 
     def pack_weights(self, reward=False):
         from . import _lib

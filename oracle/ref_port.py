@@ -58,7 +58,7 @@ class Nets:
         for m in (self.r_emb, self.r_rnn, self.r_vis, self.r_sem):
             m.requires_grad_(False)
         if not requires_grad:
-            for m in self.trainable_modules():
+            for _, m in self.trainable_modules():
                 m.requires_grad_(False)
         self.reset_state()
 
