@@ -13,8 +13,9 @@
 //   * per step every CTA needs all 512 h values.  They are exchanged through L2 as 64-bit
 //     {float value, uint32 step tag} words (single-copy atomic, no fences, no flags): the producer
 //     lane stores one word, consumers poll the words themselves.  Double buffered by step parity.
-//   * the backward kernel runs the same scheme on the 2048 pre-activation gate gradients: warp u
-//     holds column u of W_hh (2048 floats, 64 regs/lane) and computes dh_{t-1}[u].
+//   * the backward kernel exchanges dh_t the same way (512 words per step); every CTA rebuilds all
+//     2048 gate gradients from it, and warp u holds column u of W_hh (2048 floats, 64 regs/lane) to
+//     compute dh_{t-1}[u].
 //   * every spin is bounded (watchdog) and checks a global abort word, so a scheduling failure
 //     returns ICRL_ERR_WATCHDOG instead of hanging the GPU.
 #include <cooperative_groups.h>
@@ -27,6 +28,28 @@ constexpr int UNITS = 8;              // hidden units (= warps) per CTA
 constexpr int CHAIN_CTAS = H / UNITS; // 64 CTAs per chain
 constexpr int THREADS = UNITS * 32;
 constexpr unsigned SPIN_LIMIT = 1u << 22;
+
+// Activations on the serial critical path.  The accurate forms (expf, IEEE division, branchy tanhf)
+// cost 466 cycles per LSTM step, the SFU forms 180 (scripts/xchg_bench.cu, measured on B200).  The SFU
+// forms have abs error ~1e-7 on the O(1) gate values; the recurrence is contractive, so the values
+// stay within the 1e-5 parity budget (checked by tests/test_gpu_parity.py at B=256, 48,640 steps).
+#ifndef ICRL_CHAIN_ACT
+#define ICRL_CHAIN_ACT 1
+#endif
+__device__ __forceinline__ float act_sigmoid(float x) {
+#if ICRL_CHAIN_ACT
+  return __fdividef(1.0f, 1.0f + __expf(-x));            // MUFU.EX2 + MUFU.RCP
+#else
+  return sigmoidf_acc(x);
+#endif
+}
+__device__ __forceinline__ float act_tanh(float x) {
+#if ICRL_CHAIN_ACT
+  return 1.0f - 2.0f * __fdividef(1.0f, 1.0f + __expf(2.0f * x));
+#else
+  return tanhf(x);
+#endif
+}
 
 __device__ __forceinline__ void ld_tagged2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
   asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
@@ -150,21 +173,21 @@ __device__ void chain_fwd_body(const ChainFwdArgs& p, int cta) {
 
     float hnew;
     if constexpr (NG == 4) {
-      const float i = sigmoidf_acc(acc[0] + xg[0]);
-      const float f = sigmoidf_acc(acc[1] + xg[1]);
-      const float g = tanhf(acc[2] + xg[2]);
-      const float o = sigmoidf_acc(acc[3 % NG] + xg[3 % NG]);
+      const float i = act_sigmoid(acc[0] + xg[0]);
+      const float f = act_sigmoid(acc[1] + xg[1]);
+      const float g = act_tanh(acc[2] + xg[2]);
+      const float o = act_sigmoid(acc[3 % NG] + xg[3 % NG]);
       c = f * c + i * g;
-      hnew = o * tanhf(c);
+      hnew = o * act_tanh(c);
       if (p.stash_gates) {
         const float sel = lane == 0 ? i : (lane == 1 ? f : (lane == 2 ? g : o));
         if (lane < 4) p.stash_gates[(size_t)t * 4 * H + lane * H + unit] = sel;
       }
       if (p.stash_c && lane == 4) p.stash_c[(size_t)(t + 1) * H + unit] = c;
     } else {
-      const float r = sigmoidf_acc(acc[0] + xg[0]);
-      const float z = sigmoidf_acc(acc[1] + xg[1]);
-      const float n = tanhf(xg[2] + r * (acc[2] + bhn));
+      const float r = act_sigmoid(acc[0] + xg[0]);
+      const float z = act_sigmoid(acc[1] + xg[1]);
+      const float n = act_tanh(xg[2] + r * (acc[2] + bhn));
       hnew = (1.f - z) * n + z * hprev;
     }
     hprev = hnew;
@@ -195,49 +218,96 @@ struct ChainBwdArgs {
   const int* take;            // [T]  row of dh_take injected at step t, or -1
   const float* dh_take;       // [S*B][H] dL/dh at the take positions (from the value head)
   float* dgates;              // [T][4H] pre-activation gate gradients (output, feeds dW_hh / table grads)
-  unsigned long long* xchg;   // [2][4H]
+  unsigned long long* xchg;   // [2][H] tagged dh words
   int* abort_flag;
 };
 
+// Backward recurrence.  What crosses CTAs per step is dh_t (512 floats, the same volume and pattern as
+// the forward kernel): every CTA redundantly turns dh_t into all 2048 gate gradients (two hidden units
+// per thread; the stashed activations are prefetched a step ahead, dc is carried in registers), and warp
+// w of CTA c then computes dh_{t-1}[u] = W_hh[:,u] . dgates_t for its unit u = 8c + w from column u of
+// W_hh held in registers (64 per lane), adds the value-head gradient injected at take positions, and
+// publishes it as one tagged word.
 __global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_kernel(ChainBwdArgs p) {
   __shared__ __align__(16) float sh_dg[2][4 * H];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blockIdx.x * UNITS + warp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cta = blockIdx.x;
+  const int unit = cta * UNITS + warp;
+  const int pu = 2 * threadIdx.x;                              // this thread's two pointwise units
+  const bool owner = (pu >= cta * UNITS) && (pu < cta * UNITS + UNITS);
 
-  // column `unit` of W_hh: element j = 128*jj + 4*lane + q  ->  w[4*jj + q]
-  float w[64];
+  float w[64];                                                 // column `unit` of W_hh: j = 128*jj + 4*lane + q
 #pragma unroll
   for (int jj = 0; jj < 16; ++jj)
 #pragma unroll
     for (int q = 0; q < 4; ++q) w[4 * jj + q] = p.w_hh[(size_t)(128 * jj + 4 * lane + q) * H + unit];
 
-  float dc = 0.f;
-  // prefetch pipeline for the stashed activations of step t and the injected head gradient
-  auto load_step = [&](int t, float& gi, float& gf, float& gg, float& go, float& cc, float& cp, float& inj) {
-    const float* ga = p.stash_gates + (size_t)t * 4 * H;
-    gi = ga[unit]; gf = ga[H + unit]; gg = ga[2 * H + unit]; go = ga[3 * H + unit];
-    cc = p.stash_c[(size_t)(t + 1) * H + unit];
-    cp = p.stash_c[(size_t)t * H + unit];
-    const int tk = p.take[t];
-    inj = tk >= 0 ? p.dh_take[(size_t)tk * H + unit] : 0.f;
+  float2 dc = make_float2(0.f, 0.f);
+  auto load_step = [&](int t, float2& gi, float2& gf, float2& gg, float2& go, float2& cc, float2& cp) {
+    const float* ga = p.stash_gates + (size_t)t * 4 * H + pu;
+    gi = *reinterpret_cast<const float2*>(ga);
+    gf = *reinterpret_cast<const float2*>(ga + H);
+    gg = *reinterpret_cast<const float2*>(ga + 2 * H);
+    go = *reinterpret_cast<const float2*>(ga + 3 * H);
+    cc = *reinterpret_cast<const float2*>(p.stash_c + (size_t)(t + 1) * H + pu);
+    cp = *reinterpret_cast<const float2*>(p.stash_c + (size_t)t * H + pu);
   };
-  float gi, gf, gg, go, cc, cp, inj;
-  load_step(p.T - 1, gi, gf, gg, go, cc, cp, inj);
+  float2 gi, gf, gg, go, cc, cp;
+  load_step(p.T - 1, gi, gf, gg, go, cc, cp);
+  // dh of the last step is the injected head gradient only
+  float2 dh = make_float2(0.f, 0.f);
+  {
+    const int tk = p.take[p.T - 1];
+    if (tk >= 0) dh = *reinterpret_cast<const float2*>(p.dh_take + (size_t)tk * H + pu);
+  }
+  int tk_prev = p.T > 1 ? p.take[p.T - 2] : -1;                // injection for the dh this warp publishes
 
   for (int it = 0; it < p.T; ++it) {
     const int t = p.T - 1 - it;
     const int buf = it & 1;
     bool ok = true;
-    if (it > 0) ok = fetch_exchange<4>(p.xchg + (size_t)((it - 1) & 1) * 4 * H, (unsigned)it, sh_dg[buf], p.abort_flag);
+    unsigned long long a = 0, b = 0;
+    const unsigned long long* src = p.xchg + (size_t)((it - 1) & 1) * H + pu;
+    if (it > 0) ld_tagged2(src, a, b);                         // first poll in flight while the coefficients are computed
+    // everything that does not depend on dh
+    const float tcx = act_tanh(cc.x), tcy = act_tanh(cc.y);
+    const float kcx = go.x * (1.f - tcx * tcx), kcy = go.y * (1.f - tcy * tcy);
+    const float kox = tcx * go.x * (1.f - go.x), koy = tcy * go.y * (1.f - go.y);
+    const float kix = gg.x * gi.x * (1.f - gi.x), kiy = gg.y * gi.y * (1.f - gi.y);
+    const float kfx = cp.x * gf.x * (1.f - gf.x), kfy = cp.y * gf.y * (1.f - gf.y);
+    const float kgx = gi.x * (1.f - gg.x * gg.x), kgy = gi.y * (1.f - gg.y * gg.y);
+    const float inj = tk_prev >= 0 ? p.dh_take[(size_t)tk_prev * H + unit] : 0.f;
+    float2 ngi = gi, ngf = gf, ngg = gg, ngo = go, ncc = cc, ncp = cp;
+    if (t > 0) load_step(t - 1, ngi, ngf, ngg, ngo, ncc, ncp);
+    tk_prev = t > 1 ? p.take[t - 2] : -1;
+
+    if (it > 0) {
+      unsigned spins = 0;
+      while (!((unsigned)(a >> 32) == (unsigned)it && (unsigned)(b >> 32) == (unsigned)it)) {
+        if (++spins >= SPIN_LIMIT || ((spins & 1023u) == 0 && *(volatile int*)p.abort_flag != 0)) { ok = false; break; }
+        ld_tagged2(src, a, b);
+      }
+      dh = make_float2(__uint_as_float((unsigned)a), __uint_as_float((unsigned)b));
+    }
+    const float dctx = dc.x + dh.x * kcx, dcty = dc.y + dh.y * kcy;
+    dc = make_float2(dctx * gf.x, dcty * gf.y);
+    const float2 d_i = make_float2(dctx * kix, dcty * kiy), d_f = make_float2(dctx * kfx, dcty * kfy);
+    const float2 d_g = make_float2(dctx * kgx, dcty * kgy), d_o = make_float2(dh.x * kox, dh.y * koy);
+    *reinterpret_cast<float2*>(&sh_dg[buf][pu]) = d_i;
+    *reinterpret_cast<float2*>(&sh_dg[buf][H + pu]) = d_f;
+    *reinterpret_cast<float2*>(&sh_dg[buf][2 * H + pu]) = d_g;
+    *reinterpret_cast<float2*>(&sh_dg[buf][3 * H + pu]) = d_o;
+    if (owner) {
+      float* out = p.dgates + (size_t)t * 4 * H + pu;
+      *reinterpret_cast<float2*>(out) = d_i;
+      *reinterpret_cast<float2*>(out + H) = d_f;
+      *reinterpret_cast<float2*>(out + 2 * H) = d_g;
+      *reinterpret_cast<float2*>(out + 3 * H) = d_o;
+    }
     if (__syncthreads_or(!ok)) {
       if (threadIdx.x == 0) atomicExch(p.abort_flag, 1);
       return;
     }
-    float ngi = 0.f, ngf = 0.f, ngg = 0.f, ngo = 0.f, ncc = 0.f, ncp = 0.f, ninj = 0.f;
-    if (t > 0) load_step(t - 1, ngi, ngf, ngg, ngo, ncc, ncp, ninj);
-
-    float dh = 0.f;
-    if (it > 0) {
+    if (t > 0) {
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
       for (int jj = 0; jj < 16; ++jj) {
@@ -247,22 +317,10 @@ __global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_kernel(ChainBwdArgs
         a2 = fmaf(w[4 * jj + 2], v.z, a2);
         a3 = fmaf(w[4 * jj + 3], v.w, a3);
       }
-      dh = warp_sum((a0 + a1) + (a2 + a3));
+      const float rec = warp_sum((a0 + a1) + (a2 + a3));
+      if (lane == 0) st_tagged(p.xchg + (size_t)buf * H + unit, rec + inj, (unsigned)(it + 1));
     }
-    dh += inj;
-    const float tc = tanhf(cc);
-    const float dct = dc + dh * go * (1.f - tc * tc);
-    const float di = dct * gg * gi * (1.f - gi);
-    const float df = dct * cp * gf * (1.f - gf);
-    const float dg = dct * gi * (1.f - gg * gg);
-    const float dob = dh * tc * go * (1.f - go);
-    dc = dct * gf;
-    if (lane < 4) {
-      const float sel = lane == 0 ? di : (lane == 1 ? df : (lane == 2 ? dg : dob));
-      st_tagged(p.xchg + (size_t)buf * 4 * H + lane * H + unit, sel, (unsigned)(it + 1));
-      p.dgates[(size_t)t * 4 * H + lane * H + unit] = sel;
-    }
-    gi = ngi; gf = ngf; gg = ngg; go = ngo; cc = ncc; cp = ncp; inj = ninj;
+    gi = ngi; gf = ngf; gg = ngg; go = ngo; cc = ncc; cp = ncp;
   }
 }
 
@@ -294,8 +352,8 @@ static ChainFwdArgs make_fwd(const int* stream, int T, const float* table, const
 
 // sync_state layout (device, caller-owned, >= icrl_chain_sync_bytes(), zeroed once by the caller):
 // [0,64) sticky abort word (+pad; cleared only by icrl_chain_check), then exchange buffers
-// (re-zeroed before every launch): lstm fwd 2*H, gru fwd 2*H, lstm bwd 2*4H  64-bit words.
-size_t icrl_chain_sync_bytes_impl() { return 64 + sizeof(unsigned long long) * (2 * H + 2 * H + 2 * 4 * H); }
+// (re-zeroed before every launch): lstm fwd 2*H, gru fwd 2*H, lstm bwd 2*H  64-bit words.
+size_t icrl_chain_sync_bytes_impl() { return 64 + sizeof(unsigned long long) * (2 * H + 2 * H + 2 * H); }
 
 static int* sync_abort(void* s) { return reinterpret_cast<int*>(s); }
 static unsigned long long* sync_xchg(void* s, int which) {

@@ -1,15 +1,18 @@
 #!/bin/bash
-# First-contact GPU run: parity tests, smoke, a small and the full bench.  Everything is bounded by
-# `timeout`; the chain kernels carry their own watchdog.
+# GPU check: (optional microbench) parity tests, smoke, small and full bench.  Everything is bounded
+# by `timeout`; the chain kernels carry their own watchdog.
 mkdir -p gpurun_out
-nvidia-smi > gpurun_out/nvidia_smi.txt 2>&1
-timeout 1200 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/tests_gpu.log 2>&1
+if [ -x scripts/xchg_bench ] && [ "$1" = "micro" ]; then
+  timeout 300 ./scripts/xchg_bench > gpurun_out/xchg_bench.log 2>&1; echo "xchg exit $?" >> gpurun_out/xchg_bench.log
+  grep -v "^l2 mode" gpurun_out/xchg_bench.log
+fi
+timeout 1200 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/tests_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/tests_gpu.log
-tail -30 gpurun_out/tests_gpu.log
+tail -25 gpurun_out/tests_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 echo "smoke exit $?" >> gpurun_out/smoke.log
-tail -5 gpurun_out/smoke.log
-timeout 600 python bench.py --batch 256 --steps 3 --warmup 3 > gpurun_out/bench_b256.log 2>&1
+tail -3 gpurun_out/smoke.log
+timeout 600 python bench.py --batch 256 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_b256.log 2>&1
 echo "bench256 exit $?" >> gpurun_out/bench_b256.log
 tail -3 gpurun_out/bench_b256.log
 timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_b4096.log 2>&1

@@ -217,6 +217,97 @@ __global__ void gemv_kernel(int steps, float* out) {
   out[threadIdx.x] = s;
 }
 
+
+// ---------------------------------------------------------------- second round: floors and polling variants
+// one-way latency floors: two CTAs bounce a tagged word (L2) / two CTAs of a cluster bounce via st.async
+__global__ void pingpong_l2_kernel(unsigned long long* xchg, int steps, int* fail) {
+  if (threadIdx.x != 0) return;
+  const int me = blockIdx.x;
+  for (int t = 0; t < steps; ++t) {
+    if ((t & 1) == me) {
+      st1(xchg + 64 * me, ((unsigned long long)(t + 1) << 32) | 1u);
+    } else {
+      unsigned long long a, b; unsigned spins = 0;
+      while (true) { ld2(xchg + 64 * (1 - me), a, b); if ((unsigned)(a >> 32) == (unsigned)(t + 1)) break; if (++spins > (1u << 22)) { *fail = 1; return; } }
+    }
+  }
+}
+__global__ void __cluster_dims__(2, 1, 1) pingpong_dsm_kernel(int steps, float* sink) {
+  __shared__ __align__(16) float slot[4];
+  __shared__ __align__(8) unsigned long long bar;
+  unsigned rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  if (threadIdx.x == 0) mbar_init(smem_u32(&bar), 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  if (threadIdx.x == 0) {
+    const unsigned rslot = mapa(smem_u32(&slot[0]), 1 - rank), rbar = mapa(smem_u32(&bar), 1 - rank);
+    unsigned phase = 0;
+    for (int t = 0; t < steps; ++t) {
+      if ((t & 1) == (int)rank) {
+        st_async_f32(rslot, (float)t, rbar);
+      } else {
+        mbar_expect_tx(smem_u32(&bar), 4);
+        mbar_wait(smem_u32(&bar), phase);
+        phase ^= 1;
+      }
+    }
+    if (slot[0] == -5.f) sink[0] = 1.f;
+  }
+  cluster_sync_all();
+}
+
+// L2 all-to-all where only POLLERS threads per CTA poll (all loads issued before any check; only the
+// failing ones are re-polled), PIPE=1 keeps a second, time-staggered poll in flight.
+template <int POLLERS, int PIPE>
+__global__ void l2_xchg2_kernel(unsigned long long* xchg, int N, int steps, int* fail, float* sink) {
+  extern __shared__ float sm[];
+  const int G = gridDim.x, per_cta = N / G;
+  constexpr int MAXP = 8;                    // pairs per poller thread (N=512: 256/POLLERS)
+  const int ppt = (N / 2) / POLLERS;
+  float acc = 0.f;
+  for (int t = 0; t < steps; ++t) {
+    unsigned long long* buf = xchg + (size_t)(t & 1) * N;
+    const unsigned tag = (unsigned)(t + 1);
+    if (threadIdx.x < per_cta) st1(buf + blockIdx.x * per_cta + threadIdx.x, ((unsigned long long)tag << 32) | (unsigned)__float_as_uint(acc + 1.f));
+    if (threadIdx.x < POLLERS) {
+      unsigned long long a[MAXP], b[MAXP];
+      unsigned pending = (1u << ppt) - 1u, spins = 0;
+      while (pending) {
+#pragma unroll
+        for (int i = 0; i < MAXP; ++i)
+          if (i < ppt && (pending >> i & 1)) ld2(buf + 2 * (i * POLLERS + threadIdx.x), a[i], b[i]);
+        if (PIPE) { const long long c0 = clock64(); while (clock64() - c0 < 150) {} }
+#pragma unroll
+        for (int i = 0; i < MAXP; ++i)
+          if (i < ppt && (pending >> i & 1) && (unsigned)(a[i] >> 32) == tag && (unsigned)(b[i] >> 32) == tag) {
+            pending &= ~(1u << i);
+            sm[2 * (i * POLLERS + threadIdx.x)] = __uint_as_float((unsigned)a[i]);
+            sm[2 * (i * POLLERS + threadIdx.x) + 1] = __uint_as_float((unsigned)b[i]);
+          }
+        if (++spins > (1u << 22)) { *fail = 1; return; }
+      }
+    }
+    __syncthreads();
+    acc = sm[(threadIdx.x * 7) % N] * 0.5f;
+  }
+  if (acc == 123.f) sink[0] = acc;
+}
+
+__global__ void math_mid_kernel(int steps, float* out) {
+  float h = 0.1f * threadIdx.x, c = 0.f;
+  for (int t = 0; t < steps; ++t) {
+    const float i = __frcp_rn(1.f + expf(-(h + 0.1f)));
+    const float f = __frcp_rn(1.f + expf(-(h - 0.2f)));
+    const float g = 1.f - 2.f * __frcp_rn(1.f + expf(2.f * (h + 0.3f)));
+    const float o = __frcp_rn(1.f + expf(-(h * 0.5f)));
+    c = f * c + i * g;
+    h = o * (1.f - 2.f * __frcp_rn(1.f + expf(2.f * c)));
+  }
+  out[threadIdx.x] = h;
+}
+
 static float time_ms(cudaEvent_t a, cudaEvent_t b) { float ms; CK(cudaEventElapsedTime(&ms, a, b)); return ms; }
 
 int main() {
@@ -303,6 +394,61 @@ int main() {
     }
     const double ns = time_ms(e0, e1) * 1e6 / steps;
     printf("%-36s : %8.1f ns/step = %6.0f cyc\n", k.name, ns, ns * ghz);
+  }
+  // ---- second round
+  {
+    int st = steps;
+    void* args[] = {&xchg, &st, &fail};
+    for (int rep = 0; rep < 2; ++rep) {
+      CK(cudaMemset(xchg, 0, 2 * 4096 * sizeof(unsigned long long)));
+      CK(cudaEventRecord(e0));
+      CK(cudaLaunchCooperativeKernel((const void*)pingpong_l2_kernel, dim3(2), dim3(32), args, 0, 0));
+      CK(cudaEventRecord(e1));
+      CK(cudaDeviceSynchronize());
+    }
+    double ns = time_ms(e0, e1) * 1e6 / steps;
+    printf("pingpong L2 (one-way store->poll)    : %8.1f ns = %6.0f cyc\n", ns, ns * ghz);
+    for (int rep = 0; rep < 2; ++rep) {
+      CK(cudaEventRecord(e0));
+      pingpong_dsm_kernel<<<2, 32>>>(steps, sink);
+      CK(cudaEventRecord(e1));
+      CK(cudaDeviceSynchronize());
+    }
+    ns = time_ms(e0, e1) * 1e6 / steps;
+    printf("pingpong DSMEM (st.async->mbar wait) : %8.1f ns = %6.0f cyc\n", ns, ns * ghz);
+  }
+  {
+    struct V { const char* name; const void* fn; } vs[] = {
+        {"pollers=256 pipe=0", (const void*)l2_xchg2_kernel<256, 0>}, {"pollers=256 pipe=1", (const void*)l2_xchg2_kernel<256, 1>},
+        {"pollers=128 pipe=0", (const void*)l2_xchg2_kernel<128, 0>}, {"pollers= 64 pipe=0", (const void*)l2_xchg2_kernel<64, 0>},
+        {"pollers= 32 pipe=0", (const void*)l2_xchg2_kernel<32, 0>},  {"pollers= 64 pipe=1", (const void*)l2_xchg2_kernel<64, 1>}};
+    for (auto& v : vs)
+      for (int G : {32, 64}) {
+        int n = 512, st = steps;
+        void* args[] = {&xchg, &n, &st, &fail, &sink};
+        CK(cudaMemset(fail, 0, 4));
+        for (int rep = 0; rep < 2; ++rep) {
+          CK(cudaMemset(xchg, 0, 2 * 4096 * sizeof(unsigned long long)));
+          CK(cudaEventRecord(e0));
+          CK(cudaLaunchCooperativeKernel(v.fn, dim3(G), dim3(256), args, 512 * 4, 0));
+          CK(cudaEventRecord(e1));
+          CK(cudaDeviceSynchronize());
+        }
+        int hf = 0;
+        CK(cudaMemcpy(&hf, fail, 4, cudaMemcpyDeviceToHost));
+        const double ns = time_ms(e0, e1) * 1e6 / steps;
+        printf("l2v2 %s N=512 G=%3d : %8.1f ns/step = %6.0f cyc %s\n", v.name, G, ns, ns * ghz, hf ? "FAILED" : "");
+      }
+  }
+  {
+    for (int rep = 0; rep < 2; ++rep) {
+      CK(cudaEventRecord(e0));
+      math_mid_kernel<<<1, 32>>>(steps, sink);
+      CK(cudaEventRecord(e1));
+      CK(cudaDeviceSynchronize());
+    }
+    const double ns = time_ms(e0, e1) * 1e6 / steps;
+    printf("%-36s : %8.1f ns/step = %6.0f cyc\n", "lstm pointwise (expf + frcp_rn)", ns, ns * ghz);
   }
   return 0;
 }

@@ -1,12 +1,13 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the golden vectors produced by the
 unmodified reference and against the CPU oracle.
 
-Tolerances (fp32 path, stated per BASELINE north_star):
+Tolerances (fp32 path, stated per BASELINE north_star; measured errors are dumped to
+gpurun_out/parity_errors.json -- round 1: values 5.5e-7, rewards 1.1e-7, log-probs 4.8e-7, grads 2.0e-6):
   token ids                      bit-exact
-  logits / log-probs             1e-5 abs
-  values / rewards               1e-5 abs   (the reference's own formulations differ by ~2e-7)
-  loss, mean reward / advantage  1e-5 abs
-  gradients                      2e-4 of the tensor's max |entry| (sampled entries) and of its L2 norm
+  logits / log-probs             2e-6 abs
+  values / rewards               2e-6 abs   (the reference's own formulations differ by ~2e-7)
+  loss, mean reward / advantage  2e-6 abs
+  gradients                      2e-5 of the tensor's max |entry| (sampled entries) and of its L2 norm
 """
 import numpy as np
 import pytest
@@ -17,8 +18,8 @@ from tests.helpers import (check_grads_vs_golden, check_grads_vs_oracle, load_ca
 
 pytestmark = pytest.mark.gpu
 
-TOL = 1e-5
-GTOL = 2e-4
+TOL = 2e-6
+GTOL = 2e-5
 
 
 def _engine(seed):
@@ -27,11 +28,26 @@ def _engine(seed):
     return A2CEngine(A, R), A, R, w
 
 
-def _compare_forward(res, g):
+ERRORS = {}
+
+
+def _record(name, **kv):
+    """Measured parity errors, dumped to gpurun_out/parity_errors.json (margin vs the tolerances)."""
+    import json, os
+    ERRORS.setdefault(name, {}).update({k: float(v) for k, v in kv.items()})
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        json.dump(ERRORS, open("gpurun_out/parity_errors.json", "w"), indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+def _compare_forward(res, g, name="case"):
     toks = res["tokens"].cpu().numpy()
     assert np.array_equal(toks, g["tokens"]), "token ids differ in %d places" % int((toks != g["tokens"]).sum())
     for k in ("values", "rewards", "logp"):
         err = float(np.abs(res[k].cpu().numpy() - g[k]).max())
+        _record(name, **{k: err})
         assert err <= TOL, "%s: %.3e" % (k, err)
     assert abs(res.loss - float(g["loss"])) <= TOL
     assert abs(res.mean_reward - float(g["mean_reward"])) <= TOL
@@ -77,8 +93,8 @@ def test_a2c_step_vs_reference_golden(name):
     g, seed, f, c, u, level = load_case(name)
     eng, A, R, w = _engine(seed)
     res = eng.step(f, c, uniforms=u, level=level)
-    _compare_forward(res, g)
-    check_grads_vs_golden(named_grads(A), g, GTOL)
+    _compare_forward(res, g, name)
+    _record(name, grad_worst=check_grads_vs_golden(named_grads(A), g, GTOL))
 
 
 def test_a2c_config2_vs_reference_golden():
@@ -86,12 +102,12 @@ def test_a2c_config2_vs_reference_golden():
     g, seed, f, c, u, level = load_case("a2c_b256_l20")
     eng, A, R, w = _engine(seed)
     res = eng.step(f, c, uniforms=u, backward=False)
-    _compare_forward(res, g)
+    _compare_forward(res, g, "a2c_b256_l20")
     last = eng._bufs["p_logits"][18 * 256 * 1004:19 * 256 * 1004].view(256, 1004).cpu().numpy()
     assert float(np.abs(last - g["last_logits"]).max()) <= TOL
     res = eng.step(f, c, uniforms=u)
-    _compare_forward(res, g)
-    check_grads_vs_golden(named_grads(A), g, GTOL)
+    _compare_forward(res, g, "a2c_b256_l20")
+    _record("a2c_b256_l20", grad_worst=check_grads_vs_golden(named_grads(A), g, GTOL))
 
 
 def test_sampling_from_global_numpy_stream():
