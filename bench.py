@@ -135,7 +135,9 @@ def main():
     if args.impl == "reference":
         return main_reference(args, rank)
 
+    import ctypes
     import torch.distributed as dist
+    from icrl_b200 import _lib
     from icrl_b200.dp import DataParallelA2C, shard_bounds
     from icrl_b200.engine import A2CEngine
     from tests.helpers import make_nets
@@ -193,8 +195,6 @@ def main():
     clk = clocks.stop()
     phases = {k: sum(v) / len(v) for k, v in eng.phase_times_ms().items()}
     eng.phase_events = None
-    from icrl_b200 import _lib
-    import ctypes
     _lib.call("icrl_chain_check", ctypes.c_void_p(torch.cuda.current_stream().cuda_stream),
               ctypes.c_void_p(eng.sync_state.data_ptr()))
 
@@ -218,24 +218,56 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- tensor-pipe figure of the decode-step gate GEMM (B_local x 2048 x 512, 3-part bf16 split = 6 MMAs)
+    decode = None
+    try:
+        from icrl_b200.engine import _p
+        Bl_ = hi - lo
+        bufs = eng._bufs
+        st_ = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        for i in range(reps + 3):
+            if i == 3:
+                ev0.record()
+            _lib.call("icrl_gemm_bf16x3", st_, Bl_, 2048, 512, _p(bufs["p_h_parts"]), _p(bufs["p_whh_parts"]),
+                      _p(bufs["p_gpre"]), 2048, None, None)
+        ev1.record()
+        torch.cuda.synchronize()
+        us = ev0.elapsed_time(ev1) * 1e3 / reps
+        alg = 2.0 * Bl_ * 2048 * 512
+        decode = {"kernel": "gemm_bf16x3_kernel (gate GEMM of one decode step)", "bound": "tensor",
+                  "achieved": alg / us / 1e6, "executed_tflops": 6 * alg / us / 1e6, "unit": "TFLOP/s",
+                  "us_per_launch": us, "shape": [Bl_, 2048, 512], "mma_passes": 6,
+                  "note": "achieved counts the algorithmic 2MNK once; the tensor pipe executes 6x that (3-part split)"}
+    except Exception as exc:                                   # never let the side measurement kill the bench line
+        decode = {"error": str(exc)}
+
     # ---- roofline of the dominant kernel (serial chains: latency bound -- see DESIGN.md)
     Bl = hi - lo
     Tv, Tr = Bl * 190, Bl * 209
     fwd_ms, bwd_ms = phases.get("chains_fwd_fused", 0.0), phases.get("chain_lstm_bwd", 0.0)
+    ktraffic = None
     if bwd_ms >= fwd_ms:
         kname, kms, kbytes, ksteps = "chain_lstm_bwd_kernel", bwd_ms, Tv * (6 * H * 4 + 4 + 4 * H * 4), Tv
     else:
         kname, kms = "chains_fwd_fused_kernel", fwd_ms
         kbytes, ksteps = Tv * (4 * H * 4 + 6 * H * 4 + 4) + Tr * (3 * H * 4 + H * 4 + 4), max(Tv, Tr)
+        # profiles/r01_chain_fwd_ncu.md: dram read+write = 695.5 MB per launch at B=256 (linear in rows)
+        ktraffic = 695.5e6 * Bl / 256.0
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    if decode and "achieved" in decode:
+        tp = float(peaks.get("bf16_tflops", 1590.0))
+        decode.update(peak=tp, frac=decode["achieved"] / tp, frac_executed=decode["executed_tflops"] / tp,
+                      peak_source="measured" if peaks else "fallback")
     ach = kbytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
     roofline = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                "traffic": ktraffic, "peak_source": "measured" if peaks else "fallback",
                 "ms_per_launch": kms, "serial_steps_per_launch": ksteps,
                 "ns_per_serial_step": kms * 1e6 / ksteps if ksteps else None,
                 "note": "serial batch-1 recurrence: latency bound, neither HBM nor tensor pipe is the limiter"}
@@ -248,6 +280,7 @@ def main():
                    "global_batch": B, "local_batch": Bl, "parallelism": "dp%d" % world, "vocab": 1004,
                    "l2_flush": "not needed: per-step working set (chain stash, GBs) >> 126 MB L2"},
         "clocks": clk, "gpu_launches": int(launches), "phases_ms": phases, "roofline": roofline,
+        "roofline_decode": decode,
     }
     if e2e:
         out["e2e"] = e2e

@@ -23,6 +23,9 @@ SIGNATURES = {
     "icrl_version": [],
     "icrl_device_info": [LP],
     "icrl_gemm_f32": [P, I, I, I, I, I, P, I, P, I, P, I, P, F, P, Z, LP],
+    "icrl_split_bf16x3": [P, L, P, P, LP],
+    "icrl_gemm_bf16x3": [P, I, I, I, P, P, P, I, P, LP],
+    "icrl_policy_rollout_fwd_tc": [P, I, I, I, I, I] + [P] * 18 + [LP],
     "icrl_pack_gate_table": [P, I, I, I, P, P, P, P, P, LP],
     "icrl_pack_value_head": [P, P, P, P, P, P, P, LP],
     "icrl_policy_rollout_fwd": [P, I, I, I, I, I] + [P] * 17 + [LP],

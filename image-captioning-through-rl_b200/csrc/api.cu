@@ -94,6 +94,51 @@ int icrl_policy_rollout_fwd(void* stream, int B, int V, int p0, int S, int greed
   return ICRL_OK;
 }
 
+int icrl_split_bf16x3(void* stream, long long n, const float* x, void* parts, int* launches) {
+  TRY(icrl_split_bf16x3_impl(S_(stream), n, x, parts));
+  bump(launches, 1);
+  return ICRL_OK;
+}
+
+int icrl_gemm_bf16x3(void* stream, int M, int N, int K, const void* a_parts, const void* b_parts, float* C, int ldc,
+                     const float* bias, int* launches) {
+  TRY(icrl_gemm_bf16x3_impl(S_(stream), M, N, K, a_parts, b_parts, C, ldc, bias));
+  bump(launches, 1);
+  return ICRL_OK;
+}
+
+int icrl_policy_rollout_fwd_tc(void* stream, int B, int V, int p0, int S, int greedy, const float* features,
+                               const float* W_cnn, const float* b_cnn, const float* table, const void* whh_parts,
+                               const void* wv_parts, const float* b_v, const double* uniforms,
+                               const long long* forced, int* tokcm, long long* tokens_out, float* logp, float* Hs,
+                               float* Cs, float* Gs, float* logits, float* gpre, void* h_parts, int* launches) {
+  ICRL_REQUIRE(B > 0 && V > 0 && p0 >= 1 && S >= 1, "bad rollout shape");
+  ICRL_REQUIRE(greedy || uniforms || forced, "sampling needs uniforms");
+  cudaStream_t st = S_(stream);
+  const int n_cell = p0 - 1 + S;
+  const size_t BH = (size_t)B * H;
+  TRY(icrl_gemm_f32_impl(st, 0, 1, B, H, H, features, H, W_cnn, H, Hs, H, b_cnn, 0.f, nullptr, 0, launches));
+  ICRL_CUDA(cudaMemsetAsync(Cs, 0, BH * sizeof(float), st));
+  TRY(icrl_split_bf16x3_impl(st, (long long)BH, Hs, h_parts));
+  bump(launches, 1);
+  for (int j = 0; j < n_cell; ++j) {
+    TRY(icrl_gemm_bf16x3_impl(st, B, 4 * H, H, h_parts, whh_parts, gpre, 4 * H, nullptr));
+    TRY(icrl_lstm_pointwise_fwd(st, B, gpre, table, tokcm + (size_t)j * B, Cs + j * BH, Gs + (size_t)j * B * 4 * H,
+                                Cs + (j + 1) * BH, Hs + (j + 1) * BH));
+    TRY(icrl_split_bf16x3_impl(st, (long long)BH, Hs + (j + 1) * BH, h_parts));
+    bump(launches, 3);
+    const int s = j - (p0 - 1);
+    if (s >= 0) {
+      float* lg = logits + (size_t)s * B * V;
+      TRY(icrl_gemm_bf16x3_impl(st, B, V, H, h_parts, wv_parts, lg, V, b_v));
+      TRY(icrl_softmax_sample(st, B, V, lg, V, (greedy || !uniforms) ? nullptr : uniforms + (size_t)s * B, greedy, forced,
+                              tokcm + (size_t)(p0 + s) * B, tokens_out, logp, S, s, nullptr));
+      bump(launches, 2);
+    }
+  }
+  return ICRL_OK;
+}
+
 size_t icrl_colsum_ws_floats(long long rows, int cols) { return (size_t)icrl_wcolsum_chunks(rows) * cols; }
 
 int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, const float* features, const float* E,

@@ -48,3 +48,7 @@ int icrl_chains_fwd_fused_impl(cudaStream_t st, const int* v_stream, int v_T, co
 int icrl_chain_lstm_bwd_impl(cudaStream_t st, int T, const float* w_hh, const float* stash_gates, const float* stash_c,
                              const int* take, const float* dh_take, float* dgates, void* sync_state);
 int icrl_chain_check_impl(cudaStream_t st, void* sync_state);
+
+int icrl_split_bf16x3_impl(cudaStream_t st, long long n, const float* x, void* parts);
+int icrl_gemm_bf16x3_impl(cudaStream_t st, int M, int N, int K, const void* a_parts, const void* b_parts, float* C,
+                          int ldc, const float* bias);

@@ -71,7 +71,7 @@ def plan_rollout(captions, level=None):
 
 
 class A2CEngine:
-    def __init__(self, a2c_network, reward_network):
+    def __init__(self, a2c_network, reward_network, use_tc=True):
         self.policy = a2c_network.policy_network
         self.value = a2c_network.value_network
         self.reward = reward_network
@@ -85,6 +85,7 @@ class A2CEngine:
         self._bufs = {}
         self.launches = _lib.Launches()
         self.phase_events = None          # set to [] to record (name, start, end) CUDA events per phase
+        self.use_tc = bool(use_tc)        # per-step decode GEMMs on the tcgen05 pipe (split-bf16) vs fp32 SIMT
         with torch.cuda.device(dev):
             self.sync_state = torch.zeros(int(_lib.call("icrl_chain_sync_bytes")), dtype=torch.uint8, device=dev)
         self._check_params()
@@ -176,8 +177,18 @@ class A2CEngine:
           _p(self._buf("v_table", V * 4 * H)), L)
         c("icrl_pack_value_head", st, _p(Vn.linear1.weight), _p(Vn.linear1.bias), _p(Vn.linear2.weight),
           _p(Vn.linear2.bias), _p(self._buf("v_weff", 2 * H)), _p(self._buf("v_beff", 1)), L)
+        if self.use_tc:
+            self._pack_policy_tc()
         if reward:
             self.pack_reward()
+
+    def _pack_policy_tc(self):
+        """3-part bf16 splits of the two decode-step weight matrices (tensor-core operands)."""
+        P = self.policy
+        for name, w in (("whh", P.lstm.weight_hh_l0), ("wv", P.linear2vocab.weight)):
+            n = w.numel()
+            _lib.call("icrl_split_bf16x3", self._stream, n, _p(w), _p(self._buf("p_%s_parts" % name, 3 * n, torch.bfloat16)),
+                      self.launches.ref)
 
     def pack_reward(self):
         R, V = self.reward, self.V
@@ -231,9 +242,17 @@ class A2CEngine:
         Gs = self._buf("p_Gs", n_cell * B * 4 * H)
         logits = self._buf("p_logits", S * B * V)
         gpre = self._buf("p_gpre", B * 4 * H)
+        b = self._bufs
         with self._phase("policy_fwd"):
-          _lib.call("icrl_policy_rollout_fwd", self._stream, B, V, p0, S, int(bool(greedy)), _p(f),
-                  _p(P.cnn2linear.weight), _p(P.cnn2linear.bias), _p(self._bufs["p_table"]),
+          if self.use_tc:
+            _lib.call("icrl_policy_rollout_fwd_tc", self._stream, B, V, p0, S, int(bool(greedy)), _p(f),
+                  _p(P.cnn2linear.weight), _p(P.cnn2linear.bias), _p(b["p_table"]), _p(b["p_whh_parts"]),
+                  _p(b["p_wv_parts"]), _p(P.linear2vocab.bias), _p(u), _p(fo), _p(tokcm), _p(tokens),
+                  _p(logp), _p(Hs), _p(Cs), _p(Gs), _p(logits), _p(gpre),
+                  _p(self._buf("p_h_parts", 3 * B * H, torch.bfloat16)), self.launches.ref)
+          else:
+            _lib.call("icrl_policy_rollout_fwd", self._stream, B, V, p0, S, int(bool(greedy)), _p(f),
+                  _p(P.cnn2linear.weight), _p(P.cnn2linear.bias), _p(b["p_table"]),
                   _p(P.lstm.weight_hh_l0), _p(P.linear2vocab.weight), _p(P.linear2vocab.bias), _p(u), _p(fo),
                   _p(tokcm), _p(tokens), _p(logp), _p(Hs), _p(Cs), _p(Gs), _p(logits), _p(gpre), self.launches.ref)
         return tokens, logp

@@ -42,6 +42,14 @@ int icrl_gemm_f32(void* stream, int transA, int transB, int M, int N, int K, con
                   const float* B, int ldb, float* C, int ldc, const float* bias, float beta, float* ws,
                   size_t ws_bytes, int* launches);
 
+/* ---- tensor-core contraction (tcgen05, sm_100a): C[M][ldc] = A B^T + bias, fp32-grade: each fp32 operand is
+ *      split into three bf16 parts (icrl_split_bf16x3: parts is bf16 [3][n], x ~= p0 + p1 + p2) and the six
+ *      products with i + j <= 2 are accumulated in f32 in tensor memory.  a_parts [3][M][K], b_parts [3][N][K];
+ *      K % 64 == 0. */
+int icrl_split_bf16x3(void* stream, long long n, const float* x, void* parts, int* launches);
+int icrl_gemm_bf16x3(void* stream, int M, int N, int K, const void* a_parts, const void* b_parts, float* C, int ldc,
+                     const float* bias, int* launches);
+
 /* ---- weight packing, once per optimizer step (new; the reference recomputes these products at every
  *      RNN step).  table[v][:] = W_ih E[v] + b_ih + (b_hh for the first `fold` gate rows).
  *      LSTM: G = 2048, fold = 2048.  GRU: G = 1536, fold = 1024 (b_hn stays inside r*(.), models.py:215). */
@@ -65,6 +73,14 @@ int icrl_policy_rollout_fwd(void* stream, int B, int V, int p0, int S, int greed
                             const float* W_v, const float* b_v, const double* uniforms, const long long* forced,
                             int* tokcm, long long* tokens_out, float* logp, float* Hs, float* Cs, float* Gs, float* logits,
                             float* gpre, int* launches);
+/*      Same rollout with the two per-step GEMMs (h W_hh^T and h W_v^T) on the tcgen05 pipe.  Extra operands:
+ *      3-part bf16 splits of W_hh ([3][2048][512]) and W_v ([3][V][512]) (icrl_split_bf16x3, once per optimizer
+ *      step) and scratch h_parts [3][B][512] bf16. */
+int icrl_policy_rollout_fwd_tc(void* stream, int B, int V, int p0, int S, int greedy, const float* features,
+                               const float* W_cnn, const float* b_cnn, const float* table, const void* whh_parts,
+                               const void* wv_parts, const float* b_v, const double* uniforms,
+                               const long long* forced, int* tokcm, long long* tokens_out, float* logp, float* Hs,
+                               float* Cs, float* Gs, float* logits, float* gpre, void* h_parts, int* launches);
 
 /* ---- policy backward through time (replaces autograd over the S prefix re-runs, trainers.py:479).
  *      dlogp [B][S].  logits is overwritten with dL/dlogits.  Workspaces: dHv [S*B][512],

@@ -22,10 +22,10 @@ TOL = 2e-6
 GTOL = 2e-5
 
 
-def _engine(seed):
+def _engine(seed, use_tc=True):
     from icrl_b200.engine import A2CEngine
     A, R, w = make_nets(seed)
-    return A2CEngine(A, R), A, R, w
+    return A2CEngine(A, R, use_tc=use_tc), A, R, w
 
 
 ERRORS = {}
@@ -75,6 +75,35 @@ def test_gemm_f32(trans, shape):
     assert err < 2e-6, err
 
 
+@pytest.mark.parametrize("shape", [(128, 256, 512), (4096, 2048, 512), (300, 1004, 512), (8, 2048, 512), (256, 1004, 64)])
+def test_gemm_bf16x3_tcgen05(shape):
+    """tcgen05 split-bf16 GEMM vs float64.  Measured 2.6e-6..3.3e-6 of max|C| for K=512 (2-part split: 4.9e-6):
+    what remains is the tensor core's f32 accumulation, not the operand split."""
+    import ctypes
+    from icrl_b200 import _lib
+    M, N, K = shape
+    rs = np.random.RandomState(1)
+    A = torch.from_numpy(rs.standard_normal((M, K)).astype(np.float32)).cuda()
+    Bm = torch.from_numpy((rs.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)).cuda()
+    bias = torch.from_numpy(rs.standard_normal(N).astype(np.float32)).cuda()
+    C = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    parts = []
+    for x in (A, Bm):
+        pr = torch.empty((3,) + tuple(x.shape), dtype=torch.bfloat16, device="cuda")
+        _lib.call("icrl_split_bf16x3", st, x.numel(), p(x), p(pr), None)
+        assert float((x - pr.float().sum(0)).abs().max()) <= 2.0 ** -22 * float(x.abs().max())
+        parts.append(pr)
+    _lib.call("icrl_gemm_bf16x3", st, M, N, K, p(parts[0]), p(parts[1]), p(C), N, p(bias), None)
+    torch.cuda.synchronize()
+    ref = A.double() @ Bm.double().t() + bias.double()
+    assert torch.isfinite(C).all()
+    err = float((C.double() - ref).abs().max() / ref.abs().max())
+    _record("gemm_bf16x3_%dx%dx%d" % shape, rel_err=err)
+    assert err < 5e-6, err
+
+
 def test_greedy_config1():
     """BASELINE config 1: greedy decode, B=32, 16 steps."""
     import icrl_b200.trainers as T
@@ -88,19 +117,21 @@ def test_greedy_config1():
     assert float(np.abs(last.cpu().numpy() - g["last_logits"]).max()) <= TOL
 
 
+@pytest.mark.parametrize("use_tc", [False, True])
 @pytest.mark.parametrize("name", ["a2c_b8_l6", "a2c_b32_l9", "curr_b16_l10_lv4", "curr_b24_l20_lv6"])
-def test_a2c_step_vs_reference_golden(name):
+def test_a2c_step_vs_reference_golden(name, use_tc):
     g, seed, f, c, u, level = load_case(name)
-    eng, A, R, w = _engine(seed)
+    eng, A, R, w = _engine(seed, use_tc)
     res = eng.step(f, c, uniforms=u, level=level)
-    _compare_forward(res, g, name)
-    _record(name, grad_worst=check_grads_vs_golden(named_grads(A), g, GTOL))
+    _compare_forward(res, g, name + ("_tc" if use_tc else "_simt"))
+    _record(name + ("_tc" if use_tc else "_simt"), grad_worst=check_grads_vs_golden(named_grads(A), g, GTOL))
 
 
-def test_a2c_config2_vs_reference_golden():
+@pytest.mark.parametrize("use_tc", [False, True])
+def test_a2c_config2_vs_reference_golden(use_tc):
     """BASELINE config 2: B=256, L=20, S=19, fixed uniforms."""
     g, seed, f, c, u, level = load_case("a2c_b256_l20")
-    eng, A, R, w = _engine(seed)
+    eng, A, R, w = _engine(seed, use_tc)
     res = eng.step(f, c, uniforms=u, backward=False)
     _compare_forward(res, g, "a2c_b256_l20")
     last = eng._bufs["p_logits"][18 * 256 * 1004:19 * 256 * 1004].view(256, 1004).cpu().numpy()
