@@ -8,7 +8,7 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libicrl_b200.so")
+LIB_PATH = os.environ.get("ICRL_LIB_PATH") or os.path.join(_HERE, "libicrl_b200.so")   # override: A/B builds only
 
 P = c_void_p          # device pointer / stream
 I = c_int

@@ -54,9 +54,18 @@ __device__ __forceinline__ float act_tanh(float x) {
 __device__ __forceinline__ void ld_tagged2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
   asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
 }
+// A fence after the publishing store shortens the isolated two-CTA ping-pong (968 -> 821 cycles one way,
+// scripts/chain_micro.cu) but LENGTHENS the real step (B=256: fwd 69.7 -> 76.2 ms, bwd 66.8 -> 81.2 ms): the
+// warp reconverges behind the fenced lane and its next poll issues late.  Kept as a build switch, off.
+#ifndef ICRL_CHAIN_FENCE
+#define ICRL_CHAIN_FENCE 0
+#endif
 __device__ __forceinline__ void st_tagged(unsigned long long* p, float v, unsigned tag) {
   const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
   asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+#if ICRL_CHAIN_FENCE
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
 }
 
 struct ChainFwdArgs {
@@ -191,7 +200,7 @@ __device__ void chain_fwd_body(const ChainFwdArgs& p, int cta) {
       hnew = (1.f - z) * n + z * hprev;
     }
     hprev = hnew;
-    if (lane == 0) st_tagged(p.xchg + (size_t)buf * H + unit, hnew, (unsigned)(t + 1));
+    if (lane == 8) st_tagged(p.xchg + (size_t)buf * H + unit, hnew, (unsigned)(t + 1));
     if (lane == 5) p.stash_h[(size_t)(t + 1) * H + unit] = hnew;
 #pragma unroll
     for (int g = 0; g < NG; ++g) xg[g] = xg_n[g];

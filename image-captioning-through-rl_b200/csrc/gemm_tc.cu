@@ -10,9 +10,17 @@
 // Structure (one CTA per 128x128 output tile, 192 threads, warp-specialised):
 //   warp 0      TMA producer: per 64-wide K block loads the three A parts and three B parts (128x64 bf16
 //               each, 128B-swizzled) into a 2-stage ring (96 KB per stage), completion on `full` mbarriers
-//   warp 1      tcgen05.mma issuer (one lane): 6 operand pairs x 4 K-steps of 16 per stage, M=128 N=128,
-//               accumulator = 128 TMEM columns; tcgen05.commit releases the stage / signals the epilogue
+//   warp 1      tcgen05.mma issuer (one lane): 6 operand pairs x 4 K-steps of 16 per stage, M=128 N=128;
+//               tcgen05.commit releases the stage / signals the epilogue
 //   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns at a time -> + bias -> global (f32)
+//
+// Accumulator layout.  The tensor core truncates (toward zero) when it adds an MMA's products into the f32
+// accumulator: measured on B200 (scripts/tc_accuracy_probe.py) the relative bias is ~ -1.5e-8 per MMA
+// instruction that touches an accumulator, i.e. -4.7e-7 after 32 (K = 512, bf16-exact operands) but -3.5e-6
+// when all 192 MMAs of the 6-term split share one accumulator.  So the A0 B0' term -- the only one of full
+// magnitude -- goes to two accumulators by K-block parity (16 MMAs each at K = 512) and the five correction
+// terms (2^-8 and 2^-16 of the magnitude, so their truncation is 2^-8 smaller too) go to a third; the epilogue
+// adds the three in f32 with round-to-nearest.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
@@ -23,7 +31,7 @@ constexpr int BM = 128, BN = 128, BK = 64, STAGES = 2, UMMA_K = 16, PARTS = 3;
 constexpr int A_TILE = BM * BK * 2, B_TILE = BN * BK * 2;
 constexpr int STAGE_BYTES = PARTS * (A_TILE + B_TILE);            // 98,304
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;     // + alignment slack + barriers
-constexpr int TMEM_COLS = 128;
+constexpr int TMEM_COLS = 512;   // three 128-column accumulators (main even/odd K blocks, correction); allocation must be a power of two
 constexpr int THREADS = 192;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -150,9 +158,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_cons
           const unsigned a = base + pi * A_TILE;
           const unsigned b = base + 3 * A_TILE + pj * B_TILE;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            tc_mma(tmem_base, smem_desc(a + k * UMMA_K * 2), smem_desc(b + k * UMMA_K * 2), IDESC,
-                   (kb | pair | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // main term -> accumulator kb & 1; corrections -> accumulator 2
+            const unsigned acc = pair == 0 ? (unsigned)(kb & 1) * BN : 2u * BN;
+            const unsigned accumulate = pair == 0 ? ((kb >= 2 || k != 0) ? 1u : 0u) : ((kb != 0 || pair != 1 || k != 0) ? 1u : 0u);
+            tc_mma(tmem_base + acc, smem_desc(a + k * UMMA_K * 2), smem_desc(b + k * UMMA_K * 2), IDESC, accumulate);
+          }
         }
         tc_commit(smem_u32(&bars[STAGES + s]));                   // stage reusable once these MMAs retire
       }
@@ -165,8 +176,17 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_cons
     tc_fence_after();
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
-      unsigned v[32];
-      tmem_ld32(tmem_base + ((unsigned)(32 * q) << 16) + (unsigned)(c * 32), v);
+      unsigned v[32], v1[32], v2[32];
+      const unsigned tl = tmem_base + ((unsigned)(32 * q) << 16) + (unsigned)(c * 32);
+      tmem_ld32(tl, v);
+      tmem_ld32(tl + 2 * BN, v2);
+      if (KB > 1) {
+        tmem_ld32(tl + BN, v1);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v1[j]));
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
       const int col0 = n0 + c * 32;
       if (row < M && col0 < N) {
         float* dst = C + (size_t)row * ldc + col0;

@@ -77,8 +77,9 @@ def test_gemm_f32(trans, shape):
 
 @pytest.mark.parametrize("shape", [(128, 256, 512), (4096, 2048, 512), (300, 1004, 512), (8, 2048, 512), (256, 1004, 64)])
 def test_gemm_bf16x3_tcgen05(shape):
-    """tcgen05 split-bf16 GEMM vs float64.  Measured 2.6e-6..3.3e-6 of max|C| for K=512 (2-part split: 4.9e-6):
-    what remains is the tensor core's f32 accumulation, not the operand split."""
+    """tcgen05 split-bf16 GEMM vs float64: fp32-grade (measured 3.6e-7 of max|C| at K=512, torch fp32 matmul
+    8.7e-7) once the full-magnitude term and the correction terms use separate TMEM accumulators
+    (gemm_tc.cu header; one shared accumulator gave 3.9e-6 through the tensor core's truncating adds)."""
     import ctypes
     from icrl_b200 import _lib
     M, N, K = shape
@@ -101,7 +102,7 @@ def test_gemm_bf16x3_tcgen05(shape):
     assert torch.isfinite(C).all()
     err = float((C.double() - ref).abs().max() / ref.abs().max())
     _record("gemm_bf16x3_%dx%dx%d" % shape, rel_err=err)
-    assert err < 5e-6, err
+    assert err < 1e-6, err
 
 
 def test_greedy_config1():
