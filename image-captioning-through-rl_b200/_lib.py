@@ -26,6 +26,9 @@ SIGNATURES = {
     "icrl_split_bf16x3": [P, L, P, P, LP],
     "icrl_gemm_bf16x3": [P, I, I, I, P, P, P, I, P, LP],
     "icrl_policy_rollout_fwd_tc": [P, I, I, I, I, I] + [P] * 18 + [LP],
+    "icrl_decode_weight_halves": [],
+    "icrl_pack_decode_weights": [P, I, P, P, P, LP],
+    "icrl_policy_rollout_fwd_fused": [P, I, I, I, I, I] + [P] * 17 + [LP],
     "icrl_pack_gate_table": [P, I, I, I, P, P, P, P, P, LP],
     "icrl_pack_value_head": [P, P, P, P, P, P, P, LP],
     "icrl_policy_rollout_fwd": [P, I, I, I, I, I] + [P] * 17 + [LP],
@@ -46,7 +49,7 @@ SIGNATURES = {
     "icrl_reward_cosine_fwd": [P, I, I, P, P, P, LP],
     "icrl_a2c_loss_fwd_bwd": [P, I, I, P, P, P, F, P, P, P, P, LP],
 }
-_RESTYPES = {"icrl_last_error": c_char_p, "icrl_colsum_ws_floats": c_size_t, "icrl_stream_len": c_longlong,
+_RESTYPES = {"icrl_last_error": c_char_p, "icrl_decode_weight_halves": c_size_t, "icrl_colsum_ws_floats": c_size_t, "icrl_stream_len": c_longlong,
              "icrl_chain_sync_bytes": c_size_t}
 _NO_STATUS = set(_RESTYPES) | {"icrl_version"}
 

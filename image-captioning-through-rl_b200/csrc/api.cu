@@ -139,6 +139,29 @@ int icrl_policy_rollout_fwd_tc(void* stream, int B, int V, int p0, int S, int gr
   return ICRL_OK;
 }
 
+size_t icrl_decode_weight_halves(void) { return icrl_decode_weight_halves_impl(); }
+
+int icrl_pack_decode_weights(void* stream, int V, const float* W_hh, const float* W_v, void* packed, int* launches) {
+  TRY(icrl_pack_decode_weights_impl(S_(stream), V, W_hh, W_v, packed));
+  bump(launches, 1);
+  return ICRL_OK;
+}
+
+int icrl_policy_rollout_fwd_fused(void* stream, int B, int V, int p0, int S, int greedy, const float* features,
+                                  const float* W_cnn, const float* b_cnn, const float* table, const void* packed,
+                                  const float* b_v, const double* uniforms, const long long* forced, int* tokcm,
+                                  long long* tokens_out, float* logp, float* Hs, float* Cs, float* Gs, float* logits,
+                                  float* last_logits, void* hparts, int* launches) {
+  cudaStream_t st = S_(stream);
+  // h0 = cnn2linear(features), c0 = 0   (models.py:75-78)
+  TRY(icrl_gemm_f32_impl(st, 0, 1, B, H, H, features, H, W_cnn, H, Hs, H, b_cnn, 0.f, nullptr, 0, launches));
+  ICRL_CUDA(cudaMemsetAsync(Cs, 0, (size_t)B * H * sizeof(float), st));
+  TRY(icrl_policy_decode_impl(st, B, V, p0, S, greedy, table, packed, b_v, uniforms, forced, tokcm, tokens_out, logp,
+                              Hs, Cs, Gs, logits, last_logits, hparts));
+  bump(launches, 2);                       // h split + the persistent decode kernel
+  return ICRL_OK;
+}
+
 size_t icrl_colsum_ws_floats(long long rows, int cols) { return (size_t)icrl_wcolsum_chunks(rows) * cols; }
 
 int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, const float* features, const float* E,

@@ -52,3 +52,10 @@ int icrl_chain_check_impl(cudaStream_t st, void* sync_state);
 int icrl_split_bf16x3_impl(cudaStream_t st, long long n, const float* x, void* parts);
 int icrl_gemm_bf16x3_impl(cudaStream_t st, int M, int N, int K, const void* a_parts, const void* b_parts, float* C,
                           int ldc, const float* bias);
+
+size_t icrl_decode_weight_halves_impl();
+int icrl_pack_decode_weights_impl(cudaStream_t st, int V, const float* W_hh, const float* W_v, void* packed);
+int icrl_policy_decode_impl(cudaStream_t st, int B, int V, int p0, int S, int greedy, const float* table,
+                            const void* packed, const float* b_v, const double* uniforms, const long long* forced,
+                            int* tokcm, long long* tokens_out, float* logp, float* Hs, float* Cs, float* Gs,
+                            float* logits, float* last_logits, void* hparts);

@@ -71,7 +71,9 @@ def plan_rollout(captions, level=None):
 
 
 class A2CEngine:
-    def __init__(self, a2c_network, reward_network, use_tc=True):
+    DECODE_MODES = ("fused", "tc", "simt")
+
+    def __init__(self, a2c_network, reward_network, use_tc=None, decode="fused"):
         self.policy = a2c_network.policy_network
         self.value = a2c_network.value_network
         self.reward = reward_network
@@ -85,7 +87,15 @@ class A2CEngine:
         self._bufs = {}
         self.launches = _lib.Launches()
         self.phase_events = None          # set to [] to record (name, start, end) CUDA events per phase
-        self.use_tc = bool(use_tc)        # per-step decode GEMMs on the tcgen05 pipe (split-bf16) vs fp32 SIMT
+        # policy decode path: "fused" = the persistent cluster kernel (decode.cu: tcgen05 GEMMs with the cell
+        # update / softmax / sampling in their epilogues, one launch per rollout); "tc" = per-step kernels with
+        # the two GEMMs on tcgen05 (gemm_tc.cu); "simt" = per-step kernels, fp32 CUDA-core GEMMs.
+        if use_tc is not None:
+            decode = "tc" if use_tc else "simt"
+        if decode not in self.DECODE_MODES:
+            raise ValueError("decode must be one of %s" % (self.DECODE_MODES,))
+        self.decode = decode
+        self.use_tc = decode == "tc"
         with torch.cuda.device(dev):
             self.sync_state = torch.zeros(int(_lib.call("icrl_chain_sync_bytes")), dtype=torch.uint8, device=dev)
         self._check_params()
@@ -179,6 +189,10 @@ class A2CEngine:
           _p(Vn.linear2.bias), _p(self._buf("v_weff", 2 * H)), _p(self._buf("v_beff", 1)), L)
         if self.use_tc:
             self._pack_policy_tc()
+        if self.decode == "fused":
+            n = int(_lib.call("icrl_decode_weight_halves"))
+            _lib.call("icrl_pack_decode_weights", st, V, _p(P.lstm.weight_hh_l0), _p(P.linear2vocab.weight),
+                      _p(self._buf("p_decode_pk", n, torch.float16)), L)
         if reward:
             self.pack_reward()
 
@@ -244,7 +258,12 @@ class A2CEngine:
         gpre = self._buf("p_gpre", B * 4 * H)
         b = self._bufs
         with self._phase("policy_fwd"):
-          if self.use_tc:
+          if self.decode == "fused":
+            _lib.call("icrl_policy_rollout_fwd_fused", self._stream, B, V, p0, S, int(bool(greedy)), _p(f),
+                  _p(P.cnn2linear.weight), _p(P.cnn2linear.bias), _p(b["p_table"]), _p(b["p_decode_pk"]),
+                  _p(P.linear2vocab.bias), _p(u), _p(fo), _p(tokcm), _p(tokens), _p(logp), _p(Hs), _p(Cs), _p(Gs),
+                  _p(logits), None, _p(self._buf("p_hparts", 4 * B * H, torch.float16)), self.launches.ref)
+          elif self.use_tc:
             _lib.call("icrl_policy_rollout_fwd_tc", self._stream, B, V, p0, S, int(bool(greedy)), _p(f),
                   _p(P.cnn2linear.weight), _p(P.cnn2linear.bias), _p(b["p_table"]), _p(b["p_whh_parts"]),
                   _p(b["p_wv_parts"]), _p(P.linear2vocab.bias), _p(u), _p(fo), _p(tokcm), _p(tokens),

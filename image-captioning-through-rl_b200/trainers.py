@@ -97,7 +97,8 @@ class _PolicyOnlyEngine(A2CEngine):
         from . import _lib
         _lib.load()
         self.device, self.V = dev, policy_network.linear2vocab.weight.shape[0]
-        self._bufs, self.launches, self.phase_events, self.use_tc = {}, _lib.Launches(), None, True
+        self._bufs, self.launches, self.phase_events = {}, _lib.Launches(), None
+        self.decode, self.use_tc = "fused", False
 
     def pack_weights(self, reward=False):
         from . import _lib
@@ -106,8 +107,9 @@ class _PolicyOnlyEngine(A2CEngine):
         _lib.call("icrl_pack_gate_table", self._stream, self.V, 4 * H, 4 * H, _p(P.caption_embedding.weight),
                   _p(P.lstm.weight_ih_l0), _p(P.lstm.bias_ih_l0), _p(P.lstm.bias_hh_l0),
                   _p(self._buf("p_table", self.V * 4 * H)), self.launches.ref)
-        if self.use_tc:
-            self._pack_policy_tc()
+        n = int(_lib.call("icrl_decode_weight_halves"))
+        _lib.call("icrl_pack_decode_weights", self._stream, self.V, _p(P.lstm.weight_hh_l0), _p(P.linear2vocab.weight),
+                  _p(self._buf("p_decode_pk", n, torch.float16)), self.launches.ref)
 
 
 def _run_minibatches(train_data, a2c_network, reward_network, optimizer, writer, batch_size, epoch, level, tag, best):

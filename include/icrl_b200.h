@@ -82,6 +82,20 @@ int icrl_policy_rollout_fwd_tc(void* stream, int B, int V, int p0, int S, int gr
                                const long long* forced, int* tokcm, long long* tokens_out, float* logp, float* Hs,
                                float* Cs, float* Gs, float* logits, float* gpre, void* h_parts, int* launches);
 
+/*      The same rollout as ONE persistent kernel (decode.cu): clusters of 8 CTAs own 128 rows each for all
+ *      timesteps; gate and vocab GEMMs on tcgen05 (2-part fp16 split, 3 MMAs, f32 accumulation in TMEM) with the
+ *      cell update, softmax, inverse-CDF sampling / argmax and log-prob fused into their epilogues.
+ *      packed: icrl_decode_weight_halves() fp16 values written by icrl_pack_decode_weights (once per optimizer
+ *      step; needs V <= 1024, V % 4 == 0).  hparts: scratch, 4*B*512 fp16.  Gs / logits may be null (inference:
+ *      no backward stash); last_logits (nullable) [B][V] receives the logits of the final step. */
+size_t icrl_decode_weight_halves(void);
+int icrl_pack_decode_weights(void* stream, int V, const float* W_hh, const float* W_v, void* packed, int* launches);
+int icrl_policy_rollout_fwd_fused(void* stream, int B, int V, int p0, int S, int greedy, const float* features,
+                                  const float* W_cnn, const float* b_cnn, const float* table, const void* packed,
+                                  const float* b_v, const double* uniforms, const long long* forced, int* tokcm,
+                                  long long* tokens_out, float* logp, float* Hs, float* Cs, float* Gs, float* logits,
+                                  float* last_logits, void* hparts, int* launches);
+
 /* ---- policy backward through time (replaces autograd over the S prefix re-runs, trainers.py:479).
  *      dlogp [B][S].  logits is overwritten with dL/dlogits.  Workspaces: dHv [S*B][512],
  *      DG [n_cell*B][2048], dh [2][B][512], dc [B][512], dtable [V][2048], colsum_ws

@@ -22,10 +22,13 @@ TOL = 2e-6
 GTOL = 2e-5
 
 
-def _engine(seed, use_tc=True):
+DECODES = ["fused", "tc", "simt"]     # persistent tcgen05 kernel / per-step tcgen05 GEMMs / per-step fp32 SIMT
+
+
+def _engine(seed, decode="fused"):
     from icrl_b200.engine import A2CEngine
     A, R, w = make_nets(seed)
-    return A2CEngine(A, R, use_tc=use_tc), A, R, w
+    return A2CEngine(A, R, decode=decode), A, R, w
 
 
 ERRORS = {}
@@ -118,23 +121,23 @@ def test_greedy_config1():
     assert float(np.abs(last.cpu().numpy() - g["last_logits"]).max()) <= TOL
 
 
-@pytest.mark.parametrize("use_tc", [False, True])
+@pytest.mark.parametrize("decode", DECODES)
 @pytest.mark.parametrize("name", ["a2c_b8_l6", "a2c_b32_l9", "curr_b16_l10_lv4", "curr_b24_l20_lv6"])
-def test_a2c_step_vs_reference_golden(name, use_tc):
+def test_a2c_step_vs_reference_golden(name, decode):
     g, seed, f, c, u, level = load_case(name)
-    eng, A, R, w = _engine(seed, use_tc)
+    eng, A, R, w = _engine(seed, decode)
     res = eng.step(f, c, uniforms=u, level=level)
-    _compare_forward(res, g, name + ("_tc" if use_tc else "_simt"))
-    _record(name + ("_tc" if use_tc else "_simt"), grad_worst=check_grads_vs_golden(named_grads(A), g, GTOL))
+    _compare_forward(res, g, name + "_" + decode)
+    _record(name + "_" + decode, grad_worst=check_grads_vs_golden(named_grads(A), g, GTOL))
 
 
-@pytest.mark.parametrize("use_tc", [False, True])
-def test_a2c_config2_vs_reference_golden(use_tc):
+@pytest.mark.parametrize("decode", DECODES)
+def test_a2c_config2_vs_reference_golden(decode):
     """BASELINE config 2: B=256, L=20, S=19, fixed uniforms."""
     g, seed, f, c, u, level = load_case("a2c_b256_l20")
-    eng, A, R, w = _engine(seed, use_tc)
+    eng, A, R, w = _engine(seed, decode)
     res = eng.step(f, c, uniforms=u, backward=False)
-    _compare_forward(res, g, "a2c_b256_l20")
+    _compare_forward(res, g, "a2c_b256_l20_" + decode)
     last = eng._bufs["p_logits"][18 * 256 * 1004:19 * 256 * 1004].view(256, 1004).cpu().numpy()
     assert float(np.abs(last - g["last_logits"]).max()) <= TOL
     res = eng.step(f, c, uniforms=u)
@@ -229,3 +232,27 @@ def test_determinism_and_row_independence_full_size():
     assert torch.isfinite(eng.flat_grad).all()
     r3 = eng.step(f[256:512], c[256:512], uniforms=u[:, 256:512], backward=False)
     assert torch.equal(r3["tokens"], t1[256:512])
+
+
+def test_decode_paths_agree_large_batch():
+    """B=2048 (16 clusters of the persistent kernel, ragged last tile at B=2000): the fused tcgen05 kernel and
+    the fp32 SIMT path sample the same tokens from the same uniforms, greedy and forced modes included."""
+    seed, B, L = 41, 2000, 20
+    f, c = synth.make_inputs(seed, B, L)
+    u = synth.make_uniforms(seed, L - 1, B)
+    ef, A, R, w = _engine(seed, "fused")
+    from icrl_b200.engine import A2CEngine
+    es = A2CEngine(A, R, decode="simt")
+    rf = ef.step(f, c, uniforms=u, backward=False)
+    rs = es.step(f, c, uniforms=u, backward=False)
+    nflip = int((rf["tokens"] != rs["tokens"]).sum())
+    _record("decode_agree_b2000", flips=nflip, logp=float((rf["logp"] - rs["logp"]).abs().max()))
+    assert nflip == 0
+    assert float((rf["logp"] - rs["logp"]).abs().max()) <= TOL
+    gf = ef.step(f, c, greedy=True, backward=False)
+    gs = es.step(f, c, greedy=True, backward=False)
+    assert torch.equal(gf["tokens"], gs["tokens"])
+    forced = rs["tokens"].cpu().numpy()
+    ff = ef.step(f, c, forced_tokens=forced, backward=False)
+    assert torch.equal(ff["tokens"], rs["tokens"])
+    assert float((ff["logp"] - rs["logp"]).abs().max()) <= TOL
