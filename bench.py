@@ -218,28 +218,22 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- tensor-pipe figure of the decode-step gate GEMM (B_local x 2048 x 512, 3-part bf16 split = 6 MMAs)
+    # ---- tensor-pipe figure of the persistent decode kernel (policy_decode_kernel: all S steps in one launch).
+    # Timed live as the policy_fwd phase (h0 GEMM + h split + the decode kernel; the kernel is >95 % of it).
     decode = None
     try:
-        from icrl_b200.engine import _p
         Bl_ = hi - lo
-        bufs = eng._bufs
-        st_ = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 20
-        for i in range(reps + 3):
-            if i == 3:
-                ev0.record()
-            _lib.call("icrl_gemm_bf16x3", st_, Bl_, 2048, 512, _p(bufs["p_h_parts"]), _p(bufs["p_whh_parts"]),
-                      _p(bufs["p_gpre"]), 2048, None, None)
-        ev1.record()
-        torch.cuda.synchronize()
-        us = ev0.elapsed_time(ev1) * 1e3 / reps
-        alg = 2.0 * Bl_ * 2048 * 512
-        decode = {"kernel": "gemm_bf16x3_kernel (gate GEMM of one decode step)", "bound": "tensor",
-                  "achieved": alg / us / 1e6, "executed_tflops": 6 * alg / us / 1e6, "unit": "TFLOP/s",
-                  "us_per_launch": us, "shape": [Bl_, 2048, 512], "mma_passes": 6,
-                  "note": "achieved counts the algorithmic 2MNK once; the tensor pipe executes 6x that (3-part split)"}
+        us = phases.get("policy_fwd", 0.0) * 1e3
+        n_cell = S                                    # p0 = 1: S cell steps, each followed by a vocab projection
+        alg = Bl_ * (n_cell * 2.0 * 2048 * 512 + S * 2.0 * 1004 * 512)
+        rows_pad = ((Bl_ + 127) // 128) * 128
+        executed = 3.0 * rows_pad * (n_cell * 2.0 * 2048 * 512 + S * 2.0 * 1024 * 512)
+        decode = {"kernel": "policy_decode_kernel (gate GEMM + cell update + vocab GEMM + softmax + sampling, all %d steps)" % S,
+                  "bound": "tensor", "achieved": alg / us / 1e6, "executed_tflops": executed / us / 1e6, "unit": "TFLOP/s",
+                  "us_per_launch": us, "rows": Bl_, "mma_passes": 3,
+                  "note": "achieved counts the algorithmic 2MNK of the recurrent gate GEMM and the vocab GEMM once; the "
+                          "tensor pipe executes 3x that (2-part fp16 split) on rows padded to 128 and V padded to 1024; "
+                          "ncu sm__pipe_tensor_cycles_active of this kernel: profiles/"}
     except Exception as exc:                                   # never let the side measurement kill the bench line
         decode = {"error": str(exc)}
 

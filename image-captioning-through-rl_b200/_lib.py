@@ -27,6 +27,7 @@ SIGNATURES = {
     "icrl_gemm_bf16x3": [P, I, I, I, P, P, P, I, P, LP],
     "icrl_policy_rollout_fwd_tc": [P, I, I, I, I, I] + [P] * 18 + [LP],
     "icrl_decode_weight_halves": [],
+    "icrl_decode_set_profile": [P],
     "icrl_pack_decode_weights": [P, I, P, P, P, LP],
     "icrl_policy_rollout_fwd_fused": [P, I, I, I, I, I] + [P] * 17 + [LP],
     "icrl_pack_gate_table": [P, I, I, I, P, P, P, P, P, LP],

@@ -139,6 +139,8 @@ int icrl_policy_rollout_fwd_tc(void* stream, int B, int V, int p0, int S, int gr
   return ICRL_OK;
 }
 
+int icrl_decode_set_profile(void* buf) { icrl_decode_set_profile_impl(reinterpret_cast<long long*>(buf)); return ICRL_OK; }
+
 size_t icrl_decode_weight_halves(void) { return icrl_decode_weight_halves_impl(); }
 
 int icrl_pack_decode_weights(void* stream, int V, const float* W_hh, const float* W_v, void* packed, int* launches) {

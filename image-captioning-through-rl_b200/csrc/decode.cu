@@ -18,9 +18,18 @@
 // scripts/tc_accuracy_probe.py).  The vocab GEMM further splits the main term over two accumulators by
 // K-block parity.  Operand-split error 7e-8 of max|C| (emulated), i.e. below fp32 rounding of the dot itself.
 //
-// Per CTA: warp 0 = TMA producer (2-stage ring of 64-wide K blocks: A hi/lo 2 x 16 KB, B hi/lo 2 x 32 KB),
-// warp 1 = tcgen05.mma issuer (M=128, N=256 gates / N=128 vocab, 12 MMAs per stage), warps 2..9 = epilogue
-// (TMEM lane quarter = warp % 4, two warps per quarter each taking half of the columns).
+// Per CTA (384 threads): warp 0 = TMA producer (4-stage ring of 32-wide K blocks: A hi/lo 2 x 8 KB, B hi/lo
+// 2 x 16 KB), warp 1 = tcgen05.mma issuer (M=128, N=256 gates / N=128 vocab, 6 MMAs per stage), warps 4..11 =
+// epilogue (TMEM lane quarter = warp % 4, two warps per quarter each taking half of the columns).  Warpgroup 0
+// gives its registers to the two epilogue warpgroups (setmaxnreg 40 / 232).
+//
+// Global-memory access of the epilogues.  tcgen05.ld hands a thread one accumulator ROW, and a warp-wide
+// float4 access with one row per lane touches 32 cache lines (32 L1 tag cycles): the first version of the gate
+// epilogue spent 42 K of its 100 K cycles per step there.  So the gate epilogue stages through shared memory
+// (the TMA ring is idle between the gate GEMM and the cluster barrier): cp.async gathers the gate-table rows
+// and c_{t-1} as [32 rows][32 units] tiles with 8 lanes per row (4 lines per access), the cell update runs
+// thread-per-row on the swizzled tile in place, and the stash goes out the same coalesced way.  The logits
+// stash is staged through the second exchange buffer 16 columns at a time.
 //
 // Per cell step j:   G-MMA -> G-epilogue (gate table gather by token + activations + c,h update; writes the
 // fp32 stash for backward and the fp16 split of h for the next GEMMs) -> cluster barrier (all 512 h columns
@@ -41,15 +50,17 @@ constexpr int GN = 4 * H / CL;              // 256 gate columns per CTA
 constexpr int UN = H / CL;                  // 64 hidden units per CTA
 constexpr int VN = 128;                     // vocab columns per CTA
 constexpr int VPAD = CL * VN;               // 1024
-constexpr int BK = 64, KB = H / BK, UMMA_K = 16, STAGES = 2;
-constexpr int A_TILE = BM * BK * 2;         // 16 KB
-constexpr int BG_TILE = GN * BK * 2;        // 32 KB
-constexpr int BV_TILE = VN * BK * 2;        // 16 KB
-constexpr int STAGE_BYTES = 2 * A_TILE + 2 * BG_TILE;      // 96 KB
+constexpr int BK = 32, KB = H / BK, UMMA_K = 16, STAGES = 4;   // 64-byte rows (SWIZZLE_64B); 4 stages cover the L2->SMEM latency
+constexpr int A_TILE = BM * BK * 2;         // 8 KB
+constexpr int BG_TILE = GN * BK * 2;        // 16 KB
+constexpr int BV_TILE = VN * BK * 2;        // 8 KB
+constexpr int STAGE_BYTES = 2 * A_TILE + 2 * BG_TILE;      // 48 KB
 constexpr int XCHG_SLOTS = 2 * CL;          // partials per row: 8 CTAs x 2 column halves
 constexpr int XCHG_BYTES = XCHG_SLOTS * BM * 8;            // 16 KB per exchange buffer
 constexpr int EPI_WARPS = 8;
-constexpr int THREADS = 64 + 32 * EPI_WARPS;               // 320
+constexpr int EPI_WARP0 = 4;                // warps 0..3 = warpgroup 0 (TMA, MMA, 2 idle); 4..11 = epilogue warpgroups
+constexpr int THREADS = 32 * (EPI_WARP0 + EPI_WARPS);      // 384
+constexpr int GSTAGE_WARP = 6 * 4096;       // gate-epilogue staging per warp: 6 arrays of [32 rows][32 units] f32
 constexpr int NBARS = 2 * STAGES + 2 + 2;   // full[2], empty[2], acc_full, acc_empty, xchg[2]
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * XCHG_BYTES + 256 + 1024;
 constexpr int TMEM_COLS = 512;
@@ -70,6 +81,7 @@ struct DecodeArgs {
   float* logits;             // [S][B][V]                             (nullable: inference)
   float* last_logits;        // [B][V] logits of the last step        (nullable)
   __half* hparts;            // [2 buffers][2 parts][B][512]
+  long long* prof;           // optional [n_cell][16] clock64 stamps of CTA 0's first epilogue warp (icrl_decode_set_profile)
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -110,9 +122,11 @@ __device__ __forceinline__ void tc_mma(unsigned tmem_d, unsigned long long da, u
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc),
       "r"(accumulate) : "memory");
 }
-// K-major, 128B-swizzle operand descriptor (see gemm_tc.cu)
+// K-major, 64B-swizzle operand descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 = 1 [16,30) (unused
+// for swizzled K-major), SBO>>4 = 32 [32,46) (8 rows x 64 B between row groups), version = 1 [46,48), layout
+// SWIZZLE_64B = 4 [61,64).
 __device__ __forceinline__ unsigned long long smem_desc(unsigned addr) {
-  return (unsigned long long)((addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+  return (unsigned long long)((addr & 0x3FFFF) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
 }
 // c_format F32 [4,6) = 1, a/b_format F16 = 0, K-major, n_dim = N>>3 [17,23), m_dim = M>>4 [24,29)
 constexpr unsigned idesc_f16(int n) { return (1u << 4) | ((unsigned)(n >> 3) << 17) | ((unsigned)(BM >> 4) << 24); }
@@ -209,8 +223,13 @@ policy_decode_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
   cluster_arrive();                      // every CTA's mbarriers are initialised before anyone sends to them
   cluster_wait();
 
-  if (warp == 0) {
+  if (warp == 2 || warp == 3) {
+    // idle warps of warpgroup 0: only keep the cluster barrier counts complete
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    for (int j = 0; j < n_cell; ++j) { cluster_arrive(); cluster_wait(); }
+  } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     unsigned it = 0;
     for (int j = 0; j < n_cell; ++j) {
       if (lane == 0) {
@@ -251,6 +270,7 @@ policy_decode_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     unsigned it = 0, nphase = 0;
     for (int j = 0; j < n_cell; ++j) {
       if (lane == 0) {
@@ -308,7 +328,8 @@ policy_decode_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int ew = warp - 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int ew = warp - EPI_WARP0;
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
     const int ch = ew >> 2;                    // column half
     const int rl = 32 * q + lane;              // row inside the cluster tile
@@ -316,86 +337,134 @@ policy_decode_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
     const bool valid = row < B;
     const unsigned tq = tmem_base + ((unsigned)(32 * q) << 16);
     const int slot = (int)rank * 2 + ch;
+    unsigned rxb[CL], rbar[CL];                // this CTA's exchange buffer 0 / barrier 0 as seen in every peer
+#pragma unroll
+    for (unsigned d = 0; d < (unsigned)CL; ++d) { rxb[d] = mapa(smem_u32(xbuf), d); rbar[d] = mapa(bar_x, d); }
+    const unsigned xoff = (unsigned)(slot * BM + rl) * 8u;
+    auto xsend = [&](int which, unsigned long long v) {
+#pragma unroll
+      for (int d = 0; d < CL; ++d) st_async_b64(rxb[d] + which * XCHG_BYTES + xoff, v, rbar[d] + which * 8);
+    };
+    unsigned char* gst = smem + ew * GSTAGE_WARP;          // gate-epilogue staging of this warp (inside the TMA ring)
+    float* lst = reinterpret_cast<float*>(xbuf + XCHG_BYTES + ew * 2048);   // logits staging [32 rows][16 cols]
+    const int ucol0 = (int)rank * UN + 32 * ch;
     unsigned ephase = 0;                       // accumulator phases consumed
     unsigned xph0 = 0, xph1 = 0;               // exchange barrier phases
     int tok = valid ? p.tokcm[row] : 0;        // token consumed by cell 0 (prefix column 0)
 
+    const bool prof = p.prof != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0;
+#define STAMP(k) do { if (prof) p.prof[(size_t)j * 16 + (k)] = clock64(); } while (0)
     for (int j = 0; j < n_cell; ++j) {
       const size_t BH = (size_t)B * H;
-      // ---------------- gate epilogue: cell update for this thread's 32 hidden units
+      STAMP(0);
+      // ---------------- gate epilogue: cell update of [32 rows] x [32 hidden units] per warp
       mbar_wait(bar_acc_full, ephase & 1u);
       ++ephase;
       tc_fence_after();
-      const float* trow = p.table + (size_t)tok * (4 * H) + rank * UN + 32 * ch;
-      const size_t hoff = (size_t)row * H + rank * UN + 32 * ch;
-      __half* hp_hi = p.hparts + ((size_t)(((j + 1) & 1) * 2) * B + row) * H + rank * UN + 32 * ch;
-      __half* hp_lo = hp_hi + BH;
-#pragma unroll 1
+      STAMP(1);
+      // (L) gate-table rows of the consumed tokens (arrays 0..3 = i,f,g,o) and c_{j-1} (array 4) -> staging,
+      //     8 lanes per row; element (row, 16-byte chunk c) lives at row*128 + ((c ^ (row & 7)) << 4).
+      {
+        const int c4 = lane & 7;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + (lane >> 3);
+          const int tokr = __shfl_sync(0xffffffffu, tok, r);
+          const int growr = m0 + 32 * q + r;
+          if (growr < B) {
+            const unsigned dst = smem_u32(gst) + (unsigned)(r * 128 + ((c4 ^ (r & 7)) << 4));
+            const float* tsrc = p.table + (size_t)tokr * (4 * H) + ucol0 + c4 * 4;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + a * 4096), "l"(tsrc + a * H) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 4 * 4096),
+                         "l"(p.Cs + (size_t)j * BH + (size_t)growr * H + ucol0 + c4 * 4) : "memory");
+          }
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+      }
+      STAMP(11);
+      // (C) cell update, one row per lane, in place on the staging tile
+#pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
         float acc[4][8], cor[4][8];
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           tmem_ld8x2(tq + (unsigned)(g * UN + 32 * ch + 8 * c8), tq + (unsigned)(GN + g * UN + 32 * ch + 8 * c8), acc[g], cor[g]);
-        if (valid) {
-          float tb[4][8], cp[8];
+        unsigned char* e0 = gst + lane * 128 + (((2 * c8) ^ (lane & 7)) << 4);
+        unsigned char* e1 = gst + lane * 128 + (((2 * c8 + 1) ^ (lane & 7)) << 4);
+        float tin[5][8];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const float4 t0 = *reinterpret_cast<const float4*>(trow + g * H + 8 * c8);
-            const float4 t1 = *reinterpret_cast<const float4*>(trow + g * H + 8 * c8 + 4);
-            tb[g][0] = t0.x; tb[g][1] = t0.y; tb[g][2] = t0.z; tb[g][3] = t0.w;
-            tb[g][4] = t1.x; tb[g][5] = t1.y; tb[g][6] = t1.z; tb[g][7] = t1.w;
-          }
-          {
-            const float4 c0 = *reinterpret_cast<const float4*>(p.Cs + (size_t)j * BH + hoff + 8 * c8);
-            const float4 c1 = *reinterpret_cast<const float4*>(p.Cs + (size_t)j * BH + hoff + 8 * c8 + 4);
-            cp[0] = c0.x; cp[1] = c0.y; cp[2] = c0.z; cp[3] = c0.w; cp[4] = c1.x; cp[5] = c1.y; cp[6] = c1.z; cp[7] = c1.w;
-          }
-          float gi[8], gf[8], gg[8], go[8], cn[8], hn[8];
+        for (int a = 0; a < 5; ++a) {
+          const float4 u0 = *reinterpret_cast<const float4*>(e0 + a * 4096);
+          const float4 u1 = *reinterpret_cast<const float4*>(e1 + a * 4096);
+          tin[a][0] = u0.x; tin[a][1] = u0.y; tin[a][2] = u0.z; tin[a][3] = u0.w;
+          tin[a][4] = u1.x; tin[a][5] = u1.y; tin[a][6] = u1.z; tin[a][7] = u1.w;
+        }
+        float gi[8], gf[8], gg[8], go[8], cn[8], hn[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            gi[i] = sigmoidf_acc(fmaf(cor[0][i], LO_INV, acc[0][i]) + tb[0][i]);
-            gf[i] = sigmoidf_acc(fmaf(cor[1][i], LO_INV, acc[1][i]) + tb[1][i]);
-            gg[i] = tanhf(fmaf(cor[2][i], LO_INV, acc[2][i]) + tb[2][i]);
-            go[i] = sigmoidf_acc(fmaf(cor[3][i], LO_INV, acc[3][i]) + tb[3][i]);
-            cn[i] = gf[i] * cp[i] + gi[i] * gg[i];
-            hn[i] = go[i] * tanhf(cn[i]);
-          }
-          if (p.Gs) {
-            float* gs = p.Gs + ((size_t)j * B + row) * (4 * H) + rank * UN + 32 * ch + 8 * c8;
-            *reinterpret_cast<float4*>(gs) = make_float4(gi[0], gi[1], gi[2], gi[3]);
-            *reinterpret_cast<float4*>(gs + 4) = make_float4(gi[4], gi[5], gi[6], gi[7]);
-            *reinterpret_cast<float4*>(gs + H) = make_float4(gf[0], gf[1], gf[2], gf[3]);
-            *reinterpret_cast<float4*>(gs + H + 4) = make_float4(gf[4], gf[5], gf[6], gf[7]);
-            *reinterpret_cast<float4*>(gs + 2 * H) = make_float4(gg[0], gg[1], gg[2], gg[3]);
-            *reinterpret_cast<float4*>(gs + 2 * H + 4) = make_float4(gg[4], gg[5], gg[6], gg[7]);
-            *reinterpret_cast<float4*>(gs + 3 * H) = make_float4(go[0], go[1], go[2], go[3]);
-            *reinterpret_cast<float4*>(gs + 3 * H + 4) = make_float4(go[4], go[5], go[6], go[7]);
-          }
-          float* cs = p.Cs + (size_t)(j + 1) * BH + hoff + 8 * c8;
-          float* hs = p.Hs + (size_t)(j + 1) * BH + hoff + 8 * c8;
-          *reinterpret_cast<float4*>(cs) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-          *reinterpret_cast<float4*>(cs + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
-          *reinterpret_cast<float4*>(hs) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-          *reinterpret_cast<float4*>(hs + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
-          __half2 hi2[4], lo2[4];
+        for (int i = 0; i < 8; ++i) {
+          gi[i] = sigmoidf_sfu(fmaf(cor[0][i], LO_INV, acc[0][i]) + tin[0][i]);
+          gf[i] = sigmoidf_sfu(fmaf(cor[1][i], LO_INV, acc[1][i]) + tin[1][i]);
+          gg[i] = tanhf_sfu(fmaf(cor[2][i], LO_INV, acc[2][i]) + tin[2][i]);
+          go[i] = sigmoidf_sfu(fmaf(cor[3][i], LO_INV, acc[3][i]) + tin[3][i]);
+          cn[i] = gf[i] * tin[4][i] + gi[i] * gg[i];
+          hn[i] = go[i] * tanhf_sfu(cn[i]);
+        }
+        *reinterpret_cast<float4*>(e0) = make_float4(gi[0], gi[1], gi[2], gi[3]);
+        *reinterpret_cast<float4*>(e1) = make_float4(gi[4], gi[5], gi[6], gi[7]);
+        *reinterpret_cast<float4*>(e0 + 4096) = make_float4(gf[0], gf[1], gf[2], gf[3]);
+        *reinterpret_cast<float4*>(e1 + 4096) = make_float4(gf[4], gf[5], gf[6], gf[7]);
+        *reinterpret_cast<float4*>(e0 + 2 * 4096) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+        *reinterpret_cast<float4*>(e1 + 2 * 4096) = make_float4(gg[4], gg[5], gg[6], gg[7]);
+        *reinterpret_cast<float4*>(e0 + 3 * 4096) = make_float4(go[0], go[1], go[2], go[3]);
+        *reinterpret_cast<float4*>(e1 + 3 * 4096) = make_float4(go[4], go[5], go[6], go[7]);
+        *reinterpret_cast<float4*>(e0 + 4 * 4096) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+        *reinterpret_cast<float4*>(e1 + 4 * 4096) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+        *reinterpret_cast<float4*>(e0 + 5 * 4096) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        *reinterpret_cast<float4*>(e1 + 5 * 4096) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+      }
+      __syncwarp();
+      STAMP(12);
+      // (S) stash for backward: activated gates, c_j, h_j -- 8 lanes per row again
+      {
+        const int c4 = lane & 7;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const __half h0 = __float2half_rn(hn[2 * i]), h1 = __float2half_rn(hn[2 * i + 1]);
-            hi2[i] = __halves2half2(h0, h1);
-            lo2[i] = __halves2half2(__float2half_rn((hn[2 * i] - __half2float(h0)) * LO_SCALE),
-                                    __float2half_rn((hn[2 * i + 1] - __half2float(h1)) * LO_SCALE));
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + (lane >> 3);
+          const int growr = m0 + 32 * q + r;
+          if (growr < B) {
+            const unsigned char* e = gst + r * 128 + ((c4 ^ (r & 7)) << 4);
+            if (p.Gs) {
+              float* gs = p.Gs + ((size_t)j * B + growr) * (4 * H) + ucol0 + c4 * 4;
+#pragma unroll
+              for (int a = 0; a < 4; ++a) *reinterpret_cast<float4*>(gs + a * H) = *reinterpret_cast<const float4*>(e + a * 4096);
+            }
+            const size_t o = (size_t)(j + 1) * BH + (size_t)growr * H + ucol0 + c4 * 4;
+            *reinterpret_cast<float4*>(p.Cs + o) = *reinterpret_cast<const float4*>(e + 4 * 4096);
+            const float4 h4 = *reinterpret_cast<const float4*>(e + 5 * 4096);
+            *reinterpret_cast<float4*>(p.Hs + o) = h4;
+            // fp16 split of h for the next GEMMs
+            const __half a0 = __float2half_rn(h4.x), a1 = __float2half_rn(h4.y), a2 = __float2half_rn(h4.z), a3 = __float2half_rn(h4.w);
+            __half2 hi2[2] = {__halves2half2(a0, a1), __halves2half2(a2, a3)};
+            __half2 lo2[2] = {__halves2half2(__float2half_rn((h4.x - __half2float(a0)) * LO_SCALE), __float2half_rn((h4.y - __half2float(a1)) * LO_SCALE)),
+                              __halves2half2(__float2half_rn((h4.z - __half2float(a2)) * LO_SCALE), __float2half_rn((h4.w - __half2float(a3)) * LO_SCALE))};
+            __half* hp = p.hparts + ((size_t)(((j + 1) & 1) * 2) * B + growr) * H + ucol0 + c4 * 4;
+            *reinterpret_cast<uint2*>(hp) = *reinterpret_cast<const uint2*>(hi2);
+            *reinterpret_cast<uint2*>(hp + BH) = *reinterpret_cast<const uint2*>(lo2);
           }
-          *reinterpret_cast<uint4*>(hp_hi + 8 * c8) = *reinterpret_cast<const uint4*>(hi2);
-          *reinterpret_cast<uint4*>(hp_lo + 8 * c8) = *reinterpret_cast<const uint4*>(lo2);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty);
+      STAMP(2);
       __threadfence();
       fence_proxy_async();                     // generic-proxy writes of the h split -> visible to the peers' TMA loads
       cluster_arrive();
       cluster_wait();
+      STAMP(3);
 
       const int s = j - (p.p0 - 1);
       if (s < 0) {                             // teacher-forced prefix cell: next token comes from the caption
@@ -406,6 +475,7 @@ policy_decode_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
       mbar_wait(bar_acc_full, ephase & 1u);
       ++ephase;
       tc_fence_after();
+      STAMP(4);
       float x[64];
       const int v0 = (int)rank * VN + 64 * ch;
 #pragma unroll
@@ -413,27 +483,50 @@ policy_decode_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
         float m0v[8], m1v[8], cv[8];
         tmem_ld8x3(tq + (unsigned)(64 * ch + 8 * c8), tq + (unsigned)(VN + 64 * ch + 8 * c8),
                    tq + (unsigned)(2 * VN + 64 * ch + 8 * c8), m0v, m1v, cv);
+        float bz[8];
+#pragma unroll
+        for (int h4 = 0; h4 < 2; ++h4) {                  // V % 4 == 0: a float4 of bias is all valid or all padding
+          const int v = v0 + 8 * c8 + 4 * h4;
+          const float4 b4 = v < V ? __ldg(reinterpret_cast<const float4*>(p.b_v + v)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          bz[4 * h4] = b4.x; bz[4 * h4 + 1] = b4.y; bz[4 * h4 + 2] = b4.z; bz[4 * h4 + 3] = b4.w;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int v = v0 + 8 * c8 + i;
-          x[8 * c8 + i] = v < V ? fmaf(cv[i], LO_INV, m0v[i] + m1v[i]) + __ldg(p.b_v + v) : -INFINITY;
+          x[8 * c8 + i] = v < V ? fmaf(cv[i], LO_INV, m0v[i] + m1v[i]) + bz[i] : -INFINITY;
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty);          // the next gate GEMM may overwrite TMEM now
-      if (valid) {
-        float* lg = p.logits ? p.logits + ((size_t)s * B + row) * V + v0 : nullptr;
-        float* ll = (p.last_logits && s == p.S - 1) ? p.last_logits + (size_t)row * V + v0 : nullptr;
+      STAMP(13);
+      if (p.logits || (p.last_logits && s == p.S - 1)) {
+        // logits stash, 16 columns per pass: one row per lane into staging, 4 lanes per row out (8 lines per access)
+        float* lgw = p.logits ? p.logits + (size_t)s * B * V : nullptr;
+        float* llw = (p.last_logits && s == p.S - 1) ? p.last_logits : nullptr;
 #pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) {
-          if (v0 + 4 * c4 + 3 < V) {                       // V % 4 == 0 is required by the host wrapper
-            const float4 o = make_float4(x[4 * c4], x[4 * c4 + 1], x[4 * c4 + 2], x[4 * c4 + 3]);
-            if (lg) *reinterpret_cast<float4*>(lg + 4 * c4) = o;
-            if (ll) *reinterpret_cast<float4*>(ll + 4 * c4) = o;
+        for (int ps = 0; ps < 4; ++ps) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<float4*>(lst + lane * 16 + ((c ^ ((lane >> 1) & 3)) << 2)) =
+                make_float4(x[16 * ps + 4 * c], x[16 * ps + 4 * c + 1], x[16 * ps + 4 * c + 2], x[16 * ps + 4 * c + 3]);
+          __syncwarp();
+          const int c = lane & 3;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int r = it * 8 + (lane >> 2);
+            const int growr = m0 + 32 * q + r;
+            const int v = v0 + 16 * ps + 4 * c;
+            if (growr < B && v + 3 < V) {                  // V % 4 == 0 is required by the host wrapper
+              const float4 o = *reinterpret_cast<const float4*>(lst + r * 16 + ((c ^ ((r >> 1) & 3)) << 2));
+              if (lgw) *reinterpret_cast<float4*>(lgw + (size_t)growr * V + v) = o;
+              if (llw) *reinterpret_cast<float4*>(llw + (size_t)growr * V + v) = o;
+            }
           }
+          __syncwarp();
         }
       }
+      STAMP(5);
       // ---------------- part 2: softmax + sampling across the cluster (trainers.py:444-458)
       // E1: row max and first argmax
       float mx = -INFINITY;
@@ -442,7 +535,7 @@ policy_decode_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
       for (int i = 0; i < 64; ++i)
         if (x[i] > mx) { mx = x[i]; amax = v0 + i; }
       if (ew == 0 && lane == 0) mbar_expect_tx(bar_x, XCHG_BYTES);
-      xchg_send(smem_u32(xbuf), bar_x, slot, rl, ((unsigned long long)(unsigned)amax << 32) | __float_as_uint(mx));
+      xsend(0, ((unsigned long long)(unsigned)amax << 32) | __float_as_uint(mx));
       mbar_wait(bar_x, xph0 & 1u);
       ++xph0;
       {
@@ -456,12 +549,13 @@ policy_decode_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
           if (m > mx) { mx = m; amax = (int)(w >> 32); }
         }
       }
+      STAMP(6);
       // E2: sum of exp(x - max) in f32 (F.softmax)
       float lsum = 0.f;
 #pragma unroll
       for (int i = 0; i < 64; ++i) { x[i] = expf(x[i] - mx); lsum += x[i]; }
       if (ew == 0 && lane == 0) mbar_expect_tx(bar_x + 8, XCHG_BYTES);
-      xchg_send(smem_u32(xbuf + XCHG_BYTES), bar_x + 8, slot, rl, (unsigned long long)__float_as_uint(lsum));
+      xsend(1, (unsigned long long)__float_as_uint(lsum));
       mbar_wait(bar_x + 8, xph1 & 1u);
       ++xph1;
       float tot = 0.f;
@@ -471,41 +565,57 @@ policy_decode_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
         for (int k = 0; k < XCHG_SLOTS; ++k) tot += __uint_as_float((unsigned)xs[k * BM]);
       }
       const float inv = 1.0f / tot;
+      STAMP(7);
       int a;
       if (p.forced) {
         a = valid ? (int)p.forced[(size_t)row * p.S + s] : 0;
       } else if (p.greedy) {
         a = min(amax, V - 1);
       } else {
-        // E3: float64 cdf (np.random.choice: cdf = cumsum(float64(p)); cdf /= cdf[-1]; searchsorted(u, 'right'))
-        double loc = 0.0;
+        // E3: the cdf of np.random.choice (cdf = cumsum(float64(p)); cdf /= cdf[-1]; searchsorted(u, 'right')),
+        // carried in 62-bit fixed point: fx(p) = floor(p * 2^62) is exact for every f32 probability >= 2^-38 and
+        // integer prefix sums are exact and independent of how the row is cut into partials, where the f64
+        // cumsum rounds at 2^-53 per add.  (FP64 adds run at ~1/32 rate on this part: the f64 form of this
+        // phase cost 21 K cycles per step, this one 3 K.)
+        unsigned long long loc = 0;
 #pragma unroll
-        for (int i = 0; i < 64; ++i) loc += (double)(x[i] * inv);
+        for (int i = 0; i < 64; ++i) loc += __float2ull_rz(x[i] * inv * 0x1p62f);
         if (ew == 0 && lane == 0) mbar_expect_tx(bar_x, XCHG_BYTES);
-        xchg_send(smem_u32(xbuf), bar_x, slot, rl, (unsigned long long)__double_as_longlong(loc));
+        xsend(0, loc);
         mbar_wait(bar_x, xph0 & 1u);
         ++xph0;
-        double pre = 0.0, total = 0.0;
+        unsigned long long pre = 0, total = 0;
         {
           const unsigned long long* xs = reinterpret_cast<const unsigned long long*>(xbuf) + rl;
 #pragma unroll
           for (int k = 0; k < XCHG_SLOTS; ++k) {
-            const double d = __longlong_as_double((long long)xs[k * BM]);
+            const unsigned long long d = xs[k * BM];
             if (k < slot) pre += d;
             total += d;
           }
         }
-        const double u = valid ? p.uniforms[(size_t)s * B + row] : 0.0;
-        double run = pre;
+        STAMP(8);
+        // threshold: cdf_k / total <= u  <=>  cdf_k <= floor(u * total), evaluated exactly (u = mu * 2^(eb-1075))
+        unsigned long long thr;
+        {
+          const unsigned long long ub = (unsigned long long)__double_as_longlong(valid ? p.uniforms[(size_t)s * B + row] : 0.0);
+          const int eb = (int)((ub >> 52) & 0x7FF);
+          const unsigned long long mu = (ub & ((1ull << 52) - 1)) | (eb ? (1ull << 52) : 0ull);
+          const unsigned long long hi = __umul64hi(mu, total), lo = mu * total;
+          const int sh = 1075 - (eb ? eb : 1);                 // >= 53 because u < 1
+          thr = sh >= 128 ? 0ull : (sh >= 64 ? (hi >> (sh - 64)) : ((hi << (64 - sh)) | (lo >> sh)));
+        }
+        unsigned long long run = pre;
         int cnt = 0;
 #pragma unroll
         for (int i = 0; i < 64; ++i) {
-          run += (double)(x[i] * inv);
-          cnt += (v0 + i < V && run / total <= u) ? 1 : 0;
+          run += __float2ull_rz(x[i] * inv * 0x1p62f);
+          cnt += (v0 + i < V && run <= thr) ? 1 : 0;
         }
+        STAMP(9);
         // E4: count of cdf entries <= u
         if (ew == 0 && lane == 0) mbar_expect_tx(bar_x + 8, XCHG_BYTES);
-        xchg_send(smem_u32(xbuf + XCHG_BYTES), bar_x + 8, slot, rl, (unsigned long long)(unsigned)cnt);
+        xsend(1, (unsigned long long)(unsigned)cnt);
         mbar_wait(bar_x + 8, xph1 & 1u);
         ++xph1;
         int total_cnt = 0;
@@ -529,7 +639,9 @@ policy_decode_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
         }
       }
       tok = a;
+      STAMP(10);
     }
+#undef STAMP
   }
   tc_fence_before();
   __syncthreads();
@@ -595,7 +707,7 @@ int make_map_f16(CUtensorMap* map, const void* ptr, long long rows, int box_rows
   const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     icrl_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %lld)", (int)r, rows);
@@ -605,6 +717,9 @@ int make_map_f16(CUtensorMap* map, const void* ptr, long long rows, int box_rows
 }
 
 }  // namespace
+
+static long long* g_decode_prof = nullptr;
+void icrl_decode_set_profile_impl(long long* buf) { g_decode_prof = buf; }
 
 size_t icrl_decode_weight_halves_impl() { return (size_t)2 * (4 * H + VPAD) * H; }
 
@@ -653,7 +768,7 @@ int icrl_policy_decode_impl(cudaStream_t st, int B, int V, int p0, int S, int gr
   a.B = B; a.V = V; a.p0 = p0; a.S = S; a.greedy = greedy;
   a.table = table; a.b_v = b_v; a.uniforms = (greedy || forced) ? nullptr : uniforms; a.forced = forced;
   a.tokcm = tokcm; a.tokens_out = tokens_out; a.logp = logp; a.Hs = Hs; a.Cs = Cs; a.Gs = Gs; a.logits = logits;
-  a.last_logits = last_logits; a.hparts = reinterpret_cast<__half*>(hparts);
+  a.last_logits = last_logits; a.hparts = reinterpret_cast<__half*>(hparts); a.prof = g_decode_prof;
   const int n_mtiles = icrl_cdiv(B, BM);
   policy_decode_kernel<<<dim3(CL * n_mtiles), dim3(THREADS), SMEM_BYTES, st>>>(mh, mw, mv, a);
   ICRL_LAUNCH_CHECK();

@@ -59,3 +59,4 @@ int icrl_policy_decode_impl(cudaStream_t st, int B, int V, int p0, int S, int gr
                             const void* packed, const float* b_v, const double* uniforms, const long long* forced,
                             int* tokcm, long long* tokens_out, float* logp, float* Hs, float* Cs, float* Gs,
                             float* logits, float* last_logits, void* hparts);
+void icrl_decode_set_profile_impl(long long* buf);

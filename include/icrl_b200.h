@@ -89,6 +89,9 @@ int icrl_policy_rollout_fwd_tc(void* stream, int B, int V, int p0, int S, int gr
  *      step; needs V <= 1024, V % 4 == 0).  hparts: scratch, 4*B*512 fp16.  Gs / logits may be null (inference:
  *      no backward stash); last_logits (nullable) [B][V] receives the logits of the final step. */
 size_t icrl_decode_weight_halves(void);
+/*      Debug aid: when buf != NULL, CTA 0 of later icrl_policy_rollout_fwd_fused launches writes clock64 stamps of
+ *      its phases to buf[n_cell][16] (device int64); NULL switches it off. */
+int icrl_decode_set_profile(void* buf);
 int icrl_pack_decode_weights(void* stream, int V, const float* W_hh, const float* W_v, void* packed, int* launches);
 int icrl_policy_rollout_fwd_fused(void* stream, int B, int V, int p0, int S, int greedy, const float* features,
                                   const float* W_cnn, const float* b_cnn, const float* table, const void* packed,
