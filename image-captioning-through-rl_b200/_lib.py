@@ -41,7 +41,7 @@ SIGNATURES = {
     "icrl_chain_lstm_fwd": [P, P, I] + [P] * 10 + [LP],
     "icrl_chain_gru_fwd": [P, P, I] + [P] * 7 + [LP],
     "icrl_chains_fwd_fused": [P, P, I, P, P, P, P, P, P, I, P, P, P, P, P, LP],
-    "icrl_chain_lstm_bwd": [P, I, P, P, P, P, P, P, P, LP],
+    "icrl_chain_lstm_bwd": [P, I, P, P, P, P, P, P, P, P, P, P, P, LP],
     "icrl_chain_check": [P, P],
     "icrl_gather_rows": [P, L, P, P, L, P, LP],
     "icrl_value_head_fwd": [P, I, I, P, P, P, P, P, LP],

@@ -177,9 +177,11 @@ int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, const flo
   const int n_cell = p0 - 1 + S;
   const size_t BH = (size_t)B * H;
   const int SB = S * B;
-  // 1. dL/dlogits in place (log(softmax(z))[a] backward)
-  TRY(icrl_softmax_bwd(st, B, S, V, logits, V, tokens_out, dlogp));
-  bump(launches, 1);
+  // 1. dL/dlogits in place (log(softmax(z))[a] backward); dlogp == NULL: `logits` already holds dL/dlogits
+  if (dlogp) {
+    TRY(icrl_softmax_bwd(st, B, S, V, logits, V, tokens_out, dlogp));
+    bump(launches, 1);
+  }
   const float* dZ = logits;
   const float* Hsel = Hs + (size_t)p0 * BH;          // h after cell step p0-1+s, s = 0..S-1
   // 2. vocab projection gradients
@@ -265,8 +267,10 @@ int icrl_chains_fwd_fused(void* stream, const int* v_stream, int v_T, const floa
 }
 
 int icrl_chain_lstm_bwd(void* stream, int T, const float* W_hh, const float* stash_gates, const float* stash_c,
-                        const int* take, const float* dh_take, float* dgates, void* sync_state, int* launches) {
-  TRY(icrl_chain_lstm_bwd_impl(S_(stream), T, W_hh, stash_gates, stash_c, take, dh_take, dgates, sync_state));
+                        const int* take, const float* dh_take, float* dgates, void* sync_state, const float* dh_init,
+                        const float* dc_init, float* dh0_out, float* dc0_out, int* launches) {
+  TRY(icrl_chain_lstm_bwd_impl(S_(stream), T, W_hh, stash_gates, stash_c, take, dh_take, dgates, sync_state, dh_init,
+                               dc_init, dh0_out, dc0_out));
   bump(launches, 1);
   return ICRL_OK;
 }

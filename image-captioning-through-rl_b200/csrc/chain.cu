@@ -229,6 +229,10 @@ struct ChainBwdArgs {
   float* dgates;              // [T][4H] pre-activation gate gradients (output, feeds dW_hh / table grads)
   unsigned long long* xchg;   // [2][H] tagged dh words
   int* abort_flag;
+  const float* dh_init;       // [H] dL/dh_T flowing in from a later call that consumed the carried state, or null
+  const float* dc_init;       // [H] dL/dc_T, or null
+  float* dh0_out;             // [H] dL/dh_0 (gradient of the incoming hidden state), or null
+  float* dc0_out;             // [H] dL/dc_0, or null
 };
 
 // Backward recurrence.  What crosses CTAs per step is dh_t (512 floats, the same volume and pattern as
@@ -250,7 +254,7 @@ __global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_kernel(ChainBwdArgs
 #pragma unroll
     for (int q = 0; q < 4; ++q) w[4 * jj + q] = p.w_hh[(size_t)(128 * jj + 4 * lane + q) * H + unit];
 
-  float2 dc = make_float2(0.f, 0.f);
+  float2 dc = p.dc_init ? *reinterpret_cast<const float2*>(p.dc_init + pu) : make_float2(0.f, 0.f);
   auto load_step = [&](int t, float2& gi, float2& gf, float2& gg, float2& go, float2& cc, float2& cp) {
     const float* ga = p.stash_gates + (size_t)t * 4 * H + pu;
     gi = *reinterpret_cast<const float2*>(ga);
@@ -267,6 +271,7 @@ __global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_kernel(ChainBwdArgs
   {
     const int tk = p.take[p.T - 1];
     if (tk >= 0) dh = *reinterpret_cast<const float2*>(p.dh_take + (size_t)tk * H + pu);
+    if (p.dh_init) { dh.x += p.dh_init[pu]; dh.y += p.dh_init[pu + 1]; }
   }
   int tk_prev = p.T > 1 ? p.take[p.T - 2] : -1;                // injection for the dh this warp publishes
 
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_kernel(ChainBwdArgs
       if (threadIdx.x == 0) atomicExch(p.abort_flag, 1);
       return;
     }
-    if (t > 0) {
+    if (t > 0 || p.dh0_out) {
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
       for (int jj = 0; jj < 16; ++jj) {
@@ -327,10 +332,14 @@ __global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_kernel(ChainBwdArgs
         a3 = fmaf(w[4 * jj + 3], v.w, a3);
       }
       const float rec = warp_sum((a0 + a1) + (a2 + a3));
-      if (lane == 0) st_tagged(p.xchg + (size_t)buf * H + unit, rec + inj, (unsigned)(it + 1));
+      if (lane == 0) {
+        if (t > 0) st_tagged(p.xchg + (size_t)buf * H + unit, rec + inj, (unsigned)(it + 1));
+        else p.dh0_out[unit] = rec;
+      }
     }
     gi = ngi; gf = ngf; gg = ngg; go = ngo; cc = ncc; cp = ncp;
   }
+  if (p.dc0_out && owner) *reinterpret_cast<float2*>(p.dc0_out + pu) = dc;
 }
 
 int coop_launch(const void* fn, int grid, void** args, cudaStream_t st) {
@@ -406,12 +415,14 @@ int icrl_chains_fwd_fused_impl(cudaStream_t st, const int* v_stream, int v_T, co
 }
 
 int icrl_chain_lstm_bwd_impl(cudaStream_t st, int T, const float* w_hh, const float* stash_gates, const float* stash_c,
-                             const int* take, const float* dh_take, float* dgates, void* sync_state) {
+                             const int* take, const float* dh_take, float* dgates, void* sync_state, const float* dh_init,
+                             const float* dc_init, float* dh0_out, float* dc0_out) {
   ICRL_REQUIRE(T > 0, "empty chain");
   ICRL_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(sync_state) + 64, 0, icrl_chain_sync_bytes_impl() - 64, st));
   ChainBwdArgs a;
   a.T = T; a.w_hh = w_hh; a.stash_gates = stash_gates; a.stash_c = stash_c; a.take = take; a.dh_take = dh_take;
   a.dgates = dgates; a.xchg = sync_xchg(sync_state, 2); a.abort_flag = sync_abort(sync_state);
+  a.dh_init = dh_init; a.dc_init = dc_init; a.dh0_out = dh0_out; a.dc0_out = dc0_out;
   void* args[] = {&a};
   return coop_launch((const void*)chain_lstm_bwd_kernel, CHAIN_CTAS, args, st);
 }

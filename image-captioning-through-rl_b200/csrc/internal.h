@@ -46,7 +46,8 @@ int icrl_chains_fwd_fused_impl(cudaStream_t st, const int* v_stream, int v_T, co
                                const int* r_stream, int r_T, const float* r_table, const float* r_w_hh,
                                const float* r_b_hn, float* r_stash_h, void* sync_state);
 int icrl_chain_lstm_bwd_impl(cudaStream_t st, int T, const float* w_hh, const float* stash_gates, const float* stash_c,
-                             const int* take, const float* dh_take, float* dgates, void* sync_state);
+                             const int* take, const float* dh_take, float* dgates, void* sync_state, const float* dh_init,
+                             const float* dc_init, float* dh0_out, float* dc0_out);
 int icrl_chain_check_impl(cudaStream_t st, void* sync_state);
 
 int icrl_split_bf16x3_impl(cudaStream_t st, long long n, const float* x, void* parts);

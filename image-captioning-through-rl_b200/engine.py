@@ -333,7 +333,7 @@ class A2CEngine:
         dgates = self._buf("v_dgates", Tv * 4 * H)
         with self._phase("chain_lstm_bwd"):
           _lib.call("icrl_chain_lstm_bwd", st, Tv, _p(Vn.valrnn.lstm.weight_hh_l0), _p(b["v_stash_g"]), _p(b["v_stash_c"]),
-                  _p(b["v_take"]), _p(dh_take), _p(dgates), _p(self.sync_state), L)
+                  _p(b["v_take"]), _p(dh_take), _p(dgates), _p(self.sync_state), None, None, None, None, L)
         dtable = self._buf("dtable", V * 4 * H)
         lstm = Vn.valrnn.lstm
         with self._phase("value_param_grads"):

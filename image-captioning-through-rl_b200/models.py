@@ -12,10 +12,14 @@ either side load in the other (``load_state_dict(strict=False)``, ``trainers.py:
 containers' own ``forward`` is never called -- every ``forward`` below launches the CUDA kernels and
 raises if the tensors are not on a CUDA device (there is no CPU fallback).
 
-Training goes through ``engine.A2CEngine`` (the fused minibatch, used by our ``trainers.py``); the
-per-call ``forward`` methods here reproduce the reference call semantics (growing prefix, hidden
-state carried in ``valrnn.hidden_cell`` / ``rewrnn.hidden_cell`` until ``init_hidden()``) for
-inference and for step-by-step parity checks.
+Fast training goes through ``engine.A2CEngine`` (the fused minibatch, used by our ``trainers.py``).
+The per-call ``forward`` methods here reproduce the reference call semantics (growing prefix, hidden
+state carried in ``valrnn.hidden_cell`` / ``rewrnn.hidden_cell`` until ``init_hidden()``) AND carry
+autograd history (``torch.autograd.Function`` wrappers around the same CUDA kernels), so
+the reference's own rollout loop (``trainers.py:441-480``: softmax / gather / log / stack /
+``loss.backward(retain_graph=True)`` / Adam) trains these modules unmodified; like the reference,
+``valrnn.hidden_cell`` keeps its graph from call to call, so gradients flow through the whole
+carried-state chain.  Both routes give the same numbers (tests/test_gpu_parity.py).
 """
 import ctypes
 import warnings
@@ -55,6 +59,175 @@ def _unsupported(bidirectional, pretrained_embeddings):
         raise NotImplementedError("frozen pretrained_embeddings are outside the B200 hot path (SURVEY.md 8f)")
 
 
+
+def _st(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _sync_state(dev, cache={}):
+    t = cache.get(dev)
+    if t is None:
+        t = torch.zeros(int(_lib.call("icrl_chain_sync_bytes")), dtype=torch.uint8, device=dev)
+        cache[dev] = t
+    return t
+
+
+def _gemm_ws(dev, cache={}):
+    t = cache.get(dev)
+    if t is None:
+        t = torch.empty(24 * 4 * HID * HID, dtype=torch.float32, device=dev)
+        cache[dev] = t
+    return t
+
+
+class _PolicyFn(torch.autograd.Function):
+    """PolicyNetwork.forward (models.py:71-84) with a hand-written backward: logits of all n positions
+    from one incremental pass, BPTT through the n cells in backward."""
+
+    @staticmethod
+    def forward(ctx, f, captions, E, Wc, bc, W_ih, W_hh, b_ih, b_hh, Wv, bv):
+        dev = f.device
+        B, n = captions.shape
+        V = Wv.shape[0]
+        st = _st(dev)
+        with torch.cuda.device(dev):
+            table = torch.empty(V * 4 * HID, dtype=torch.float32, device=dev)
+            _lib.call("icrl_pack_gate_table", st, V, 4 * HID, 4 * HID, _p(E), _p(W_ih), _p(b_ih), _p(b_hh), _p(table), None)
+            tokcm = torch.empty((n + 1) * B, dtype=torch.int32, device=dev)
+            tokcm[:B] = captions[:, 0].to(torch.int32)
+            forced = torch.zeros((B, n), dtype=torch.int64, device=dev)
+            if n > 1:
+                forced[:, :n - 1] = captions[:, 1:]
+            tokens = torch.empty((B, n), dtype=torch.int64, device=dev)
+            logp = torch.empty((B, n), dtype=torch.float32, device=dev)
+            logits = torch.empty((n, B, V), dtype=torch.float32, device=dev)
+            Hs = torch.empty((n + 1) * B * HID, dtype=torch.float32, device=dev)
+            Cs = torch.empty((n + 1) * B * HID, dtype=torch.float32, device=dev)
+            Gs = torch.empty(n * B * 4 * HID, dtype=torch.float32, device=dev)
+            gpre = torch.empty(B * 4 * HID, dtype=torch.float32, device=dev)
+            _lib.call("icrl_policy_rollout_fwd", st, B, V, 1, n, 0, _p(f), _p(Wc), _p(bc), _p(table), _p(W_hh), _p(Wv),
+                      _p(bv), None, _p(forced), _p(tokcm), _p(tokens), _p(logp), _p(Hs), _p(Cs), _p(Gs), _p(logits),
+                      _p(gpre), None)
+        ctx.save_for_backward(f, E, W_ih, W_hh, Wv, tokcm, tokens, Hs, Cs, Gs)
+        ctx.shape = (B, n, V)
+        return logits.permute(1, 0, 2)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        f, E, W_ih, W_hh, Wv, tokcm, tokens, Hs, Cs, Gs = ctx.saved_tensors
+        B, n, V = ctx.shape
+        dev = f.device
+        st = _st(dev)
+        new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            dZ = dlogits.permute(1, 0, 2).contiguous().clone()          # [n][B][V], consumed in place
+            dE, dWc, dbc, dWih, dWhh = new(V, HID), new(HID, HID), new(HID), new(4 * HID, HID), new(4 * HID, HID)
+            dbih, dbhh, dWv, dbv = new(4 * HID), new(4 * HID), new(V, HID), new(V)
+            cs = int(_lib.call("icrl_colsum_ws_floats", max(n * B, V, B), 4 * HID)) + 2 * HID + 4 * HID * 8
+            ws = _gemm_ws(dev)
+            # scratch tensors are held in locals until the call returns (a temporary would be recycled at once)
+            dHv, DG, dh, dc, dtable, csws = new(n * B, HID), new(n * B, 4 * HID), new(2 * B, HID), new(B, HID), new(V, 4 * HID), new(cs)
+            _lib.call("icrl_policy_rollout_bwd", st, B, V, 1, n, _p(f), _p(E), _p(W_ih), _p(W_hh), _p(Wv), _p(tokcm),
+                      _p(tokens), None, _p(Hs), _p(Cs), _p(Gs), _p(dZ), _p(dHv), _p(DG),
+                      _p(dh), _p(dc), _p(dtable), _p(csws), _p(ws), ws.numel() * 4,
+                      _p(dE), _p(dWc), _p(dbc), _p(dWih), _p(dWhh), _p(dbih), _p(dbhh), _p(dWv), _p(dbv), None)
+        return None, None, dE, dWc, dbc, dWih, dWhh, dbih, dbhh, dWv, dbv
+
+
+class _ChainLSTMFn(torch.autograd.Function):
+    """One ValueNetworkRNN segment: the columns of one call fed as a serial batch-1 LSTM from the carried
+    state (models.py:130-135, 166-169).  Returns (h after every row of the last column, final h, final c);
+    backward runs the serial BPTT kernel and hands dL/d(initial h, c) to the previous segment."""
+
+    @staticmethod
+    def forward(ctx, tok_cm, h0, c0, E, W_ih, W_hh, b_ih, b_hh):
+        dev = E.device
+        n, B = tok_cm.shape
+        V, T = E.shape[0], n * B
+        st = _st(dev)
+        with torch.cuda.device(dev):
+            table = torch.empty(V * 4 * HID, dtype=torch.float32, device=dev)
+            _lib.call("icrl_pack_gate_table", st, V, 4 * HID, 4 * HID, _p(E), _p(W_ih), _p(b_ih), _p(b_hh), _p(table), None)
+            stream = tok_cm.reshape(-1).contiguous()
+            stash_h = torch.empty((T + 1, HID), dtype=torch.float32, device=dev)
+            stash_c = torch.empty((T + 1, HID), dtype=torch.float32, device=dev)
+            stash_g = torch.empty((T, 4 * HID), dtype=torch.float32, device=dev)
+            h_out = torch.empty(HID, dtype=torch.float32, device=dev)
+            c_out = torch.empty(HID, dtype=torch.float32, device=dev)
+            sync = _sync_state(dev)
+            h0f, c0f = h0.reshape(-1).contiguous(), c0.reshape(-1).contiguous()
+            _lib.call("icrl_chain_lstm_fwd", st, _p(stream), T, _p(table), _p(W_hh), _p(h0f),
+                      _p(c0f), _p(stash_h), _p(stash_c), _p(stash_g), _p(h_out), _p(c_out),
+                      _p(sync), None)
+            _lib.call("icrl_chain_check", st, _p(sync))
+        ctx.save_for_backward(stream, E, W_ih, W_hh, stash_h, stash_c, stash_g)
+        ctx.dims = (n, B, V)
+        ctx.state_shapes = (tuple(h0.shape), tuple(c0.shape))
+        return stash_h[T - B + 1:T + 1].clone(), h_out, c_out
+
+    @staticmethod
+    def backward(ctx, dh_last, dh_out, dc_out):
+        stream, E, W_ih, W_hh, stash_h, stash_c, stash_g = ctx.saved_tensors
+        n, B, V = ctx.dims
+        T = n * B
+        dev = E.device
+        st = _st(dev)
+        new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            take = torch.full((T,), -1, dtype=torch.int32, device=dev)
+            take[T - B:] = torch.arange(B, dtype=torch.int32, device=dev)
+            dh_take = (dh_last if dh_last is not None else torch.zeros((B, HID), device=dev)).contiguous()
+            dgates, dh0, dc0 = new(T, 4 * HID), new(HID), new(HID)
+            sync = _sync_state(dev)
+            dh_in = dh_out.contiguous() if dh_out is not None else None
+            dc_in = dc_out.contiguous() if dc_out is not None else None
+            _lib.call("icrl_chain_lstm_bwd", st, T, _p(W_hh), _p(stash_g), _p(stash_c), _p(take), _p(dh_take), _p(dgates),
+                      _p(sync), _p(dh_in), _p(dc_in), _p(dh0), _p(dc0), None)
+            _lib.call("icrl_chain_check", st, _p(sync))
+            dE, dWih, dWhh, dbih, dbhh = new(V, HID), new(4 * HID, HID), new(4 * HID, HID), new(4 * HID), new(4 * HID)
+            cs = int(_lib.call("icrl_colsum_ws_floats", max(T, V), 4 * HID))
+            ws = _gemm_ws(dev)
+            dtable, csws = new(V, 4 * HID), new(cs)
+            _lib.call("icrl_value_chain_param_grads", st, T, V, _p(stream), _p(dgates), _p(stash_h), _p(E), _p(W_ih),
+                      _p(dtable), _p(csws), _p(ws), ws.numel() * 4, _p(dE), _p(dWih), _p(dWhh), _p(dbih),
+                      _p(dbhh), None)
+        return None, dh0.view(ctx.state_shapes[0]), dc0.view(ctx.state_shapes[1]), dE, dWih, dWhh, dbih, dbhh
+
+
+class _ValueHeadFn(torch.autograd.Function):
+    """linear2(linear1(cat(features, h))) (models.py:175-178; no activation in between)."""
+
+    @staticmethod
+    def forward(ctx, f, h, W1, b1, W2, b2):
+        dev = f.device
+        B = f.shape[0]
+        st = _st(dev)
+        with torch.cuda.device(dev):
+            weff, beff = torch.empty(2 * HID, device=dev), torch.empty(1, device=dev)
+            _lib.call("icrl_pack_value_head", st, _p(W1), _p(b1), _p(W2), _p(b2), _p(weff), _p(beff), None)
+            values = torch.empty((B, 1), dtype=torch.float32, device=dev)
+            h = h.contiguous()
+            _lib.call("icrl_value_head_fwd", st, B, 1, _p(f), _p(h), _p(weff), _p(beff), _p(values), None)
+        ctx.save_for_backward(f, h, W1, b1, W2, weff)
+        return values
+
+    @staticmethod
+    def backward(ctx, dv):
+        f, h, W1, b1, W2, weff = ctx.saved_tensors
+        dev = f.device
+        B = f.shape[0]
+        st = _st(dev)
+        new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            dv = dv.reshape(-1).contiguous()
+            sum_dv = dv.sum().reshape(1)
+            dh, dW1, db1, dW2, db2 = new(B, HID), new(HID, 2 * HID), new(HID), new(1, HID), new(1)
+            ws = new(2 * HID + int(_lib.call("icrl_colsum_ws_floats", B, HID)) + 1024)
+            _lib.call("icrl_value_head_bwd", st, B, 1, _p(f), _p(h), _p(dv), _p(sum_dv), _p(W1), _p(b1), _p(W2), _p(weff),
+                      _p(dh), _p(dW1), _p(db1), _p(dW2), _p(db2), _p(ws), None)
+        return None, dh, dW1, db1, dW2, db2
+
+
 class _KernelModule(nn.Module):
     """Workspace + stream plumbing shared by the drop-in modules."""
 
@@ -84,8 +257,8 @@ class _KernelModule(nn.Module):
     def _grad_note(self):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and not self._warned:
             object.__setattr__(self, "_warned", True)
-            warnings.warn("%s.forward returns tensors without autograd history; train through "
-                          "icrl_b200.trainers / A2CEngine (fused rollout + hand-written backward)"
+            warnings.warn("%s.forward returns tensors without autograd history (the reward network is frozen "
+                          "in A2C training, trainers.py:372-373; its pretraining is out of scope)"
                           % type(self).__name__)
 
     def _tokcm(self, captions, dev):
@@ -113,31 +286,14 @@ class PolicyNetwork(_KernelModule):
         self._rt_init()
 
     def forward(self, features, captions):
-        """features (1,B,512), captions (B,n) int64 -> logits (B,n,V) (models.py:71-84)."""
+        """features (1,B,512), captions (B,n) int64 -> logits (B,n,V) (models.py:71-84), with autograd history
+        w.r.t. the nine policy parameters."""
         dev = self._dev()
-        self._grad_note()
         B, n = captions.shape
-        V = self.linear2vocab.weight.shape[0]
-        st, L = self._stream(dev), self._launches.ref
-        with torch.cuda.device(dev):
-            f = features.reshape(B, HID).to(dev, torch.float32).contiguous()
-            table = self._buf("table", V * 4 * HID, dev=dev)
-            _lib.call("icrl_pack_gate_table", st, V, 4 * HID, 4 * HID, _p(self.caption_embedding.weight),
-                      _p(self.lstm.weight_ih_l0), _p(self.lstm.bias_ih_l0), _p(self.lstm.bias_hh_l0), _p(table), L)
-            tokcm = self._buf("tokcm", (n + 1) * B, torch.int32, dev)
-            tokcm[:B] = captions[:, 0].to(dev).to(torch.int32)
-            forced = torch.zeros((B, n), dtype=torch.int64, device=dev)
-            if n > 1:
-                forced[:, :n - 1] = captions[:, 1:].to(dev)
-            tokens = torch.empty((B, n), dtype=torch.int64, device=dev)
-            logp = torch.empty((B, n), dtype=torch.float32, device=dev)
-            logits = torch.empty((n, B, V), dtype=torch.float32, device=dev)
-            _lib.call("icrl_policy_rollout_fwd", st, B, V, 1, n, 0, _p(f), _p(self.cnn2linear.weight),
-                      _p(self.cnn2linear.bias), _p(table), _p(self.lstm.weight_hh_l0), _p(self.linear2vocab.weight),
-                      _p(self.linear2vocab.bias), None, _p(forced), _p(tokcm), _p(tokens), _p(logp),
-                      _p(self._buf("Hs", (n + 1) * B * HID, dev=dev)), _p(self._buf("Cs", (n + 1) * B * HID, dev=dev)),
-                      _p(self._buf("Gs", n * B * 4 * HID, dev=dev)), _p(logits), _p(self._buf("gpre", B * 4 * HID, dev=dev)), L)
-        return logits.permute(1, 0, 2)
+        f = features.reshape(B, HID).to(dev, torch.float32).contiguous()
+        return _PolicyFn.apply(f, captions.to(dev).to(torch.int64).contiguous(), self.caption_embedding.weight,
+                               self.cnn2linear.weight, self.cnn2linear.bias, self.lstm.weight_ih_l0, self.lstm.weight_hh_l0,
+                               self.lstm.bias_ih_l0, self.lstm.bias_hh_l0, self.linear2vocab.weight, self.linear2vocab.bias)
 
 
 class _ChainRNN(_KernelModule):
@@ -153,9 +309,18 @@ class _ChainRNN(_KernelModule):
 
     def _run_columns(self, captions_cm, kind):
         """Feed columns [n][B] through the serial chain from the carried state; returns the hidden
-        state after every row of the LAST column, (B,512), and updates ``hidden_cell``."""
+        state after every row of the LAST column, (B,512), and updates ``hidden_cell``.  The LSTM
+        (value) path records autograd history, including through the carried state."""
         dev = self._dev()
         n, B = captions_cm.shape
+        if kind == "lstm":
+            rnn = self.lstm
+            h0 = self.hidden_cell[0].to(dev, torch.float32)
+            c0 = self.hidden_cell[1].to(dev, torch.float32)
+            h_last, h_out, c_out = _ChainLSTMFn.apply(captions_cm.contiguous(), h0, c0, self.caption_embedding.weight,
+                                                      rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0)
+            self.hidden_cell = (h_out.view(1, 1, HID), c_out.view(1, 1, HID))
+            return h_last
         V = self.caption_embedding.weight.shape[0]
         st, L = self._stream(dev), self._launches.ref
         with torch.cuda.device(dev):
@@ -190,7 +355,6 @@ class _ChainRNN(_KernelModule):
 
     def forward(self, captions):
         """captions (B,) -> (B,1,512): the column is a length-B sequence (models.py:130-135 / 223-228)."""
-        self._grad_note()
         kind = "lstm" if hasattr(self, "lstm") else "gru"
         cm = captions.reshape(1, -1).to(self._dev()).to(torch.int32)
         return self._run_columns(cm, kind).unsqueeze(1)
@@ -227,18 +391,9 @@ class ValueNetwork(_KernelModule):
         """features (B,512), captions (B,n) -> (B,1); all n columns run through the carried-state
         chain, the head uses the h after each row of the last column (models.py:166-180)."""
         dev = self._dev()
-        self._grad_note()
-        B = captions.shape[0]
         h = self.valrnn._run_columns(self.valrnn._tokcm(captions, dev), "lstm")
-        st, L = self._stream(dev), self._launches.ref
-        with torch.cuda.device(dev):
-            f = features.to(dev, torch.float32).contiguous()
-            weff, beff = self._buf("weff", 2 * HID, dev=dev), self._buf("beff", 1, dev=dev)
-            _lib.call("icrl_pack_value_head", st, _p(self.linear1.weight), _p(self.linear1.bias), _p(self.linear2.weight),
-                      _p(self.linear2.bias), _p(weff), _p(beff), L)
-            values = torch.empty((B, 1), dtype=torch.float32, device=dev)
-            _lib.call("icrl_value_head_fwd", st, B, 1, _p(f), _p(h), _p(weff), _p(beff), _p(values), L)
-        return values
+        f = features.to(dev, torch.float32).contiguous()
+        return _ValueHeadFn.apply(f, h, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias)
 
 
 class RewardNetworkRNN(_ChainRNN):

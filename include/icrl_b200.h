@@ -100,7 +100,8 @@ int icrl_policy_rollout_fwd_fused(void* stream, int B, int V, int p0, int S, int
                                   float* last_logits, void* hparts, int* launches);
 
 /* ---- policy backward through time (replaces autograd over the S prefix re-runs, trainers.py:479).
- *      dlogp [B][S].  logits is overwritten with dL/dlogits.  Workspaces: dHv [S*B][512],
+ *      dlogp [B][S]; when dlogp is NULL, `logits` must already hold dL/dlogits [S][B][V] (module-level autograd).
+ *      logits is overwritten with dL/dlogits.  Workspaces: dHv [S*B][512],
  *      DG [n_cell*B][2048], dh [2][B][512], dc [B][512], dtable [V][2048], colsum_ws
  *      [icrl_colsum_ws_floats(max(S*B, V), 2048)], gemm_ws/gemm_ws_bytes.  Gradients are OVERWRITTEN. */
 int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, const float* features, const float* E,
@@ -139,9 +140,13 @@ int icrl_chains_fwd_fused(void* stream, const int* v_stream, int v_T, const floa
                           const float* r_table, const float* r_W_hh, const float* r_b_hn, float* r_stash_h,
                           void* sync_state, int* launches);
 /* BPTT through the value chain (replaces autograd through the carried-state LSTM, trainers.py:479):
- * dgates [T][2048] = dL/d(pre-activation gates); dh_take [S*B][512] injected at take[t] >= 0. */
+ * dgates [T][2048] = dL/d(pre-activation gates); dh_take [S*B][512] injected at take[t] >= 0.
+ * The reference carries hidden_cell WITH its autograd history from one call to the next (models.py:133), so a
+ * segment's backward may receive dL/d(final h, c) from the call that consumed its state (dh_init, dc_init [512],
+ * nullable = zero) and must hand dL/d(initial h, c) to the call before it (dh0_out, dc0_out [512], nullable). */
 int icrl_chain_lstm_bwd(void* stream, int T, const float* W_hh, const float* stash_gates, const float* stash_c,
-                        const int* take, const float* dh_take, float* dgates, void* sync_state, int* launches);
+                        const int* take, const float* dh_take, float* dgates, void* sync_state, const float* dh_init,
+                        const float* dc_init, float* dh0_out, float* dc0_out, int* launches);
 /* synchronises `stream`; ICRL_ERR_WATCHDOG if any chain launch since the last check gave up waiting */
 int icrl_chain_check(void* stream, void* sync_state);
 /* dst[r][:] = src[idx[r] + row_offset][:]  (rows of 512 floats; h at the take positions) */

@@ -256,3 +256,54 @@ def test_decode_paths_agree_large_batch():
     ff = ef.step(f, c, forced_tokens=forced, backward=False)
     assert torch.equal(ff["tokens"], rs["tokens"])
     assert float((ff["logp"] - rs["logp"]).abs().max()) <= TOL
+
+
+@pytest.mark.parametrize("name", ["a2c_b8_l6", "curr_b16_l10_lv4"])
+def test_reference_rollout_loop_trains_dropin_modules(name):
+    """The reference's own loop body (trainers.py:428-480 / 544-594, restated verbatim below) run on the drop-in
+    modules with torch autograd: module outputs carry autograd history, the value RNN's
+    hidden_cell keeps its graph from call to call, and loss.backward() reaches all 18 parameters with the
+    gradients of the unmodified reference (golden fixtures)."""
+    import icrl_b200.trainers as T
+    from torch.nn import functional as F
+    g, seed, f, c, u, level = load_case(name)
+    A, R, w = make_nets(seed)
+    R.requires_grad_(False)
+    features = torch.tensor(f, device="cuda").float()
+    captions = torch.tensor(c, device="cuda").long()
+    caplen = int(np.nonzero(c == 2)[1].max() + 1)
+    if level is None:
+        captions_in, steps = captions[:, :1], caplen - 1
+    else:
+        captions_in, steps = captions[:, :caplen - level], level
+    np.random.seed(seed)
+    A.value_network.valrnn.init_hidden()
+    R.rewrnn.init_hidden()
+    values, rewards, log_probs = [], [], []
+    for step in range(steps):
+        value, probs = A(features, captions_in)
+        probs = F.softmax(probs, dim=2)
+        dist = probs.cpu().detach().numpy()[:, 0]
+        actions = [np.random.choice(probs.shape[-1], p=dist[i]) for i in range(captions.shape[0])]
+        gen_cap = torch.from_numpy(np.array(actions)).unsqueeze(-1).to(captions_in.device)
+        captions_in = torch.cat((captions_in, gen_cap), axis=1)
+        log_prob = torch.log(probs[:, 0, :].gather(1, gen_cap))
+        reward = T.GetRewards(features, captions_in, R)
+        values.append(value)
+        rewards.append(reward)
+        log_probs.append(log_prob)
+    values = torch.stack(values, axis=1).squeeze()
+    rewards = torch.stack(rewards, axis=1).squeeze()
+    log_probs = torch.stack(log_probs, axis=1).squeeze()
+    advantage = values - rewards
+    loss = (-log_probs * advantage).mean() + 0.5 * advantage.pow(2).mean()
+    for p in A.parameters():
+        p.grad = None
+    loss.mean().backward(retain_graph=True)
+    p0 = captions_in.shape[1] - steps
+    assert np.array_equal(captions_in[:, p0:].cpu().numpy(), g["tokens"])
+    assert float(np.abs(values.detach().cpu().numpy() - g["values"]).max()) <= TOL
+    assert float(np.abs(rewards.detach().cpu().numpy() - g["rewards"]).max()) <= TOL
+    assert abs(float(loss) - float(g["loss"])) <= TOL
+    assert all(p.grad is not None for p in A.parameters())
+    _record(name + "_autograd_loop", grad_worst=check_grads_vs_golden(named_grads(A), g, GTOL))
