@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="global batch (captions per step)")
     ap.add_argument("--cpu-sample", type=int, default=256, help="rows of the workload timed on the host cores")
+    ap.add_argument("--chain-shards", type=int, default=1, choices=[1, 2, 4, 8],
+                    help="value/reward recurrences per rank (1 = the reference's single carried-state chain)")
+    ap.add_argument("--no-sharded-leg", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -148,7 +151,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(dev))
     A, R, _ = make_nets(0, dev)
     opt = torch.optim.Adam(A.parameters(), lr=1e-4)
-    eng = A2CEngine(A, R)
+    eng = A2CEngine(A, R, chain_shards=args.chain_shards)
     dp = DataParallelA2C(eng, opt)
     B = args.batch
     S = L_CAP - 1
@@ -213,6 +216,21 @@ def main():
         e2e = {"value": B / (ms_e2e * 1e-3), "unit": "captions/s",
                "h2d_bytes_per_step": int(fl.nbytes + (hi - lo) * 4 + ul.nbytes), "d2h_bytes_per_step": 8}
 
+    # ---- leg 3 (reported separately, never the headline): the same workload with 8 chain shards per rank
+    sharded = None
+    if args.chain_shards == 1 and not args.no_sharded_leg and (hi - lo) % 8 == 0:
+        eng8 = A2CEngine(A, R, chain_shards=8)
+        dp8 = DataParallelA2C(eng8, opt)
+        ms8, _ = timed(lambda: dp8.step(prep, global_rows=B, check=False), args.steps, 2)
+        _lib.call("icrl_chain_check", ctypes.c_void_p(torch.cuda.current_stream().cuda_stream),
+                  ctypes.c_void_p(eng8.sync_state.data_ptr()))
+        sharded = {"chain_shards_per_rank": 8, "value": B / (ms8 * 1e-3), "unit": "captions/s", "ms_per_step": ms8,
+                   "note": "value/reward recurrences restart from zero state every local_batch/8 rows and run in lockstep "
+                           "(numerically = the reference on 8x%d row shards with averaged gradients, i.e. %d-rank data "
+                           "parallel, SURVEY 8e); NOT the single carried-state chain of `value`" % (world, 8 * world)}
+        del eng8, dp8
+        eng._attach_grads()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -272,12 +290,15 @@ def main():
         "config": {"workload": "configs[3]: full A2C training step (rollout+reward+value+loss+backward+allreduce+Adam), "
                                "global batch %d, max_len %d, S=%d" % (B, L_CAP, S),
                    "global_batch": B, "local_batch": Bl, "parallelism": "dp%d" % world, "vocab": 1004,
+                   "chain_shards_per_rank": args.chain_shards,
                    "l2_flush": "not needed: per-step working set (chain stash, GBs) >> 126 MB L2"},
         "clocks": clk, "gpu_launches": int(launches), "phases_ms": phases, "roofline": roofline,
         "roofline_decode": decode,
     }
     if e2e:
         out["e2e"] = e2e
+    if sharded:
+        out["sharded"] = sharded
     if world == 1 and not args.no_cpu_baseline:
         Bs = min(args.cpu_sample, B)
         cps, cores, dt = cpu_reference(Bs, 1, 0)

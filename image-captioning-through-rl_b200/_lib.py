@@ -37,6 +37,9 @@ SIGNATURES = {
     "icrl_colsum_ws_floats": [L, I],
     "icrl_stream_len": [I, I, I, I],
     "icrl_build_stream": [P, I, I, I, I, P, P, P, P, LP],
+    "icrl_build_stream_sharded": [P, I, I, I, I, I, P, P, P, P, LP],
+    "icrl_chains_fwd_fused_sharded": [P, I, P, I, P, P, P, P, P, P, I, P, P, P, P, P, LP],
+    "icrl_chain_lstm_bwd_sharded": [P, I, I, P, P, P, P, P, P, P, LP],
     "icrl_chain_sync_bytes": [],
     "icrl_chain_lstm_fwd": [P, P, I] + [P] * 10 + [LP],
     "icrl_chain_gru_fwd": [P, P, I] + [P] * 7 + [LP],

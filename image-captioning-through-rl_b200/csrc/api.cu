@@ -237,6 +237,34 @@ int icrl_build_stream(void* stream, int B, int p0, int S, int extra, const int* 
   return ICRL_OK;
 }
 
+int icrl_build_stream_sharded(void* stream, int B, int p0, int S, int extra, int shards, const int* tokcm,
+                              int* stream_out, int* take, int* take_pos, int* launches) {
+  ICRL_REQUIRE(shards >= 1 && B % shards == 0, "the batch must split evenly into chain shards");
+  ICRL_REQUIRE(icrl_stream_len(B / shards, p0, S, extra) + 1 < (1ll << 31) / shards, "token stream longer than 2^31");
+  TRY(icrl_build_stream_sharded_impl(S_(stream), B, p0, S, extra, shards, tokcm, stream_out, take, take_pos));
+  bump(launches, 1);
+  return ICRL_OK;
+}
+
+int icrl_chains_fwd_fused_sharded(void* stream, int shards, const int* v_stream, int v_T, const float* v_table,
+                                  const float* v_W_hh, float* v_stash_h, float* v_stash_c, float* v_stash_gates,
+                                  const int* r_stream, int r_T, const float* r_table, const float* r_W_hh,
+                                  const float* r_b_hn, float* r_stash_h, void* sync_state, int* launches) {
+  TRY(icrl_chains_fwd_fused_batched_impl(S_(stream), shards, v_stream, v_T, v_table, v_W_hh, v_stash_h, v_stash_c,
+                                         v_stash_gates, r_stream, r_T, r_table, r_W_hh, r_b_hn, r_stash_h, sync_state));
+  bump(launches, 1);
+  return ICRL_OK;
+}
+
+int icrl_chain_lstm_bwd_sharded(void* stream, int shards, int T, const float* W_hh, const float* stash_gates,
+                                const float* stash_c, const int* take, const float* dh_take, float* dgates,
+                                void* sync_state, int* launches) {
+  TRY(icrl_chain_lstm_bwd_batched_impl(S_(stream), shards, T, W_hh, stash_gates, stash_c, take, dh_take, dgates,
+                                       sync_state));
+  bump(launches, 1);
+  return ICRL_OK;
+}
+
 size_t icrl_chain_sync_bytes(void) { return icrl_chain_sync_bytes_impl(); }
 
 int icrl_chain_lstm_fwd(void* stream, const int* tok_stream, int T, const float* table, const float* W_hh,

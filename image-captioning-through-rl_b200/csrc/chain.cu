@@ -106,6 +106,28 @@ __device__ __forceinline__ bool fetch_exchange(const unsigned long long* buf, un
   return ok;
 }
 
+// Batched form: all NV polls are in flight before the first tag is examined (one L2 round trip for the whole
+// batch instead of one per vector); only words that had not arrived yet are polled again.
+template <int NV>
+__device__ __forceinline__ bool fetch_exchange_all(const unsigned long long* buf, unsigned tag, float* sm,
+                                                   volatile int* abort_flag) {
+  unsigned long long a[NV], b[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) ld_tagged2(buf + (v * THREADS + threadIdx.x) * 2, a[v], b[v]);
+  bool ok = true;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    unsigned spins = 0;
+    while (!((unsigned)(a[v] >> 32) == tag && (unsigned)(b[v] >> 32) == tag)) {
+      if (++spins >= SPIN_LIMIT || ((spins & 1023u) == 0 && *abort_flag != 0)) { ok = false; break; }
+      ld_tagged2(buf + (v * THREADS + threadIdx.x) * 2, a[v], b[v]);
+    }
+    reinterpret_cast<float2*>(sm)[v * THREADS + threadIdx.x] =
+        make_float2(__uint_as_float((unsigned)a[v]), __uint_as_float((unsigned)b[v]));
+  }
+  return ok;
+}
+
 template <int NG>   // 4 = LSTM (i,f,g,o), 3 = GRU (r,z,n)
 __device__ void chain_fwd_body(const ChainFwdArgs& p, int cta) {
   __shared__ __align__(16) float sh_h[2][H];
@@ -342,6 +364,310 @@ __global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_kernel(ChainBwdArgs
   if (p.dc0_out && owner) *reinterpret_cast<float2*>(p.dc0_out + pu) = dc;
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Batched chains: NB independent recurrences ("chain shards": row shards of the minibatch, each starting
+// from zero state = the reference run on that shard, which is also what each data-parallel rank computes,
+// SURVEY.md 8e/H6) advance in lockstep on the same CTAs.  They share W_hh in registers, and one L2 exchange
+// round trip now carries NB hidden vectors, so the latency that bounds the single chain is amortised:
+// the step becomes FMA-bound instead of exchange-bound.
+// All per-step arrays of a shard use the same row stride (T + 1): stream [NB][stride], stash_h / stash_c
+// [NB][stride][H], stash_gates / dgates [NB][stride][4H] (row T unused / zero), take [NB][stride].
+
+constexpr int NB_MAX = 8;
+
+// transposed butterfly: v[0..NB) per lane in, afterwards lane l holds in v[0] the warp-wide sum of element
+// b = l >> (5 - log2 NB)
+template <int NB>
+__device__ __forceinline__ float reduce_transposed(float (&v)[NB], int lane) {
+  int o = 16;
+#pragma unroll
+  for (int n = NB; n > 1; n >>= 1, o >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = upper ? v[i] : v[i + n / 2];
+      const float keep = upper ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  for (; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+  return v[0];
+}
+
+struct ChainFwdBatchArgs {
+  const int* stream;          // [NB][stride]
+  int T;
+  long long stride;           // rows per shard (T + 1)
+  const float* table;         // [V][NG*H]
+  const float* w_hh;          // [NG*H][H]
+  const float* b_hn;          // GRU only
+  float* stash_h;             // [NB][stride][H]; row 0 = 0, row t+1 = h_t
+  float* stash_c;             // LSTM: [NB][stride][H] or null
+  float* stash_gates;         // LSTM: [NB][stride][4H] or null
+  unsigned long long* xchg;   // [2][NB][H] tagged words, zeroed before launch
+  int* abort_flag;
+};
+
+template <int NG, int NB>
+__device__ void chain_fwd_batched_body(const ChainFwdBatchArgs& p, int cta, float* sh_h /* [2][NB][H] */) {
+  constexpr int GL = 32 / NB;                          // lanes per shard group after the transposed reduction
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = cta * UNITS + warp;
+  const int b = lane / GL, sub = lane % GL;            // this lane's shard for the pointwise stage
+
+  float w[NG][16];
+#pragma unroll
+  for (int g = 0; g < NG; ++g)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 t = *reinterpret_cast<const float4*>(p.w_hh + (size_t)(g * H + unit) * H + 128 * j + 4 * lane);
+      w[g][4 * j + 0] = t.x; w[g][4 * j + 1] = t.y; w[g][4 * j + 2] = t.z; w[g][4 * j + 3] = t.w;
+    }
+  const float bhn = (NG == 3) ? p.b_hn[unit] : 0.f;
+  float c = 0.f, hprev = 0.f;
+  const int* my_stream = p.stream + (size_t)b * p.stride;
+  float* my_h = p.stash_h + (size_t)b * p.stride * H;
+  float* my_c = p.stash_c ? p.stash_c + (size_t)b * p.stride * H : nullptr;
+  float* my_g = p.stash_gates ? p.stash_gates + (size_t)b * p.stride * (4 * H) : nullptr;
+  if (sub == 0) {
+    my_h[unit] = 0.f;
+    if (NG == 4 && my_c) my_c[unit] = 0.f;
+  }
+  for (int i = threadIdx.x; i < NB * H; i += THREADS) sh_h[i] = 0.f;      // step-0 vectors: zero state
+
+  int tok_next = p.T > 1 ? my_stream[1] : 0;
+  float xg[NG];
+  {
+    const int tok0 = my_stream[0];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) xg[g] = p.table[(size_t)tok0 * (NG * H) + g * H + unit];
+  }
+
+  for (int t = 0; t < p.T; ++t) {
+    const int buf = t & 1;
+    float* hb = sh_h + buf * NB * H;
+    bool ok = true;
+    if (t > 0) ok = fetch_exchange_all<NB>(p.xchg + (size_t)((t - 1) & 1) * NB * H, (unsigned)t, hb, p.abort_flag);
+    if (__syncthreads_or(!ok)) {
+      if (threadIdx.x == 0) atomicExch(p.abort_flag, 1);
+      return;
+    }
+    float xg_n[NG];
+    {
+      const int tk = tok_next;
+      if (t + 1 < p.T) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) xg_n[g] = p.table[(size_t)tk * (NG * H) + g * H + unit];
+      } else {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) xg_n[g] = 0.f;
+      }
+      tok_next = (t + 2 < p.T) ? my_stream[t + 2] : 0;
+    }
+    // batch-NB GEMV: NG rows x 512 against NB hidden vectors, weights in registers
+    float acc[NG][NB];
+#pragma unroll
+    for (int g = 0; g < NG; ++g)
+#pragma unroll
+      for (int v = 0; v < NB; ++v) acc[g][v] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int v = 0; v < NB; ++v) {
+        const float4 hv = *reinterpret_cast<const float4*>(&hb[v * H + 128 * j + 4 * lane]);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          acc[g][v] = fmaf(w[g][4 * j + 0], hv.x, acc[g][v]);
+          acc[g][v] = fmaf(w[g][4 * j + 1], hv.y, acc[g][v]);
+          acc[g][v] = fmaf(w[g][4 * j + 2], hv.z, acc[g][v]);
+          acc[g][v] = fmaf(w[g][4 * j + 3], hv.w, acc[g][v]);
+        }
+      }
+    }
+    float sum[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) sum[g] = reduce_transposed<NB>(acc[g], lane);
+
+    float hnew;
+    if constexpr (NG == 4) {
+      const float i = act_sigmoid(sum[0] + xg[0]);
+      const float f = act_sigmoid(sum[1] + xg[1]);
+      const float g = act_tanh(sum[2] + xg[2]);
+      const float o = act_sigmoid(sum[3 % NG] + xg[3 % NG]);
+      c = f * c + i * g;
+      hnew = o * act_tanh(c);
+      if (my_g && sub < 4) {
+        const float sel = sub == 0 ? i : (sub == 1 ? f : (sub == 2 ? g : o));
+        my_g[(size_t)t * 4 * H + sub * H + unit] = sel;
+      }
+      if (my_c && sub == 4 % GL) my_c[(size_t)(t + 1) * H + unit] = c;
+    } else {
+      const float r = act_sigmoid(sum[0] + xg[0]);
+      const float z = act_sigmoid(sum[1] + xg[1]);
+      const float n = act_tanh(xg[2] + r * (sum[2] + bhn));
+      hnew = (1.f - z) * n + z * hprev;
+    }
+    hprev = hnew;
+    if (sub == 6 % GL) st_tagged(p.xchg + ((size_t)buf * NB + b) * H + unit, hnew, (unsigned)(t + 1));
+    if (sub == 5 % GL) my_h[(size_t)(t + 1) * H + unit] = hnew;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) xg[g] = xg_n[g];
+  }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(THREADS, 1) chains_fwd_fused_batched_kernel(ChainFwdBatchArgs lstm, ChainFwdBatchArgs gru) {
+  extern __shared__ __align__(16) float sh_dyn[];
+  if (blockIdx.x < CHAIN_CTAS) chain_fwd_batched_body<4, NB>(lstm, blockIdx.x, sh_dyn);
+  else chain_fwd_batched_body<3, NB>(gru, blockIdx.x - CHAIN_CTAS, sh_dyn);
+}
+template <int NB>
+__global__ void __launch_bounds__(THREADS, 1) chain_gru_fwd_batched_kernel(ChainFwdBatchArgs gru) {
+  extern __shared__ __align__(16) float sh_dyn[];
+  chain_fwd_batched_body<3, NB>(gru, blockIdx.x, sh_dyn);
+}
+
+struct ChainBwdBatchArgs {
+  int T;
+  long long stride;
+  const float* w_hh;          // [4H][H]
+  const float* stash_gates;   // [shards][stride][4H]
+  const float* stash_c;       // [shards][stride][H]
+  const int* take;            // [shards][stride]
+  const float* dh_take;       // [S*B][H]
+  float* dgates;              // [shards][stride][4H]; row T of every shard is zeroed by the launcher
+  unsigned long long* xchg;   // [2][shards][H]
+  int shards;                 // total shards = gridDim.x / CHAIN_CTAS * NB
+  int* abort_flag;
+};
+
+// Backward recurrence of NB shards per 64-CTA group (see chain_lstm_bwd_kernel for the single-chain scheme).
+template <int NB>
+__global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_batched_kernel(ChainBwdBatchArgs p) {
+  extern __shared__ __align__(16) float sh_dyn[];      // [2][NB][4H]
+  constexpr int GL = 32 / NB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = blockIdx.x / CHAIN_CTAS, cta = blockIdx.x % CHAIN_CTAS;
+  const int sb = group * NB;                           // first shard of this group
+  const int unit = cta * UNITS + warp;
+  const int pu = 2 * threadIdx.x;
+  const bool owner = (pu >= cta * UNITS) && (pu < cta * UNITS + UNITS);
+  const int myb = lane / GL, sub = lane % GL;          // shard whose dh this lane publishes
+
+  float w[64];
+#pragma unroll
+  for (int jj = 0; jj < 16; ++jj)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[4 * jj + q] = p.w_hh[(size_t)(128 * jj + 4 * lane + q) * H + unit];
+
+  float2 dc[NB], gi[NB], gf[NB], gg[NB], go[NB], cc[NB], cp[NB], dh[NB];
+  auto load_step = [&](int v, int t, float2& a_i, float2& a_f, float2& a_g, float2& a_o, float2& a_cc, float2& a_cp) {
+    const float* ga = p.stash_gates + ((size_t)(sb + v) * p.stride + t) * 4 * H + pu;
+    const float* ca = p.stash_c + ((size_t)(sb + v) * p.stride + t) * H + pu;
+    a_i = *reinterpret_cast<const float2*>(ga);
+    a_f = *reinterpret_cast<const float2*>(ga + H);
+    a_g = *reinterpret_cast<const float2*>(ga + 2 * H);
+    a_o = *reinterpret_cast<const float2*>(ga + 3 * H);
+    a_cc = *reinterpret_cast<const float2*>(ca + H);
+    a_cp = *reinterpret_cast<const float2*>(ca);
+  };
+#pragma unroll
+  for (int v = 0; v < NB; ++v) {
+    dc[v] = make_float2(0.f, 0.f);
+    load_step(v, p.T - 1, gi[v], gf[v], gg[v], go[v], cc[v], cp[v]);
+    dh[v] = make_float2(0.f, 0.f);
+    const int tk = p.take[(size_t)(sb + v) * p.stride + p.T - 1];
+    if (tk >= 0) dh[v] = *reinterpret_cast<const float2*>(p.dh_take + (size_t)tk * H + pu);
+  }
+  const int* my_take = p.take + (size_t)(sb + myb) * p.stride;
+  int tk_prev = p.T > 1 ? my_take[p.T - 2] : -1;
+
+  for (int it = 0; it < p.T; ++it) {
+    const int t = p.T - 1 - it;
+    const int buf = it & 1;
+    float* dgb = sh_dyn + buf * NB * 4 * H;
+    bool ok = true;
+    unsigned long long pa[NB], pb[NB];
+    const unsigned long long* src = p.xchg + ((size_t)((it - 1) & 1) * p.shards + sb) * H + pu;
+    if (it > 0) {
+#pragma unroll
+      for (int v = 0; v < NB; ++v) ld_tagged2(src + (size_t)v * H, pa[v], pb[v]);
+    }
+    // coefficients that do not depend on dh
+    float2 kc[NB], ko[NB], ki[NB], kf[NB], kg[NB], fgate[NB];
+#pragma unroll
+    for (int v = 0; v < NB; ++v) {
+      const float tcx = act_tanh(cc[v].x), tcy = act_tanh(cc[v].y);
+      kc[v] = make_float2(go[v].x * (1.f - tcx * tcx), go[v].y * (1.f - tcy * tcy));
+      ko[v] = make_float2(tcx * go[v].x * (1.f - go[v].x), tcy * go[v].y * (1.f - go[v].y));
+      ki[v] = make_float2(gg[v].x * gi[v].x * (1.f - gi[v].x), gg[v].y * gi[v].y * (1.f - gi[v].y));
+      kf[v] = make_float2(cp[v].x * gf[v].x * (1.f - gf[v].x), cp[v].y * gf[v].y * (1.f - gf[v].y));
+      kg[v] = make_float2(gi[v].x * (1.f - gg[v].x * gg[v].x), gi[v].y * (1.f - gg[v].y * gg[v].y));
+      fgate[v] = gf[v];
+    }
+    const float inj = tk_prev >= 0 ? p.dh_take[(size_t)tk_prev * H + unit] : 0.f;
+    if (t > 0) {
+#pragma unroll
+      for (int v = 0; v < NB; ++v) load_step(v, t - 1, gi[v], gf[v], gg[v], go[v], cc[v], cp[v]);
+    }
+    tk_prev = t > 1 ? my_take[t - 2] : -1;
+
+    if (it > 0) {
+#pragma unroll
+      for (int v = 0; v < NB; ++v) {
+        unsigned spins = 0;
+        while (!((unsigned)(pa[v] >> 32) == (unsigned)it && (unsigned)(pb[v] >> 32) == (unsigned)it)) {
+          if (++spins >= SPIN_LIMIT || ((spins & 1023u) == 0 && *(volatile int*)p.abort_flag != 0)) { ok = false; break; }
+          ld_tagged2(src + (size_t)v * H, pa[v], pb[v]);
+        }
+        dh[v] = make_float2(__uint_as_float((unsigned)pa[v]), __uint_as_float((unsigned)pb[v]));
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < NB; ++v) {
+      const float dctx = dc[v].x + dh[v].x * kc[v].x, dcty = dc[v].y + dh[v].y * kc[v].y;
+      dc[v] = make_float2(dctx * fgate[v].x, dcty * fgate[v].y);
+      const float2 d_i = make_float2(dctx * ki[v].x, dcty * ki[v].y), d_f = make_float2(dctx * kf[v].x, dcty * kf[v].y);
+      const float2 d_g = make_float2(dctx * kg[v].x, dcty * kg[v].y), d_o = make_float2(dh[v].x * ko[v].x, dh[v].y * ko[v].y);
+      float* sd = dgb + v * 4 * H + pu;
+      *reinterpret_cast<float2*>(sd) = d_i;
+      *reinterpret_cast<float2*>(sd + H) = d_f;
+      *reinterpret_cast<float2*>(sd + 2 * H) = d_g;
+      *reinterpret_cast<float2*>(sd + 3 * H) = d_o;
+      if (owner) {
+        float* out = p.dgates + ((size_t)(sb + v) * p.stride + t) * 4 * H + pu;
+        *reinterpret_cast<float2*>(out) = d_i;
+        *reinterpret_cast<float2*>(out + H) = d_f;
+        *reinterpret_cast<float2*>(out + 2 * H) = d_g;
+        *reinterpret_cast<float2*>(out + 3 * H) = d_o;
+      }
+    }
+    if (__syncthreads_or(!ok)) {
+      if (threadIdx.x == 0) atomicExch(p.abort_flag, 1);
+      return;
+    }
+    if (t > 0) {
+      float rec[NB];
+#pragma unroll
+      for (int v = 0; v < NB; ++v) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          const float4 x = *reinterpret_cast<const float4*>(&dgb[v * 4 * H + 128 * jj + 4 * lane]);
+          a0 = fmaf(w[4 * jj + 0], x.x, a0);
+          a1 = fmaf(w[4 * jj + 1], x.y, a1);
+          a2 = fmaf(w[4 * jj + 2], x.z, a2);
+          a3 = fmaf(w[4 * jj + 3], x.w, a3);
+        }
+        rec[v] = (a0 + a1) + (a2 + a3);
+      }
+      const float r = reduce_transposed<NB>(rec, lane);
+      if (sub == 0) st_tagged(p.xchg + ((size_t)buf * p.shards + sb + myb) * H + unit, r + inj, (unsigned)(it + 1));
+    }
+  }
+}
+
 int coop_launch(const void* fn, int grid, void** args, cudaStream_t st) {
   int dev = 0, coop = 0, sms = 0, per_sm = 0;
   ICRL_CUDA(cudaGetDevice(&dev));
@@ -371,12 +697,12 @@ static ChainFwdArgs make_fwd(const int* stream, int T, const float* table, const
 // sync_state layout (device, caller-owned, >= icrl_chain_sync_bytes(), zeroed once by the caller):
 // [0,64) sticky abort word (+pad; cleared only by icrl_chain_check), then exchange buffers
 // (re-zeroed before every launch): lstm fwd 2*H, gru fwd 2*H, lstm bwd 2*H  64-bit words.
-size_t icrl_chain_sync_bytes_impl() { return 64 + sizeof(unsigned long long) * (2 * H + 2 * H + 2 * H); }
+size_t icrl_chain_sync_bytes_impl() { return 64 + sizeof(unsigned long long) * 3 * (2 * NB_MAX * H); }
 
 static int* sync_abort(void* s) { return reinterpret_cast<int*>(s); }
 static unsigned long long* sync_xchg(void* s, int which) {
   unsigned long long* base = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(s) + 64);
-  return base + (which == 0 ? 0 : (which == 1 ? 2 * H : 4 * H));
+  return base + (size_t)which * (2 * NB_MAX * H);
 }
 
 int icrl_chain_lstm_fwd_impl(cudaStream_t st, const int* stream, int T, const float* table, const float* w_hh,
@@ -438,4 +764,66 @@ int icrl_chain_check_impl(cudaStream_t st, void* sync_state) {
     return ICRL_ERR_WATCHDOG;
   }
   return ICRL_OK;
+}
+
+
+// ---- batched launchers (nb chain shards; see the kernels above)
+static int coop_launch_smem(const void* fn, int grid, void** args, size_t smem, cudaStream_t st) {
+  int dev = 0, sms = 0, per_sm = 0;
+  ICRL_CUDA(cudaGetDevice(&dev));
+  ICRL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  ICRL_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ICRL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, THREADS, smem));
+  ICRL_REQUIRE(per_sm * sms >= grid, "chain grid is not co-resident on this device");
+  ICRL_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(THREADS), args, smem, st));
+  return ICRL_OK;
+}
+
+int icrl_chains_fwd_fused_batched_impl(cudaStream_t st, int nb, const int* v_stream, int v_T, const float* v_table,
+                                       const float* v_w_hh, float* v_stash_h, float* v_stash_c, float* v_stash_gates,
+                                       const int* r_stream, int r_T, const float* r_table, const float* r_w_hh,
+                                       const float* r_b_hn, float* r_stash_h, void* sync_state) {
+  ICRL_REQUIRE(nb == 2 || nb == 4 || nb == 8, "chain shards per launch must be 2, 4 or 8");
+  ICRL_REQUIRE(r_T > 0, "empty chain");
+  ICRL_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(sync_state) + 64, 0, icrl_chain_sync_bytes_impl() - 64, st));
+  ChainFwdBatchArgs a, b;
+  a.stream = v_stream; a.T = v_T; a.stride = (long long)v_T + 1; a.table = v_table; a.w_hh = v_w_hh; a.b_hn = nullptr;
+  a.stash_h = v_stash_h; a.stash_c = v_stash_c; a.stash_gates = v_stash_gates; a.xchg = sync_xchg(sync_state, 0);
+  a.abort_flag = sync_abort(sync_state);
+  b.stream = r_stream; b.T = r_T; b.stride = (long long)r_T + 1; b.table = r_table; b.w_hh = r_w_hh; b.b_hn = r_b_hn;
+  b.stash_h = r_stash_h; b.stash_c = nullptr; b.stash_gates = nullptr; b.xchg = sync_xchg(sync_state, 1);
+  b.abort_flag = sync_abort(sync_state);
+  const size_t smem = (size_t)2 * nb * H * sizeof(float);
+  if (v_T > 0) {
+    void* args[] = {&a, &b};
+    const void* fn = nb == 2 ? (const void*)chains_fwd_fused_batched_kernel<2>
+                             : (nb == 4 ? (const void*)chains_fwd_fused_batched_kernel<4> : (const void*)chains_fwd_fused_batched_kernel<8>);
+    return coop_launch_smem(fn, 2 * CHAIN_CTAS, args, smem, st);
+  }
+  void* args[] = {&b};
+  const void* fn = nb == 2 ? (const void*)chain_gru_fwd_batched_kernel<2>
+                           : (nb == 4 ? (const void*)chain_gru_fwd_batched_kernel<4> : (const void*)chain_gru_fwd_batched_kernel<8>);
+  return coop_launch_smem(fn, CHAIN_CTAS, args, smem, st);
+}
+
+// shards = 2, 4 or 8 total; they are split over two 64-CTA groups (1, 2 or 4 shards per group).
+int icrl_chain_lstm_bwd_batched_impl(cudaStream_t st, int shards, int T, const float* w_hh, const float* stash_gates,
+                                     const float* stash_c, const int* take, const float* dh_take, float* dgates,
+                                     void* sync_state) {
+  ICRL_REQUIRE(shards == 2 || shards == 4 || shards == 8, "chain shards must be 2, 4 or 8");
+  ICRL_REQUIRE(T > 0, "empty chain");
+  ICRL_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(sync_state) + 64, 0, icrl_chain_sync_bytes_impl() - 64, st));
+  const long long stride = (long long)T + 1;
+  for (int k = 0; k < shards; ++k)                      // padding row T of every shard (feeds the weight-gradient GEMM)
+    ICRL_CUDA(cudaMemsetAsync(dgates + ((size_t)k * stride + T) * 4 * H, 0, 4 * H * sizeof(float), st));
+  ChainBwdBatchArgs a;
+  a.T = T; a.stride = stride; a.w_hh = w_hh; a.stash_gates = stash_gates; a.stash_c = stash_c; a.take = take;
+  a.dh_take = dh_take; a.dgates = dgates; a.xchg = sync_xchg(sync_state, 2); a.shards = shards;
+  a.abort_flag = sync_abort(sync_state);
+  void* args[] = {&a};
+  const int nb = shards / 2;
+  const size_t smem = (size_t)2 * nb * 4 * H * sizeof(float);
+  const void* fn = nb == 1 ? (const void*)chain_lstm_bwd_batched_kernel<1>
+                           : (nb == 2 ? (const void*)chain_lstm_bwd_batched_kernel<2> : (const void*)chain_lstm_bwd_batched_kernel<4>);
+  return coop_launch_smem(fn, 2 * CHAIN_CTAS, args, smem, st);
 }

@@ -155,6 +155,31 @@ __global__ void build_stream_kernel(int B, int p0, int S, int extra, const int* 
   }
 }
 
+// The same streams for `shards` contiguous row shards of Bs = B / shards rows, each an independent chain:
+// shard k's arrays start at k * stride (stride = T_shard + 1; the padding entry gets token 0 / take -1);
+// take holds GLOBAL rows s*B + b, take_pos GLOBAL stash rows k * stride + position.
+__global__ void build_stream_sharded_kernel(int B, int Bs, int p0, int S, int extra, long long stride,
+                                            const int* __restrict__ tokcm, int* __restrict__ stream,
+                                            int* __restrict__ take, int* __restrict__ take_pos) {
+  const int s = blockIdx.y, k = blockIdx.z;
+  const int n = p0 + s + extra;
+  const long long start = (long long)Bs * ((long long)s * (p0 + extra) + (long long)s * (s - 1) / 2);
+  const long long len = (long long)n * Bs;
+  const long long base = (long long)k * stride;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i / Bs), bl = (int)(i % Bs);
+    const int row = k * Bs + bl;
+    stream[base + start + i] = tokcm[(long long)col * B + row];
+    const int tk = col == n - 1 ? s * B + row : -1;
+    if (take) take[base + start + i] = tk;
+    if (tk >= 0 && take_pos) take_pos[tk] = (int)(base + start + i);
+  }
+  if (s == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+    stream[base + stride - 1] = 0;
+    if (take) take[base + stride - 1] = -1;
+  }
+}
+
 // dst[r] = src[idx[r] + row_offset]  (rows of H floats)
 __global__ void gather_rows_kernel(long long R, const float* __restrict__ src, const int* __restrict__ idx,
                                    long long row_offset, float* __restrict__ dst) {
@@ -221,6 +246,16 @@ int icrl_build_stream_impl(cudaStream_t st, int B, int p0, int S, int extra, con
                            int* take_pos) {
   dim3 grid(icrl_cdiv((long long)(p0 + S + extra) * B, 256 * 4), S);
   build_stream_kernel<<<grid, 256, 0, st>>>(B, p0, S, extra, tokcm, stream, take, take_pos);
+  ICRL_LAUNCH_CHECK();
+  return ICRL_OK;
+}
+
+int icrl_build_stream_sharded_impl(cudaStream_t st, int B, int p0, int S, int extra, int shards, const int* tokcm,
+                                   int* stream, int* take, int* take_pos) {
+  const int Bs = B / shards;
+  const long long T = (long long)Bs * ((long long)S * (p0 + extra) + (long long)S * (S - 1) / 2);
+  dim3 grid(icrl_cdiv((long long)(p0 + S + extra) * Bs, 256 * 4), S, shards);
+  build_stream_sharded_kernel<<<grid, 256, 0, st>>>(B, Bs, p0, S, extra, T + 1, tokcm, stream, take, take_pos);
   ICRL_LAUNCH_CHECK();
   return ICRL_OK;
 }

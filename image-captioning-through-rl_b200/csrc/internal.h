@@ -61,3 +61,12 @@ int icrl_policy_decode_impl(cudaStream_t st, int B, int V, int p0, int S, int gr
                             int* tokcm, long long* tokens_out, float* logp, float* Hs, float* Cs, float* Gs,
                             float* logits, float* last_logits, void* hparts);
 void icrl_decode_set_profile_impl(long long* buf);
+int icrl_build_stream_sharded_impl(cudaStream_t st, int B, int p0, int S, int extra, int shards, const int* tokcm,
+                                   int* stream, int* take, int* take_pos);
+int icrl_chains_fwd_fused_batched_impl(cudaStream_t st, int nb, const int* v_stream, int v_T, const float* v_table,
+                                       const float* v_w_hh, float* v_stash_h, float* v_stash_c, float* v_stash_gates,
+                                       const int* r_stream, int r_T, const float* r_table, const float* r_w_hh,
+                                       const float* r_b_hn, float* r_stash_h, void* sync_state);
+int icrl_chain_lstm_bwd_batched_impl(cudaStream_t st, int shards, int T, const float* w_hh, const float* stash_gates,
+                                     const float* stash_c, const int* take, const float* dh_take, float* dgates,
+                                     void* sync_state);

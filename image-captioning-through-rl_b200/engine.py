@@ -73,7 +73,7 @@ def plan_rollout(captions, level=None):
 class A2CEngine:
     DECODE_MODES = ("fused", "tc", "simt")
 
-    def __init__(self, a2c_network, reward_network, use_tc=None, decode="fused"):
+    def __init__(self, a2c_network, reward_network, use_tc=None, decode="fused", chain_shards=1):
         self.policy = a2c_network.policy_network
         self.value = a2c_network.value_network
         self.reward = reward_network
@@ -96,6 +96,13 @@ class A2CEngine:
             raise ValueError("decode must be one of %s" % (self.DECODE_MODES,))
         self.decode = decode
         self.use_tc = decode == "tc"
+        # chain_shards = K > 1 cuts the (local) batch into K contiguous row shards whose value / reward recurrences
+        # each start from zero state -- the reference run on K minibatches of B/K rows with averaged gradients,
+        # i.e. exactly what K data-parallel ranks compute.  K = 1 is the reference's single
+        # carried-state chain over the whole batch.  The K chains advance in lockstep on the same CTAs.
+        if chain_shards not in (1, 2, 4, 8):
+            raise ValueError("chain_shards must be 1, 2, 4 or 8")
+        self.chain_shards = int(chain_shards)
         with torch.cuda.device(dev):
             self.sync_state = torch.zeros(int(_lib.call("icrl_chain_sync_bytes")), dtype=torch.uint8, device=dev)
         self._check_params()
@@ -278,9 +285,21 @@ class A2CEngine:
 
     def _streams(self, tokcm, B, p0, S):
         st, L = self._stream, self.launches.ref
+        K = self.chain_shards
+        i32 = torch.int32
+        if K > 1:
+            if B % K:
+                raise ValueError("batch of %d rows does not split into %d chain shards" % (B, K))
+            Tv = int(_lib.call("icrl_stream_len", B // K, p0, S, 0))
+            Tr = int(_lib.call("icrl_stream_len", B // K, p0, S, 1))
+            v_stream, v_take = self._buf("v_stream", K * (Tv + 1), i32), self._buf("v_take", K * (Tv + 1), i32)
+            r_stream = self._buf("r_stream", K * (Tr + 1), i32)
+            v_pos, r_pos = self._buf("v_pos", S * B, i32), self._buf("r_pos", S * B, i32)
+            _lib.call("icrl_build_stream_sharded", st, B, p0, S, 0, K, _p(tokcm), _p(v_stream), _p(v_take), _p(v_pos), L)
+            _lib.call("icrl_build_stream_sharded", st, B, p0, S, 1, K, _p(tokcm), _p(r_stream), None, _p(r_pos), L)
+            return Tv, Tr
         Tv = int(_lib.call("icrl_stream_len", B, p0, S, 0))
         Tr = int(_lib.call("icrl_stream_len", B, p0, S, 1))
-        i32 = torch.int32
         v_stream, v_take, v_pos = self._buf("v_stream", Tv, i32), self._buf("v_take", Tv, i32), self._buf("v_pos", S * B, i32)
         r_stream, r_pos = self._buf("r_stream", Tr, i32), self._buf("r_pos", S * B, i32)
         _lib.call("icrl_build_stream", st, B, p0, S, 0, _p(tokcm), _p(v_stream), _p(v_take), _p(v_pos), L)
@@ -290,12 +309,18 @@ class A2CEngine:
     def _chains_forward(self, f, B, S, Tv, Tr, train):
         st, L, b = self._stream, self.launches.ref, self._bufs
         Vn, R = self.value, self.reward
-        v_h = self._buf("v_stash_h", (Tv + 1) * H)
-        v_c = self._buf("v_stash_c", (Tv + 1) * H)
-        v_g = self._buf("v_stash_g", Tv * 4 * H)
-        r_h = self._buf("r_stash_h", (Tr + 1) * H)
+        K = self.chain_shards
+        v_h = self._buf("v_stash_h", K * (Tv + 1) * H)
+        v_c = self._buf("v_stash_c", K * (Tv + 1) * H)
+        v_g = self._buf("v_stash_g", K * (Tv + 1) * 4 * H)
+        r_h = self._buf("r_stash_h", K * (Tr + 1) * H)
         with self._phase("chains_fwd_fused"):
-          _lib.call("icrl_chains_fwd_fused", st, _p(b["v_stream"]), Tv, _p(b["v_table"]), _p(Vn.valrnn.lstm.weight_hh_l0),
+          if K > 1:
+            _lib.call("icrl_chains_fwd_fused_sharded", st, K, _p(b["v_stream"]), Tv, _p(b["v_table"]),
+                  _p(Vn.valrnn.lstm.weight_hh_l0), _p(v_h), _p(v_c), _p(v_g), _p(b["r_stream"]), Tr, _p(b["r_table"]),
+                  _p(R.rewrnn.gru.weight_hh_l0), _p(R.rewrnn.gru.bias_hh_l0[2 * H:]), _p(r_h), _p(self.sync_state), L)
+          else:
+            _lib.call("icrl_chains_fwd_fused", st, _p(b["v_stream"]), Tv, _p(b["v_table"]), _p(Vn.valrnn.lstm.weight_hh_l0),
                   _p(v_h), _p(v_c), _p(v_g), _p(b["r_stream"]), Tr, _p(b["r_table"]), _p(R.rewrnn.gru.weight_hh_l0),
                   _p(R.rewrnn.gru.bias_hh_l0[2 * H:]), _p(r_h), _p(self.sync_state), L)
         SB = S * B
@@ -330,14 +355,19 @@ class A2CEngine:
                   _p(g(Vn.linear1.weight)), _p(g(Vn.linear1.bias)), _p(g(Vn.linear2.weight)), _p(g(Vn.linear2.bias)),
                   _p(colsum_ws), L)
         # value chain BPTT (serial) and its parameter gradients (contractions over all T steps)
-        dgates = self._buf("v_dgates", Tv * 4 * H)
+        K = self.chain_shards
+        dgates = self._buf("v_dgates", K * (Tv + 1) * 4 * H)
         with self._phase("chain_lstm_bwd"):
-          _lib.call("icrl_chain_lstm_bwd", st, Tv, _p(Vn.valrnn.lstm.weight_hh_l0), _p(b["v_stash_g"]), _p(b["v_stash_c"]),
+          if K > 1:
+            _lib.call("icrl_chain_lstm_bwd_sharded", st, K, Tv, _p(Vn.valrnn.lstm.weight_hh_l0), _p(b["v_stash_g"]),
+                  _p(b["v_stash_c"]), _p(b["v_take"]), _p(dh_take), _p(dgates), _p(self.sync_state), L)
+          else:
+            _lib.call("icrl_chain_lstm_bwd", st, Tv, _p(Vn.valrnn.lstm.weight_hh_l0), _p(b["v_stash_g"]), _p(b["v_stash_c"]),
                   _p(b["v_take"]), _p(dh_take), _p(dgates), _p(self.sync_state), None, None, None, None, L)
         dtable = self._buf("dtable", V * 4 * H)
         lstm = Vn.valrnn.lstm
         with self._phase("value_param_grads"):
-          _lib.call("icrl_value_chain_param_grads", st, Tv, V, _p(b["v_stream"]), _p(dgates), _p(b["v_stash_h"]),
+          _lib.call("icrl_value_chain_param_grads", st, Tv if K == 1 else K * (Tv + 1), V, _p(b["v_stream"]), _p(dgates), _p(b["v_stash_h"]),
                   _p(Vn.valrnn.caption_embedding.weight), _p(lstm.weight_ih_l0), _p(dtable), _p(colsum_ws), _p(gemm_ws),
                   gemm_ws_floats * 4, _p(g(Vn.valrnn.caption_embedding.weight)), _p(g(lstm.weight_ih_l0)),
                   _p(g(lstm.weight_hh_l0)), _p(g(lstm.bias_ih_l0)), _p(g(lstm.bias_hh_l0)), L)

@@ -147,6 +147,23 @@ int icrl_chains_fwd_fused(void* stream, const int* v_stream, int v_T, const floa
 int icrl_chain_lstm_bwd(void* stream, int T, const float* W_hh, const float* stash_gates, const float* stash_c,
                         const int* take, const float* dh_take, float* dgates, void* sync_state, const float* dh_init,
                         const float* dc_init, float* dh0_out, float* dc0_out, int* launches);
+/* ---- chain shards (new; the reference has no equivalent).  The batch is cut into `shards` (2, 4 or 8) contiguous
+ *      row shards and the value / reward recurrences of every shard start from zero state: exactly the reference
+ *      run on `shards` minibatches of B/shards rows with the gradients averaged, i.e. what `shards` data-parallel
+ *      ranks compute.  The shards advance in lockstep on the same CTAs, sharing W_hh in registers, so
+ *      one exchange round trip carries `shards` hidden vectors.  Layout: every per-step array of shard k starts at
+ *      row k * (T + 1) with T = icrl_stream_len(B / shards, p0, S, extra); take holds global rows s*B + b and take_pos
+ *      global stash rows, so heads, loss and the parameter-gradient entry points are used unchanged with
+ *      T_total = shards * (T + 1). */
+int icrl_build_stream_sharded(void* stream, int B, int p0, int S, int extra, int shards, const int* tokcm,
+                              int* stream_out, int* take, int* take_pos, int* launches);
+int icrl_chains_fwd_fused_sharded(void* stream, int shards, const int* v_stream, int v_T, const float* v_table,
+                                  const float* v_W_hh, float* v_stash_h, float* v_stash_c, float* v_stash_gates,
+                                  const int* r_stream, int r_T, const float* r_table, const float* r_W_hh,
+                                  const float* r_b_hn, float* r_stash_h, void* sync_state, int* launches);
+int icrl_chain_lstm_bwd_sharded(void* stream, int shards, int T, const float* W_hh, const float* stash_gates,
+                                const float* stash_c, const int* take, const float* dh_take, float* dgates,
+                                void* sync_state, int* launches);
 /* synchronises `stream`; ICRL_ERR_WATCHDOG if any chain launch since the last check gave up waiting */
 int icrl_chain_check(void* stream, void* sync_state);
 /* dst[r][:] = src[idx[r] + row_offset][:]  (rows of 512 floats; h at the take positions) */

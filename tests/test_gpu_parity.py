@@ -307,3 +307,33 @@ def test_reference_rollout_loop_trains_dropin_modules(name):
     assert abs(float(loss) - float(g["loss"])) <= TOL
     assert all(p.grad is not None for p in A.parameters())
     _record(name + "_autograd_loop", grad_worst=check_grads_vs_golden(named_grads(A), g, GTOL))
+
+
+@pytest.mark.parametrize("shards", [2, 4, 8])
+@pytest.mark.parametrize("level", [None, 4])
+def test_chain_shards_equal_independent_shard_runs(shards, level):
+    """chain_shards=K (K value/reward recurrences in lockstep, each from zero state) must equal K independent
+    single-chain runs on the row shards with the global loss normalisation and summed gradients -- the N-rank
+    data-parallel oracle of SURVEY 8e, which tests/test_oracle_golden.py pins to the reference on CPU."""
+    from icrl_b200.engine import A2CEngine
+    seed, B, L = 51, 32, 9
+    A, R, w = make_nets(seed)
+    f, c = synth.make_inputs(seed, B, L)
+    S = (L - 1) if level is None else level
+    u = synth.make_uniforms(seed, S, B)
+    e1 = A2CEngine(A, R, chain_shards=1)
+    Bs = B // shards
+    gsum, vals, rews, toks = None, [], [], []
+    for k in range(shards):
+        sl = slice(k * Bs, (k + 1) * Bs)
+        r = e1.step(f[sl], c[sl], uniforms=np.ascontiguousarray(u[:, sl]), level=level, global_rows=B)
+        vals.append(r["values"].clone()); rews.append(r["rewards"].clone()); toks.append(r["tokens"].clone())
+        gsum = e1.flat_grad.clone() if gsum is None else gsum + e1.flat_grad
+    ek = A2CEngine(A, R, chain_shards=shards)
+    rk = ek.step(f, c, uniforms=u, level=level)
+    assert torch.equal(rk["tokens"], torch.cat(toks))
+    assert float((rk["values"] - torch.cat(vals)).abs().max()) <= TOL
+    assert float((rk["rewards"] - torch.cat(rews)).abs().max()) <= TOL
+    err = float((ek.flat_grad - gsum).abs().max() / gsum.abs().max())
+    _record("chain_shards_%d_%s" % (shards, level), grad_rel=err)
+    assert err <= GTOL
