@@ -106,6 +106,25 @@ __device__ __forceinline__ bool fetch_exchange(const unsigned long long* buf, un
   return ok;
 }
 
+// transposed butterfly: v[0..NB) per lane in, afterwards lane l holds in v[0] the warp-wide sum of element
+// b = l >> (5 - log2 NB)
+template <int NB>
+__device__ __forceinline__ float reduce_transposed(float (&v)[NB], int lane) {
+  int o = 16;
+#pragma unroll
+  for (int n = NB; n > 1; n >>= 1, o >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = upper ? v[i] : v[i + n / 2];
+      const float keep = upper ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  for (; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+  return v[0];
+}
+
 // Batched form: all NV polls are in flight before the first tag is examined (one L2 round trip for the whole
 // batch instead of one per vector); only words that had not arrived yet are polled again.
 template <int NV>
@@ -270,11 +289,19 @@ __global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_kernel(ChainBwdArgs
   const int pu = 2 * threadIdx.x;                              // this thread's two pointwise units
   const bool owner = (pu >= cta * UNITS) && (pu < cta * UNITS + UNITS);
 
-  float w[64];                                                 // column `unit` of W_hh: j = 128*jj + 4*lane + q
+  // dh_{t-1}[u] = sum_j W_hh[j][u] dg[j] for the CTA's 8 units u.  The 2048 j are split over the 8 warps (warp w:
+  // j in [256w, 256w+256), lane: 8 consecutive j) so that every dg value is read from shared memory by ONE lane
+  // (the earlier warp-per-unit mapping had all 8 warps read all 2048 values: 64 KB of LDS per step, ~500 cycles).
+  // wl[i][k] = W_hh[256w + 8 lane + k][8 cta + i]
+  __shared__ float sh_part[UNITS][UNITS];                      // [warp][unit] partial sums
+  float wl[UNITS][8];
 #pragma unroll
-  for (int jj = 0; jj < 16; ++jj)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) w[4 * jj + q] = p.w_hh[(size_t)(128 * jj + 4 * lane + q) * H + unit];
+  for (int k = 0; k < 8; ++k) {
+    const float* src = p.w_hh + (size_t)(256 * warp + 8 * lane + k) * H + cta * UNITS;
+    const float4 x0 = *reinterpret_cast<const float4*>(src), x1 = *reinterpret_cast<const float4*>(src + 4);
+    wl[0][k] = x0.x; wl[1][k] = x0.y; wl[2][k] = x0.z; wl[3][k] = x0.w;
+    wl[4][k] = x1.x; wl[5][k] = x1.y; wl[6][k] = x1.z; wl[7][k] = x1.w;
+  }
 
   float2 dc = p.dc_init ? *reinterpret_cast<const float2*>(p.dc_init + pu) : make_float2(0.f, 0.f);
   auto load_step = [&](int t, float2& gi, float2& gf, float2& gg, float2& go, float2& cc, float2& cp) {
@@ -344,19 +371,28 @@ __global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_kernel(ChainBwdArgs
       return;
     }
     if (t > 0 || p.dh0_out) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const float4 d0 = *reinterpret_cast<const float4*>(&sh_dg[buf][256 * warp + 8 * lane]);
+      const float4 d1 = *reinterpret_cast<const float4*>(&sh_dg[buf][256 * warp + 8 * lane + 4]);
+      float part[UNITS];
 #pragma unroll
-      for (int jj = 0; jj < 16; ++jj) {
-        const float4 v = *reinterpret_cast<const float4*>(&sh_dg[buf][128 * jj + 4 * lane]);
-        a0 = fmaf(w[4 * jj + 0], v.x, a0);
-        a1 = fmaf(w[4 * jj + 1], v.y, a1);
-        a2 = fmaf(w[4 * jj + 2], v.z, a2);
-        a3 = fmaf(w[4 * jj + 3], v.w, a3);
+      for (int i = 0; i < UNITS; ++i) {
+        float a = wl[i][0] * d0.x;
+        a = fmaf(wl[i][1], d0.y, a); a = fmaf(wl[i][2], d0.z, a); a = fmaf(wl[i][3], d0.w, a);
+        a = fmaf(wl[i][4], d1.x, a); a = fmaf(wl[i][5], d1.y, a); a = fmaf(wl[i][6], d1.z, a); a = fmaf(wl[i][7], d1.w, a);
+        part[i] = a;
       }
-      const float rec = warp_sum((a0 + a1) + (a2 + a3));
-      if (lane == 0) {
-        if (t > 0) st_tagged(p.xchg + (size_t)buf * H + unit, rec + inj, (unsigned)(it + 1));
-        else p.dh0_out[unit] = rec;
+      const float ps = reduce_transposed<UNITS>(part, lane);      // lane l: unit l >> 2, summed over the warp's 256 j
+      if ((lane & 3) == 0) sh_part[warp][lane >> 2] = ps;
+      __syncthreads();
+      if (lane < UNITS) {
+        float rec = sh_part[lane][warp];                           // this warp finishes unit `warp`
+        rec += __shfl_xor_sync(0xffu, rec, 1);
+        rec += __shfl_xor_sync(0xffu, rec, 2);
+        rec += __shfl_xor_sync(0xffu, rec, 4);
+        if (lane == 0) {
+          if (t > 0) st_tagged(p.xchg + (size_t)buf * H + unit, rec + inj, (unsigned)(it + 1));
+          else p.dh0_out[unit] = rec;
+        }
       }
     }
     gi = ngi; gf = ngf; gg = ngg; go = ngo; cc = ncc; cp = ncp;
@@ -375,25 +411,6 @@ __global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_kernel(ChainBwdArgs
 // [NB][stride][H], stash_gates / dgates [NB][stride][4H] (row T unused / zero), take [NB][stride].
 
 constexpr int NB_MAX = 8;
-
-// transposed butterfly: v[0..NB) per lane in, afterwards lane l holds in v[0] the warp-wide sum of element
-// b = l >> (5 - log2 NB)
-template <int NB>
-__device__ __forceinline__ float reduce_transposed(float (&v)[NB], int lane) {
-  int o = 16;
-#pragma unroll
-  for (int n = NB; n > 1; n >>= 1, o >>= 1) {
-    const bool upper = (lane & o) != 0;
-#pragma unroll
-    for (int i = 0; i < n / 2; ++i) {
-      const float send = upper ? v[i] : v[i + n / 2];
-      const float keep = upper ? v[i + n / 2] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-    }
-  }
-  for (; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
-  return v[0];
-}
 
 struct ChainFwdBatchArgs {
   const int* stream;          // [NB][stride]
