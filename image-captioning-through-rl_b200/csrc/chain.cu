@@ -563,20 +563,24 @@ struct ChainBwdBatchArgs {
 template <int NB>
 __global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_batched_kernel(ChainBwdBatchArgs p) {
   extern __shared__ __align__(16) float sh_dyn[];      // [2][NB][4H]
-  constexpr int GL = 32 / NB;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int group = blockIdx.x / CHAIN_CTAS, cta = blockIdx.x % CHAIN_CTAS;
   const int sb = group * NB;                           // first shard of this group
   const int unit = cta * UNITS + warp;
   const int pu = 2 * threadIdx.x;
   const bool owner = (pu >= cta * UNITS) && (pu < cta * UNITS + UNITS);
-  const int myb = lane / GL, sub = lane % GL;          // shard whose dh this lane publishes
+  const int myb = (lane >> 3) < NB ? (lane >> 3) : 0;  // shard whose dh lane 8*myb publishes
 
-  float w[64];
+  // contraction split over the warps as in chain_lstm_bwd_kernel: wl[i][k] = W_hh[256w + 8 lane + k][8 cta + i]
+  __shared__ float sh_part[UNITS][NB * UNITS];         // [warp][shard * 8 + unit]
+  float wl[UNITS][8];
 #pragma unroll
-  for (int jj = 0; jj < 16; ++jj)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) w[4 * jj + q] = p.w_hh[(size_t)(128 * jj + 4 * lane + q) * H + unit];
+  for (int k = 0; k < 8; ++k) {
+    const float* src = p.w_hh + (size_t)(256 * warp + 8 * lane + k) * H + cta * UNITS;
+    const float4 x0 = *reinterpret_cast<const float4*>(src), x1 = *reinterpret_cast<const float4*>(src + 4);
+    wl[0][k] = x0.x; wl[1][k] = x0.y; wl[2][k] = x0.z; wl[3][k] = x0.w;
+    wl[4][k] = x1.x; wl[5][k] = x1.y; wl[6][k] = x1.z; wl[7][k] = x1.w;
+  }
 
   float2 dc[NB], gi[NB], gf[NB], gg[NB], go[NB], cc[NB], cp[NB], dh[NB];
   auto load_step = [&](int v, int t, float2& a_i, float2& a_f, float2& a_g, float2& a_o, float2& a_cc, float2& a_cp) {
@@ -665,22 +669,30 @@ __global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_batched_kernel(Chai
       return;
     }
     if (t > 0) {
-      float rec[NB];
+      float part[NB * UNITS];
 #pragma unroll
       for (int v = 0; v < NB; ++v) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float4 d0 = *reinterpret_cast<const float4*>(&dgb[v * 4 * H + 256 * warp + 8 * lane]);
+        const float4 d1 = *reinterpret_cast<const float4*>(&dgb[v * 4 * H + 256 * warp + 8 * lane + 4]);
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-          const float4 x = *reinterpret_cast<const float4*>(&dgb[v * 4 * H + 128 * jj + 4 * lane]);
-          a0 = fmaf(w[4 * jj + 0], x.x, a0);
-          a1 = fmaf(w[4 * jj + 1], x.y, a1);
-          a2 = fmaf(w[4 * jj + 2], x.z, a2);
-          a3 = fmaf(w[4 * jj + 3], x.w, a3);
+        for (int i = 0; i < UNITS; ++i) {
+          float a = wl[i][0] * d0.x;
+          a = fmaf(wl[i][1], d0.y, a); a = fmaf(wl[i][2], d0.z, a); a = fmaf(wl[i][3], d0.w, a);
+          a = fmaf(wl[i][4], d1.x, a); a = fmaf(wl[i][5], d1.y, a); a = fmaf(wl[i][6], d1.z, a); a = fmaf(wl[i][7], d1.w, a);
+          part[v * UNITS + i] = a;
         }
-        rec[v] = (a0 + a1) + (a2 + a3);
       }
-      const float r = reduce_transposed<NB>(rec, lane);
-      if (sub == 0) st_tagged(p.xchg + ((size_t)buf * p.shards + sb + myb) * H + unit, r + inj, (unsigned)(it + 1));
+      constexpr int R = NB * UNITS;                     // 8, 16 or 32 values: lane l ends with element l >> (5 - log2 R)
+      const float ps = reduce_transposed<R>(part, lane);
+      if ((lane & (32 / R - 1)) == 0) sh_part[warp][lane / (32 / R)] = ps;
+      __syncthreads();
+      if (lane < R) {
+        float r = sh_part[lane & 7][(lane >> 3) * UNITS + warp];     // lane 8v + w': warp w' partial of (shard v, unit `warp`)
+        r += __shfl_xor_sync((unsigned)((1ull << R) - 1), r, 1);
+        r += __shfl_xor_sync((unsigned)((1ull << R) - 1), r, 2);
+        r += __shfl_xor_sync((unsigned)((1ull << R) - 1), r, 4);
+        if ((lane & 7) == 0) st_tagged(p.xchg + ((size_t)buf * p.shards + sb + (lane >> 3)) * H + unit, r + inj, (unsigned)(it + 1));
+      }
     }
   }
 }
