@@ -7,6 +7,9 @@ Same function names, argument order and return values as the reference
 global MT19937 stream exactly like the reference's ``np.random.choice`` calls (one double per row
 per step, step-major), so ``np.random.seed(s)`` reproduces the reference's token ids.
 
+``GenerateCaptionsWithActorCriticLookAhead`` / ``test_a2c_network`` (``:73-105``, ``:619-665``) run
+the reference's beam look-ahead on the drop-in modules.
+
 Supervised pretraining (``train_policy_network`` etc.) is outside the hot path: when a
 pretrained file is missing ``train_a2c_network`` raises instead of pretraining from scratch.
 """
@@ -83,6 +86,80 @@ def GenerateCaptionsGreedy(features, captions, policy_network):
         object.__setattr__(policy_network, "_icrl_greedy", eng)
     tokens, _ = eng.greedy_decode(np.asarray(features, dtype=np.float32), np.asarray(captions)[:, 0], MAX_SEQ_LEN - 1)
     return tokens
+
+
+def GenerateCaptionsWithActorCriticLookAhead(features, captions, policy_network, value_network, beamSize=5,
+                                             most_likely=False):
+    """Value-guided beam search of the reference's evaluation path (trainers.py:73-105).
+
+    Keeps `beamSize` candidate caption BATCHES.  Each of the MAX_SEQ_LEN-1 steps expands every candidate with
+    the policy's top-`beamSize` words of the last position, scores an expansion as
+    ``score - (0.6 * V(features, caption) + 0.4 * log(top-k logit))`` (the reference takes the log of the raw
+    top-k logit, a NaN where it is negative -- reproduced, the ordering key is the batch MEAN of the score), and
+    keeps the `beamSize` expansions with the smallest mean.  The value network's hidden_cell is carried through
+    every call and never reset inside (Q1), exactly as in the reference; callers reset it per batch
+    (trainers.py:661).  Policy and value forwards run on the CUDA kernels through the drop-in modules; top-k,
+    log and the sort are torch plumbing on (B,1,beam) tensors."""
+    dev = policy_network.linear2vocab.weight.device
+    feats = torch.as_tensor(np.asarray(features), device=dev).float().unsqueeze(0)
+    start = torch.as_tensor(np.asarray(captions)[:, 0:1], device=dev).long()
+    beam = [(start, 0)]
+    with torch.no_grad():
+        for _ in range(MAX_SEQ_LEN - 1):
+            grown = []
+            for cap, score in beam:
+                logits = policy_network(feats, cap)[:, -1:, :]
+                top, words = torch.topk(logits, beamSize)
+                for i in range(beamSize):
+                    longer = torch.cat((cap, words[:, :, i]), dim=1)
+                    value = value_network(feats.squeeze(0), longer).detach()
+                    grown.append((longer, score - (0.6 * value + 0.4 * torch.log(top[:, :, i]))))
+            grown.sort(key=lambda cs: cs[1].mean())
+            beam = grown[:beamSize]
+    return beam[0][0] if most_likely else beam
+
+
+def decode_captions(captions, idx_to_word):
+    """ids -> sentences, stopping at <END> and skipping <NULL> (utilities.py:116-140)."""
+    caps = np.asarray(captions.cpu() if isinstance(captions, torch.Tensor) else captions)
+    single = caps.ndim == 1
+    caps = caps[None] if single else caps
+    out = []
+    for row in caps:
+        words = []
+        for t in row:
+            w = idx_to_word[int(t)]
+            if w != "<NULL>":
+                words.append(w)
+            if w == "<END>":
+                break
+        out.append(" ".join(words))
+    return out[0] if single else out
+
+
+def test_a2c_network(a2c_network, test_data, image_caption_data, data_size, validation_batch_size=128):
+    """Validation-set caption dump with the look-ahead decoder (trainers.py:619-665): appends real captions,
+    generated captions and urls to the three files, resetting the value RNN state after every batch.  The
+    reference slices `i : i + validation_batch_size - 1` (one row of every batch is skipped) -- kept."""
+    a2c_network.train(False)
+    n = min(int(data_size), test_data["val_captions"].shape[0])
+    mask = np.random.choice(test_data["val_captions"].shape[0], n)            # get_coco_batch, utilities.py:143-157
+    caps_all = test_data["val_captions"][mask]
+    idxs = test_data["val_image_idxs"][mask]
+    feats_all, urls_all = test_data["val_features"][idxs], test_data["val_urls"][idxs]
+    with open(image_caption_data["real_captions_path"], "a") as f_real, \
+            open(image_caption_data["generated_captions_path"], "a") as f_gen, \
+            open(image_caption_data["image_urls_path"], "a") as f_url:
+        for i in range(0, len(caps_all), validation_batch_size):
+            sl = slice(i, i + validation_batch_size - 1)
+            if len(caps_all[sl]) == 0:
+                continue
+            gen = GenerateCaptionsWithActorCriticLookAhead(feats_all[sl], caps_all[sl], a2c_network.policy_network,
+                                                           a2c_network.value_network, most_likely=True)
+            f_real.write("\n".join(decode_captions(caps_all[sl], test_data["idx_to_word"])))
+            f_gen.write("\n".join(decode_captions(gen, test_data["idx_to_word"])))
+            f_url.write("\n".join(str(u) for u in urls_all[sl]))
+            a2c_network.value_network.valrnn.init_hidden()
 
 
 class _PolicyOnlyEngine(A2CEngine):

@@ -185,7 +185,24 @@ def case_rewards(name, seed, B, L):
     print(name, r.shape, float(r.mean()))
 
 
+def case_lookahead(name, seed, B, beam=5):
+    """Value-guided beam look-ahead (trainers.py:73-105), all `beam` final candidates and their scores."""
+    T = import_reference()
+    w = synth.make_weights(seed)
+    f, _ = synth.make_inputs(seed, B, 17)
+    P, V, _, _ = build_reference_nets(T, w)
+    caps = np.ones((B, 17), dtype=np.int64)
+    V.valrnn.init_hidden()
+    with torch.no_grad():
+        cands = T.GenerateCaptionsWithActorCriticLookAhead(f, caps, P, V, beamSize=beam, most_likely=False)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), seed=seed, B=B, beam=beam,
+                        captions=np.stack([c.numpy() for c, _ in cands]),
+                        scores=np.stack([s.numpy().reshape(-1) for _, s in cands]))
+    print(name, [float(s.mean()) for _, s in cands])
+
+
 CASES = {
+    "lookahead_b6": lambda: case_lookahead("lookahead_b6", 7, 6),              # SURVEY 8f row 1
     "greedy_b32": lambda: case_greedy("greedy_b32", 0, 32),                    # BASELINE config 1
     "a2c_b8_l6": lambda: case_a2c("a2c_b8_l6", 1, 8, 6),
     "a2c_b32_l9": lambda: case_a2c("a2c_b32_l9", 2, 32, 9),

@@ -337,3 +337,28 @@ def test_chain_shards_equal_independent_shard_runs(shards, level):
     err = float((ek.flat_grad - gsum).abs().max() / gsum.abs().max())
     _record("chain_shards_%d_%s" % (shards, level), grad_rel=err)
     assert err <= GTOL
+
+
+def test_lookahead_beam_vs_reference_golden():
+    """value-guided beam look-ahead (trainers.py:73-105) on the drop-in modules vs the unmodified
+    reference: all 5 final candidate caption batches identical, scores within 2e-5 (16 steps of accumulated
+    0.6 V + 0.4 log(logit); the value RNN state is carried through all ~400 calls)."""
+    import icrl_b200.trainers as T
+    g = np.load(GOLDEN + "/lookahead_b6.npz")
+    seed, B, beam = int(g["seed"]), int(g["B"]), int(g["beam"])
+    A, R, w = make_nets(seed)
+    f, _ = synth.make_inputs(seed, B, 17)
+    A.value_network.valrnn.init_hidden()
+    cands = T.GenerateCaptionsWithActorCriticLookAhead(f, np.ones((B, 17), dtype=np.int64), A.policy_network,
+                                                       A.value_network, beamSize=beam, most_likely=False)
+    assert len(cands) == beam
+    for k, (cap, score) in enumerate(cands):
+        assert np.array_equal(cap.cpu().numpy(), g["captions"][k]), "candidate %d differs" % k
+        ref = g["scores"][k]
+        got = score.cpu().numpy().reshape(-1)
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        ok = ~np.isnan(ref)
+        assert float(np.abs(got[ok] - ref[ok]).max()) <= 2e-5
+    best = T.GenerateCaptionsWithActorCriticLookAhead(f, np.ones((B, 17), dtype=np.int64), A.policy_network,
+                                                      A.value_network, most_likely=True)
+    assert tuple(best.shape) == (B, 17)
