@@ -276,6 +276,7 @@ policy_decode_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
       if (lane == 0) {
         if (nphase > 0) mbar_wait(bar_acc_empty, (nphase - 1) & 1u);       // previous epilogue drained TMEM
         tc_fence_after();
+        const long long tg0 = (p.prof && blockIdx.x == 0) ? clock64() : 0;
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(bar_full + 8 * s, (it / STAGES) & 1u);
@@ -296,6 +297,7 @@ policy_decode_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
         }
         tc_commit(bar_acc_full);
         ++nphase;
+        if (p.prof && blockIdx.x == 0) p.prof[(size_t)j * 16 + 14] = clock64() - tg0;   // gate-GEMM phase (issue span)
       }
       __syncwarp();
       cluster_arrive();
@@ -303,6 +305,7 @@ policy_decode_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
       if (lane == 0 && j >= p.p0 - 1) {
         mbar_wait(bar_acc_empty, (nphase - 1) & 1u);
         tc_fence_after();
+        const long long tv0 = (p.prof && blockIdx.x == 0) ? clock64() : 0;
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(bar_full + 8 * s, (it / STAGES) & 1u);
@@ -323,6 +326,7 @@ policy_decode_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
         }
         tc_commit(bar_acc_full);
         ++nphase;
+        if (p.prof && blockIdx.x == 0) p.prof[(size_t)j * 16 + 15] = clock64() - tv0;   // vocab-GEMM phase (issue span)
       }
       __syncwarp();
     }

@@ -39,3 +39,9 @@ for j in range(19):
         out.append(t[j, k] - prev)
         prev = t[j, k]
     print(" ".join("%8d" % v for v in out), " %8d" % (t[j, 10] - t[j, 0]))
+
+g, v = t[2:, 14].mean(), t[2:, 15].mean()
+step = (t[2:, 10] - t[2:, 0]).mean()
+print("MMA issue spans (mean cycles): gate GEMM phase %.0f (96 MMAs N=256 = 12,288 tensor cycles -> %.0f %% busy inside the phase), "
+      "vocab GEMM phase %.0f (96 MMAs N=128 = 6,144 -> %.0f %%); whole step %.0f -> %.0f %% tensor-pipe busy"
+      % (g, 100 * 12288 / g, v, 100 * 6144 / v, step, 100 * (12288 + 6144) / step))
