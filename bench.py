@@ -87,16 +87,32 @@ class ClockSampler:
 
 
 def workload(batch):
-    from oracle import synth          # synthetic inputs only (seeded); not the oracle's arithmetic
+    from icrl_b200 import synth       # seeded synthetic inputs (product-side helper; oracle/ is not touched here)
     f, c = synth.make_inputs(100, batch, L_CAP)
     u = synth.make_uniforms(100, L_CAP - 1, batch)
     return f, c, u
 
 
+def make_nets(seed, dev):
+    """Drop-in modules with random-init weights of the reference architecture (the .pt blobs are absent)."""
+    import icrl_b200.models as M
+    from icrl_b200 import synth
+    w = synth.make_weights(seed)
+    w2i = synth.word_to_idx()
+    P, V, R = M.PolicyNetwork(w2i), M.ValueNetwork(w2i), M.RewardNetwork(w2i)
+    P.load_state_dict(w["policy"])
+    V.load_state_dict(w["value"])
+    R.load_state_dict(w["reward"])
+    R.requires_grad_(False)
+    R.train(False)
+    return M.AdvantageActorCriticNetwork(V, P).to(dev), R.to(dev)
+
+
 def cpu_reference(batch_sample, steps, warmup):
     """The reference algorithm as executed (oracle/ref_port: per-step prefix re-runs, batch-as-time RNN
     calls, numpy sampling, autograd backward, Adam) on the host cores; returns (captions/s, cores, s/step)."""
-    from oracle import ref_port, synth
+    from oracle import ref_port        # the one place bench.py executes oracle/: the CPU reference being timed
+    from icrl_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     nets = ref_port.Nets(synth.make_weights(0))
@@ -143,13 +159,12 @@ def main():
     from icrl_b200 import _lib
     from icrl_b200.dp import DataParallelA2C, shard_bounds
     from icrl_b200.engine import A2CEngine
-    from tests.helpers import make_nets
 
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
-    A, R, _ = make_nets(0, dev)
+    A, R = make_nets(0, dev)
     opt = torch.optim.Adam(A.parameters(), lr=1e-4)
     eng = A2CEngine(A, R, chain_shards=args.chain_shards)
     dp = DataParallelA2C(eng, opt)

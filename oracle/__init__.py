@@ -15,7 +15,8 @@ every CPU run, and against the live reference when ``/root/reference`` exists.
 
 Modules
 -------
-synth        deterministic synthetic weights / inputs (numpy MT19937, portable)
+synth        re-export of icrl_b200.synth (seeded synthetic weights / inputs; lives product-side so that
+             bench.py's GPU arm imports nothing from oracle/)
 ref_port     the reference algorithm *as executed* (per-step prefix re-runs, the
              batch-as-time value/reward RNN calls with carried state) on torch
              CPU library layers -- the CPU baseline that bench.py times

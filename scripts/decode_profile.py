@@ -5,7 +5,7 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from icrl_b200 import _lib
 from icrl_b200.engine import A2CEngine
-from oracle import synth
+from icrl_b200 import synth
 from tests.helpers import make_nets
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
