@@ -42,7 +42,10 @@ SIGNATURES = {
     "icrl_chain_lstm_bwd_sharded": [P, I, I, P, P, P, P, P, P, P, LP],
     "icrl_chain_sync_bytes": [],
     "icrl_chain_lstm_fwd": [P, P, I] + [P] * 10 + [LP],
-    "icrl_chain_gru_fwd": [P, P, I] + [P] * 7 + [LP],
+    "icrl_chain_gru_fwd": [P, P, I] + [P] * 8 + [LP],
+    "icrl_chain_gru_bwd": [P, I] + [P] * 10 + [LP],
+    "icrl_reward_chain_param_grads": [P, I, I] + [P] * 9 + [Z] + [P] * 5 + [LP],
+    "icrl_linear_bwd": [P, I, I, I] + [P] * 8 + [Z, LP],
     "icrl_chains_fwd_fused": [P, P, I, P, P, P, P, P, P, I, P, P, P, P, P, LP],
     "icrl_chain_lstm_bwd": [P, I, P, P, P, P, P, P, P, P, P, P, P, LP],
     "icrl_chain_check": [P, P],

@@ -278,8 +278,8 @@ int icrl_chain_lstm_fwd(void* stream, const int* tok_stream, int T, const float*
 
 int icrl_chain_gru_fwd(void* stream, const int* tok_stream, int T, const float* table, const float* W_hh,
                        const float* b_hn, const float* h0, float* stash_h, float* h_out, void* sync_state,
-                       int* launches) {
-  TRY(icrl_chain_gru_fwd_impl(S_(stream), tok_stream, T, table, W_hh, b_hn, h0, stash_h, h_out, sync_state));
+                       float* stash_gates, int* launches) {
+  TRY(icrl_chain_gru_fwd_impl(S_(stream), tok_stream, T, table, W_hh, b_hn, h0, stash_h, h_out, sync_state, stash_gates));
   bump(launches, 1);
   return ICRL_OK;
 }
@@ -300,6 +300,49 @@ int icrl_chain_lstm_bwd(void* stream, int T, const float* W_hh, const float* sta
   TRY(icrl_chain_lstm_bwd_impl(S_(stream), T, W_hh, stash_gates, stash_c, take, dh_take, dgates, sync_state, dh_init,
                                dc_init, dh0_out, dc0_out));
   bump(launches, 1);
+  return ICRL_OK;
+}
+
+int icrl_chain_gru_bwd(void* stream, int T, const float* W_hh, const float* stash_gates, const float* stash_h,
+                       const int* take, const float* dh_take, float* dgh, float* dgx, void* sync_state,
+                       const float* dh_init, float* dh0_out, int* launches) {
+  TRY(icrl_chain_gru_bwd_impl(S_(stream), T, W_hh, stash_gates, stash_h, take, dh_take, dgh, dgx, sync_state, dh_init,
+                              dh0_out));
+  bump(launches, 1);
+  return ICRL_OK;
+}
+
+int icrl_reward_chain_param_grads(void* stream, int T, int V, const int* tok_stream, const float* dgh, const float* dgx,
+                                  const float* stash_h, const float* E, const float* W_ih, float* dtable,
+                                  float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE, float* dW_ih,
+                                  float* dW_hh, float* db_ih, float* db_hh, int* launches) {
+  cudaStream_t st = S_(stream);
+  const int G = 3 * H;
+  // dW_hh = sum_t (da_r, da_z, da_nh)_t (x) h_{t-1}
+  TRY(icrl_gemm_f32_impl(st, 1, 0, G, H, T, dgh, G, stash_h, H, dW_hh, H, nullptr, 0.f, gemm_ws, gemm_ws_bytes, launches));
+  // gate-table gradient from the input-side gradients, then its factors
+  ICRL_CUDA(cudaMemsetAsync(dtable, 0, (size_t)V * G * sizeof(float), st));
+  TRY(icrl_scatter_add_rows(st, T, G, dgx, tok_stream, dtable));
+  bump(launches, 1);
+  TRY(icrl_gemm_f32_impl(st, 1, 0, G, H, V, dtable, G, E, H, dW_ih, H, nullptr, 0.f, nullptr, 0, launches));
+  TRY(icrl_gemm_f32_impl(st, 0, 0, V, H, G, dtable, G, W_ih, H, dE, H, nullptr, 0.f, nullptr, 0, launches));
+  TRY(icrl_wcolsum(st, V, G, dtable, nullptr, 0, colsum_ws, db_ih));
+  // b_hh: the r,z rows are folded into the table (same gradient as b_ih); b_hn sits inside r*(.) -> column sums of da_nh
+  float* tmp = colsum_ws + (size_t)icrl_wcolsum_chunks(T > V ? T : V) * G;
+  TRY(icrl_wcolsum(st, T, G, dgh, nullptr, 0, colsum_ws, tmp));
+  bump(launches, 4);
+  ICRL_CUDA(cudaMemcpyAsync(db_hh, db_ih, 2 * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  ICRL_CUDA(cudaMemcpyAsync(db_hh + 2 * H, tmp + 2 * H, H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return ICRL_OK;
+}
+
+int icrl_linear_bwd(void* stream, int M, int N, int K, const float* x, const float* W, const float* dy, float* dx,
+                    float* dW, float* db, float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, int* launches) {
+  cudaStream_t st = S_(stream);
+  if (dx) TRY(icrl_gemm_f32_impl(st, 0, 0, M, K, N, dy, N, W, K, dx, K, nullptr, 0.f, nullptr, 0, launches));
+  TRY(icrl_gemm_f32_impl(st, 1, 0, N, K, M, dy, N, x, K, dW, K, nullptr, 0.f, gemm_ws, gemm_ws_bytes, launches));
+  TRY(icrl_wcolsum(st, M, N, dy, nullptr, 0, colsum_ws, db));
+  bump(launches, 2);
   return ICRL_OK;
 }
 

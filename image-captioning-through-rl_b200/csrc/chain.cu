@@ -78,7 +78,7 @@ struct ChainFwdArgs {
   const float* c0;            // [H] or null (LSTM)
   float* stash_h;             // [(T+1)][H]; row 0 = initial h, row t+1 = h_t
   float* stash_c;             // LSTM: [(T+1)][H] or null
-  float* stash_gates;         // LSTM: [T][4H] activated i,f,g,o, or null
+  float* stash_gates;         // [T][4H] or null.  LSTM: activated i,f,g,o.  GRU: r, z, n, W_hn h + b_hn
   float* h_out;               // [H] final h or null
   float* c_out;               // [H] final c or null
   unsigned long long* xchg;   // [2][H] tagged exchange words, zeroed before launch
@@ -237,8 +237,13 @@ __device__ void chain_fwd_body(const ChainFwdArgs& p, int cta) {
     } else {
       const float r = act_sigmoid(acc[0] + xg[0]);
       const float z = act_sigmoid(acc[1] + xg[1]);
-      const float n = act_tanh(xg[2] + r * (acc[2] + bhn));
+      const float anh = acc[2] + bhn;
+      const float n = act_tanh(xg[2] + r * anh);
       hnew = (1.f - z) * n + z * hprev;
+      if (p.stash_gates && lane < 4) {                 // training stash of the reward GRU: r, z, n, W_hn h + b_hn
+        const float sel = lane == 0 ? r : (lane == 1 ? z : (lane == 2 ? n : anh));
+        p.stash_gates[(size_t)t * 4 * H + lane * H + unit] = sel;
+      }
     }
     hprev = hnew;
     if (lane == 8) st_tagged(p.xchg + (size_t)buf * H + unit, hnew, (unsigned)(t + 1));
@@ -697,6 +702,133 @@ __global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_batched_kernel(Chai
   }
 }
 
+
+struct ChainGruBwdArgs {
+  int T;
+  const float* w_hh;          // [3H][H]
+  const float* stash_gates;   // [T][4H]: r, z, n, a_nh = W_hn h_{t-1} + b_hn
+  const float* stash_h;       // [(T+1)][H]; row t = h_{t-1}
+  const int* take;            // [T]
+  const float* dh_take;       // [rows][H]
+  float* dgh;                 // [T][3H] hidden-side pre-activation gradients (da_r, da_z, da_nh): feeds dW_hh, db_hn
+  float* dgx;                 // [T][3H] input-side gradients (da_r, da_z, da_n): feeds the gate table, W_ih, E, b_ih
+  unsigned long long* xchg;   // [2][H]
+  int* abort_flag;
+  const float* dh_init;       // [H] or null
+  float* dh0_out;             // [H] or null
+};
+
+// BPTT through the reward GRU chain (the reference trains it in train_reward_network, trainers.py:260-309; the
+// A2C step keeps it frozen).  h_t = (1-z) n + z h_{t-1}, n = tanh(x_n + r a_nh):
+//   da_n = dh (1-z)(1-n^2), da_nh = da_n r, da_r = da_n a_nh r(1-r), da_z = dh (h_{t-1} - n) z(1-z),
+//   dh_{t-1} = dh z + W_hh^T (da_r, da_z, da_nh).
+// Same scheme as chain_lstm_bwd_kernel: dh_t crosses CTAs as tagged words, every CTA rebuilds all 1536 gate
+// gradients, the contraction over them is split across the warps (192 each, 6 per lane).
+__global__ void __launch_bounds__(THREADS, 1) chain_gru_bwd_kernel(ChainGruBwdArgs p) {
+  __shared__ __align__(16) float sh_dg[2][3 * H];
+  __shared__ float sh_direct[2][H];
+  __shared__ float sh_part[UNITS][UNITS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cta = blockIdx.x;
+  const int unit = cta * UNITS + warp;
+  const int pu = 2 * threadIdx.x;
+  const bool owner = (pu >= cta * UNITS) && (pu < cta * UNITS + UNITS);
+
+  float wl[UNITS][6];                                  // wl[i][k] = W_hh[192 warp + 6 lane + k][8 cta + i]
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const float* src = p.w_hh + (size_t)(192 * warp + 6 * lane + k) * H + cta * UNITS;
+    const float4 x0 = *reinterpret_cast<const float4*>(src), x1 = *reinterpret_cast<const float4*>(src + 4);
+    wl[0][k] = x0.x; wl[1][k] = x0.y; wl[2][k] = x0.z; wl[3][k] = x0.w;
+    wl[4][k] = x1.x; wl[5][k] = x1.y; wl[6][k] = x1.z; wl[7][k] = x1.w;
+  }
+  auto load_step = [&](int t, float2& r, float2& z, float2& n, float2& a, float2& hp) {
+    const float* ga = p.stash_gates + (size_t)t * 4 * H + pu;
+    r = *reinterpret_cast<const float2*>(ga);
+    z = *reinterpret_cast<const float2*>(ga + H);
+    n = *reinterpret_cast<const float2*>(ga + 2 * H);
+    a = *reinterpret_cast<const float2*>(ga + 3 * H);
+    hp = *reinterpret_cast<const float2*>(p.stash_h + (size_t)t * H + pu);
+  };
+  float2 r, z, n, a, hp;
+  load_step(p.T - 1, r, z, n, a, hp);
+  float2 dh = make_float2(0.f, 0.f);
+  {
+    const int tk = p.take[p.T - 1];
+    if (tk >= 0) dh = *reinterpret_cast<const float2*>(p.dh_take + (size_t)tk * H + pu);
+    if (p.dh_init) { dh.x += p.dh_init[pu]; dh.y += p.dh_init[pu + 1]; }
+  }
+  int tk_prev = p.T > 1 ? p.take[p.T - 2] : -1;
+
+  for (int it = 0; it < p.T; ++it) {
+    const int t = p.T - 1 - it;
+    const int buf = it & 1;
+    bool ok = true;
+    unsigned long long wa = 0, wb = 0;
+    const unsigned long long* src = p.xchg + (size_t)((it - 1) & 1) * H + pu;
+    if (it > 0) ld_tagged2(src, wa, wb);
+    const float knx = (1.f - z.x) * (1.f - n.x * n.x), kny = (1.f - z.y) * (1.f - n.y * n.y);
+    const float khx = knx * r.x, khy = kny * r.y;
+    const float krx = knx * a.x * r.x * (1.f - r.x), kry = kny * a.y * r.y * (1.f - r.y);
+    const float kzx = (hp.x - n.x) * z.x * (1.f - z.x), kzy = (hp.y - n.y) * z.y * (1.f - z.y);
+    const float2 zz = z;
+    const float inj = tk_prev >= 0 ? p.dh_take[(size_t)tk_prev * H + unit] : 0.f;
+    if (t > 0) load_step(t - 1, r, z, n, a, hp);
+    tk_prev = t > 1 ? p.take[t - 2] : -1;
+    if (it > 0) {
+      unsigned spins = 0;
+      while (!((unsigned)(wa >> 32) == (unsigned)it && (unsigned)(wb >> 32) == (unsigned)it)) {
+        if (++spins >= SPIN_LIMIT || ((spins & 1023u) == 0 && *(volatile int*)p.abort_flag != 0)) { ok = false; break; }
+        ld_tagged2(src, wa, wb);
+      }
+      dh = make_float2(__uint_as_float((unsigned)wa), __uint_as_float((unsigned)wb));
+    }
+    const float2 d_r = make_float2(dh.x * krx, dh.y * kry), d_z = make_float2(dh.x * kzx, dh.y * kzy);
+    const float2 d_h = make_float2(dh.x * khx, dh.y * khy), d_n = make_float2(dh.x * knx, dh.y * kny);
+    *reinterpret_cast<float2*>(&sh_dg[buf][pu]) = d_r;
+    *reinterpret_cast<float2*>(&sh_dg[buf][H + pu]) = d_z;
+    *reinterpret_cast<float2*>(&sh_dg[buf][2 * H + pu]) = d_h;
+    *reinterpret_cast<float2*>(&sh_direct[buf][pu]) = make_float2(dh.x * zz.x, dh.y * zz.y);
+    if (owner) {
+      float* oh = p.dgh + (size_t)t * 3 * H + pu;
+      float* ox = p.dgx + (size_t)t * 3 * H + pu;
+      *reinterpret_cast<float2*>(oh) = d_r;          *reinterpret_cast<float2*>(ox) = d_r;
+      *reinterpret_cast<float2*>(oh + H) = d_z;      *reinterpret_cast<float2*>(ox + H) = d_z;
+      *reinterpret_cast<float2*>(oh + 2 * H) = d_h;  *reinterpret_cast<float2*>(ox + 2 * H) = d_n;
+    }
+    if (__syncthreads_or(!ok)) {
+      if (threadIdx.x == 0) atomicExch(p.abort_flag, 1);
+      return;
+    }
+    if (t > 0 || p.dh0_out) {
+      const float2 q0 = *reinterpret_cast<const float2*>(&sh_dg[buf][192 * warp + 6 * lane]);
+      const float2 q1 = *reinterpret_cast<const float2*>(&sh_dg[buf][192 * warp + 6 * lane + 2]);
+      const float2 q2 = *reinterpret_cast<const float2*>(&sh_dg[buf][192 * warp + 6 * lane + 4]);
+      float part[UNITS];
+#pragma unroll
+      for (int i = 0; i < UNITS; ++i) {
+        float acc = wl[i][0] * q0.x;
+        acc = fmaf(wl[i][1], q0.y, acc); acc = fmaf(wl[i][2], q1.x, acc); acc = fmaf(wl[i][3], q1.y, acc);
+        acc = fmaf(wl[i][4], q2.x, acc); acc = fmaf(wl[i][5], q2.y, acc);
+        part[i] = acc;
+      }
+      const float ps = reduce_transposed<UNITS>(part, lane);
+      if ((lane & 3) == 0) sh_part[warp][lane >> 2] = ps;
+      __syncthreads();
+      if (lane < UNITS) {
+        float rec = sh_part[lane][warp];
+        rec += __shfl_xor_sync(0xffu, rec, 1);
+        rec += __shfl_xor_sync(0xffu, rec, 2);
+        rec += __shfl_xor_sync(0xffu, rec, 4);
+        if (lane == 0) {
+          rec += sh_direct[buf][unit];
+          if (t > 0) st_tagged(p.xchg + (size_t)buf * H + unit, rec + inj, (unsigned)(it + 1));
+          else p.dh0_out[unit] = rec;
+        }
+      }
+    }
+  }
+}
+
 int coop_launch(const void* fn, int grid, void** args, cudaStream_t st) {
   int dev = 0, coop = 0, sms = 0, per_sm = 0;
   ICRL_CUDA(cudaGetDevice(&dev));
@@ -746,10 +878,11 @@ int icrl_chain_lstm_fwd_impl(cudaStream_t st, const int* stream, int T, const fl
 }
 
 int icrl_chain_gru_fwd_impl(cudaStream_t st, const int* stream, int T, const float* table, const float* w_hh,
-                            const float* b_hn, const float* h0, float* stash_h, float* h_out, void* sync_state) {
+                            const float* b_hn, const float* h0, float* stash_h, float* h_out, void* sync_state,
+                            float* stash_gates) {
   ICRL_REQUIRE(T > 0 && stash_h, "empty chain");
   ICRL_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(sync_state) + 64, 0, icrl_chain_sync_bytes_impl() - 64, st));
-  ChainFwdArgs a = make_fwd(stream, T, table, w_hh, b_hn, h0, nullptr, stash_h, nullptr, nullptr, h_out, nullptr,
+  ChainFwdArgs a = make_fwd(stream, T, table, w_hh, b_hn, h0, nullptr, stash_h, nullptr, stash_gates, h_out, nullptr,
                             sync_xchg(sync_state, 1), sync_abort(sync_state));
   void* args[] = {&a};
   return coop_launch((const void*)chain_gru_fwd_kernel, CHAIN_CTAS, args, st);
@@ -780,6 +913,19 @@ int icrl_chain_lstm_bwd_impl(cudaStream_t st, int T, const float* w_hh, const fl
   a.dh_init = dh_init; a.dc_init = dc_init; a.dh0_out = dh0_out; a.dc0_out = dc0_out;
   void* args[] = {&a};
   return coop_launch((const void*)chain_lstm_bwd_kernel, CHAIN_CTAS, args, st);
+}
+
+int icrl_chain_gru_bwd_impl(cudaStream_t st, int T, const float* w_hh, const float* stash_gates, const float* stash_h,
+                            const int* take, const float* dh_take, float* dgh, float* dgx, void* sync_state,
+                            const float* dh_init, float* dh0_out) {
+  ICRL_REQUIRE(T > 0, "empty chain");
+  ICRL_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(sync_state) + 64, 0, icrl_chain_sync_bytes_impl() - 64, st));
+  ChainGruBwdArgs a;
+  a.T = T; a.w_hh = w_hh; a.stash_gates = stash_gates; a.stash_h = stash_h; a.take = take; a.dh_take = dh_take;
+  a.dgh = dgh; a.dgx = dgx; a.xchg = sync_xchg(sync_state, 2); a.abort_flag = sync_abort(sync_state);
+  a.dh_init = dh_init; a.dh0_out = dh0_out;
+  void* args[] = {&a};
+  return coop_launch((const void*)chain_gru_bwd_kernel, CHAIN_CTAS, args, st);
 }
 
 // Reads the abort word (synchronises the stream).  Returns ICRL_ERR_WATCHDOG if a chain gave up.

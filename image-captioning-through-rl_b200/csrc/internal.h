@@ -40,7 +40,11 @@ int icrl_chain_lstm_fwd_impl(cudaStream_t st, const int* stream, int T, const fl
                              const float* h0, const float* c0, float* stash_h, float* stash_c, float* stash_gates,
                              float* h_out, float* c_out, void* sync_state);
 int icrl_chain_gru_fwd_impl(cudaStream_t st, const int* stream, int T, const float* table, const float* w_hh,
-                            const float* b_hn, const float* h0, float* stash_h, float* h_out, void* sync_state);
+                            const float* b_hn, const float* h0, float* stash_h, float* h_out, void* sync_state,
+                            float* stash_gates = nullptr);
+int icrl_chain_gru_bwd_impl(cudaStream_t st, int T, const float* w_hh, const float* stash_gates, const float* stash_h,
+                            const int* take, const float* dh_take, float* dgh, float* dgx, void* sync_state,
+                            const float* dh_init, float* dh0_out);
 int icrl_chains_fwd_fused_impl(cudaStream_t st, const int* v_stream, int v_T, const float* v_table,
                                const float* v_w_hh, float* v_stash_h, float* v_stash_c, float* v_stash_gates,
                                const int* r_stream, int r_T, const float* r_table, const float* r_w_hh,

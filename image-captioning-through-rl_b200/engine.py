@@ -439,7 +439,7 @@ class A2CEngine:
             _lib.call("icrl_build_stream", st, B, Lc, 1, 0, _p(tokcm), _p(r_stream), None, _p(r_pos), L)
             r_h = self._buf("r_stash_h", (T + 1) * H)
             _lib.call("icrl_chain_gru_fwd", st, _p(r_stream), T, _p(b["r_table"]), _p(R.rewrnn.gru.weight_hh_l0),
-                      _p(R.rewrnn.gru.bias_hh_l0[2 * H:]), None, _p(r_h), None, _p(self.sync_state), L)
+                      _p(R.rewrnn.gru.bias_hh_l0[2 * H:]), None, _p(r_h), None, _p(self.sync_state), None, L)
             r_take_h = self._buf("r_take_h", B * H)
             _lib.call("icrl_gather_rows", st, B, _p(r_h), _p(r_pos), 1, _p(r_take_h), L)
             se, ve = self._buf("r_se", B * H), self._buf("r_ve", B * H)

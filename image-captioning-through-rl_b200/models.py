@@ -19,10 +19,11 @@ autograd history (``torch.autograd.Function`` wrappers around the same CUDA kern
 the reference's own rollout loop (``trainers.py:441-480``: softmax / gather / log / stack /
 ``loss.backward(retain_graph=True)`` / Adam) trains these modules unmodified; like the reference,
 ``valrnn.hidden_cell`` keeps its graph from call to call, so gradients flow through the whole
-carried-state chain.  Both routes give the same numbers (tests/test_gpu_parity.py).
+carried-state chain.  The reward network's forward is differentiable too (GRU BPTT kernel), which is what the
+reference's pretraining loops need (``train_reward_network``).  Both routes give the same numbers
+(tests/test_gpu_parity.py).
 """
 import ctypes
-import warnings
 
 import numpy as np
 import torch
@@ -228,13 +229,100 @@ class _ValueHeadFn(torch.autograd.Function):
         return None, dh, dW1, db1, dW2, db2
 
 
+class _ChainGRUFn(torch.autograd.Function):
+    """One RewardNetworkRNN segment (models.py:223-228, 253-255): serial batch-1 GRU from the carried state.
+    Returns (h after every row of the last column, final h); backward = serial GRU BPTT kernel.  Only needed to
+    TRAIN the reward network (train_reward_network); the A2C step keeps it frozen."""
+
+    @staticmethod
+    def forward(ctx, tok_cm, h0, E, W_ih, W_hh, b_ih, b_hh):
+        dev = E.device
+        n, B = tok_cm.shape
+        V, T = E.shape[0], n * B
+        st = _st(dev)
+        train = any(ctx.needs_input_grad)
+        with torch.cuda.device(dev):
+            table = torch.empty(V * 3 * HID, dtype=torch.float32, device=dev)
+            _lib.call("icrl_pack_gate_table", st, V, 3 * HID, 2 * HID, _p(E), _p(W_ih), _p(b_ih), _p(b_hh), _p(table), None)
+            stream = tok_cm.reshape(-1).contiguous()
+            stash_h = torch.empty((T + 1, HID), dtype=torch.float32, device=dev)
+            stash_g = torch.empty((T, 4 * HID), dtype=torch.float32, device=dev) if train else None
+            h_out = torch.empty(HID, dtype=torch.float32, device=dev)
+            h0f, bhn = h0.reshape(-1).contiguous(), b_hh[2 * HID:].contiguous()
+            sync = _sync_state(dev)
+            _lib.call("icrl_chain_gru_fwd", st, _p(stream), T, _p(table), _p(W_hh), _p(bhn), _p(h0f), _p(stash_h), _p(h_out),
+                      _p(sync), _p(stash_g), None)
+            _lib.call("icrl_chain_check", st, _p(sync))
+        if train:
+            ctx.save_for_backward(stream, E, W_ih, W_hh, stash_h, stash_g)
+        ctx.dims = (n, B, V)
+        ctx.state_shape = tuple(h0.shape)
+        return stash_h[T - B + 1:T + 1].clone(), h_out
+
+    @staticmethod
+    def backward(ctx, dh_last, dh_out):
+        stream, E, W_ih, W_hh, stash_h, stash_g = ctx.saved_tensors
+        n, B, V = ctx.dims
+        T = n * B
+        dev = E.device
+        st = _st(dev)
+        new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            take = torch.full((T,), -1, dtype=torch.int32, device=dev)
+            take[T - B:] = torch.arange(B, dtype=torch.int32, device=dev)
+            dh_take = (dh_last if dh_last is not None else torch.zeros((B, HID), device=dev)).contiguous()
+            dgh, dgx, dh0 = new(T, 3 * HID), new(T, 3 * HID), new(HID)
+            dh_in = dh_out.contiguous() if dh_out is not None else None
+            sync = _sync_state(dev)
+            _lib.call("icrl_chain_gru_bwd", st, T, _p(W_hh), _p(stash_g), _p(stash_h), _p(take), _p(dh_take), _p(dgh), _p(dgx),
+                      _p(sync), _p(dh_in), _p(dh0), None)
+            _lib.call("icrl_chain_check", st, _p(sync))
+            dE, dWih, dWhh, dbih, dbhh = new(V, HID), new(3 * HID, HID), new(3 * HID, HID), new(3 * HID), new(3 * HID)
+            cs = int(_lib.call("icrl_colsum_ws_floats", max(T, V), 3 * HID)) + 3 * HID
+            dtable, csws, ws = new(V, 3 * HID), new(cs), _gemm_ws(dev)
+            _lib.call("icrl_reward_chain_param_grads", st, T, V, _p(stream), _p(dgh), _p(dgx), _p(stash_h), _p(E), _p(W_ih),
+                      _p(dtable), _p(csws), _p(ws), ws.numel() * 4, _p(dE), _p(dWih), _p(dWhh), _p(dbih), _p(dbhh), None)
+        return None, dh0.view(ctx.state_shape), dE, dWih, dWhh, dbih, dbhh
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b on the library's GEMM (visual_embed / semantic_embed, models.py:259-260)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        dev = x.device
+        M, K = x.shape
+        N = W.shape[0]
+        with torch.cuda.device(dev):
+            x = x.contiguous()
+            y = torch.empty((M, N), dtype=torch.float32, device=dev)
+            _lib.call("icrl_gemm_f32", _st(dev), 0, 1, M, N, K, _p(x), K, _p(W), K, _p(y), N, _p(b), 0.0, None, 0, None)
+        ctx.save_for_backward(x, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        dev = x.device
+        M, K = x.shape
+        N = W.shape[0]
+        new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            dy = dy.contiguous()
+            dx = new(M, K) if ctx.needs_input_grad[0] else None
+            dW, db = new(N, K), new(N)
+            csws, ws = new(int(_lib.call("icrl_colsum_ws_floats", M, N))), _gemm_ws(dev)
+            _lib.call("icrl_linear_bwd", _st(dev), M, N, K, _p(x), _p(W), _p(dy), _p(dx), _p(dW), _p(db), _p(csws), _p(ws),
+                      ws.numel() * 4, None)
+        return dx, dW, db
+
+
 class _KernelModule(nn.Module):
     """Workspace + stream plumbing shared by the drop-in modules."""
 
     def _rt_init(self):
         object.__setattr__(self, "_ws", {})
         object.__setattr__(self, "_launches", _lib.Launches())
-        object.__setattr__(self, "_warned", False)
 
     def _dev(self):
         d = next(self.parameters()).device
@@ -253,13 +341,6 @@ class _KernelModule(nn.Module):
 
     def _stream(self, dev):
         return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-
-    def _grad_note(self):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and not self._warned:
-            object.__setattr__(self, "_warned", True)
-            warnings.warn("%s.forward returns tensors without autograd history (the reward network is frozen "
-                          "in A2C training, trainers.py:372-373; its pretraining is out of scope)"
-                          % type(self).__name__)
 
     def _tokcm(self, captions, dev):
         caps = captions.to(dev).to(torch.int32)
@@ -321,37 +402,12 @@ class _ChainRNN(_KernelModule):
                                                       rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0)
             self.hidden_cell = (h_out.view(1, 1, HID), c_out.view(1, 1, HID))
             return h_last
-        V = self.caption_embedding.weight.shape[0]
-        st, L = self._stream(dev), self._launches.ref
-        with torch.cuda.device(dev):
-            rnn = self.lstm if kind == "lstm" else self.gru
-            G = 4 * HID if kind == "lstm" else 3 * HID
-            table = self._buf("table", V * G, dev=dev)
-            _lib.call("icrl_pack_gate_table", st, V, G, G if kind == "lstm" else 2 * HID,
-                      _p(self.caption_embedding.weight), _p(rnn.weight_ih_l0), _p(rnn.bias_ih_l0), _p(rnn.bias_hh_l0),
-                      _p(table), L)
-            T = n * B
-            stream = captions_cm.reshape(-1).contiguous()
-            stash_h = self._buf("stash_h", (T + 1) * HID, dev=dev)
-            sync = self._ws.get("sync")
-            if sync is None or sync.device != dev:
-                sync = torch.zeros(int(_lib.call("icrl_chain_sync_bytes")), dtype=torch.uint8, device=dev)
-                self._ws["sync"] = sync
-            h_out = torch.empty(HID, dtype=torch.float32, device=dev)
-            if kind == "lstm":
-                h0 = self.hidden_cell[0].to(dev, torch.float32).reshape(-1).contiguous()
-                c0 = self.hidden_cell[1].to(dev, torch.float32).reshape(-1).contiguous()
-                c_out = torch.empty(HID, dtype=torch.float32, device=dev)
-                _lib.call("icrl_chain_lstm_fwd", st, _p(stream), T, _p(table), _p(rnn.weight_hh_l0), _p(h0), _p(c0),
-                          _p(stash_h), None, None, _p(h_out), _p(c_out), _p(sync), L)
-                self.hidden_cell = (h_out.view(1, 1, HID), c_out.view(1, 1, HID))
-            else:
-                h0 = self.hidden_cell.to(dev, torch.float32).reshape(-1).contiguous()
-                _lib.call("icrl_chain_gru_fwd", st, _p(stream), T, _p(table), _p(rnn.weight_hh_l0),
-                          _p(rnn.bias_hh_l0[2 * HID:]), _p(h0), _p(stash_h), _p(h_out), _p(sync), L)
-                self.hidden_cell = h_out.view(1, 1, HID)
-            _lib.call("icrl_chain_check", st, _p(sync))
-            return stash_h[(T - B + 1) * HID:(T + 1) * HID].view(B, HID).clone()
+        rnn = self.gru
+        h0 = self.hidden_cell.to(dev, torch.float32)
+        h_last, h_out = _ChainGRUFn.apply(captions_cm.contiguous(), h0, self.caption_embedding.weight, rnn.weight_ih_l0,
+                                          rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0)
+        self.hidden_cell = h_out.view(1, 1, HID)
+        return h_last
 
     def forward(self, captions):
         """captions (B,) -> (B,1,512): the column is a length-B sequence (models.py:130-135 / 223-228)."""
@@ -424,18 +480,13 @@ class RewardNetwork(_KernelModule):
         self._rt_init()
 
     def forward(self, features, captions):
+        """features (B,512), captions (B,n) -> (visual embedding (B,512), semantic embedding (B,512))
+        (models.py:253-262), with autograd history w.r.t. the nine reward-network parameters."""
         dev = self._dev()
-        self._grad_note()
-        B = captions.shape[0]
         h = self.rewrnn._run_columns(self.rewrnn._tokcm(captions, dev), "gru")
-        st, L = self._stream(dev), self._launches.ref
-        with torch.cuda.device(dev):
-            f = features.to(dev, torch.float32).contiguous()
-            se = torch.empty((B, HID), dtype=torch.float32, device=dev)
-            ve = torch.empty((B, HID), dtype=torch.float32, device=dev)
-            for x, lin, out in ((h, self.semantic_embed, se), (f, self.visual_embed, ve)):
-                _lib.call("icrl_gemm_f32", st, 0, 1, B, HID, HID, _p(x), HID, _p(lin.weight), HID, _p(out), HID,
-                          _p(lin.bias), 0.0, None, 0, L)
+        f = features.to(dev, torch.float32).contiguous()
+        se = _LinearFn.apply(h, self.semantic_embed.weight, self.semantic_embed.bias)
+        ve = _LinearFn.apply(f, self.visual_embed.weight, self.visual_embed.bias)
         return ve, se
 
 

@@ -10,11 +10,15 @@ per step, step-major), so ``np.random.seed(s)`` reproduces the reference's token
 ``GenerateCaptionsWithActorCriticLookAhead`` / ``test_a2c_network`` (``:73-105``, ``:619-665``) run
 the reference's beam look-ahead on the drop-in modules.
 
-Supervised pretraining (``train_policy_network`` etc.) is outside the hot path: when a
-pretrained file is missing ``train_a2c_network`` raises instead of pretraining from scratch.
+The supervised pretraining loops (``train_policy_network :202``, ``train_reward_network :260``,
+``train_value_network :125``, ``VisualSemanticEmbeddingLoss :23``) run on the drop-in modules through
+their autograd wrappers: the recurrent forwards / backwards are the CUDA kernels, the loss arithmetic on the module
+outputs (cross entropy, MSE, hinge) is torch host code exactly as in the reference.  As in the reference, a missing
+pretrained file makes ``train_a2c_network`` pretrain that network.
 """
 import math
 import os
+import random
 
 import numpy as np
 import torch
@@ -78,8 +82,13 @@ def GetRewards(features, captions, reward_network):
     return out
 
 
+def _np(x):
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
 def GenerateCaptionsGreedy(features, captions, policy_network):
     """MAX_SEQ_LEN-1 greedy steps from column 0, no early stop: (B,17) int64 (trainers.py:57-70)."""
+    features, captions = _np(features), _np(captions)
     eng = getattr(policy_network, "_icrl_greedy", None)
     if eng is None:
         eng = _PolicyOnlyEngine(policy_network)
@@ -189,6 +198,116 @@ class _PolicyOnlyEngine(A2CEngine):
                   _p(self._buf("p_decode_pk", n, torch.float16)), self.launches.ref)
 
 
+def VisualSemanticEmbeddingLoss(visuals, semantics):
+    """Bidirectional hinge ranking loss of the reward pretraining (trainers.py:23-54), beta = 0.2:
+    sum(relu(S - diag(S)[:,None] + (beta/N)(1 - I))) / N for S = V S^T and for its transpose."""
+    from .models import _LinearFn
+    N = visuals.shape[0]
+    margin = (0.2 / N) * (1.0 - torch.eye(N, device=visuals.device))
+    zero = torch.zeros(N, device=visuals.device)
+
+    def side(a, b):
+        sim = _LinearFn.apply(a, b, zero)                      # a b^T on the library GEMM (with autograd)
+        return torch.relu(sim - torch.diag(sim).unsqueeze(1) + margin).sum() / N
+
+    return side(visuals, semantics) + side(semantics, visuals)
+
+
+def _minibatches(train_data, batch_size):
+    return get_coco_minibatches(train_data, batch_size=batch_size, split="train")
+
+
+def train_policy_network(train_data, network_paths, plot_dir, bidirectional, epochs=100, batch_size=512):
+    """Cross-entropy pretraining of the policy (trainers.py:202-257): teacher-forced logits of captions[:, :-1]
+    against captions[:, 1:], each row weighted by caplen/B and averaged over its first caplen positions."""
+    policy_network = PolicyNetwork(train_data["word_to_idx"], pretrained_embeddings=train_data.get("embeddings"),
+                                   bidirectional=bidirectional).to(device)
+    criterion = nn.CrossEntropyLoss().to(device)
+    optimizer = optim.Adam(policy_network.parameters(), lr=0.001)
+    writer = SummaryWriter(log_dir=os.path.join(plot_dir, "runs"))
+    best = float("inf")
+    for epoch in range(epochs):
+        for minibatch_id, (captions, features, _) in enumerate(_minibatches(train_data, batch_size)):
+            feats = torch.as_tensor(np.asarray(features), device=device).float().unsqueeze(0)
+            caps_in = torch.as_tensor(captions[:, :-1], device=device).long()
+            caps_out = torch.as_tensor(captions[:, 1:], device=device).long()
+            output = policy_network(feats, caps_in)
+            loss = 0
+            for i in range(captions.shape[0]):
+                caplen = int(np.nonzero(captions[i] == 2)[0][0]) + 1          # <END> = 2 marks the caption length
+                loss = loss + (caplen / captions.shape[0]) * criterion(output[i][:caplen], caps_out[i][:caplen])
+            if loss.item() < best:
+                best = loss.item()
+                torch.save(policy_network.state_dict(), network_paths["policy_network"])
+            writer.add_scalar("Policy Network-loss", loss, global_minibatch_number(epoch, minibatch_id, batch_size))
+            optimizer.zero_grad()
+            loss.backward()
+            optimizer.step()
+    return policy_network
+
+
+def train_reward_network(train_data, network_paths, plot_dir, bidirectional, epochs=50, batch_size=512):
+    """Visual-semantic-embedding pretraining of the reward network (trainers.py:260-309)."""
+    writer = SummaryWriter(log_dir=os.path.join(plot_dir, "runs"))
+    reward_network = RewardNetwork(train_data["word_to_idx"], pretrained_embeddings=train_data.get("embeddings"),
+                                   bidirectional=bidirectional).to(device)
+    optimizer = optim.Adam(reward_network.parameters(), lr=0.0001)
+    best = float("inf")
+    for epoch in range(epochs):
+        for minibatch_id, (captions, features, _) in enumerate(_minibatches(train_data, batch_size)):
+            feats = torch.as_tensor(np.asarray(features), device=device).float()
+            caps = torch.as_tensor(captions, device=device).long()
+            ve, se = reward_network(feats, caps)
+            loss = VisualSemanticEmbeddingLoss(ve, se)
+            if loss.item() < best:
+                best = loss.item()
+                torch.save(reward_network.state_dict(), network_paths["reward_network"])
+            writer.add_scalar("Reward Network-loss", loss, global_minibatch_number(epoch, minibatch_id, batch_size))
+            optimizer.zero_grad()
+            loss.backward(retain_graph=True)
+            optimizer.step()
+            reward_network.rewrnn.init_hidden()
+    return reward_network
+
+
+def train_value_network(train_data, network_paths, plot_dir, bidirectional, epochs=50, batch_size=512):
+    """MSE pretraining of the value network (trainers.py:125-199): greedy captions of the frozen policy, their
+    reward under the frozen reward network, and the value of a random-length prefix regressed onto it."""
+    writer = SummaryWriter(log_dir=os.path.join(plot_dir, "runs"))
+    frozen = {}
+    for key, cls in (("reward_network", RewardNetwork), ("policy_network", PolicyNetwork)):
+        net = cls(train_data["word_to_idx"], pretrained_embeddings=train_data.get("embeddings"),
+                  bidirectional=bidirectional).to(device)
+        net.load_state_dict(torch.load(network_paths[key], map_location=device), strict=False)
+        net.train(False)
+        net.requires_grad_(False)
+        frozen[key] = net
+    reward_network, policy_network = frozen["reward_network"], frozen["policy_network"]
+    value_network = ValueNetwork(train_data["word_to_idx"], pretrained_embeddings=train_data.get("embeddings"),
+                                 bidirectional=bidirectional).to(device)
+    criterion = nn.MSELoss().to(device)
+    optimizer = optim.Adam(value_network.parameters(), lr=0.001)
+    value_network.train(mode=True)
+    best = float("inf")
+    for epoch in range(epochs):
+        for minibatch_id, (captions, features, _) in enumerate(_minibatches(train_data, batch_size)):
+            feats = torch.as_tensor(np.asarray(features), device=device).float()
+            gen = GenerateCaptionsGreedy(feats, captions, policy_network)
+            rewards = GetRewards(feats, gen, reward_network)
+            values = value_network(feats, gen[:, :random.randint(1, MAX_SEQ_LEN)])
+            loss = criterion(values, rewards)
+            if loss.item() < best:
+                best = loss.item()
+                torch.save(value_network.state_dict(), network_paths["value_network"])
+            writer.add_scalar("Value Network-loss", loss, global_minibatch_number(epoch, minibatch_id, batch_size))
+            optimizer.zero_grad()
+            loss.backward(retain_graph=True)
+            optimizer.step()
+            value_network.valrnn.init_hidden()
+            reward_network.rewrnn.init_hidden()
+    return value_network
+
+
 def _run_minibatches(train_data, a2c_network, reward_network, optimizer, writer, batch_size, epoch, level, tag, best):
     eng = _engine_for(a2c_network, reward_network)
     for minibatch_id, (captions, features, _) in enumerate(get_coco_minibatches(train_data, batch_size=batch_size)):
@@ -238,15 +357,16 @@ def train_a2c_network(train_data, save_paths, network_paths, plot_dir, bidirecti
     """trainers.py:312-399: build the three networks, load the pretrained state dicts
     (``torch.load(path, map_location=device)`` + ``load_state_dict(strict=False)``), freeze the
     reward network, wrap, Adam(lr=1e-4), dispatch."""
-    if retrain_all:
-        raise NotImplementedError("supervised pretraining is outside the B200 hot path (SURVEY.md 8f row 2)")
     w2i, emb = train_data["word_to_idx"], train_data.get("embeddings")
+    trainers_ = {"reward_network": train_reward_network, "policy_network": train_policy_network,
+                 "value_network": train_value_network}
     nets = {}
     for key, cls in (("reward_network", RewardNetwork), ("policy_network", PolicyNetwork), ("value_network", ValueNetwork)):
+        if retrain_all or not os.path.exists(network_paths[key]):
+            # trainers.py:330-370: retrain everything, or fall back to pretraining the network whose file is missing
+            nets[key] = trainers_[key](train_data, network_paths, plot_dir, bidirectional, batch_size=batch_size)
+            continue
         net = cls(w2i, pretrained_embeddings=emb, bidirectional=bidirectional).to(device)
-        if not os.path.exists(network_paths[key]):
-            raise FileNotFoundError("%s not found at %s; the reference would pretrain it from scratch "
-                                    "(trainers.py:345-370), which is outside the hot path" % (key, network_paths[key]))
         net.load_state_dict(torch.load(network_paths[key], map_location=device), strict=False)
         nets[key] = net
     reward_network = nets["reward_network"]

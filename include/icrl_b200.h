@@ -131,9 +131,25 @@ size_t icrl_chain_sync_bytes(void);
 int icrl_chain_lstm_fwd(void* stream, const int* tok_stream, int T, const float* table, const float* W_hh,
                         const float* h0, const float* c0, float* stash_h, float* stash_c, float* stash_gates,
                         float* h_out, float* c_out, void* sync_state, int* launches);
+/* stash_gates (nullable) [T][2048]: r, z, n, W_hn h + b_hn per step -- only for training the reward network. */
 int icrl_chain_gru_fwd(void* stream, const int* tok_stream, int T, const float* table, const float* W_hh,
                        const float* b_hn, const float* h0, float* stash_h, float* h_out, void* sync_state,
-                       int* launches);
+                       float* stash_gates, int* launches);
+/* BPTT through the reward GRU chain (train_reward_network, trainers.py:260-309; the A2C step keeps the reward net
+ * frozen).  dgh [T][1536] = hidden-side gate gradients (da_r, da_z, da_nh), dgx [T][1536] = input-side
+ * (da_r, da_z, da_n); dh_init / dh0_out as in icrl_chain_lstm_bwd. */
+int icrl_chain_gru_bwd(void* stream, int T, const float* W_hh, const float* stash_gates, const float* stash_h,
+                       const int* take, const float* dh_take, float* dgh, float* dgx, void* sync_state,
+                       const float* dh_init, float* dh0_out, int* launches);
+/* reward-chain parameter gradients (overwritten); colsum_ws: icrl_colsum_ws_floats(max(T,V), 1536) + 1536 floats. */
+int icrl_reward_chain_param_grads(void* stream, int T, int V, const int* tok_stream, const float* dgh, const float* dgx,
+                                  const float* stash_h, const float* E, const float* W_ih, float* dtable,
+                                  float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE, float* dW_ih,
+                                  float* dW_hh, float* db_ih, float* db_hh, int* launches);
+/* backward of y = x W^T + b (nn.Linear; visual_embed / semantic_embed, models.py:259-260): dx [M][K] (nullable),
+ * dW [N][K], db [N] (overwritten); colsum_ws: icrl_colsum_ws_floats(M, N) floats. */
+int icrl_linear_bwd(void* stream, int M, int N, int K, const float* x, const float* W, const float* dy, float* dx,
+                    float* dW, float* db, float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, int* launches);
 /* value LSTM chain and reward GRU chain side by side in one launch (both from zero state) */
 int icrl_chains_fwd_fused(void* stream, const int* v_stream, int v_T, const float* v_table, const float* v_W_hh,
                           float* v_stash_h, float* v_stash_c, float* v_stash_gates, const int* r_stream, int r_T,

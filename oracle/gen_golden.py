@@ -201,7 +201,76 @@ def case_lookahead(name, seed, B, beam=5):
     print(name, [float(s.mean()) for _, s in cands])
 
 
+def case_pretrain(name, seed, B):
+    """One minibatch of each supervised pretraining loop of the reference (train_policy_network :202-257,
+    train_reward_network :260-309, train_value_network :125-199): loss and gradients.
+    The loops construct their networks themselves, so the class names inside the reference's trainers module are
+    wrapped by factories that load the synthetic weights right after construction (no source is modified)."""
+    import random
+    T = import_reference()
+    import utilities
+    w = synth.make_weights(seed)
+    f, c = synth.make_inputs(seed, B, 17)
+    data = {"train_captions": c, "train_image_idxs": np.arange(B), "train_features": f,
+            "train_urls": np.array(["u"] * B), "word_to_idx": synth.word_to_idx(), "embeddings": None}
+    tmp = tempfile.mkdtemp()
+    paths = {k: os.path.join(tmp, k + ".pt") for k in ("policy_network", "reward_network", "value_network")}
+    torch.save(w["policy"], paths["policy_network"])
+    torch.save(w["reward"], paths["reward_network"])
+    orig = dict(P=T.PolicyNetwork, V=T.ValueNetwork, R=T.RewardNetwork, sw=T.SummaryWriter, perm=utilities.torch.randperm,
+                tqdm=T.tqdm, ri=random.randint)
+
+    def factory(cls, sd):
+        def make(*a, **k):
+            net = cls(*a, **k)
+            net.load_state_dict(sd)
+            return net
+        return make
+
+    picked = []
+
+    def randint(a, b):
+        v = orig["ri"](a, b)
+        picked.append(v)
+        return v
+
+    T.PolicyNetwork, T.ValueNetwork, T.RewardNetwork = factory(orig["P"], w["policy"]), factory(orig["V"], w["value"]), factory(orig["R"], w["reward"])
+    T.SummaryWriter = _Recorder
+    utilities.torch.randperm = lambda n: torch.arange(n)
+    T.tqdm = lambda it, **k: _Quiet(it)
+    random.randint = randint
+    out = dict(seed=seed, B=B)
+    try:
+        for key, fn in (("policy", T.train_policy_network), ("reward", T.train_reward_network), ("value", T.train_value_network)):
+            _Recorder.scalars = []
+            random.seed(seed)
+            net = fn(data, paths, tmp, False, epochs=1, batch_size=B)
+            out[key + "_loss"] = np.float64(_Recorder.scalars[0][1])
+            grads = {k: p.grad.detach().numpy() for k, p in net.named_parameters()}
+            out.update({key + "/" + k: v for k, v in summarize_grads(grads).items()})
+            print(name, key, "loss", out[key + "_loss"])
+        out["value_prefix_len"] = np.int64(picked[-1])
+    finally:
+        T.PolicyNetwork, T.ValueNetwork, T.RewardNetwork = orig["P"], orig["V"], orig["R"]
+        T.SummaryWriter, utilities.torch.randperm, T.tqdm, random.randint = orig["sw"], orig["perm"], orig["tqdm"], orig["ri"]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+
+
+class _Quiet:
+    """tqdm stand-in: iterable with the two methods the loops call on the progress bar."""
+
+    def __init__(self, it):
+        self.it = it
+
+    def __iter__(self):
+        return iter(self.it)
+
+    def set_description_str(self, *a, **k):
+        pass
+
+
 CASES = {
+    "pretrain_b12": lambda: case_pretrain("pretrain_b12", 8, 12),              # SURVEY 8f row 2
     "lookahead_b6": lambda: case_lookahead("lookahead_b6", 7, 6),              # SURVEY 8f row 1
     "greedy_b32": lambda: case_greedy("greedy_b32", 0, 32),                    # BASELINE config 1
     "a2c_b8_l6": lambda: case_a2c("a2c_b8_l6", 1, 8, 6),

@@ -15,6 +15,7 @@ import torch
 
 from oracle import ref_port, single_pass, synth
 from tests.helpers import (check_grads_vs_golden, check_grads_vs_oracle, load_case, make_nets, named_grads, GOLDEN)
+from oracle.gen_golden import grad_sample_index
 
 pytestmark = pytest.mark.gpu
 
@@ -420,3 +421,71 @@ def test_curriculum_full_size_properties():
         assert torch.isfinite(eng.flat_grad).all()
         r2 = eng.step(f, c, uniforms=u, level=level, backward=False)
         assert torch.equal(r["tokens"], r2["tokens"])
+
+
+def _pretrain_case():
+    g = np.load(GOLDEN + "/pretrain_b12.npz")
+    seed, B = int(g["seed"]), int(g["B"])
+    w = synth.make_weights(seed)
+    f, c = synth.make_inputs(seed, B, 17)
+    data = {"train_captions": c, "train_image_idxs": np.arange(B), "train_features": f,
+            "train_urls": np.array(["u"] * B), "word_to_idx": synth.word_to_idx(), "embeddings": None}
+    return g, seed, B, w, data
+
+
+def _check_pretrain_grads(net, g, key, tol=GTOL):
+    worst = 0.0
+    for k, p_ in net.named_parameters():
+        assert p_.grad is not None, k
+        flat = p_.grad.detach().float().cpu().numpy().reshape(-1)
+        ref = g["%s/gsamp/%s" % (key, k)]
+        got = flat[grad_sample_index(flat.size)]
+        err = float(np.abs(got - ref).max()) / max(float(np.abs(ref).max()), 1e-12)
+        worst = max(worst, err)
+        assert err <= tol, "%s %s: %.3e" % (key, k, err)
+        nrm = float(np.sqrt((flat.astype(np.float64) ** 2).sum()))
+        assert abs(nrm - float(g["%s/gnorm/%s" % (key, k)])) <= tol * max(float(g["%s/gnorm/%s" % (key, k)]), 1e-12), k
+    return worst
+
+
+@pytest.mark.parametrize("key", ["policy", "reward", "value"])
+def test_pretraining_loops_vs_reference_golden(key, tmp_path, monkeypatch):
+    """one minibatch of train_policy_network / train_reward_network / train_value_network on the
+    drop-in modules (autograd through the CUDA kernels, GRU BPTT included) against the unmodified reference: loss and
+    all gradients.  As in the golden generator, the loops' own network constructors are wrapped to load the
+    synthetic weights."""
+    import random
+    import icrl_b200.trainers as T
+    g, seed, B, w, data = _pretrain_case()
+    paths = {k: str(tmp_path / (k + ".pt")) for k in ("policy_network", "reward_network", "value_network")}
+    torch.save(w["policy"], paths["policy_network"])
+    torch.save(w["reward"], paths["reward_network"])
+
+    def factory(cls, sd):
+        def make(*a, **k):
+            net = cls(*a, **k)
+            net.load_state_dict(sd)
+            return net
+        return make
+
+    losses = []
+
+    class Rec:
+        def __init__(self, *a, **k):
+            pass
+
+        def add_scalar(self, tag, val, step):
+            losses.append(float(val))
+
+    monkeypatch.setattr(T, "PolicyNetwork", factory(T.PolicyNetwork, w["policy"]))
+    monkeypatch.setattr(T, "ValueNetwork", factory(T.ValueNetwork, w["value"]))
+    monkeypatch.setattr(T, "RewardNetwork", factory(T.RewardNetwork, w["reward"]))
+    monkeypatch.setattr(T, "SummaryWriter", Rec)
+    monkeypatch.setattr(T.torch, "randperm", lambda n: torch.arange(n))
+    random.seed(seed)
+    fn = {"policy": T.train_policy_network, "reward": T.train_reward_network, "value": T.train_value_network}[key]
+    net = fn(data, paths, str(tmp_path), False, epochs=1, batch_size=B)
+    ref_loss = float(g[key + "_loss"])
+    assert abs(losses[0] - ref_loss) <= 2e-6 * max(1.0, abs(ref_loss)), (losses[0], ref_loss)
+    # gradients survive the optimizer step (zero_grad precedes backward in the loops)
+    _record("pretrain_" + key, loss=losses[0], grad_worst=_check_pretrain_grads(net, g, key))
