@@ -30,10 +30,10 @@ SIGNATURES = {
     "icrl_decode_set_profile": [P],
     "icrl_pack_decode_weights": [P, I, P, P, P, LP],
     "icrl_policy_rollout_fwd_fused": [P, I, I, I, I, I] + [P] * 17 + [LP],
-    "icrl_pack_gate_table": [P, I, I, I, P, P, P, P, P, LP],
+    "icrl_pack_gate_table": [P, I, I, I, I, P, P, P, P, P, LP],
     "icrl_pack_value_head": [P, P, P, P, P, P, P, LP],
     "icrl_policy_rollout_fwd": [P, I, I, I, I, I] + [P] * 17 + [LP],
-    "icrl_policy_rollout_bwd": [P, I, I, I, I] + [P] * 19 + [Z] + [P] * 9 + [LP],
+    "icrl_policy_rollout_bwd": [P, I, I, I, I, I] + [P] * 19 + [Z] + [P] * 9 + [LP],
     "icrl_colsum_ws_floats": [L, I],
     "icrl_stream_len": [I, I, I, I],
     "icrl_build_stream": [P, I, I, I, I, P, P, P, P, LP],
@@ -44,7 +44,7 @@ SIGNATURES = {
     "icrl_chain_lstm_fwd": [P, P, I] + [P] * 10 + [LP],
     "icrl_chain_gru_fwd": [P, P, I] + [P] * 8 + [LP],
     "icrl_chain_gru_bwd": [P, I] + [P] * 10 + [LP],
-    "icrl_reward_chain_param_grads": [P, I, I] + [P] * 9 + [Z] + [P] * 5 + [LP],
+    "icrl_reward_chain_param_grads": [P, I, I, I] + [P] * 9 + [Z] + [P] * 5 + [LP],
     "icrl_linear_bwd": [P, I, I, I] + [P] * 8 + [Z, LP],
     "icrl_chains_fwd_fused": [P, P, I, P, P, P, P, P, P, I, P, P, P, P, P, LP],
     "icrl_chain_lstm_bwd": [P, I, P, P, P, P, P, P, P, P, P, P, P, LP],
@@ -52,7 +52,7 @@ SIGNATURES = {
     "icrl_gather_rows": [P, L, P, P, L, P, LP],
     "icrl_value_head_fwd": [P, I, I, P, P, P, P, P, LP],
     "icrl_value_head_bwd": [P, I, I] + [P] * 14 + [LP],
-    "icrl_value_chain_param_grads": [P, I, I] + [P] * 8 + [Z] + [P] * 5 + [LP],
+    "icrl_value_chain_param_grads": [P, I, I, I] + [P] * 8 + [Z] + [P] * 5 + [LP],
     "icrl_reward_cosine_fwd": [P, I, I, P, P, P, LP],
     "icrl_a2c_loss_fwd_bwd": [P, I, I, P, P, P, F, P, P, P, P, LP],
 }

@@ -46,10 +46,11 @@ int icrl_gemm_f32(void* stream, int transA, int transB, int M, int N, int K, con
                             launches);
 }
 
-int icrl_pack_gate_table(void* stream, int V, int G, int fold, const float* E, const float* W_ih,
+int icrl_pack_gate_table(void* stream, int V, int G, int fold, int D, const float* E, const float* W_ih,
                          const float* b_ih, const float* b_hh, float* table, int* launches) {
-  // table = E [V][512] * W_ih^T ([G][512], K contiguous)
-  TRY(icrl_gemm_f32_impl(S_(stream), 0, 1, V, G, H, E, H, W_ih, H, table, G, nullptr, 0.f, nullptr, 0, launches));
+  // table = E [V][D] * W_ih^T ([G][D], K contiguous); D = embedding width (512, or that of frozen pretrained vectors)
+  ICRL_REQUIRE(D > 0, "embedding width");
+  TRY(icrl_gemm_f32_impl(S_(stream), 0, 1, V, G, D, E, D, W_ih, D, table, G, nullptr, 0.f, nullptr, 0, launches));
   TRY(icrl_add_gate_bias_impl(S_(stream), V, G, fold, b_ih, b_hh, table));
   bump(launches, 1);
   return ICRL_OK;
@@ -166,7 +167,7 @@ int icrl_policy_rollout_fwd_fused(void* stream, int B, int V, int p0, int S, int
 
 size_t icrl_colsum_ws_floats(long long rows, int cols) { return (size_t)icrl_wcolsum_chunks(rows) * cols; }
 
-int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, const float* features, const float* E,
+int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, int D, const float* features, const float* E,
                             const float* W_ih, const float* W_hh, const float* W_v, const int* tokcm,
                             const long long* tokens_out, const float* dlogp, const float* Hs, const float* Cs,
                             const float* Gs, float* logits, float* dHv, float* DG, float* dh, float* dc,
@@ -213,8 +214,9 @@ int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, const flo
   ICRL_CUDA(cudaMemsetAsync(dtable, 0, (size_t)V * 4 * H * sizeof(float), st));
   TRY(icrl_scatter_add_rows(st, nB, 4 * H, DG, tokcm, dtable));
   bump(launches, 1);
-  TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, H, V, dtable, 4 * H, E, H, dW_ih, H, nullptr, 0.f, nullptr, 0, launches));
-  TRY(icrl_gemm_f32_impl(st, 0, 0, V, H, 4 * H, dtable, 4 * H, W_ih, H, dE, H, nullptr, 0.f, nullptr, 0, launches));
+  TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, D, V, dtable, 4 * H, E, D, dW_ih, D, nullptr, 0.f, nullptr, 0, launches));
+  if (dE)                                            // null: frozen pretrained embedding (models.py:61-63)
+    TRY(icrl_gemm_f32_impl(st, 0, 0, V, D, 4 * H, dtable, 4 * H, W_ih, D, dE, D, nullptr, 0.f, nullptr, 0, launches));
   TRY(icrl_wcolsum(st, V, 4 * H, dtable, nullptr, 0, colsum_ws, db_ih));
   bump(launches, 2);
   ICRL_CUDA(cudaMemcpyAsync(db_hh, db_ih, 4 * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -312,7 +314,7 @@ int icrl_chain_gru_bwd(void* stream, int T, const float* W_hh, const float* stas
   return ICRL_OK;
 }
 
-int icrl_reward_chain_param_grads(void* stream, int T, int V, const int* tok_stream, const float* dgh, const float* dgx,
+int icrl_reward_chain_param_grads(void* stream, int T, int V, int D, const int* tok_stream, const float* dgh, const float* dgx,
                                   const float* stash_h, const float* E, const float* W_ih, float* dtable,
                                   float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE, float* dW_ih,
                                   float* dW_hh, float* db_ih, float* db_hh, int* launches) {
@@ -324,8 +326,8 @@ int icrl_reward_chain_param_grads(void* stream, int T, int V, const int* tok_str
   ICRL_CUDA(cudaMemsetAsync(dtable, 0, (size_t)V * G * sizeof(float), st));
   TRY(icrl_scatter_add_rows(st, T, G, dgx, tok_stream, dtable));
   bump(launches, 1);
-  TRY(icrl_gemm_f32_impl(st, 1, 0, G, H, V, dtable, G, E, H, dW_ih, H, nullptr, 0.f, nullptr, 0, launches));
-  TRY(icrl_gemm_f32_impl(st, 0, 0, V, H, G, dtable, G, W_ih, H, dE, H, nullptr, 0.f, nullptr, 0, launches));
+  TRY(icrl_gemm_f32_impl(st, 1, 0, G, D, V, dtable, G, E, D, dW_ih, D, nullptr, 0.f, nullptr, 0, launches));
+  if (dE) TRY(icrl_gemm_f32_impl(st, 0, 0, V, D, G, dtable, G, W_ih, D, dE, D, nullptr, 0.f, nullptr, 0, launches));
   TRY(icrl_wcolsum(st, V, G, dtable, nullptr, 0, colsum_ws, db_ih));
   // b_hh: the r,z rows are folded into the table (same gradient as b_ih); b_hn sits inside r*(.) -> column sums of da_nh
   float* tmp = colsum_ws + (size_t)icrl_wcolsum_chunks(T > V ? T : V) * G;
@@ -377,7 +379,7 @@ int icrl_value_head_bwd(void* stream, int B, int S, const float* features, const
   return ICRL_OK;
 }
 
-int icrl_value_chain_param_grads(void* stream, int T, int V, const int* tok_stream, const float* dgates,
+int icrl_value_chain_param_grads(void* stream, int T, int V, int D, const int* tok_stream, const float* dgates,
                                  const float* stash_h, const float* E, const float* W_ih, float* dtable,
                                  float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE, float* dW_ih,
                                  float* dW_hh, float* db_ih, float* db_hh, int* launches) {
@@ -388,8 +390,9 @@ int icrl_value_chain_param_grads(void* stream, int T, int V, const int* tok_stre
   ICRL_CUDA(cudaMemsetAsync(dtable, 0, (size_t)V * 4 * H * sizeof(float), st));
   TRY(icrl_scatter_add_rows(st, T, 4 * H, dgates, tok_stream, dtable));
   bump(launches, 1);
-  TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, H, V, dtable, 4 * H, E, H, dW_ih, H, nullptr, 0.f, nullptr, 0, launches));
-  TRY(icrl_gemm_f32_impl(st, 0, 0, V, H, 4 * H, dtable, 4 * H, W_ih, H, dE, H, nullptr, 0.f, nullptr, 0, launches));
+  TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, D, V, dtable, 4 * H, E, D, dW_ih, D, nullptr, 0.f, nullptr, 0, launches));
+  if (dE)
+    TRY(icrl_gemm_f32_impl(st, 0, 0, V, D, 4 * H, dtable, 4 * H, W_ih, D, dE, D, nullptr, 0.f, nullptr, 0, launches));
   TRY(icrl_wcolsum(st, V, 4 * H, dtable, nullptr, 0, colsum_ws, db_ih));
   bump(launches, 2);
   ICRL_CUDA(cudaMemcpyAsync(db_hh, db_ih, 4 * H * sizeof(float), cudaMemcpyDeviceToDevice, st));

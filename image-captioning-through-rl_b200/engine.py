@@ -135,11 +135,14 @@ class A2CEngine:
             if p.grad is None or p.grad.data_ptr() != v.data_ptr():
                 p.grad = v
 
-    def _g(self, p):
-        """Gradient destination for parameter p (a scratch buffer if p is frozen)."""
+    def _g(self, p, optional=False):
+        """Gradient destination for parameter p (frozen: a scratch buffer, or None where the ABI lets a gradient
+        be skipped -- the frozen pretrained embeddings, models.py:61-63)."""
         for q, v in self._grad_views:
             if q is p:
                 return v
+        if optional:
+            return None
         return self._buf("frozen_grad_%d" % id(p), p.numel())
 
     def _buf(self, name, numel, dtype=torch.float32):
@@ -187,9 +190,9 @@ class A2CEngine:
         st, L, V = self._stream, self.launches.ref, self.V
         P, Vn, R = self.policy, self.value, self.reward
         c = _lib.call
-        c("icrl_pack_gate_table", st, V, 4 * H, 4 * H, _p(P.caption_embedding.weight), _p(P.lstm.weight_ih_l0),
+        c("icrl_pack_gate_table", st, V, 4 * H, 4 * H, P.caption_embedding.weight.shape[1], _p(P.caption_embedding.weight), _p(P.lstm.weight_ih_l0),
           _p(P.lstm.bias_ih_l0), _p(P.lstm.bias_hh_l0), _p(self._buf("p_table", V * 4 * H)), L)
-        c("icrl_pack_gate_table", st, V, 4 * H, 4 * H, _p(Vn.valrnn.caption_embedding.weight),
+        c("icrl_pack_gate_table", st, V, 4 * H, 4 * H, Vn.valrnn.caption_embedding.weight.shape[1], _p(Vn.valrnn.caption_embedding.weight),
           _p(Vn.valrnn.lstm.weight_ih_l0), _p(Vn.valrnn.lstm.bias_ih_l0), _p(Vn.valrnn.lstm.bias_hh_l0),
           _p(self._buf("v_table", V * 4 * H)), L)
         c("icrl_pack_value_head", st, _p(Vn.linear1.weight), _p(Vn.linear1.bias), _p(Vn.linear2.weight),
@@ -213,7 +216,7 @@ class A2CEngine:
 
     def pack_reward(self):
         R, V = self.reward, self.V
-        _lib.call("icrl_pack_gate_table", self._stream, V, 3 * H, 2 * H, _p(R.rewrnn.caption_embedding.weight),
+        _lib.call("icrl_pack_gate_table", self._stream, V, 3 * H, 2 * H, R.rewrnn.caption_embedding.weight.shape[1], _p(R.rewrnn.caption_embedding.weight),
                   _p(R.rewrnn.gru.weight_ih_l0), _p(R.rewrnn.gru.bias_ih_l0), _p(R.rewrnn.gru.bias_hh_l0),
                   _p(self._buf("r_table", V * 3 * H)), self.launches.ref)
 
@@ -367,18 +370,18 @@ class A2CEngine:
         dtable = self._buf("dtable", V * 4 * H)
         lstm = Vn.valrnn.lstm
         with self._phase("value_param_grads"):
-          _lib.call("icrl_value_chain_param_grads", st, Tv if K == 1 else K * (Tv + 1), V, _p(b["v_stream"]), _p(dgates), _p(b["v_stash_h"]),
+          _lib.call("icrl_value_chain_param_grads", st, Tv if K == 1 else K * (Tv + 1), V, Vn.valrnn.caption_embedding.weight.shape[1], _p(b["v_stream"]), _p(dgates), _p(b["v_stash_h"]),
                   _p(Vn.valrnn.caption_embedding.weight), _p(lstm.weight_ih_l0), _p(dtable), _p(colsum_ws), _p(gemm_ws),
-                  gemm_ws_floats * 4, _p(g(Vn.valrnn.caption_embedding.weight)), _p(g(lstm.weight_ih_l0)),
+                  gemm_ws_floats * 4, _p(g(Vn.valrnn.caption_embedding.weight, True)), _p(g(lstm.weight_ih_l0)),
                   _p(g(lstm.weight_hh_l0)), _p(g(lstm.bias_ih_l0)), _p(g(lstm.bias_hh_l0)), L)
         # policy BPTT
         pl = P.lstm
         with self._phase("policy_bwd"):
-          _lib.call("icrl_policy_rollout_bwd", st, B, V, p0, S, _p(f), _p(P.caption_embedding.weight), _p(pl.weight_ih_l0),
+          _lib.call("icrl_policy_rollout_bwd", st, B, V, p0, S, P.caption_embedding.weight.shape[1], _p(f), _p(P.caption_embedding.weight), _p(pl.weight_ih_l0),
                   _p(pl.weight_hh_l0), _p(P.linear2vocab.weight), _p(tokcm), _p(tokens), _p(b["dlogp"]), _p(b["p_Hs"]),
                   _p(b["p_Cs"]), _p(b["p_Gs"]), _p(b["p_logits"]), _p(self._buf("p_dHv", SB * H)),
                   _p(self._buf("p_DG", n_cell * B * 4 * H)), _p(self._buf("p_dh", 2 * B * H)), _p(self._buf("p_dc", B * H)),
-                  _p(dtable), _p(colsum_ws), _p(gemm_ws), gemm_ws_floats * 4, _p(g(P.caption_embedding.weight)),
+                  _p(dtable), _p(colsum_ws), _p(gemm_ws), gemm_ws_floats * 4, _p(g(P.caption_embedding.weight, True)),
                   _p(g(P.cnn2linear.weight)), _p(g(P.cnn2linear.bias)), _p(g(pl.weight_ih_l0)), _p(g(pl.weight_hh_l0)),
                   _p(g(pl.bias_ih_l0)), _p(g(pl.bias_hh_l0)), _p(g(P.linear2vocab.weight)), _p(g(P.linear2vocab.bias)), L)
 

@@ -52,12 +52,18 @@ def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def _unsupported(bidirectional, pretrained_embeddings):
-    # variants outside the A2C hot path (no BASELINE config uses them)
+def _unsupported(bidirectional, pretrained_embeddings=None):
+    # the bidirectional variant is outside the built scope (no BASELINE config uses it)
     if bidirectional:
         raise NotImplementedError("bidirectional=True is outside the B200 hot path (SURVEY.md 8f)")
+
+
+def _embedding(vocab_size, wordvec_dim, pretrained_embeddings):
+    """Trainable (V, wordvec_dim) table, or the frozen pretrained vectors and their width (models.py:61-65)."""
     if pretrained_embeddings is not None:
-        raise NotImplementedError("frozen pretrained_embeddings are outside the B200 hot path (SURVEY.md 8f)")
+        emb = nn.Embedding.from_pretrained(torch.FloatTensor(np.asarray(pretrained_embeddings)), freeze=True)
+        return emb, int(emb.weight.shape[1])
+    return nn.Embedding(vocab_size, wordvec_dim), wordvec_dim
 
 
 
@@ -93,7 +99,7 @@ class _PolicyFn(torch.autograd.Function):
         st = _st(dev)
         with torch.cuda.device(dev):
             table = torch.empty(V * 4 * HID, dtype=torch.float32, device=dev)
-            _lib.call("icrl_pack_gate_table", st, V, 4 * HID, 4 * HID, _p(E), _p(W_ih), _p(b_ih), _p(b_hh), _p(table), None)
+            _lib.call("icrl_pack_gate_table", st, V, 4 * HID, 4 * HID, E.shape[1], _p(E), _p(W_ih), _p(b_ih), _p(b_hh), _p(table), None)
             tokcm = torch.empty((n + 1) * B, dtype=torch.int32, device=dev)
             tokcm[:B] = captions[:, 0].to(torch.int32)
             forced = torch.zeros((B, n), dtype=torch.int64, device=dev)
@@ -122,13 +128,15 @@ class _PolicyFn(torch.autograd.Function):
         new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             dZ = dlogits.permute(1, 0, 2).contiguous().clone()          # [n][B][V], consumed in place
-            dE, dWc, dbc, dWih, dWhh = new(V, HID), new(HID, HID), new(HID), new(4 * HID, HID), new(4 * HID, HID)
+            D = E.shape[1]
+            dE = new(V, D) if ctx.needs_input_grad[2] else None           # frozen pretrained embedding: skipped
+            dWc, dbc, dWih, dWhh = new(HID, HID), new(HID), new(4 * HID, D), new(4 * HID, HID)
             dbih, dbhh, dWv, dbv = new(4 * HID), new(4 * HID), new(V, HID), new(V)
             cs = int(_lib.call("icrl_colsum_ws_floats", max(n * B, V, B), 4 * HID)) + 2 * HID + 4 * HID * 8
             ws = _gemm_ws(dev)
             # scratch tensors are held in locals until the call returns (a temporary would be recycled at once)
             dHv, DG, dh, dc, dtable, csws = new(n * B, HID), new(n * B, 4 * HID), new(2 * B, HID), new(B, HID), new(V, 4 * HID), new(cs)
-            _lib.call("icrl_policy_rollout_bwd", st, B, V, 1, n, _p(f), _p(E), _p(W_ih), _p(W_hh), _p(Wv), _p(tokcm),
+            _lib.call("icrl_policy_rollout_bwd", st, B, V, 1, n, D, _p(f), _p(E), _p(W_ih), _p(W_hh), _p(Wv), _p(tokcm),
                       _p(tokens), None, _p(Hs), _p(Cs), _p(Gs), _p(dZ), _p(dHv), _p(DG),
                       _p(dh), _p(dc), _p(dtable), _p(csws), _p(ws), ws.numel() * 4,
                       _p(dE), _p(dWc), _p(dbc), _p(dWih), _p(dWhh), _p(dbih), _p(dbhh), _p(dWv), _p(dbv), None)
@@ -148,7 +156,7 @@ class _ChainLSTMFn(torch.autograd.Function):
         st = _st(dev)
         with torch.cuda.device(dev):
             table = torch.empty(V * 4 * HID, dtype=torch.float32, device=dev)
-            _lib.call("icrl_pack_gate_table", st, V, 4 * HID, 4 * HID, _p(E), _p(W_ih), _p(b_ih), _p(b_hh), _p(table), None)
+            _lib.call("icrl_pack_gate_table", st, V, 4 * HID, 4 * HID, E.shape[1], _p(E), _p(W_ih), _p(b_ih), _p(b_hh), _p(table), None)
             stream = tok_cm.reshape(-1).contiguous()
             stash_h = torch.empty((T + 1, HID), dtype=torch.float32, device=dev)
             stash_c = torch.empty((T + 1, HID), dtype=torch.float32, device=dev)
@@ -185,11 +193,13 @@ class _ChainLSTMFn(torch.autograd.Function):
             _lib.call("icrl_chain_lstm_bwd", st, T, _p(W_hh), _p(stash_g), _p(stash_c), _p(take), _p(dh_take), _p(dgates),
                       _p(sync), _p(dh_in), _p(dc_in), _p(dh0), _p(dc0), None)
             _lib.call("icrl_chain_check", st, _p(sync))
-            dE, dWih, dWhh, dbih, dbhh = new(V, HID), new(4 * HID, HID), new(4 * HID, HID), new(4 * HID), new(4 * HID)
+            D = E.shape[1]
+            dE = new(V, D) if ctx.needs_input_grad[3] else None
+            dWih, dWhh, dbih, dbhh = new(4 * HID, D), new(4 * HID, HID), new(4 * HID), new(4 * HID)
             cs = int(_lib.call("icrl_colsum_ws_floats", max(T, V), 4 * HID))
             ws = _gemm_ws(dev)
             dtable, csws = new(V, 4 * HID), new(cs)
-            _lib.call("icrl_value_chain_param_grads", st, T, V, _p(stream), _p(dgates), _p(stash_h), _p(E), _p(W_ih),
+            _lib.call("icrl_value_chain_param_grads", st, T, V, D, _p(stream), _p(dgates), _p(stash_h), _p(E), _p(W_ih),
                       _p(dtable), _p(csws), _p(ws), ws.numel() * 4, _p(dE), _p(dWih), _p(dWhh), _p(dbih),
                       _p(dbhh), None)
         return None, dh0.view(ctx.state_shapes[0]), dc0.view(ctx.state_shapes[1]), dE, dWih, dWhh, dbih, dbhh
@@ -243,7 +253,7 @@ class _ChainGRUFn(torch.autograd.Function):
         train = any(ctx.needs_input_grad)
         with torch.cuda.device(dev):
             table = torch.empty(V * 3 * HID, dtype=torch.float32, device=dev)
-            _lib.call("icrl_pack_gate_table", st, V, 3 * HID, 2 * HID, _p(E), _p(W_ih), _p(b_ih), _p(b_hh), _p(table), None)
+            _lib.call("icrl_pack_gate_table", st, V, 3 * HID, 2 * HID, E.shape[1], _p(E), _p(W_ih), _p(b_ih), _p(b_hh), _p(table), None)
             stream = tok_cm.reshape(-1).contiguous()
             stash_h = torch.empty((T + 1, HID), dtype=torch.float32, device=dev)
             stash_g = torch.empty((T, 4 * HID), dtype=torch.float32, device=dev) if train else None
@@ -277,10 +287,12 @@ class _ChainGRUFn(torch.autograd.Function):
             _lib.call("icrl_chain_gru_bwd", st, T, _p(W_hh), _p(stash_g), _p(stash_h), _p(take), _p(dh_take), _p(dgh), _p(dgx),
                       _p(sync), _p(dh_in), _p(dh0), None)
             _lib.call("icrl_chain_check", st, _p(sync))
-            dE, dWih, dWhh, dbih, dbhh = new(V, HID), new(3 * HID, HID), new(3 * HID, HID), new(3 * HID), new(3 * HID)
+            D = E.shape[1]
+            dE = new(V, D) if ctx.needs_input_grad[2] else None
+            dWih, dWhh, dbih, dbhh = new(3 * HID, D), new(3 * HID, HID), new(3 * HID), new(3 * HID)
             cs = int(_lib.call("icrl_colsum_ws_floats", max(T, V), 3 * HID)) + 3 * HID
             dtable, csws, ws = new(V, 3 * HID), new(cs), _gemm_ws(dev)
-            _lib.call("icrl_reward_chain_param_grads", st, T, V, _p(stream), _p(dgh), _p(dgx), _p(stash_h), _p(E), _p(W_ih),
+            _lib.call("icrl_reward_chain_param_grads", st, T, V, D, _p(stream), _p(dgh), _p(dgx), _p(stash_h), _p(E), _p(W_ih),
                       _p(dtable), _p(csws), _p(ws), ws.numel() * 4, _p(dE), _p(dWih), _p(dWhh), _p(dbih), _p(dbhh), None)
         return None, dh0.view(ctx.state_shape), dE, dWih, dWhh, dbih, dbhh
 
@@ -354,13 +366,13 @@ class PolicyNetwork(_KernelModule):
                  pretrained_embeddings=None, bidirectional=False):
         super().__init__()
         _unsupported(bidirectional, pretrained_embeddings)
-        if (input_dim, wordvec_dim, hidden_dim) != (HID, HID, HID):
-            raise NotImplementedError("the B200 kernels are specialised for 512-wide layers (models.py:41)")
+        if (input_dim, hidden_dim) != (HID, HID):
+            raise NotImplementedError("the B200 kernels are specialised for 512-wide features / hidden state (models.py:41)")
         self.bidirectional = bidirectional
         self.word_to_idx = word_to_idx
         self.idx_to_word = {i: w for w, i in word_to_idx.items()}
         vocab_size = len(word_to_idx)
-        self.caption_embedding = nn.Embedding(vocab_size, wordvec_dim)
+        self.caption_embedding, wordvec_dim = _embedding(vocab_size, wordvec_dim, pretrained_embeddings)
         self.cnn2linear = nn.Linear(input_dim, hidden_dim)
         self.lstm = nn.LSTM(wordvec_dim, hidden_dim, batch_first=True)
         self.linear2vocab = nn.Linear(hidden_dim, vocab_size)
@@ -421,7 +433,7 @@ class ValueNetworkRNN(_ChainRNN):
                  pretrained_embeddings=None, bidirectional=False):
         super().__init__()
         self._common_init(word_to_idx, hidden_dim, pretrained_embeddings, bidirectional)
-        self.caption_embedding = nn.Embedding(len(word_to_idx), wordvec_dim)
+        self.caption_embedding, wordvec_dim = _embedding(len(word_to_idx), wordvec_dim, pretrained_embeddings)
         self.init_hidden()
         self.lstm = nn.LSTM(wordvec_dim, hidden_dim)
 
@@ -457,7 +469,7 @@ class RewardNetworkRNN(_ChainRNN):
                  pretrained_embeddings=None, bidirectional=False):
         super().__init__()
         self._common_init(word_to_idx, hidden_dim, pretrained_embeddings, bidirectional)
-        self.caption_embedding = nn.Embedding(len(word_to_idx), wordvec_dim)
+        self.caption_embedding, wordvec_dim = _embedding(len(word_to_idx), wordvec_dim, pretrained_embeddings)
         self.init_hidden()
         self.gru = nn.GRU(wordvec_dim, hidden_dim)
 

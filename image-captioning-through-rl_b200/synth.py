@@ -25,15 +25,17 @@ def _uni(rs, shape, fan):
     return rs.uniform(-k, k, size=shape).astype(np.float32)
 
 
-def make_weights(seed=0, vocab=VOCAB, emb_scale=1.0):
-    """Return {'policy','value','reward'} -> state_dict of float32 torch tensors."""
+def make_weights(seed=0, vocab=VOCAB, emb_scale=1.0, wordvec_dim=H):
+    """Return {'policy','value','reward'} -> state_dict of float32 torch tensors.  wordvec_dim != 512 gives the
+    layout of the frozen-pretrained-embedding variant (models.py:61-63): E (V, D), W_ih (gates, D)."""
+    D = wordvec_dim
     rs = np.random.RandomState(1000 + seed)
     nrm = lambda *s: (emb_scale * rs.standard_normal(s)).astype(np.float32)
     policy = {
-        "caption_embedding.weight": nrm(vocab, H),
+        "caption_embedding.weight": nrm(vocab, D),
         "cnn2linear.weight": _uni(rs, (H, H), H),
         "cnn2linear.bias": _uni(rs, (H,), H),
-        "lstm.weight_ih_l0": _uni(rs, (4 * H, H), H),
+        "lstm.weight_ih_l0": _uni(rs, (4 * H, D), H),
         "lstm.weight_hh_l0": _uni(rs, (4 * H, H), H),
         "lstm.bias_ih_l0": _uni(rs, (4 * H,), H),
         "lstm.bias_hh_l0": _uni(rs, (4 * H,), H),
@@ -41,8 +43,8 @@ def make_weights(seed=0, vocab=VOCAB, emb_scale=1.0):
         "linear2vocab.bias": _uni(rs, (vocab,), H),
     }
     value = {
-        "valrnn.caption_embedding.weight": nrm(vocab, H),
-        "valrnn.lstm.weight_ih_l0": _uni(rs, (4 * H, H), H),
+        "valrnn.caption_embedding.weight": nrm(vocab, D),
+        "valrnn.lstm.weight_ih_l0": _uni(rs, (4 * H, D), H),
         "valrnn.lstm.weight_hh_l0": _uni(rs, (4 * H, H), H),
         "valrnn.lstm.bias_ih_l0": _uni(rs, (4 * H,), H),
         "valrnn.lstm.bias_hh_l0": _uni(rs, (4 * H,), H),
@@ -52,8 +54,8 @@ def make_weights(seed=0, vocab=VOCAB, emb_scale=1.0):
         "linear2.bias": _uni(rs, (1,), H),
     }
     reward = {
-        "rewrnn.caption_embedding.weight": nrm(vocab, H),
-        "rewrnn.gru.weight_ih_l0": _uni(rs, (3 * H, H), H),
+        "rewrnn.caption_embedding.weight": nrm(vocab, D),
+        "rewrnn.gru.weight_ih_l0": _uni(rs, (3 * H, D), H),
         "rewrnn.gru.weight_hh_l0": _uni(rs, (3 * H, H), H),
         "rewrnn.gru.bias_ih_l0": _uni(rs, (3 * H,), H),
         "rewrnn.gru.bias_hh_l0": _uni(rs, (3 * H,), H),

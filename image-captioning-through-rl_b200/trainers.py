@@ -190,7 +190,7 @@ class _PolicyOnlyEngine(A2CEngine):
         from . import _lib
         from .engine import _p, H
         P = self.policy
-        _lib.call("icrl_pack_gate_table", self._stream, self.V, 4 * H, 4 * H, _p(P.caption_embedding.weight),
+        _lib.call("icrl_pack_gate_table", self._stream, self.V, 4 * H, 4 * H, P.caption_embedding.weight.shape[1], _p(P.caption_embedding.weight),
                   _p(P.lstm.weight_ih_l0), _p(P.lstm.bias_ih_l0), _p(P.lstm.bias_hh_l0),
                   _p(self._buf("p_table", self.V * 4 * H)), self.launches.ref)
         n = int(_lib.call("icrl_decode_weight_halves"))

@@ -52,8 +52,10 @@ int icrl_gemm_bf16x3(void* stream, int M, int N, int K, const void* a_parts, con
 
 /* ---- weight packing, once per optimizer step (new; the reference recomputes these products at every
  *      RNN step).  table[v][:] = W_ih E[v] + b_ih + (b_hh for the first `fold` gate rows).
- *      LSTM: G = 2048, fold = 2048.  GRU: G = 1536, fold = 1024 (b_hn stays inside r*(.), models.py:215). */
-int icrl_pack_gate_table(void* stream, int V, int G, int fold, const float* E, const float* W_ih,
+ *      LSTM: G = 2048, fold = 2048.  GRU: G = 1536, fold = 1024 (b_hn stays inside r*(.), models.py:215).
+ *      D = embedding width: E [V][D], W_ih [G][D] (512, or the width of frozen pretrained vectors, models.py:61-63).
+ *      The same D is passed to the three parameter-gradient entry points, whose dE may be NULL (frozen embedding). */
+int icrl_pack_gate_table(void* stream, int V, int G, int fold, int D, const float* E, const float* W_ih,
                          const float* b_ih, const float* b_hh, float* table, int* launches);
 /* value head linear2(linear1(.)) has no activation (models.py:177-178): w_eff = W2 W1 (1024), b_eff (1). */
 int icrl_pack_value_head(void* stream, const float* W1, const float* b1, const float* W2, const float* b2,
@@ -104,7 +106,7 @@ int icrl_policy_rollout_fwd_fused(void* stream, int B, int V, int p0, int S, int
  *      logits is overwritten with dL/dlogits.  Workspaces: dHv [S*B][512],
  *      DG [n_cell*B][2048], dh [2][B][512], dc [B][512], dtable [V][2048], colsum_ws
  *      [icrl_colsum_ws_floats(max(S*B, V), 2048)], gemm_ws/gemm_ws_bytes.  Gradients are OVERWRITTEN. */
-int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, const float* features, const float* E,
+int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, int D, const float* features, const float* E,
                             const float* W_ih, const float* W_hh, const float* W_v, const int* tokcm,
                             const long long* tokens_out, const float* dlogp, const float* Hs, const float* Cs,
                             const float* Gs, float* logits, float* dHv, float* DG, float* dh, float* dc,
@@ -142,7 +144,7 @@ int icrl_chain_gru_bwd(void* stream, int T, const float* W_hh, const float* stas
                        const int* take, const float* dh_take, float* dgh, float* dgx, void* sync_state,
                        const float* dh_init, float* dh0_out, int* launches);
 /* reward-chain parameter gradients (overwritten); colsum_ws: icrl_colsum_ws_floats(max(T,V), 1536) + 1536 floats. */
-int icrl_reward_chain_param_grads(void* stream, int T, int V, const int* tok_stream, const float* dgh, const float* dgx,
+int icrl_reward_chain_param_grads(void* stream, int T, int V, int D, const int* tok_stream, const float* dgh, const float* dgx,
                                   const float* stash_h, const float* E, const float* W_ih, float* dtable,
                                   float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE, float* dW_ih,
                                   float* dW_hh, float* db_ih, float* db_hh, int* launches);
@@ -197,7 +199,7 @@ int icrl_value_head_bwd(void* stream, int B, int S, const float* features, const
                         float* dh_take, float* dW1, float* db1, float* dW2, float* db2, float* ws, int* launches);
 /*      value-chain parameter gradients from the chain backward's dgates (overwritten):
  *      dW_hh = dgates^T h_prev, gate-table scatter, dW_ih = dtable^T E, dE = dtable W_ih, db = colsum. */
-int icrl_value_chain_param_grads(void* stream, int T, int V, const int* tok_stream, const float* dgates,
+int icrl_value_chain_param_grads(void* stream, int T, int V, int D, const int* tok_stream, const float* dgates,
                                  const float* stash_h, const float* E, const float* W_ih, float* dtable,
                                  float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE, float* dW_ih,
                                  float* dW_hh, float* db_ih, float* db_hh, int* launches);

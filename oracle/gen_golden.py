@@ -83,9 +83,14 @@ def summarize_grads(named_grads):
     return out
 
 
-def build_reference_nets(T, weights):
+def build_reference_nets(T, weights, pretrained=False):
     w2i = synth.word_to_idx(weights["policy"]["caption_embedding.weight"].shape[0])
-    P, V, R = T.PolicyNetwork(w2i), T.ValueNetwork(w2i), T.RewardNetwork(w2i)
+    if pretrained:          # frozen pretrained word vectors (models.py:61-63): every net gets its own table
+        P = T.PolicyNetwork(w2i, pretrained_embeddings=weights["policy"]["caption_embedding.weight"].numpy())
+        V = T.ValueNetwork(w2i, pretrained_embeddings=weights["value"]["valrnn.caption_embedding.weight"].numpy())
+        R = T.RewardNetwork(w2i, pretrained_embeddings=weights["reward"]["rewrnn.caption_embedding.weight"].numpy())
+    else:
+        P, V, R = T.PolicyNetwork(w2i), T.ValueNetwork(w2i), T.RewardNetwork(w2i)
     P.load_state_dict(weights["policy"])
     V.load_state_dict(weights["value"])
     R.load_state_dict(weights["reward"])
@@ -95,10 +100,10 @@ def build_reference_nets(T, weights):
     return P, V, R, A
 
 
-def run_reference_a2c(weights, features, captions, seed, level=None):
+def run_reference_a2c(weights, features, captions, seed, level=None, pretrained=False):
     T = import_reference()
     import utilities
-    P, V, R, A = build_reference_nets(T, weights)
+    P, V, R, A = build_reference_nets(T, weights, pretrained)
     opt = T.optim.Adam(A.parameters(), lr=1e-4)
     B = captions.shape[0]
     data = {"train_captions": captions, "train_image_idxs": np.arange(B),
@@ -138,7 +143,7 @@ def run_reference_a2c(weights, features, captions, seed, level=None):
     logits = np.stack(rec["logits"], axis=1)                       # (B,S,V)
     z = torch.from_numpy(logits)
     logp = torch.log(torch.softmax(z, dim=2).gather(2, torch.from_numpy(tokens).unsqueeze(2)))[:, :, 0].numpy()
-    grads = {k: p.grad.detach().numpy() for k, p in A.named_parameters()}
+    grads = {k: p.grad.detach().numpy() for k, p in A.named_parameters() if p.grad is not None}
     sc = dict(_Recorder.scalars)
     loss = [v for k, v in _Recorder.scalars if k.endswith("loss")][0]
     mr = [v for k, v in _Recorder.scalars if k.endswith("mean-rewards")][0]
@@ -150,11 +155,11 @@ def run_reference_a2c(weights, features, captions, seed, level=None):
     return out
 
 
-def case_a2c(name, seed, B, L, level=None):
-    w = synth.make_weights(seed)
+def case_a2c(name, seed, B, L, level=None, wordvec_dim=512):
+    w = synth.make_weights(seed, wordvec_dim=wordvec_dim)
     f, c = synth.make_inputs(seed, B, L)
-    out = run_reference_a2c(w, f, c, seed, level)
-    out.update(seed=seed, B=B, L=L, level=-1 if level is None else level)
+    out = run_reference_a2c(w, f, c, seed, level, pretrained=wordvec_dim != 512)
+    out.update(seed=seed, B=B, L=L, level=-1 if level is None else level, wordvec_dim=wordvec_dim)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
     print(name, "loss", out["loss"], "tokens", out["tokens"].shape)
 
@@ -270,6 +275,7 @@ class _Quiet:
 
 
 CASES = {
+    "a2c_b16_l8_wemb300": lambda: case_a2c("a2c_b16_l8_wemb300", 9, 16, 8, wordvec_dim=300),   # SURVEY 8f row 3 (frozen 300-d vectors)
     "pretrain_b12": lambda: case_pretrain("pretrain_b12", 8, 12),
     "lookahead_b6": lambda: case_lookahead("lookahead_b6", 7, 6),
     "greedy_b32": lambda: case_greedy("greedy_b32", 0, 32),                    # BASELINE config 1

@@ -489,3 +489,32 @@ def test_pretraining_loops_vs_reference_golden(key, tmp_path, monkeypatch):
     assert abs(losses[0] - ref_loss) <= 2e-6 * max(1.0, abs(ref_loss)), (losses[0], ref_loss)
     # gradients survive the optimizer step (zero_grad precedes backward in the loops)
     _record("pretrain_" + key, loss=losses[0], grad_worst=_check_pretrain_grads(net, g, key))
+
+
+def test_frozen_pretrained_embeddings_variant_vs_reference_golden():
+    """SURVEY 8f row 3 (first half): `pretrained_embeddings` given -> frozen 300-d word vectors, 300-wide LSTM / GRU
+    inputs (models.py:61-63, 113-115, 208-210).  One A2C minibatch through the fused engine against the unmodified
+    reference: tokens bit-exact, values / rewards / log-probs / loss within tolerance, the 16 trainable gradients
+    match and the frozen tables get none."""
+    import icrl_b200.models as M
+    from icrl_b200.engine import A2CEngine
+    g = np.load(GOLDEN + "/a2c_b16_l8_wemb300.npz")
+    seed, B, L, D = int(g["seed"]), int(g["B"]), int(g["L"]), int(g["wordvec_dim"])
+    w = synth.make_weights(seed, wordvec_dim=D)
+    w2i = synth.word_to_idx()
+    P = M.PolicyNetwork(w2i, pretrained_embeddings=w["policy"]["caption_embedding.weight"].numpy())
+    V = M.ValueNetwork(w2i, pretrained_embeddings=w["value"]["valrnn.caption_embedding.weight"].numpy())
+    R = M.RewardNetwork(w2i, pretrained_embeddings=w["reward"]["rewrnn.caption_embedding.weight"].numpy())
+    P.load_state_dict(w["policy"]); V.load_state_dict(w["value"]); R.load_state_dict(w["reward"])
+    assert P.lstm.weight_ih_l0.shape == (2048, D) and not P.caption_embedding.weight.requires_grad
+    R.requires_grad_(False)
+    A = M.AdvantageActorCriticNetwork(V, P).cuda()
+    R = R.cuda()
+    f, c = synth.make_inputs(seed, B, L)
+    u = synth.make_uniforms(seed, L - 1, B)
+    eng = A2CEngine(A, R)
+    res = eng.step(f, c, uniforms=u)
+    _compare_forward(res, g, "a2c_b16_l8_wemb300")
+    grads = {k: p.grad.detach().float().cpu().numpy() for k, p in A.named_parameters() if p.requires_grad}
+    assert len(grads) == 16 and A.policy_network.caption_embedding.weight.grad is None
+    _record("a2c_b16_l8_wemb300", grad_worst=check_grads_vs_golden(grads, g, GTOL))
