@@ -94,6 +94,12 @@ class A2CEngine:
             decode = "tc" if use_tc else "simt"
         if decode not in self.DECODE_MODES:
             raise ValueError("decode must be one of %s" % (self.DECODE_MODES,))
+        if decode == "fused" and (self.V > 1024 or self.V % 4):
+            # the persistent kernel keeps one row of logits inside a cluster (8 x 128 columns, float4 stash)
+            import warnings
+            warnings.warn("vocabulary of %d words does not fit the fused decode kernel (V <= 1024, V %% 4 == 0): "
+                          "using the per-step kernels" % self.V)
+            decode = "simt"
         self.decode = decode
         self.use_tc = decode == "tc"
         # chain_shards = K > 1 cuts the (local) batch into K contiguous row shards whose value / reward recurrences

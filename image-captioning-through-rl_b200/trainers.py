@@ -184,7 +184,7 @@ class _PolicyOnlyEngine(A2CEngine):
         _lib.load()
         self.device, self.V = dev, policy_network.linear2vocab.weight.shape[0]
         self._bufs, self.launches, self.phase_events = {}, _lib.Launches(), None
-        self.decode, self.use_tc = "fused", False
+        self.decode, self.use_tc = ("fused" if self.V <= 1024 and self.V % 4 == 0 else "simt"), False
 
     def pack_weights(self, reward=False):
         from . import _lib
@@ -193,9 +193,10 @@ class _PolicyOnlyEngine(A2CEngine):
         _lib.call("icrl_pack_gate_table", self._stream, self.V, 4 * H, 4 * H, P.caption_embedding.weight.shape[1], _p(P.caption_embedding.weight),
                   _p(P.lstm.weight_ih_l0), _p(P.lstm.bias_ih_l0), _p(P.lstm.bias_hh_l0),
                   _p(self._buf("p_table", self.V * 4 * H)), self.launches.ref)
-        n = int(_lib.call("icrl_decode_weight_halves"))
-        _lib.call("icrl_pack_decode_weights", self._stream, self.V, _p(P.lstm.weight_hh_l0), _p(P.linear2vocab.weight),
-                  _p(self._buf("p_decode_pk", n, torch.float16)), self.launches.ref)
+        if self.decode == "fused":
+            n = int(_lib.call("icrl_decode_weight_halves"))
+            _lib.call("icrl_pack_decode_weights", self._stream, self.V, _p(P.lstm.weight_hh_l0), _p(P.linear2vocab.weight),
+                      _p(self._buf("p_decode_pk", n, torch.float16)), self.launches.ref)
 
 
 def VisualSemanticEmbeddingLoss(visuals, semantics):

@@ -518,3 +518,30 @@ def test_frozen_pretrained_embeddings_variant_vs_reference_golden():
     grads = {k: p.grad.detach().float().cpu().numpy() for k, p in A.named_parameters() if p.requires_grad}
     assert len(grads) == 16 and A.policy_network.caption_embedding.weight.grad is None
     _record("a2c_b16_l8_wemb300", grad_worst=check_grads_vs_golden(grads, g, GTOL))
+
+
+def test_odd_vocabulary_falls_back_to_per_step_decode():
+    """A vocabulary the persistent decode kernel cannot hold (V % 4 != 0) still trains: the engine switches to the
+    per-step kernels (with a warning) and matches the CPU oracle."""
+    import warnings
+    import icrl_b200.models as M
+    from icrl_b200.engine import A2CEngine
+    seed, B, L, V = 81, 10, 6, 203
+    w = synth.make_weights(seed, vocab=V)
+    w2i = synth.word_to_idx(V)
+    P, Vn, R = M.PolicyNetwork(w2i), M.ValueNetwork(w2i), M.RewardNetwork(w2i)
+    P.load_state_dict(w["policy"]); Vn.load_state_dict(w["value"]); R.load_state_dict(w["reward"])
+    R.requires_grad_(False)
+    A = M.AdvantageActorCriticNetwork(Vn, P).cuda()
+    f, c = synth.make_inputs(seed, B, L, vocab=V)
+    u = synth.make_uniforms(seed, L - 1, B)
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        eng = A2CEngine(A, R.cuda())
+    assert eng.decode == "simt" and any("fused decode" in str(x.message) for x in rec)
+    ref = single_pass.a2c_minibatch(w, f, c, u, lib=True)
+    res = eng.step(f, c, uniforms=u)
+    assert np.array_equal(res["tokens"].cpu().numpy(), ref["tokens"])
+    for k in ("values", "rewards", "logp"):
+        assert float(np.abs(res[k].cpu().numpy() - ref[k]).max()) <= TOL, k
+    check_grads_vs_oracle(named_grads(A), ref["grads"], GTOL)
