@@ -2,9 +2,10 @@
 # GPU check: (optional microbench) parity tests, smoke, small and full bench.  Everything is bounded
 # by `timeout`; the chain kernels carry their own watchdog.
 mkdir -p gpurun_out
-if [ -x scripts/xchg_bench ] && [ "$1" = "micro" ]; then
-  timeout 300 ./scripts/xchg_bench > gpurun_out/xchg_bench.log 2>&1; echo "xchg exit $?" >> gpurun_out/xchg_bench.log
-  grep -v "^l2 mode" gpurun_out/xchg_bench.log
+if [ "$1" = "micro" ]; then
+  [ -x scripts/xchg_bench ] && { timeout 300 ./scripts/xchg_bench > gpurun_out/xchg_bench.log 2>&1; echo "xchg exit $?" >> gpurun_out/xchg_bench.log; }
+  [ -x scripts/chain_micro ] && { timeout 300 ./scripts/chain_micro > gpurun_out/chain_micro.log 2>&1; echo "micro exit $?" >> gpurun_out/chain_micro.log; }
+  timeout 200 python scripts/tc_accuracy_probe.py > gpurun_out/tc_probe.log 2>&1
 fi
 timeout 1200 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/tests_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/tests_gpu.log
