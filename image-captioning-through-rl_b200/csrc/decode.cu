@@ -64,6 +64,15 @@ constexpr int GSTAGE_WARP = 6 * 4096;       // gate-epilogue staging per warp: 6
 constexpr int NBARS = 2 * STAGES + 2 + 2;   // full[2], empty[2], acc_full, acc_empty, xchg[2]
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * XCHG_BYTES + 256 + 1024;
 constexpr int TMEM_COLS = 512;
+// The A operand (fp16 split of h for the cluster's 128 rows) is the same in all 8 CTAs: each CTA fetches a 16-row
+// slice and TMA-multicasts it to the whole cluster (the stage's "empty" barrier then counts the MMA commits of all
+// 8 CTAs).  L2->SMEM bytes per stage: gate 48 -> 34 KB, vocab 32 -> 18 KB.
+#ifndef ICRL_DECODE_MCAST
+#define ICRL_DECODE_MCAST 1
+#endif
+constexpr bool MCAST = ICRL_DECODE_MCAST != 0;
+constexpr int A_SLICE_ROWS = BM / CL;                       // 16
+constexpr int A_SLICE = A_SLICE_ROWS * BK * 2;              // 1 KB
 constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
 
 struct DecodeArgs {
@@ -110,10 +119,31 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// {k, row, part} box: the hi and lo' tiles of an operand arrive with ONE instruction (a single thread issues every
+// TMA of the CTA; with four 2-D loads per 32-wide K block the GEMM phases were bound by TMA issue).
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mcast(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar,
+                                                  unsigned short mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.u32 %0, 1, 0, P1;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(unsigned bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mcast(unsigned bar, unsigned short mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tc_mma(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc,
                                        unsigned accumulate) {
@@ -185,6 +215,8 @@ __device__ __forceinline__ void xchg_send(unsigned buf, unsigned bar, int slot, 
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
 policy_decode_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_whh,
                      const __grid_constant__ CUtensorMap map_wv, const DecodeArgs p) {
+  // map_h: MCAST ? 2-D [4B rows][512] box {32,16} : 3-D {512, B, 4 = buffer*2 + part} box {32,128,2}
+  // map_whh / map_wv: 3-D {512, rows, 2 parts} box {32, 256 | 128, 2}
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* xbuf = smem + STAGES * STAGE_BYTES;                       // [2][XCHG_SLOTS][BM] 8-byte slots
@@ -202,7 +234,7 @@ policy_decode_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
   const int n_cell = p.p0 - 1 + p.S;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, MCAST ? CL : 1); }
     mbar_init(bar_acc_full, 1);
     mbar_init(bar_acc_empty, EPI_WARPS);
     mbar_init(bar_x, 1);
@@ -240,10 +272,13 @@ policy_decode_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
           const unsigned full = bar_full + 8 * s;
           mbar_expect_tx(full, 2 * A_TILE + 2 * BG_TILE);
           const unsigned base = smem_u32(smem + s * STAGE_BYTES);
-          tma_load_2d(base, &map_h, kb * BK, arow, full);
-          tma_load_2d(base + A_TILE, &map_h, kb * BK, arow + B, full);
-          tma_load_2d(base + 2 * A_TILE, &map_whh, kb * BK, (int)rank * GN, full);
-          tma_load_2d(base + 2 * A_TILE + BG_TILE, &map_whh, kb * BK, 4 * H + (int)rank * GN, full);
+          if (MCAST) {
+            tma_load_2d_mcast(base + rank * A_SLICE, &map_h, kb * BK, arow + (int)rank * A_SLICE_ROWS, full, 0xFF);
+            tma_load_2d_mcast(base + A_TILE + rank * A_SLICE, &map_h, kb * BK, arow + B + (int)rank * A_SLICE_ROWS, full, 0xFF);
+          } else {
+            tma_load_3d(base, &map_h, kb * BK, m0, 2 * (j & 1), full);
+          }
+          tma_load_3d(base + 2 * A_TILE, &map_whh, kb * BK, (int)rank * GN, 0, full);
         }
       }
       __syncwarp();
@@ -259,10 +294,13 @@ policy_decode_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
             const unsigned full = bar_full + 8 * s;
             mbar_expect_tx(full, 2 * A_TILE + 2 * BV_TILE);
             const unsigned base = smem_u32(smem + s * STAGE_BYTES);
-            tma_load_2d(base, &map_h, kb * BK, arow, full);
-            tma_load_2d(base + A_TILE, &map_h, kb * BK, arow + B, full);
-            tma_load_2d(base + 2 * A_TILE, &map_wv, kb * BK, (int)rank * VN, full);
-            tma_load_2d(base + 2 * A_TILE + BG_TILE, &map_wv, kb * BK, VPAD + (int)rank * VN, full);
+            if (MCAST) {
+              tma_load_2d_mcast(base + rank * A_SLICE, &map_h, kb * BK, arow + (int)rank * A_SLICE_ROWS, full, 0xFF);
+              tma_load_2d_mcast(base + A_TILE + rank * A_SLICE, &map_h, kb * BK, arow + B + (int)rank * A_SLICE_ROWS, full, 0xFF);
+            } else {
+              tma_load_3d(base, &map_h, kb * BK, m0, 2 * ((j + 1) & 1), full);
+            }
+            tma_load_3d(base + 2 * A_TILE, &map_wv, kb * BK, (int)rank * VN, 0, full);   // hi at +0, lo' at +BV_TILE
           }
         }
       }
@@ -270,63 +308,68 @@ policy_decode_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    // The whole warp runs the loops so that every address / descriptor stays warp-uniform (uniform registers);
+    // elect.sync picks the lane that issues.  With the loops inside `if (lane == 0)` the compiler had to move
+    // five operands per MMA from vector to uniform registers in an elect loop: ~130 cycles per MMA instead of 64.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     unsigned it = 0, nphase = 0;
+    const bool profw = p.prof != nullptr && blockIdx.x == 0;
     for (int j = 0; j < n_cell; ++j) {
-      if (lane == 0) {
+      {
         if (nphase > 0) mbar_wait(bar_acc_empty, (nphase - 1) & 1u);       // previous epilogue drained TMEM
         tc_fence_after();
-        const long long tg0 = (p.prof && blockIdx.x == 0) ? clock64() : 0;
+        const long long tg0 = profw ? clock64() : 0;
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(bar_full + 8 * s, (it / STAGES) & 1u);
           tc_fence_after();
           const unsigned base = smem_u32(smem + s * STAGE_BYTES);
+          const unsigned long long dA0 = smem_desc(base), dA1 = smem_desc(base + A_TILE);
+          const unsigned long long dB0 = smem_desc(base + 2 * A_TILE), dB1 = smem_desc(base + 2 * A_TILE + BG_TILE);
+          if (elect_one()) {
 #pragma unroll
-          for (int pair = 0; pair < 3; ++pair) {                           // (hi,hi) (hi,lo') (lo',hi)
-            const unsigned a = base + (pair == 2 ? A_TILE : 0);
-            const unsigned b = base + 2 * A_TILE + (pair == 1 ? BG_TILE : 0);
-            const unsigned acc = pair == 0 ? 0u : (unsigned)GN;
-#pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              const unsigned accumulate = pair == 0 ? ((kb | k) != 0) : !(kb == 0 && pair == 1 && k == 0);
-              tc_mma(tmem_base + acc, smem_desc(a + k * UMMA_K * 2), smem_desc(b + k * UMMA_K * 2), idesc_f16(GN), accumulate);
+            for (int k = 0; k < BK / UMMA_K; ++k) {                        // +2 = 32 bytes (16 fp16 along K) in 16-byte units
+              tc_mma(tmem_base, dA0 + 2 * k, dB0 + 2 * k, idesc_f16(GN), (kb | k) != 0);        // hi  * hi  -> main
+              tc_mma(tmem_base + GN, dA0 + 2 * k, dB1 + 2 * k, idesc_f16(GN), (kb | k) != 0);   // hi  * lo' -> correction
+              tc_mma(tmem_base + GN, dA1 + 2 * k, dB0 + 2 * k, idesc_f16(GN), 1u);              // lo' * hi  -> correction
             }
+            if (MCAST) tc_commit_mcast(bar_empty + 8 * s, 0xFF); else tc_commit(bar_empty + 8 * s);
           }
-          tc_commit(bar_empty + 8 * s);
+          __syncwarp();
         }
-        tc_commit(bar_acc_full);
+        if (elect_one()) tc_commit(bar_acc_full);
         ++nphase;
-        if (p.prof && blockIdx.x == 0) p.prof[(size_t)j * 16 + 14] = clock64() - tg0;   // gate-GEMM phase (issue span)
+        if (profw && lane == 0) p.prof[(size_t)j * 16 + 14] = clock64() - tg0;   // gate-GEMM phase (issue span)
       }
       __syncwarp();
       cluster_arrive();
       cluster_wait();
-      if (lane == 0 && j >= p.p0 - 1) {
+      if (j >= p.p0 - 1) {
         mbar_wait(bar_acc_empty, (nphase - 1) & 1u);
         tc_fence_after();
-        const long long tv0 = (p.prof && blockIdx.x == 0) ? clock64() : 0;
+        const long long tv0 = profw ? clock64() : 0;
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(bar_full + 8 * s, (it / STAGES) & 1u);
           tc_fence_after();
           const unsigned base = smem_u32(smem + s * STAGE_BYTES);
-#pragma unroll
-          for (int pair = 0; pair < 3; ++pair) {
-            const unsigned a = base + (pair == 2 ? A_TILE : 0);
-            const unsigned b = base + 2 * A_TILE + (pair == 1 ? BG_TILE : 0);
-            const unsigned acc = pair == 0 ? (unsigned)(kb & 1) * VN : 2u * VN;   // main even/odd K blocks, correction
+          const unsigned long long dA0 = smem_desc(base), dA1 = smem_desc(base + A_TILE);
+          const unsigned long long dB0 = smem_desc(base + 2 * A_TILE), dB1 = smem_desc(base + 2 * A_TILE + BV_TILE);
+          const unsigned main_acc = tmem_base + (unsigned)(kb & 1) * VN;   // main term: even / odd K blocks
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              const unsigned accumulate = pair == 0 ? (kb >= 2 || k != 0) : !(kb == 0 && pair == 1 && k == 0);
-              tc_mma(tmem_base + acc, smem_desc(a + k * UMMA_K * 2), smem_desc(b + k * UMMA_K * 2), idesc_f16(VN), accumulate);
+              tc_mma(main_acc, dA0 + 2 * k, dB0 + 2 * k, idesc_f16(VN), (kb >= 2 || k != 0) ? 1u : 0u);
+              tc_mma(tmem_base + 2 * VN, dA0 + 2 * k, dB1 + 2 * k, idesc_f16(VN), (kb | k) != 0);
+              tc_mma(tmem_base + 2 * VN, dA1 + 2 * k, dB0 + 2 * k, idesc_f16(VN), 1u);
             }
+            if (MCAST) tc_commit_mcast(bar_empty + 8 * s, 0xFF); else tc_commit(bar_empty + 8 * s);
           }
-          tc_commit(bar_empty + 8 * s);
+          __syncwarp();
         }
-        tc_commit(bar_acc_full);
+        if (elect_one()) tc_commit(bar_acc_full);
         ++nphase;
-        if (p.prof && blockIdx.x == 0) p.prof[(size_t)j * 16 + 15] = clock64() - tv0;   // vocab-GEMM phase (issue span)
+        if (profw && lane == 0) p.prof[(size_t)j * 16 + 15] = clock64() - tv0;   // vocab-GEMM phase (issue span)
       }
       __syncwarp();
     }
@@ -697,6 +740,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+int make_map_f16_3d(CUtensorMap* map, const void* ptr, long long rows, int parts, int box_rows);
+
 int make_map_f16(CUtensorMap* map, const void* ptr, long long rows, int box_rows) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
@@ -715,6 +760,29 @@ int make_map_f16(CUtensorMap* map, const void* ptr, long long rows, int box_rows
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     icrl_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %lld)", (int)r, rows);
+    return ICRL_ERR_CUDA;
+  }
+  return ICRL_OK;
+}
+
+int make_map_f16_3d(CUtensorMap* map, const void* ptr, long long rows, int parts, int box_rows) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult qres;
+    void* q = nullptr;
+    ICRL_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qres));
+    ICRL_REQUIRE(q && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled unavailable");
+    fn = reinterpret_cast<EncodeTiledFn>(q);
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)H, (cuuint64_t)rows, (cuuint64_t)parts};
+  const cuuint64_t strides[2] = {(cuuint64_t)H * 2, (cuuint64_t)rows * H * 2};
+  const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 2};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    icrl_set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult %d (rows %lld)", (int)r, rows);
     return ICRL_ERR_CUDA;
   }
   return ICRL_OK;
@@ -765,9 +833,11 @@ int icrl_policy_decode_impl(cudaStream_t st, int B, int V, int p0, int S, int gr
   }
   CUtensorMap mh, mw, mv;
   int rc;
-  if ((rc = make_map_f16(&mh, hparts, (long long)4 * B, BM))) return rc;
-  if ((rc = make_map_f16(&mw, whh_pk, (long long)2 * 4 * H, GN))) return rc;
-  if ((rc = make_map_f16(&mv, wv_pk, (long long)2 * VPAD, VN))) return rc;
+  if (MCAST) rc = make_map_f16(&mh, hparts, (long long)4 * B, A_SLICE_ROWS);
+  else rc = make_map_f16_3d(&mh, hparts, B, 4, BM);
+  if (rc) return rc;
+  if ((rc = make_map_f16_3d(&mw, whh_pk, 4 * H, 2, GN))) return rc;
+  if ((rc = make_map_f16_3d(&mv, wv_pk, VPAD, 2, VN))) return rc;
   DecodeArgs a;
   a.B = B; a.V = V; a.p0 = p0; a.S = S; a.greedy = greedy;
   a.table = table; a.b_v = b_v; a.uniforms = (greedy || forced) ? nullptr : uniforms; a.forced = forced;

@@ -57,6 +57,11 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.u32 %0, 1, 0, P1;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(unsigned bar) {
@@ -143,32 +148,33 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % STAGES;
-        const unsigned ph = (unsigned)(kb / STAGES) & 1u;
-        mbar_wait(smem_u32(&bars[s]), ph);
-        tc_fence_after();
-        const unsigned base = smem_u32(smem + s * STAGE_BYTES);
-        // pairs (i,j), i + j <= 2: (0,0) (0,1) (1,0) (0,2) (1,1) (2,0)
+    // the whole warp runs the loop (descriptors stay in uniform registers); elect.sync picks the issuing lane
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % STAGES;
+      const unsigned ph = (unsigned)(kb / STAGES) & 1u;
+      mbar_wait(smem_u32(&bars[s]), ph);
+      tc_fence_after();
+      const unsigned base = smem_u32(smem + s * STAGE_BYTES);
+      unsigned long long da[PARTS], db[PARTS];
 #pragma unroll
-        for (int pair = 0; pair < 6; ++pair) {
-          const int pi = pair == 2 || pair == 4 ? 1 : (pair == 5 ? 2 : 0);
-          const int pj = pair == 1 || pair == 4 ? 1 : (pair == 3 ? 2 : 0);
-          const unsigned a = base + pi * A_TILE;
-          const unsigned b = base + 3 * A_TILE + pj * B_TILE;
+      for (int i = 0; i < PARTS; ++i) { da[i] = smem_desc(base + i * A_TILE); db[i] = smem_desc(base + 3 * A_TILE + i * B_TILE); }
+      if (elect_one()) {
+        // pairs (i,j), i + j <= 2: (0,0) main -> accumulator kb & 1; (0,1) (1,0) (0,2) (1,1) (2,0) corrections -> accumulator 2
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // main term -> accumulator kb & 1; corrections -> accumulator 2
-            const unsigned acc = pair == 0 ? (unsigned)(kb & 1) * BN : 2u * BN;
-            const unsigned accumulate = pair == 0 ? ((kb >= 2 || k != 0) ? 1u : 0u) : ((kb != 0 || pair != 1 || k != 0) ? 1u : 0u);
-            tc_mma(tmem_base + acc, smem_desc(a + k * UMMA_K * 2), smem_desc(b + k * UMMA_K * 2), IDESC, accumulate);
-          }
+        for (int k = 0; k < BK / UMMA_K; ++k) {          // +2 = 32 bytes along K in 16-byte descriptor units
+          tc_mma(tmem_base + (unsigned)(kb & 1) * BN, da[0] + 2 * k, db[0] + 2 * k, IDESC, (kb >= 2 || k != 0) ? 1u : 0u);
+          tc_mma(tmem_base + 2 * BN, da[0] + 2 * k, db[1] + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+          tc_mma(tmem_base + 2 * BN, da[1] + 2 * k, db[0] + 2 * k, IDESC, 1u);
+          tc_mma(tmem_base + 2 * BN, da[0] + 2 * k, db[2] + 2 * k, IDESC, 1u);
+          tc_mma(tmem_base + 2 * BN, da[1] + 2 * k, db[1] + 2 * k, IDESC, 1u);
+          tc_mma(tmem_base + 2 * BN, da[2] + 2 * k, db[0] + 2 * k, IDESC, 1u);
         }
         tc_commit(smem_u32(&bars[STAGES + s]));                   // stage reusable once these MMAs retire
       }
-      tc_commit(smem_u32(&bars[2 * STAGES]));                     // accumulator complete
+      __syncwarp();
     }
+    if (elect_one()) tc_commit(smem_u32(&bars[2 * STAGES]));      // accumulator complete
+    __syncwarp();
   } else {
     const int q = warp & 3;                                       // TMEM lane quarter this warp may read
     const int row = m0 + 32 * q + lane;

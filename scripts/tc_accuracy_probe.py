@@ -42,3 +42,21 @@ for K in (64, 128, 512, 2048):
     run(256, 256, K, True, positive=True)
     run(256, 256, K, False)
     run(256, 256, K, False, positive=True)
+
+# throughput of the standalone split-bf16 GEMM (decode="tc" path): gate GEMM shape of a 4096-row decode step
+M, N, K = 4096, 2048, 512
+A = torch.randn(M, K, device="cuda"); B = torch.randn(N, K, device="cuda") / K ** 0.5
+C = torch.empty(M, N, device="cuda")
+st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+p = lambda t: ctypes.c_void_p(t.data_ptr())
+pa = torch.empty((3, M, K), dtype=torch.bfloat16, device="cuda"); pb = torch.empty((3, N, K), dtype=torch.bfloat16, device="cuda")
+_lib.call("icrl_split_bf16x3", st, A.numel(), p(A), p(pa), None)
+_lib.call("icrl_split_bf16x3", st, B.numel(), p(B), p(pb), None)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for i in range(23):
+    if i == 3:
+        e0.record()
+    _lib.call("icrl_gemm_bf16x3", st, M, N, K, p(pa), p(pb), p(C), N, None, None)
+e1.record(); torch.cuda.synchronize()
+us = e0.elapsed_time(e1) * 1e3 / 20
+print("gemm_bf16x3 %dx%dx%d: %.1f us, algorithmic %.0f TFLOP/s, executed (6 MMAs) %.0f TFLOP/s" % (M, N, K, us, 2.0 * M * N * K / us / 1e6, 12.0 * M * N * K / us / 1e6))
