@@ -40,6 +40,7 @@ SIGNATURES = {
     "icrl_build_stream_sharded": [P, I, I, I, I, I, P, P, P, P, LP],
     "icrl_chains_fwd_fused_sharded": [P, I, P, I, P, P, P, P, P, P, I, P, P, P, P, P, LP],
     "icrl_chain_lstm_bwd_sharded": [P, I, I, P, P, P, P, P, P, P, LP],
+    "icrl_chain_set_profile": [P],
     "icrl_chain_sync_bytes": [],
     "icrl_chain_lstm_fwd": [P, P, I] + [P] * 10 + [LP],
     "icrl_chain_gru_fwd": [P, P, I] + [P] * 8 + [LP],

@@ -267,6 +267,8 @@ int icrl_chain_lstm_bwd_sharded(void* stream, int shards, int T, const float* W_
   return ICRL_OK;
 }
 
+int icrl_chain_set_profile(void* buf) { icrl_chain_set_profile_impl(reinterpret_cast<long long*>(buf)); return ICRL_OK; }
+
 size_t icrl_chain_sync_bytes(void) { return icrl_chain_sync_bytes_impl(); }
 
 int icrl_chain_lstm_fwd(void* stream, const int* tok_stream, int T, const float* table, const float* W_hh,

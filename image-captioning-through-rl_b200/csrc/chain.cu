@@ -133,17 +133,25 @@ __device__ __forceinline__ bool fetch_exchange_all(const unsigned long long* buf
   unsigned long long a[NV], b[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) ld_tagged2(buf + (v * THREADS + threadIdx.x) * 2, a[v], b[v]);
+  // Poll in ROUNDS: every word that has not arrived is re-read in the same round (one L2 round trip per round).
+  // Re-polling word by word costs one round trip per word, because the first sample of every later word was
+  // taken before the data existed: measured 1,705 / 2,593 / 5,574 cycles of wait at NV = 2 / 4 / 8.
+  unsigned pending = (1u << NV) - 1u, spins = 0;
   bool ok = true;
+  while (true) {
 #pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    unsigned spins = 0;
-    while (!((unsigned)(a[v] >> 32) == tag && (unsigned)(b[v] >> 32) == tag)) {
-      if (++spins >= SPIN_LIMIT || ((spins & 1023u) == 0 && *abort_flag != 0)) { ok = false; break; }
-      ld_tagged2(buf + (v * THREADS + threadIdx.x) * 2, a[v], b[v]);
-    }
+    for (int v = 0; v < NV; ++v)
+      if ((pending >> v & 1u) && (unsigned)(a[v] >> 32) == tag && (unsigned)(b[v] >> 32) == tag) pending &= ~(1u << v);
+    if (pending == 0) break;
+    if (++spins >= SPIN_LIMIT || ((spins & 1023u) == 0 && *abort_flag != 0)) { ok = false; break; }
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      if (pending >> v & 1u) ld_tagged2(buf + (v * THREADS + threadIdx.x) * 2, a[v], b[v]);
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
     reinterpret_cast<float2*>(sm)[v * THREADS + threadIdx.x] =
         make_float2(__uint_as_float((unsigned)a[v]), __uint_as_float((unsigned)b[v]));
-  }
   return ok;
 }
 
@@ -429,8 +437,12 @@ struct ChainFwdBatchArgs {
   float* stash_gates;         // LSTM: [NB][stride][4H] or null
   unsigned long long* xchg;   // [2][NB][H] tagged words, zeroed before launch
   int* abort_flag;
+  long long* prof;            // debug: {exchange wait, GEMV + reduce, pointwise + publish} cycles of CTA 0 thread 0, T
 };
 
+// (Tried and dropped for this exchange, both slower at NB = 8: a unit-major word layout [unit][NB], 393 -> 426 ms, and
+// plain data + one release flag per unit polled with acquire loads, 393 -> 508 ms: the release store waits for the
+// warp's stash writes.)
 template <int NG, int NB>
 __device__ void chain_fwd_batched_body(const ChainFwdBatchArgs& p, int cta, float* sh_h /* [2][NB][H] */) {
   constexpr int GL = 32 / NB;                          // lanes per shard group after the transposed reduction
@@ -466,7 +478,10 @@ __device__ void chain_fwd_batched_body(const ChainFwdBatchArgs& p, int cta, floa
     for (int g = 0; g < NG; ++g) xg[g] = p.table[(size_t)tok0 * (NG * H) + g * H + unit];
   }
 
+  long long prof_wait = 0, prof_gemv = 0, prof_rest = 0;
+  const bool prof = p.prof != nullptr && cta == 0 && threadIdx.x == 0;
   for (int t = 0; t < p.T; ++t) {
+    const long long c0 = prof ? clock64() : 0;
     const int buf = t & 1;
     float* hb = sh_h + buf * NB * H;
     bool ok = true;
@@ -475,6 +490,7 @@ __device__ void chain_fwd_batched_body(const ChainFwdBatchArgs& p, int cta, floa
       if (threadIdx.x == 0) atomicExch(p.abort_flag, 1);
       return;
     }
+    const long long c1 = prof ? clock64() : 0;
     float xg_n[NG];
     {
       const int tk = tok_next;
@@ -510,6 +526,7 @@ __device__ void chain_fwd_batched_body(const ChainFwdBatchArgs& p, int cta, floa
     float sum[NG];
 #pragma unroll
     for (int g = 0; g < NG; ++g) sum[g] = reduce_transposed<NB>(acc[g], lane);
+    const long long c2 = prof ? clock64() : 0;
 
     float hnew;
     if constexpr (NG == 4) {
@@ -535,7 +552,9 @@ __device__ void chain_fwd_batched_body(const ChainFwdBatchArgs& p, int cta, floa
     if (sub == 5 % GL) my_h[(size_t)(t + 1) * H + unit] = hnew;
 #pragma unroll
     for (int g = 0; g < NG; ++g) xg[g] = xg_n[g];
+    if (prof) { const long long c3 = clock64(); prof_wait += c1 - c0; prof_gemv += c2 - c1; prof_rest += c3 - c2; }
   }
+  if (prof) { p.prof[0] = prof_wait; p.prof[1] = prof_gemv; p.prof[2] = prof_rest; p.prof[3] = p.T; }
 }
 
 template <int NB>
@@ -640,15 +659,20 @@ __global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_batched_kernel(Chai
     tk_prev = t > 1 ? my_take[t - 2] : -1;
 
     if (it > 0) {
+      unsigned pending = (1u << NB) - 1u, spins = 0;       // rounds: all missing words are re-read together
+      while (true) {
 #pragma unroll
-      for (int v = 0; v < NB; ++v) {
-        unsigned spins = 0;
-        while (!((unsigned)(pa[v] >> 32) == (unsigned)it && (unsigned)(pb[v] >> 32) == (unsigned)it)) {
-          if (++spins >= SPIN_LIMIT || ((spins & 1023u) == 0 && *(volatile int*)p.abort_flag != 0)) { ok = false; break; }
-          ld_tagged2(src + (size_t)v * H, pa[v], pb[v]);
-        }
-        dh[v] = make_float2(__uint_as_float((unsigned)pa[v]), __uint_as_float((unsigned)pb[v]));
+        for (int v = 0; v < NB; ++v)
+          if ((pending >> v & 1u) && (unsigned)(pa[v] >> 32) == (unsigned)it && (unsigned)(pb[v] >> 32) == (unsigned)it)
+            pending &= ~(1u << v);
+        if (pending == 0) break;
+        if (++spins >= SPIN_LIMIT || ((spins & 1023u) == 0 && *(volatile int*)p.abort_flag != 0)) { ok = false; break; }
+#pragma unroll
+        for (int v = 0; v < NB; ++v)
+          if (pending >> v & 1u) ld_tagged2(src + (size_t)v * H, pa[v], pb[v]);
       }
+#pragma unroll
+      for (int v = 0; v < NB; ++v) dh[v] = make_float2(__uint_as_float((unsigned)pa[v]), __uint_as_float((unsigned)pb[v]));
     }
 #pragma unroll
     for (int v = 0; v < NB; ++v) {
@@ -943,6 +967,8 @@ int icrl_chain_check_impl(cudaStream_t st, void* sync_state) {
 
 
 // ---- batched launchers (nb chain shards; see the kernels above)
+static long long* g_chain_prof = nullptr;      // icrl_chain_set_profile: 8 device int64 (LSTM then GRU shard kernels)
+void icrl_chain_set_profile_impl(long long* buf) { g_chain_prof = buf; }
 static int coop_launch_smem(const void* fn, int grid, void** args, size_t smem, cudaStream_t st) {
   int dev = 0, sms = 0, per_sm = 0;
   ICRL_CUDA(cudaGetDevice(&dev));
@@ -964,10 +990,10 @@ int icrl_chains_fwd_fused_batched_impl(cudaStream_t st, int nb, const int* v_str
   ChainFwdBatchArgs a, b;
   a.stream = v_stream; a.T = v_T; a.stride = (long long)v_T + 1; a.table = v_table; a.w_hh = v_w_hh; a.b_hn = nullptr;
   a.stash_h = v_stash_h; a.stash_c = v_stash_c; a.stash_gates = v_stash_gates; a.xchg = sync_xchg(sync_state, 0);
-  a.abort_flag = sync_abort(sync_state);
+  a.abort_flag = sync_abort(sync_state); a.prof = g_chain_prof;
   b.stream = r_stream; b.T = r_T; b.stride = (long long)r_T + 1; b.table = r_table; b.w_hh = r_w_hh; b.b_hn = r_b_hn;
   b.stash_h = r_stash_h; b.stash_c = nullptr; b.stash_gates = nullptr; b.xchg = sync_xchg(sync_state, 1);
-  b.abort_flag = sync_abort(sync_state);
+  b.abort_flag = sync_abort(sync_state); b.prof = g_chain_prof ? g_chain_prof + 4 : nullptr;
   const size_t smem = (size_t)2 * nb * H * sizeof(float);
   if (v_T > 0) {
     void* args[] = {&a, &b};

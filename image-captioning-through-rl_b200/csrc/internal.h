@@ -74,3 +74,4 @@ int icrl_chains_fwd_fused_batched_impl(cudaStream_t st, int nb, const int* v_str
 int icrl_chain_lstm_bwd_batched_impl(cudaStream_t st, int shards, int T, const float* w_hh, const float* stash_gates,
                                      const float* stash_c, const int* take, const float* dh_take, float* dgates,
                                      void* sync_state);
+void icrl_chain_set_profile_impl(long long* buf);

@@ -182,6 +182,9 @@ int icrl_chains_fwd_fused_sharded(void* stream, int shards, const int* v_stream,
 int icrl_chain_lstm_bwd_sharded(void* stream, int shards, int T, const float* W_hh, const float* stash_gates,
                                 const float* stash_c, const int* take, const float* dh_take, float* dgates,
                                 void* sync_state, int* launches);
+/* Debug aid: when buf != NULL (8 device int64), CTA 0 / thread 0 of the sharded forward chains accumulates its cycles per
+ * phase {exchange wait, GEMV + reduce, pointwise + publish, T}: [0..3] value LSTM, [4..7] reward GRU. */
+int icrl_chain_set_profile(void* buf);
 /* synchronises `stream`; ICRL_ERR_WATCHDOG if any chain launch since the last check gave up waiting */
 int icrl_chain_check(void* stream, void* sync_state);
 /* dst[r][:] = src[idx[r] + row_offset][:]  (rows of 512 floats; h at the take positions) */
