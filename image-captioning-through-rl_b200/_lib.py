@@ -35,6 +35,8 @@ SIGNATURES = {
     "icrl_policy_rollout_fwd": [P, I, I, I, I, I] + [P] * 17 + [LP],
     "icrl_policy_rollout_bwd": [P, I, I, I, I, I] + [P] * 19 + [Z] + [P] * 9 + [LP],
     "icrl_colsum_ws_floats": [L, I],
+    "icrl_lstm_seq_fwd": [P, I, I] + [P] * 8 + [LP],
+    "icrl_lstm_seq_bwd": [P, I, I, I, I] + [P] * 14 + [Z] + [P] * 6 + [LP],
     "icrl_stream_len": [I, I, I, I],
     "icrl_build_stream": [P, I, I, I, I, P, P, P, P, LP],
     "icrl_build_stream_sharded": [P, I, I, I, I, I, P, P, P, P, LP],

@@ -165,6 +165,59 @@ int icrl_policy_rollout_fwd_fused(void* stream, int B, int V, int p0, int S, int
   return ICRL_OK;
 }
 
+// ---- direction-agnostic teacher-forced LSTM sequence (bidirectional policy variant, models.py:59-78: each direction
+//      is one call; the caller reverses the token columns for the reverse direction).
+int icrl_lstm_seq_fwd(void* stream, int B, int n, const float* h0, const int* tokcm, const float* table,
+                      const float* W_hh, float* Hs, float* Cs, float* Gs, float* gpre, int* launches) {
+  ICRL_REQUIRE(B > 0 && n > 0, "bad sequence shape");
+  cudaStream_t st = S_(stream);
+  const size_t BH = (size_t)B * H;
+  ICRL_CUDA(cudaMemcpyAsync(Hs, h0, BH * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  ICRL_CUDA(cudaMemsetAsync(Cs, 0, BH * sizeof(float), st));
+  for (int j = 0; j < n; ++j) {
+    TRY(icrl_gemm_f32_impl(st, 0, 1, B, 4 * H, H, Hs + j * BH, H, W_hh, H, gpre, 4 * H, nullptr, 0.f, nullptr, 0, launches));
+    TRY(icrl_lstm_pointwise_fwd(st, B, gpre, table, tokcm + (size_t)j * B, Cs + j * BH, Gs + (size_t)j * B * 4 * H,
+                                Cs + (j + 1) * BH, Hs + (j + 1) * BH));
+    bump(launches, 1);
+  }
+  return ICRL_OK;
+}
+
+// dH [n][B][512] = dL/d(h after cell j).  Outputs (overwritten): dh0 [B][512], dE [V][D] (nullable), dW_ih [2048][D],
+// dW_hh [2048][512], db_ih, db_hh [2048].  Workspaces as icrl_policy_rollout_bwd.
+int icrl_lstm_seq_bwd(void* stream, int B, int n, int V, int D, const int* tokcm, const float* Hs, const float* Cs,
+                      const float* Gs, const float* dH, const float* W_hh, const float* E, const float* W_ih, float* DG,
+                      float* dh, float* dc, float* dtable, float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes,
+                      float* dh0, float* dE, float* dW_ih, float* dW_hh, float* db_ih, float* db_hh, int* launches) {
+  ICRL_REQUIRE(B > 0 && n > 0, "bad sequence shape");
+  cudaStream_t st = S_(stream);
+  const size_t BH = (size_t)B * H;
+  float* dh_cur = dh;
+  float* dh_nxt = dh + BH;
+  ICRL_CUDA(cudaMemsetAsync(dh_cur, 0, BH * sizeof(float), st));
+  ICRL_CUDA(cudaMemsetAsync(dc, 0, BH * sizeof(float), st));
+  for (int j = n - 1; j >= 0; --j) {
+    float* dg = DG + (size_t)j * B * 4 * H;
+    TRY(icrl_lstm_pointwise_bwd(st, B, dh_cur, dH + (size_t)j * BH, dc, Gs + (size_t)j * B * 4 * H, Cs + j * BH,
+                                Cs + (j + 1) * BH, dg));
+    bump(launches, 1);
+    TRY(icrl_gemm_f32_impl(st, 0, 0, B, H, 4 * H, dg, 4 * H, W_hh, H, dh_nxt, H, nullptr, 0.f, nullptr, 0, launches));
+    float* t = dh_cur; dh_cur = dh_nxt; dh_nxt = t;
+  }
+  ICRL_CUDA(cudaMemcpyAsync(dh0, dh_cur, BH * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  const long long nB = (long long)n * B;
+  TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, H, (int)nB, DG, 4 * H, Hs, H, dW_hh, H, nullptr, 0.f, gemm_ws, gemm_ws_bytes, launches));
+  ICRL_CUDA(cudaMemsetAsync(dtable, 0, (size_t)V * 4 * H * sizeof(float), st));
+  TRY(icrl_scatter_add_rows(st, nB, 4 * H, DG, tokcm, dtable));
+  bump(launches, 1);
+  TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, D, V, dtable, 4 * H, E, D, dW_ih, D, nullptr, 0.f, nullptr, 0, launches));
+  if (dE) TRY(icrl_gemm_f32_impl(st, 0, 0, V, D, 4 * H, dtable, 4 * H, W_ih, D, dE, D, nullptr, 0.f, nullptr, 0, launches));
+  TRY(icrl_wcolsum(st, V, 4 * H, dtable, nullptr, 0, colsum_ws, db_ih));
+  bump(launches, 2);
+  ICRL_CUDA(cudaMemcpyAsync(db_hh, db_ih, 4 * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return ICRL_OK;
+}
+
 size_t icrl_colsum_ws_floats(long long rows, int cols) { return (size_t)icrl_wcolsum_chunks(rows) * cols; }
 
 int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, int D, const float* features, const float* E,

@@ -78,6 +78,9 @@ class A2CEngine:
         self.value = a2c_network.value_network
         self.reward = reward_network
         self.a2c = a2c_network
+        if any(getattr(m, "bidirectional", False) for m in (self.policy, self.value, self.reward)):
+            raise NotImplementedError("the fused engine is built for the unidirectional networks; bidirectional=True runs "
+                                      "on the module (autograd) route -- icrl_b200.trainers switches to it by itself")
         dev = self.policy.linear2vocab.weight.device
         if dev.type != "cuda":
             raise _lib.IcrlError("A2CEngine needs the networks on a CUDA device (no CPU fallback)")

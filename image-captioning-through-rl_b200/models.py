@@ -53,9 +53,10 @@ def _p(t):
 
 
 def _unsupported(bidirectional, pretrained_embeddings=None):
-    # the bidirectional variant is outside the built scope (no BASELINE config uses it)
-    if bidirectional:
-        raise NotImplementedError("bidirectional=True is outside the B200 hot path (SURVEY.md 8f)")
+    """Both constructor variants are built: frozen pretrained embeddings run on every path; bidirectional=True runs on
+    the module (autograd) route only -- the fused A2CEngine refuses bidirectional networks and icrl_b200.trainers
+    falls back to the reference-style loop for them."""
+    return None
 
 
 def _embedding(vocab_size, wordvec_dim, pretrained_embeddings):
@@ -141,6 +142,49 @@ class _PolicyFn(torch.autograd.Function):
                       _p(dh), _p(dc), _p(dtable), _p(csws), _p(ws), ws.numel() * 4,
                       _p(dE), _p(dWc), _p(dbc), _p(dWih), _p(dWhh), _p(dbih), _p(dbhh), _p(dWv), _p(dbv), None)
         return None, None, dE, dWc, dbc, dWih, dWhh, dbih, dbhh, dWv, dbv
+
+
+class _LstmSeqFn(torch.autograd.Function):
+    """Teacher-forced LSTM over token columns [n][B] from h0 (c0 = 0): h after every cell, [n][B][512].  One
+    direction of the bidirectional policy (models.py:59-78); the reverse direction passes the columns flipped."""
+
+    @staticmethod
+    def forward(ctx, tok_cm, h0, E, W_ih, W_hh, b_ih, b_hh):
+        dev = E.device
+        n, B = tok_cm.shape
+        V = E.shape[0]
+        st = _st(dev)
+        new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            table = new(V, 4 * HID)
+            _lib.call("icrl_pack_gate_table", st, V, 4 * HID, 4 * HID, E.shape[1], _p(E), _p(W_ih), _p(b_ih), _p(b_hh), _p(table), None)
+            tok = tok_cm.contiguous()
+            h0c = h0.contiguous()
+            Hs, Cs, Gs, gpre = new(n + 1, B, HID), new(n + 1, B, HID), new(n, B, 4 * HID), new(B, 4 * HID)
+            _lib.call("icrl_lstm_seq_fwd", st, B, n, _p(h0c), _p(tok), _p(table), _p(W_hh), _p(Hs), _p(Cs), _p(Gs), _p(gpre), None)
+        ctx.save_for_backward(tok, E, W_ih, W_hh, Hs, Cs, Gs)
+        return Hs[1:].clone()
+
+    @staticmethod
+    def backward(ctx, dH):
+        tok, E, W_ih, W_hh, Hs, Cs, Gs = ctx.saved_tensors
+        n, B = tok.shape
+        V, D = E.shape
+        dev = E.device
+        st = _st(dev)
+        new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            dHc = dH.contiguous()
+            DG, dh, dc, dtable = new(n * B, 4 * HID), new(2 * B, HID), new(B, HID), new(V, 4 * HID)
+            cs = int(_lib.call("icrl_colsum_ws_floats", max(n * B, V), 4 * HID))
+            csws, ws = new(cs), _gemm_ws(dev)
+            dh0 = new(B, HID)
+            dE = new(V, D) if ctx.needs_input_grad[2] else None
+            dWih, dWhh, dbih, dbhh = new(4 * HID, D), new(4 * HID, HID), new(4 * HID), new(4 * HID)
+            _lib.call("icrl_lstm_seq_bwd", st, B, n, V, D, _p(tok), _p(Hs), _p(Cs), _p(Gs), _p(dHc), _p(W_hh), _p(E), _p(W_ih),
+                      _p(DG), _p(dh), _p(dc), _p(dtable), _p(csws), _p(ws), ws.numel() * 4, _p(dh0), _p(dE), _p(dWih), _p(dWhh),
+                      _p(dbih), _p(dbhh), None)
+        return None, dh0, dE, dWih, dWhh, dbih, dbhh
 
 
 class _ChainLSTMFn(torch.autograd.Function):
@@ -372,10 +416,11 @@ class PolicyNetwork(_KernelModule):
         self.word_to_idx = word_to_idx
         self.idx_to_word = {i: w for w, i in word_to_idx.items()}
         vocab_size = len(word_to_idx)
+        num_dim = 2 if bidirectional else 1                    # models.py:58
         self.caption_embedding, wordvec_dim = _embedding(vocab_size, wordvec_dim, pretrained_embeddings)
-        self.cnn2linear = nn.Linear(input_dim, hidden_dim)
-        self.lstm = nn.LSTM(wordvec_dim, hidden_dim, batch_first=True)
-        self.linear2vocab = nn.Linear(hidden_dim, vocab_size)
+        self.cnn2linear = nn.Linear(input_dim, hidden_dim * num_dim)
+        self.lstm = nn.LSTM(wordvec_dim, hidden_dim, batch_first=True, bidirectional=bidirectional)
+        self.linear2vocab = nn.Linear(hidden_dim * num_dim, vocab_size)
         self._rt_init()
 
     def forward(self, features, captions):
@@ -384,6 +429,19 @@ class PolicyNetwork(_KernelModule):
         dev = self._dev()
         B, n = captions.shape
         f = features.reshape(B, HID).to(dev, torch.float32).contiguous()
+        if self.bidirectional:
+            # models.py:76-82: cnn2linear gives both directions' initial states (first half forward, second half
+            # reverse); the reverse direction reads the prefix back to front; logits from [h_fwd, h_rev].
+            L = self.lstm
+            hinit = _LinearFn.apply(f, self.cnn2linear.weight, self.cnn2linear.bias)
+            tok = captions.to(dev).t().to(torch.int32).contiguous()
+            E = self.caption_embedding.weight
+            Hf = _LstmSeqFn.apply(tok, hinit[:, :HID], E, L.weight_ih_l0, L.weight_hh_l0, L.bias_ih_l0, L.bias_hh_l0)
+            Hr = _LstmSeqFn.apply(tok.flip(0), hinit[:, HID:], E, L.weight_ih_l0_reverse, L.weight_hh_l0_reverse,
+                                  L.bias_ih_l0_reverse, L.bias_hh_l0_reverse).flip(0)
+            out = torch.cat((Hf, Hr), dim=2).reshape(n * B, 2 * HID)
+            logits = _LinearFn.apply(out, self.linear2vocab.weight, self.linear2vocab.bias)
+            return logits.view(n, B, -1).permute(1, 0, 2)
         return _PolicyFn.apply(f, captions.to(dev).to(torch.int64).contiguous(), self.caption_embedding.weight,
                                self.cnn2linear.weight, self.cnn2linear.bias, self.lstm.weight_ih_l0, self.lstm.weight_hh_l0,
                                self.lstm.bias_ih_l0, self.lstm.bias_hh_l0, self.linear2vocab.weight, self.linear2vocab.bias)
@@ -406,20 +464,35 @@ class _ChainRNN(_KernelModule):
         (value) path records autograd history, including through the carried state."""
         dev = self._dev()
         n, B = captions_cm.shape
+        E = self.caption_embedding.weight
+        cm = captions_cm.contiguous()
+        # bidirectional (models.py:120, 215): the reverse direction walks every column bottom-up from its own carried
+        # state (hidden_cell[...][1]); its outputs are flipped back to row order and concatenated -> (B, 1024)
+        cm_rev = cm.flip(1).contiguous() if self.bidirectional else None
         if kind == "lstm":
             rnn = self.lstm
             h0 = self.hidden_cell[0].to(dev, torch.float32)
             c0 = self.hidden_cell[1].to(dev, torch.float32)
-            h_last, h_out, c_out = _ChainLSTMFn.apply(captions_cm.contiguous(), h0, c0, self.caption_embedding.weight,
-                                                      rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0)
-            self.hidden_cell = (h_out.view(1, 1, HID), c_out.view(1, 1, HID))
-            return h_last
+            h_last, h_out, c_out = _ChainLSTMFn.apply(cm, h0[0], c0[0], E, rnn.weight_ih_l0, rnn.weight_hh_l0,
+                                                      rnn.bias_ih_l0, rnn.bias_hh_l0)
+            if not self.bidirectional:
+                self.hidden_cell = (h_out.view(1, 1, HID), c_out.view(1, 1, HID))
+                return h_last
+            r_last, rh_out, rc_out = _ChainLSTMFn.apply(cm_rev, h0[1], c0[1], E, rnn.weight_ih_l0_reverse,
+                                                        rnn.weight_hh_l0_reverse, rnn.bias_ih_l0_reverse,
+                                                        rnn.bias_hh_l0_reverse)
+            self.hidden_cell = (torch.stack((h_out, rh_out)).view(2, 1, HID), torch.stack((c_out, rc_out)).view(2, 1, HID))
+            return torch.cat((h_last, r_last.flip(0)), dim=1)
         rnn = self.gru
         h0 = self.hidden_cell.to(dev, torch.float32)
-        h_last, h_out = _ChainGRUFn.apply(captions_cm.contiguous(), h0, self.caption_embedding.weight, rnn.weight_ih_l0,
-                                          rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0)
-        self.hidden_cell = h_out.view(1, 1, HID)
-        return h_last
+        h_last, h_out = _ChainGRUFn.apply(cm, h0[0], E, rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0)
+        if not self.bidirectional:
+            self.hidden_cell = h_out.view(1, 1, HID)
+            return h_last
+        r_last, rh_out = _ChainGRUFn.apply(cm_rev, h0[1], E, rnn.weight_ih_l0_reverse, rnn.weight_hh_l0_reverse,
+                                           rnn.bias_ih_l0_reverse, rnn.bias_hh_l0_reverse)
+        self.hidden_cell = torch.stack((h_out, rh_out)).view(2, 1, HID)
+        return torch.cat((h_last, r_last.flip(0)), dim=1)
 
     def forward(self, captions):
         """captions (B,) -> (B,1,512): the column is a length-B sequence (models.py:130-135 / 223-228)."""
@@ -435,11 +508,12 @@ class ValueNetworkRNN(_ChainRNN):
         self._common_init(word_to_idx, hidden_dim, pretrained_embeddings, bidirectional)
         self.caption_embedding, wordvec_dim = _embedding(len(word_to_idx), wordvec_dim, pretrained_embeddings)
         self.init_hidden()
-        self.lstm = nn.LSTM(wordvec_dim, hidden_dim)
+        self.lstm = nn.LSTM(wordvec_dim, hidden_dim, bidirectional=bidirectional)
 
     def init_hidden(self):
         """models.py:122-128"""
-        self.hidden_cell = (torch.zeros(1, 1, self.hidden_dim).to(device), torch.zeros(1, 1, self.hidden_dim).to(device))
+        d = 2 if self.bidirectional else 1
+        self.hidden_cell = (torch.zeros(d, 1, self.hidden_dim).to(device), torch.zeros(d, 1, self.hidden_dim).to(device))
 
 
 class ValueNetwork(_KernelModule):
@@ -453,6 +527,8 @@ class ValueNetwork(_KernelModule):
                                       bidirectional=bidirectional)
         self.linear1 = nn.Linear(1024, 512)
         self.linear2 = nn.Linear(512, 1)
+        if bidirectional:
+            self.rnn_linear = nn.Linear(1024, 512)           # models.py:163-164
         self._rt_init()
 
     def forward(self, features, captions):
@@ -460,6 +536,8 @@ class ValueNetwork(_KernelModule):
         chain, the head uses the h after each row of the last column (models.py:166-180)."""
         dev = self._dev()
         h = self.valrnn._run_columns(self.valrnn._tokcm(captions, dev), "lstm")
+        if self.bidirectional:
+            h = _LinearFn.apply(h, self.rnn_linear.weight, self.rnn_linear.bias)     # models.py:171-172
         f = features.to(dev, torch.float32).contiguous()
         return _ValueHeadFn.apply(f, h, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias)
 
@@ -471,11 +549,11 @@ class RewardNetworkRNN(_ChainRNN):
         self._common_init(word_to_idx, hidden_dim, pretrained_embeddings, bidirectional)
         self.caption_embedding, wordvec_dim = _embedding(len(word_to_idx), wordvec_dim, pretrained_embeddings)
         self.init_hidden()
-        self.gru = nn.GRU(wordvec_dim, hidden_dim)
+        self.gru = nn.GRU(wordvec_dim, hidden_dim, bidirectional=bidirectional)
 
     def init_hidden(self):
         """models.py:217-221"""
-        self.hidden_cell = torch.zeros(1, 1, self.hidden_dim).to(device)
+        self.hidden_cell = torch.zeros(2 if self.bidirectional else 1, 1, self.hidden_dim).to(device)
 
 
 class RewardNetwork(_KernelModule):
@@ -488,7 +566,7 @@ class RewardNetwork(_KernelModule):
         self.rewrnn = RewardNetworkRNN(word_to_idx, pretrained_embeddings=pretrained_embeddings,
                                        bidirectional=bidirectional)
         self.visual_embed = nn.Linear(512, 512)
-        self.semantic_embed = nn.Linear(512, 512)
+        self.semantic_embed = nn.Linear(1024 if bidirectional else 512, 512)     # models.py:247-251
         self._rt_init()
 
     def forward(self, features, captions):

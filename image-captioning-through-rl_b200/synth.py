@@ -25,7 +25,7 @@ def _uni(rs, shape, fan):
     return rs.uniform(-k, k, size=shape).astype(np.float32)
 
 
-def make_weights(seed=0, vocab=VOCAB, emb_scale=1.0, wordvec_dim=H):
+def make_weights(seed=0, vocab=VOCAB, emb_scale=1.0, wordvec_dim=H, bidirectional=False):
     """Return {'policy','value','reward'} -> state_dict of float32 torch tensors.  wordvec_dim != 512 gives the
     layout of the frozen-pretrained-embedding variant (models.py:61-63): E (V, D), W_ih (gates, D)."""
     D = wordvec_dim
@@ -64,6 +64,24 @@ def make_weights(seed=0, vocab=VOCAB, emb_scale=1.0, wordvec_dim=H):
         "semantic_embed.weight": _uni(rs, (H, H), H),
         "semantic_embed.bias": _uni(rs, (H,), H),
     }
+    if bidirectional:
+        # bidirectional variant (models.py:59-69, 120, 163-164, 215, 247-251): reverse-direction RNN weights, 1024-wide
+        # cnn2linear / linear2vocab / semantic_embed, value rnn_linear.  Drawn from a second stream so that the
+        # unidirectional draws above stay what the committed fixtures were generated with.
+        r2 = np.random.RandomState(3000 + seed)
+        for sd, pre, G in ((policy, "lstm.", 4 * H), (value, "valrnn.lstm.", 4 * H), (reward, "rewrnn.gru.", 3 * H)):
+            sd[pre + "weight_ih_l0_reverse"] = _uni(r2, (G, D), H)
+            sd[pre + "weight_hh_l0_reverse"] = _uni(r2, (G, H), H)
+            sd[pre + "bias_ih_l0_reverse"] = _uni(r2, (G,), H)
+            sd[pre + "bias_hh_l0_reverse"] = _uni(r2, (G,), H)
+        policy["cnn2linear.weight"] = _uni(r2, (2 * H, H), H)
+        policy["cnn2linear.bias"] = _uni(r2, (2 * H,), H)
+        policy["linear2vocab.weight"] = _uni(r2, (vocab, 2 * H), 2 * H)
+        policy["linear2vocab.bias"] = _uni(r2, (vocab,), 2 * H)
+        value["rnn_linear.weight"] = _uni(r2, (H, 2 * H), 2 * H)
+        value["rnn_linear.bias"] = _uni(r2, (H,), 2 * H)
+        reward["semantic_embed.weight"] = _uni(r2, (H, 2 * H), 2 * H)
+        reward["semantic_embed.bias"] = _uni(r2, (H,), 2 * H)
     out = {}
     for name, sd in (("policy", policy), ("value", value), ("reward", reward)):
         out[name] = {k: torch.from_numpy(v) for k, v in sd.items()}

@@ -89,6 +89,15 @@ def _np(x):
 def GenerateCaptionsGreedy(features, captions, policy_network):
     """MAX_SEQ_LEN-1 greedy steps from column 0, no early stop: (B,17) int64 (trainers.py:57-70)."""
     features, captions = _np(features), _np(captions)
+    if getattr(policy_network, "bidirectional", False):
+        # module route (the fused decode kernel is unidirectional): the reference's loop, trainers.py:65-69
+        dev = policy_network.linear2vocab.weight.device
+        feats = torch.as_tensor(features, device=dev).float().unsqueeze(0)
+        gen = torch.as_tensor(captions[:, 0:1], device=dev).long()
+        with torch.no_grad():
+            for _ in range(MAX_SEQ_LEN - 1):
+                gen = torch.cat((gen, policy_network(feats, gen)[:, -1:, :].argmax(dim=2)), dim=1)
+        return gen
     eng = getattr(policy_network, "_icrl_greedy", None)
     if eng is None:
         eng = _PolicyOnlyEngine(policy_network)
@@ -309,10 +318,50 @@ def train_value_network(train_data, network_paths, plot_dir, bidirectional, epoc
     return value_network
 
 
+class _ModuleRouteResult:
+    def __init__(self, loss, mean_reward, mean_adv):
+        self.loss, self.mean_reward, self.mean_adv = loss, mean_reward, mean_adv
+
+
+def _module_route_step(a2c_network, reward_network, features, captions, level):
+    """One minibatch through the modules' autograd instead of the fused engine (used for the bidirectional variant):
+    the reference's loop body, trainers.py:428-479 / 544-593.  Leaves the gradients in .grad; returns None when the
+    curriculum level does not fit (trainers.py:550)."""
+    from .engine import plan_rollout
+    p0, S = plan_rollout(captions, level)
+    if p0 < 1:
+        return None
+    dev = a2c_network.policy_network.linear2vocab.weight.device
+    feats = torch.as_tensor(np.asarray(features), device=dev).float()
+    caps_in = torch.as_tensor(np.asarray(captions)[:, :p0], device=dev).long()
+    values, rewards, log_probs = [], [], []
+    for _ in range(S):
+        value, logits = a2c_network(feats, caps_in)
+        probs = F.softmax(logits, dim=2)
+        dist = probs.detach().cpu().numpy()[:, 0]
+        acts = [np.random.choice(probs.shape[-1], p=dist[i]) for i in range(dist.shape[0])]     # trainers.py:447-450
+        gen = torch.from_numpy(np.array(acts)).unsqueeze(-1).to(dev)
+        caps_in = torch.cat((caps_in, gen), dim=1)
+        log_probs.append(torch.log(probs[:, 0, :].gather(1, gen)))
+        rewards.append(GetRewards(feats, caps_in, reward_network))
+        values.append(value)
+    values = torch.stack(values, dim=1).squeeze()
+    rewards = torch.stack(rewards, dim=1).squeeze()
+    log_probs = torch.stack(log_probs, dim=1).squeeze()
+    advantage = values - rewards
+    loss = (-log_probs * advantage).mean() + 0.5 * advantage.pow(2).mean()
+    for p in a2c_network.parameters():
+        p.grad = None
+    loss.backward()
+    return _ModuleRouteResult(float(loss), float(rewards.mean()), float(advantage.mean()))
+
+
 def _run_minibatches(train_data, a2c_network, reward_network, optimizer, writer, batch_size, epoch, level, tag, best):
-    eng = _engine_for(a2c_network, reward_network)
+    bidir = getattr(a2c_network.policy_network, "bidirectional", False)
+    eng = None if bidir else _engine_for(a2c_network, reward_network)
     for minibatch_id, (captions, features, _) in enumerate(get_coco_minibatches(train_data, batch_size=batch_size)):
-        res = eng.step(features, captions, level=level)
+        res = (_module_route_step(a2c_network, reward_network, features, captions, level) if bidir
+               else eng.step(features, captions, level=level))
         if res is not None:                           # curriculum: prefix shorter than 1 => skipped (trainers.py:550)
             optimizer.step()                          # gradients already sit in .grad (flat bucket)
             loss = res.loss

@@ -114,6 +114,18 @@ int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, int D, co
                             float* dW_cnn, float* db_cnn, float* dW_ih, float* dW_hh, float* db_ih, float* db_hh,
                             float* dW_v, float* db_v, int* launches);
 size_t icrl_colsum_ws_floats(long long rows, int cols);
+/* ---- teacher-forced LSTM sequence, one direction (bidirectional policy variant, models.py:59-78; for the reverse
+ *      direction the caller passes the token columns reversed).  Cell j consumes tokcm[j][:]; Hs/Cs [(n+1)][B][512]
+ *      (row 0 = h0 / 0), Gs [n][B][2048]; gpre: workspace [B][2048].
+ *      Backward: dH [n][B][512] = dL/d(h after cell j); outputs overwritten: dh0 [B][512], dE [V][D] (nullable),
+ *      dW_ih [2048][D], dW_hh [2048][512], db_ih, db_hh [2048]; DG [n*B][2048], dh [2][B][512], dc [B][512],
+ *      dtable [V][2048], colsum_ws / gemm_ws as icrl_policy_rollout_bwd. */
+int icrl_lstm_seq_fwd(void* stream, int B, int n, const float* h0, const int* tokcm, const float* table,
+                      const float* W_hh, float* Hs, float* Cs, float* Gs, float* gpre, int* launches);
+int icrl_lstm_seq_bwd(void* stream, int B, int n, int V, int D, const int* tokcm, const float* Hs, const float* Cs,
+                      const float* Gs, const float* dH, const float* W_hh, const float* E, const float* W_ih, float* DG,
+                      float* dh, float* dc, float* dtable, float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes,
+                      float* dh0, float* dE, float* dW_ih, float* dW_hh, float* db_ih, float* db_hh, int* launches);
 
 /* ---- token streams of the batch-as-time chains (models.py:166-169, 253-255).  Block s = columns
  *      0..p0+s-1+extra (extra = 0 value net, 1 reward net; for GetRewards on whole captions use

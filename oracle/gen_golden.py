@@ -83,9 +83,12 @@ def summarize_grads(named_grads):
     return out
 
 
-def build_reference_nets(T, weights, pretrained=False):
+def build_reference_nets(T, weights, pretrained=False, bidirectional=False):
     w2i = synth.word_to_idx(weights["policy"]["caption_embedding.weight"].shape[0])
-    if pretrained:          # frozen pretrained word vectors (models.py:61-63): every net gets its own table
+    if bidirectional:
+        P, V, R = (T.PolicyNetwork(w2i, bidirectional=True), T.ValueNetwork(w2i, bidirectional=True),
+                   T.RewardNetwork(w2i, bidirectional=True))
+    elif pretrained:          # frozen pretrained word vectors (models.py:61-63): every net gets its own table
         P = T.PolicyNetwork(w2i, pretrained_embeddings=weights["policy"]["caption_embedding.weight"].numpy())
         V = T.ValueNetwork(w2i, pretrained_embeddings=weights["value"]["valrnn.caption_embedding.weight"].numpy())
         R = T.RewardNetwork(w2i, pretrained_embeddings=weights["reward"]["rewrnn.caption_embedding.weight"].numpy())
@@ -100,10 +103,10 @@ def build_reference_nets(T, weights, pretrained=False):
     return P, V, R, A
 
 
-def run_reference_a2c(weights, features, captions, seed, level=None, pretrained=False):
+def run_reference_a2c(weights, features, captions, seed, level=None, pretrained=False, bidirectional=False):
     T = import_reference()
     import utilities
-    P, V, R, A = build_reference_nets(T, weights, pretrained)
+    P, V, R, A = build_reference_nets(T, weights, pretrained, bidirectional)
     opt = T.optim.Adam(A.parameters(), lr=1e-4)
     B = captions.shape[0]
     data = {"train_captions": captions, "train_image_idxs": np.arange(B),
@@ -155,10 +158,10 @@ def run_reference_a2c(weights, features, captions, seed, level=None, pretrained=
     return out
 
 
-def case_a2c(name, seed, B, L, level=None, wordvec_dim=512):
-    w = synth.make_weights(seed, wordvec_dim=wordvec_dim)
+def case_a2c(name, seed, B, L, level=None, wordvec_dim=512, bidirectional=False):
+    w = synth.make_weights(seed, wordvec_dim=wordvec_dim, bidirectional=bidirectional)
     f, c = synth.make_inputs(seed, B, L)
-    out = run_reference_a2c(w, f, c, seed, level, pretrained=wordvec_dim != 512)
+    out = run_reference_a2c(w, f, c, seed, level, pretrained=wordvec_dim != 512, bidirectional=bidirectional)
     out.update(seed=seed, B=B, L=L, level=-1 if level is None else level, wordvec_dim=wordvec_dim)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
     print(name, "loss", out["loss"], "tokens", out["tokens"].shape)
@@ -276,6 +279,7 @@ class _Quiet:
 
 CASES = {
     "a2c_b16_l8_wemb300": lambda: case_a2c("a2c_b16_l8_wemb300", 9, 16, 8, wordvec_dim=300),   # SURVEY 8f row 3 (frozen 300-d vectors)
+    "a2c_b12_l7_bidir": lambda: case_a2c("a2c_b12_l7_bidir", 10, 12, 7, bidirectional=True),   # SURVEY 8f row 3 (bidirectional RNNs)
     "pretrain_b12": lambda: case_pretrain("pretrain_b12", 8, 12),
     "lookahead_b6": lambda: case_lookahead("lookahead_b6", 7, 6),
     "greedy_b32": lambda: case_greedy("greedy_b32", 0, 32),                    # BASELINE config 1

@@ -81,8 +81,13 @@ def test_state_dict_layout_matches_reference_keys():
     assert list(A.state_dict().keys()) == list(synth.a2c_state_dict(w).keys())
     assert sum(p.numel() for p in A.parameters()) == 6533613
     assert V.valrnn.hidden_cell[0].shape == (1, 1, 512) and R.rewrnn.hidden_cell.shape == (1, 1, 512)
-    with pytest.raises(NotImplementedError):
-        M.PolicyNetwork(w2i, bidirectional=True)
+    # bidirectional variant: the reference's extra keys exist (models.py:68, 120, 163-164, 215, 251)
+    wb = synth.make_weights(0, bidirectional=True)
+    Pb, Vb, Rb = M.PolicyNetwork(w2i, bidirectional=True), M.ValueNetwork(w2i, bidirectional=True), M.RewardNetwork(w2i, bidirectional=True)
+    for mod, sd in ((Pb, wb["policy"]), (Vb, wb["value"]), (Rb, wb["reward"])):
+        assert set(mod.state_dict()) == set(sd)
+        mod.load_state_dict(sd)
+    assert Vb.valrnn.hidden_cell[0].shape == (2, 1, 512) and Rb.rewrnn.hidden_cell.shape == (2, 1, 512)
 
 
 def test_plan_rollout_rules():

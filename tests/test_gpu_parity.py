@@ -545,3 +545,48 @@ def test_odd_vocabulary_falls_back_to_per_step_decode():
     for k in ("values", "rewards", "logp"):
         assert float(np.abs(res[k].cpu().numpy() - ref[k]).max()) <= TOL, k
     check_grads_vs_oracle(named_grads(A), ref["grads"], GTOL)
+
+
+def test_bidirectional_variant_vs_reference_golden(tmp_path, monkeypatch):
+    """SURVEY 8f row 3 (second half): bidirectional=True networks (models.py:59-78, 120-128, 163-172, 215-221, 247-251)
+    on the module route.  One A2C minibatch driven by icrl_b200.trainers.a2c_training -- which switches to the
+    reference-style loop for bidirectional networks -- against the unmodified reference: loss, mean reward / advantage
+    and all 28 gradients (reverse-direction RNN weights, rnn_linear, 1024-wide cnn2linear / linear2vocab included)."""
+    import icrl_b200.models as M
+    import icrl_b200.trainers as T
+    g = np.load(GOLDEN + "/a2c_b12_l7_bidir.npz")
+    seed, B, L = int(g["seed"]), int(g["B"]), int(g["L"])
+    w = synth.make_weights(seed, bidirectional=True)
+    w2i = synth.word_to_idx()
+    P, V, R = M.PolicyNetwork(w2i, bidirectional=True), M.ValueNetwork(w2i, bidirectional=True), M.RewardNetwork(w2i, bidirectional=True)
+    P.load_state_dict(w["policy"]); V.load_state_dict(w["value"]); R.load_state_dict(w["reward"])
+    assert V.valrnn.hidden_cell[0].shape == (2, 1, 512) and P.linear2vocab.weight.shape == (1004, 1024)
+    R.requires_grad_(False)
+    R.train(False)
+    A = M.AdvantageActorCriticNetwork(V, P).cuda()
+    R = R.cuda()
+    f, c = synth.make_inputs(seed, B, L)
+    data = {"train_captions": c, "train_image_idxs": np.arange(B), "train_features": f, "train_urls": np.array(["u"] * B)}
+    scalars = {}
+
+    class Rec:
+        def __init__(self, *a, **k):
+            pass
+
+        def add_scalar(self, tag, val, step):
+            scalars[tag.split("episodic-")[-1]] = float(val)
+
+    monkeypatch.setattr(T, "SummaryWriter", Rec)
+    monkeypatch.setattr(T.torch, "randperm", lambda n: torch.arange(n))
+    opt = torch.optim.SGD(A.parameters(), lr=0.0)                   # keeps the weights, gradients stay in .grad
+    np.random.seed(seed)
+    T.a2c_training(data, A, R, opt, str(tmp_path), [str(tmp_path / "a.pt")], B, 1)
+    assert abs(scalars["loss"] - float(g["loss"])) <= TOL, scalars
+    assert abs(scalars["mean-rewards"] - float(g["mean_reward"])) <= TOL
+    assert abs(scalars["mean-advantage"] - float(g["mean_adv"])) <= TOL
+    grads = named_grads(A)
+    assert len(grads) == 28
+    _record("a2c_b12_l7_bidir", grad_worst=check_grads_vs_golden(grads, g, GTOL))
+    # greedy decode of a bidirectional policy goes through the module route too
+    toks = T.GenerateCaptionsGreedy(f, np.ones((B, 17), dtype=np.int64), A.policy_network)
+    assert tuple(toks.shape) == (B, 17)
