@@ -26,6 +26,8 @@ SIGNATURES = {
     "icrl_split_bf16x3": [P, L, P, P, LP],
     "icrl_gemm_bf16x3": [P, I, I, I, P, P, P, I, P, LP],
     "icrl_policy_rollout_fwd_tc": [P, I, I, I, I, I] + [P] * 18 + [LP],
+    "icrl_wgrad_tc_ws_bytes": [I, I, L, I],
+    "icrl_wgrad_tc": [P, I, I, L, P, I, P, I, P, I, P, Z, I, LP],
     "icrl_decode_weight_halves": [],
     "icrl_decode_set_profile": [P],
     "icrl_pack_decode_weights": [P, I, P, P, P, LP],
@@ -59,7 +61,7 @@ SIGNATURES = {
     "icrl_reward_cosine_fwd": [P, I, I, P, P, P, LP],
     "icrl_a2c_loss_fwd_bwd": [P, I, I, P, P, P, F, P, P, P, P, LP],
 }
-_RESTYPES = {"icrl_last_error": c_char_p, "icrl_decode_weight_halves": c_size_t, "icrl_colsum_ws_floats": c_size_t, "icrl_stream_len": c_longlong,
+_RESTYPES = {"icrl_last_error": c_char_p, "icrl_wgrad_tc_ws_bytes": c_size_t, "icrl_decode_weight_halves": c_size_t, "icrl_colsum_ws_floats": c_size_t, "icrl_stream_len": c_longlong,
              "icrl_chain_sync_bytes": c_size_t}
 _NO_STATUS = set(_RESTYPES) | {"icrl_version"}
 

@@ -142,6 +142,15 @@ int icrl_policy_rollout_fwd_tc(void* stream, int B, int V, int p0, int S, int gr
 
 int icrl_decode_set_profile(void* buf) { icrl_decode_set_profile_impl(reinterpret_cast<long long*>(buf)); return ICRL_OK; }
 
+size_t icrl_wgrad_tc_ws_bytes(int M, int N, long long T, int splits) { return icrl_wgrad_tc_ws_bytes_impl(M, N, T, splits); }
+
+int icrl_wgrad_tc(void* stream, int M, int N, long long T, const float* A, int lda, const float* B, int ldb, float* C,
+                  int ldc, void* ws, size_t ws_bytes, int splits, int* launches) {
+  TRY(icrl_wgrad_tc_impl(S_(stream), M, N, T, A, lda, B, ldb, C, ldc, ws, ws_bytes, splits));
+  bump(launches, 5);
+  return ICRL_OK;
+}
+
 size_t icrl_decode_weight_halves(void) { return icrl_decode_weight_halves_impl(); }
 
 int icrl_pack_decode_weights(void* stream, int V, const float* W_hh, const float* W_v, void* packed, int* launches) {
@@ -261,8 +270,13 @@ int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, int D, co
   // dh_cur = dL/dh0
   // 5. recurrent weight gradient: DG^T [2048 x nB] * H_prev [nB x 512]
   const long long nB = (long long)n_cell * B;
-  TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, H, (int)nB, DG, 4 * H, Hs, H, dW_hh, H, nullptr, 0.f, gemm_ws, gemm_ws_bytes,
-                         launches));
+  if (gemm_ws_bytes >= icrl_wgrad_tc_ws_bytes_impl(4 * H, H, nB, 2)) {       // tcgen05 (wgrad_tc.cu) when the workspace allows
+    TRY(icrl_wgrad_tc_impl(st, 4 * H, H, nB, DG, 4 * H, Hs, H, dW_hh, H, gemm_ws, gemm_ws_bytes, 2));
+    bump(launches, 5);
+  } else {
+    TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, H, (int)nB, DG, 4 * H, Hs, H, dW_hh, H, nullptr, 0.f, gemm_ws, gemm_ws_bytes,
+                           launches));
+  }
   // 6. gate-table gradient, then its factors
   ICRL_CUDA(cudaMemsetAsync(dtable, 0, (size_t)V * 4 * H * sizeof(float), st));
   TRY(icrl_scatter_add_rows(st, nB, 4 * H, DG, tokcm, dtable));
@@ -439,9 +453,15 @@ int icrl_value_chain_param_grads(void* stream, int T, int V, int D, const int* t
                                  float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE, float* dW_ih,
                                  float* dW_hh, float* db_ih, float* db_hh, int* launches) {
   cudaStream_t st = S_(stream);
-  // dW_hh = sum_t dgates_t (x) h_{t-1};  stash_h row t = h_{t-1}
-  TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, H, T, dgates, 4 * H, stash_h, H, dW_hh, H, nullptr, 0.f, gemm_ws,
-                         gemm_ws_bytes, launches));
+  // dW_hh = sum_t dgates_t (x) h_{t-1};  stash_h row t = h_{t-1}.  With a workspace of icrl_wgrad_tc_ws_bytes(2048, 512,
+  // T, 2) bytes the contraction runs on tcgen05 (wgrad_tc.cu), otherwise on the fp32 SIMT GEMM.
+  if (gemm_ws_bytes >= icrl_wgrad_tc_ws_bytes_impl(4 * H, H, T, 2)) {
+    TRY(icrl_wgrad_tc_impl(st, 4 * H, H, T, dgates, 4 * H, stash_h, H, dW_hh, H, gemm_ws, gemm_ws_bytes, 2));
+    bump(launches, 5);
+  } else {
+    TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, H, T, dgates, 4 * H, stash_h, H, dW_hh, H, nullptr, 0.f, gemm_ws,
+                           gemm_ws_bytes, launches));
+  }
   ICRL_CUDA(cudaMemsetAsync(dtable, 0, (size_t)V * 4 * H * sizeof(float), st));
   TRY(icrl_scatter_add_rows(st, T, 4 * H, dgates, tok_stream, dtable));
   bump(launches, 1);

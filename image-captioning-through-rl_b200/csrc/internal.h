@@ -75,3 +75,6 @@ int icrl_chain_lstm_bwd_batched_impl(cudaStream_t st, int shards, int T, const f
                                      const float* stash_c, const int* take, const float* dh_take, float* dgates,
                                      void* sync_state);
 void icrl_chain_set_profile_impl(long long* buf);
+size_t icrl_wgrad_tc_ws_bytes_impl(int M, int N, long long T, int splits);
+int icrl_wgrad_tc_impl(cudaStream_t st, int M, int N, long long T, const float* A, int lda, const float* B, int ldb,
+                       float* C, int ldc, void* ws, size_t ws_bytes, int splits);

@@ -73,7 +73,7 @@ def plan_rollout(captions, level=None):
 class A2CEngine:
     DECODE_MODES = ("fused", "tc", "simt")
 
-    def __init__(self, a2c_network, reward_network, use_tc=None, decode="fused", chain_shards=1):
+    def __init__(self, a2c_network, reward_network, use_tc=None, decode="fused", chain_shards=1, wgrad="tc"):
         self.policy = a2c_network.policy_network
         self.value = a2c_network.value_network
         self.reward = reward_network
@@ -109,6 +109,11 @@ class A2CEngine:
         # each start from zero state -- the reference run on K minibatches of B/K rows with averaged gradients,
         # i.e. exactly what K data-parallel ranks compute.  K = 1 is the reference's single
         # carried-state chain over the whole batch.  The K chains advance in lockstep on the same CTAs.
+        # wgrad: "tc" = the K = T weight-gradient contraction of the value chain on tcgen05 (wgrad_tc.cu; needs a
+        # workspace of ~10 KB per serial step), "simt" = fp32 CUDA-core GEMM with split-K.
+        if wgrad not in ("tc", "simt"):
+            raise ValueError("wgrad must be 'tc' or 'simt'")
+        self.wgrad = wgrad
         if chain_shards not in (1, 2, 4, 8):
             raise ValueError("chain_shards must be 1, 2, 4 or 8")
         self.chain_shards = int(chain_shards)
@@ -359,6 +364,9 @@ class A2CEngine:
         cs_rows = max(SB, V, B)
         colsum_ws = self._buf("colsum_ws", int(_lib.call("icrl_colsum_ws_floats", cs_rows, 4 * H)) + 2 * H + 4 * H * 8)
         gemm_ws_floats = 24 * 4 * H * H
+        if self.wgrad == "tc":
+            T_total = Tv if self.chain_shards == 1 else self.chain_shards * (Tv + 1)
+            gemm_ws_floats = max(gemm_ws_floats, (int(_lib.call("icrl_wgrad_tc_ws_bytes", 4 * H, H, T_total, 2)) + 3) // 4)
         gemm_ws = self._buf("gemm_ws", gemm_ws_floats)
         # value head -> dh at the take positions + head gradients
         dh_take = self._buf("v_dh_take", SB * H)

@@ -84,6 +84,15 @@ int icrl_policy_rollout_fwd_tc(void* stream, int B, int V, int p0, int S, int gr
                                const long long* forced, int* tokcm, long long* tokens_out, float* logp, float* Hs,
                                float* Cs, float* Gs, float* logits, float* gpre, void* h_parts, int* launches);
 
+/* ---- weight-gradient contraction on tcgen05 (wgrad_tc.cu): C [M][ldc] = A^T B for time-major fp32 operands A [T][lda]
+ *      (M columns), B [T][ldb] (N columns); M, N multiples of 128.  Operands are transposed, scaled per A column and
+ *      split into fp16 pairs by two pre-passes; f32 accumulation in TMEM is flushed to registers every 512 K elements.
+ *      ws: icrl_wgrad_tc_ws_bytes(M, N, T, splits) device bytes.  icrl_value_chain_param_grads takes this path by
+ *      itself when its gemm_ws is at least icrl_wgrad_tc_ws_bytes(2048, 512, T, 2) bytes. */
+size_t icrl_wgrad_tc_ws_bytes(int M, int N, long long T, int splits);
+int icrl_wgrad_tc(void* stream, int M, int N, long long T, const float* A, int lda, const float* B, int ldb, float* C,
+                  int ldc, void* ws, size_t ws_bytes, int splits, int* launches);
+
 /*      The same rollout as ONE persistent kernel (decode.cu): clusters of 8 CTAs own 128 rows each for all
  *      timesteps; gate and vocab GEMMs on tcgen05 (2-part fp16 split, 3 MMAs, f32 accumulation in TMEM) with the
  *      cell update, softmax, inverse-CDF sampling / argmax and log-prob fused into their epilogues.
