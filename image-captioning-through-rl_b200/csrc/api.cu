@@ -210,7 +210,7 @@ int icrl_lstm_seq_bwd(void* stream, int B, int n, int V, int D, const int* tokcm
     TRY(icrl_lstm_pointwise_bwd(st, B, dh_cur, dH + (size_t)j * BH, dc, Gs + (size_t)j * B * 4 * H, Cs + j * BH,
                                 Cs + (j + 1) * BH, dg));
     bump(launches, 1);
-    TRY(icrl_gemm_f32_impl(st, 0, 0, B, H, 4 * H, dg, 4 * H, W_hh, H, dh_nxt, H, nullptr, 0.f, nullptr, 0, launches));
+    TRY(icrl_gemm_f32_impl(st, 0, 0, B, H, 4 * H, dg, 4 * H, W_hh, H, dh_nxt, H, nullptr, 0.f, gemm_ws, gemm_ws_bytes, launches));
     float* t = dh_cur; dh_cur = dh_nxt; dh_nxt = t;
   }
   ICRL_CUDA(cudaMemcpyAsync(dh0, dh_cur, BH * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -264,7 +264,7 @@ int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, int D, co
     TRY(icrl_lstm_pointwise_bwd(st, B, dh_cur, s >= 0 ? dHv + (size_t)s * BH : nullptr, dc,
                                 Gs + (size_t)j * B * 4 * H, Cs + j * BH, Cs + (j + 1) * BH, dg));
     bump(launches, 1);
-    TRY(icrl_gemm_f32_impl(st, 0, 0, B, H, 4 * H, dg, 4 * H, W_hh, H, dh_nxt, H, nullptr, 0.f, nullptr, 0, launches));
+    TRY(icrl_gemm_f32_impl(st, 0, 0, B, H, 4 * H, dg, 4 * H, W_hh, H, dh_nxt, H, nullptr, 0.f, gemm_ws, gemm_ws_bytes, launches));
     float* t = dh_cur; dh_cur = dh_nxt; dh_nxt = t;
   }
   // dh_cur = dL/dh0
