@@ -297,7 +297,11 @@ def main():
                 "traffic": ktraffic, "peak_source": "measured" if peaks else "fallback",
                 "ms_per_launch": kms, "serial_steps_per_launch": ksteps,
                 "ns_per_serial_step": kms * 1e6 / ksteps if ksteps else None,
-                "note": "serial batch-1 recurrence: latency bound, neither HBM nor tensor pipe is the limiter"}
+                "note": "serial batch-1 recurrence: latency bound, neither HBM nor tensor pipe is the limiter",
+                "latency_floor": {"one_way_l2_store_to_poll_ns": 494, "all_to_all_512_words_64_ctas_ns": 782,
+                                  "register_gemv_plus_pointwise_ns": 230,
+                                  "source": "profiles/r01_xchg_bench.log, profiles/r01_chain_micro.log (microbenchmarks, "
+                                            "not measured in this run)"}}
     out = {
         "metric": "A2C train captions/sec", "value": B / (ms_step * 1e-3), "unit": "captions/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
