@@ -53,6 +53,7 @@ SIGNATURES = {
     "icrl_linear_bwd": [P, I, I, I] + [P] * 8 + [Z, LP],
     "icrl_chains_fwd_fused": [P, P, I, P, P, P, P, P, P, I, P, P, P, P, P, LP],
     "icrl_chain_lstm_bwd": [P, I, P, P, P, P, P, P, P, P, P, P, P, LP],
+    "icrl_adam_flat": [P, L, P, P, P, P, F, F, F, F, I, LP],
     "icrl_chain_check": [P, P],
     "icrl_gather_rows": [P, L, P, P, L, P, LP],
     "icrl_value_head_fwd": [P, I, I, P, P, P, P, P, LP],

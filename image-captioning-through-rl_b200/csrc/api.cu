@@ -417,6 +417,14 @@ int icrl_linear_bwd(void* stream, int M, int N, int K, const float* x, const flo
   return ICRL_OK;
 }
 
+int icrl_adam_flat(void* stream, long long n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                   float lr, float beta1, float beta2, float eps, int step, int* launches) {
+  ICRL_REQUIRE(n > 0 && step >= 1, "bad Adam arguments");
+  TRY(icrl_adam_flat_impl(S_(stream), n, params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step));
+  bump(launches, 1);
+  return ICRL_OK;
+}
+
 int icrl_chain_check(void* stream, void* sync_state) { return icrl_chain_check_impl(S_(stream), sync_state); }
 
 int icrl_gather_rows(void* stream, long long R, const float* src, const int* idx, long long row_offset, float* dst,

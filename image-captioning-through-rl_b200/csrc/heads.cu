@@ -200,7 +200,31 @@ __global__ void add_gate_bias_kernel(int V, int G, int fold, const float* __rest
   table[i] += b_ih[j] + (j < fold ? b_hh[j] : 0.f);
 }
 
+// torch.optim.Adam (trainers.py:378, default betas / eps, no weight decay, no amsgrad) on flat arrays, in the order of
+// torch's own kernel: m = lerp(m, g, 1-b1); v = b2 v + (1-b2) g^2; p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps).
+__global__ void adam_flat_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, float one_minus_b1, float b2, float one_minus_b2, float step_size,
+                                 float bc2_sqrt, float eps) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = m[i] + one_minus_b1 * (gi - m[i]);
+    const float vi = b2 * v[i] + one_minus_b2 * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  }
+}
+
 }  // namespace
+
+int icrl_adam_flat_impl(cudaStream_t st, long long n, float* p, const float* g, float* m, float* v, float lr, float b1,
+                        float b2, float eps, int step) {
+  const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
+  adam_flat_kernel<<<(int)min((long long)148 * 8, (n + 255) / 256), 256, 0, st>>>(
+      n, p, g, m, v, 1.f - b1, b2, 1.f - b2, (float)((double)lr / bc1), (float)sqrt(bc2), eps);
+  ICRL_LAUNCH_CHECK();
+  return ICRL_OK;
+}
 
 int icrl_pack_value_head_impl(cudaStream_t st, const float* W1, const float* b1, const float* W2, const float* b2,
                               float* w_eff, float* b_eff) {

@@ -78,3 +78,5 @@ void icrl_chain_set_profile_impl(long long* buf);
 size_t icrl_wgrad_tc_ws_bytes_impl(int M, int N, long long T, int splits);
 int icrl_wgrad_tc_impl(cudaStream_t st, int M, int N, long long T, const float* A, int lda, const float* B, int ldb,
                        float* C, int ldc, void* ws, size_t ws_bytes, int splits);
+int icrl_adam_flat_impl(cudaStream_t st, long long n, float* p, const float* g, float* m, float* v, float lr, float b1,
+                        float b2, float eps, int step);

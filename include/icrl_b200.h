@@ -236,6 +236,12 @@ int icrl_reward_cosine_fwd(void* stream, int B, int S, const float* ve, const fl
 int icrl_a2c_loss_fwd_bwd(void* stream, int B, int S, const float* values, const float* rewards, const float* logp,
                           float inv_denom, float* out3, float* dv_sb, float* dlogp, float* sum_dv, int* launches);
 
+/* ---- optimizer (replaces torch.optim.Adam.step over the 18 tensors, trainers.py:378, 480): one
+ *      kernel over the flat parameter / gradient buckets, torch's default Adam (betas 0.9/0.999, eps 1e-8, no weight
+ *      decay); `step` is the 1-based step count. */
+int icrl_adam_flat(void* stream, long long n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                   float lr, float beta1, float beta2, float eps, int step, int* launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -645,3 +645,28 @@ def test_wgrad_tcgen05_vs_float64(T):
     err = ((C.double() - ref).abs().max(dim=1).values / ref.abs().max(dim=1).values.clamp_min(1e-300)).max().item()
     _record("wgrad_tc_T%d" % T, rel_err_per_row=err)
     assert err < 2e-6, err
+
+
+def test_flat_adam_matches_torch():
+    """the one-kernel Adam over the flat buckets against torch.optim.Adam (the reference's optimizer,
+    trainers.py:378) over three training steps from identical gradients."""
+    from icrl_b200.engine import A2CEngine
+    from icrl_b200.optim import FlatAdam
+    seed, B, L = 95, 8, 6
+    A1, R1, w = make_nets(seed)
+    A2, R2, _ = make_nets(seed)
+    e1, e2 = A2CEngine(A1, R1), A2CEngine(A2, R2)
+    o1 = torch.optim.Adam(A1.parameters(), lr=1e-3)
+    o2 = FlatAdam(e2, lr=1e-3)
+    for it in range(3):
+        f, c = synth.make_inputs(seed + it, B, L)
+        u = synth.make_uniforms(seed + it, L - 1, B)
+        e1.step(f, c, uniforms=u)
+        e2.flat_grad.copy_(e1.flat_grad)            # identical gradients: this test isolates the optimizer
+        o1.step()
+        o2.step()
+        for (k, p1), (_, p2) in zip(A1.named_parameters(), A2.named_parameters()):
+            d = float((p1 - p2).abs().max())
+            assert d <= 2e-7, (it, k, d)
+            p2.data.copy_(p1.data)                  # keep both sides on the same trajectory
+    assert A2.policy_network.linear2vocab.weight.data_ptr() >= o2.flat_param.data_ptr()      # parameters live in the flat buffer
