@@ -68,6 +68,32 @@ def save_a2c_model(model, save_paths):
         torch.save(model.state_dict(), path)
 
 
+def load_a2c_models(model_path, train_data, network_paths, bidirectional):
+    """Rebuild an A2C network from its checkpoints (utilities.py:299-323): policy and value state dicts first, then the
+    a2cNetwork*.pt file over them, all with strict=False; both sub-networks in eval mode."""
+    nets = {}
+    for key, cls in (("policy_network", PolicyNetwork), ("value_network", ValueNetwork)):
+        net = cls(train_data["word_to_idx"], pretrained_embeddings=train_data.get("embeddings"),
+                  bidirectional=bidirectional).to(device)
+        net.load_state_dict(torch.load(network_paths[key], map_location=device), strict=False)
+        nets[key] = net
+    a2c_network = AdvantageActorCriticNetwork(nets["value_network"], nets["policy_network"]).to(device)
+    a2c_network.load_state_dict(torch.load(model_path, map_location=device), strict=False)
+    a2c_network.policy_network.train(mode=False)
+    a2c_network.value_network.train(mode=False)
+    return a2c_network
+
+
+def get_filename(base_name, bidirectional, curriculum=None):
+    """Checkpoint naming of the reference (utilities.py:326-338): `_bidirectional`, then `_curriculum`, before the extension."""
+    name, ext = os.path.splitext(base_name)
+    if bidirectional:
+        name += "_bidirectional"
+    if curriculum:
+        name += "_curriculum"
+    return name + ext
+
+
 def GetRewards(features, captions, reward_network):
     """Cosine similarity of the visual and semantic embeddings, (B,1) (trainers.py:108-121).
     Uses and advances ``reward_network.rewrnn.hidden_cell`` like the reference."""

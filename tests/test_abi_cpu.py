@@ -102,3 +102,28 @@ def test_plan_rollout_rules():
     assert plan_rollout(caps, 20)[0] < 1              # skipped by the caller (trainers.py:550)
     with pytest.raises(ValueError):
         plan_rollout(np.ones((2, 5), dtype=np.int64))
+
+
+def test_checkpoint_helpers_roundtrip(tmp_path):
+    """save_a2c_model / load_a2c_models / get_filename keep the reference's plain-state_dict format and naming
+    (utilities.py:286-338): a checkpoint written from one set of modules loads into freshly built ones on CPU."""
+    import icrl_b200.models as M
+    import icrl_b200.trainers as T
+    from oracle import synth
+    w = synth.make_weights(3)
+    w2i = synth.word_to_idx()
+    P, V = M.PolicyNetwork(w2i), M.ValueNetwork(w2i)
+    P.load_state_dict(w["policy"])
+    V.load_state_dict(w["value"])
+    A = M.AdvantageActorCriticNetwork(V, P)
+    paths = {"policy_network": str(tmp_path / "p.pt"), "value_network": str(tmp_path / "v.pt")}
+    torch.save(P.state_dict(), paths["policy_network"])
+    torch.save(V.state_dict(), paths["value_network"])
+    a2c_path = str(tmp_path / T.get_filename("a2cNetwork.pt", False, True))
+    assert a2c_path.endswith("a2cNetwork_curriculum.pt")
+    assert T.get_filename("x.pt", True, None) == "x_bidirectional.pt"
+    T.save_a2c_model(A, [a2c_path])
+    B = T.load_a2c_models(a2c_path, {"word_to_idx": w2i, "embeddings": None}, paths, False)
+    for (k, a), (_, b) in zip(A.state_dict().items(), B.state_dict().items()):
+        assert torch.equal(a.cpu(), b.cpu()), k
+    assert not B.policy_network.training and not B.value_network.training
