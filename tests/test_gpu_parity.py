@@ -670,3 +670,22 @@ def test_flat_adam_matches_torch():
             assert d <= 2e-7, (it, k, d)
             p2.data.copy_(p1.data)                  # keep both sides on the same trajectory
     assert A2.policy_network.linear2vocab.weight.data_ptr() >= o2.flat_param.data_ptr()      # parameters live in the flat buffer
+
+
+def test_config4_full_size_properties():
+    """BASELINE config 4 at its full single-GPU size (4096 rows, L=20: 778,240 + 856,064 serial steps): the loss equals
+    the reference's formula recomputed from the returned tensors, gradients are finite, rewards lie in [-1, 1], and --
+    rows being independent in the policy -- the tokens of a 512-row data-parallel shard equal those rows of the full batch."""
+    seed, B, L = 97, 4096, 20
+    eng, A, R, w = _engine(seed)
+    f, c = synth.make_inputs(seed, B, L)
+    u = synth.make_uniforms(seed, L - 1, B)
+    r = eng.step(f, c, uniforms=u)
+    adv = (r["values"] - r["rewards"]).double()
+    loss = float((-r["logp"].double() * adv).mean() + 0.5 * (adv ** 2).mean())
+    assert abs(loss - r.loss) <= 1e-6
+    assert torch.isfinite(eng.flat_grad).all() and float(eng.flat_grad.abs().max()) > 0
+    assert float(r["rewards"].abs().max()) <= 1.0 + 1e-6
+    toks = r["tokens"].clone()
+    rs = eng.step(f[1024:1536], c[1024:1536], uniforms=np.ascontiguousarray(u[:, 1024:1536]), backward=False)
+    assert torch.equal(rs["tokens"], toks[1024:1536])
