@@ -43,7 +43,11 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=256, help="rows of the workload timed on the host cores")
     ap.add_argument("--chain-shards", type=int, default=1, choices=[1, 2, 4, 8],
                     help="value/reward recurrences per rank (1 = the reference's single carried-state chain)")
-    ap.add_argument("--no-sharded-leg", action="store_true")
+    ap.add_argument("--chain-segments", type=int, default=8, choices=[1, 2, 4, 8],
+                    help="lockstep pieces of the single carried-state chain (verified warm-up; 1 = serial kernels only)")
+    ap.add_argument("--chain-warmup", type=int, default=512, help="warm-up positions of every chain piece")
+    ap.add_argument("--sharded-leg", action="store_true", help="also time 8 zero-state row shards per rank")
+    ap.add_argument("--no-serial-leg", action="store_true", help="skip the serial-kernel leg (chain_segments = 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -166,7 +170,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(dev))
     A, R = make_nets(0, dev)
     opt = torch.optim.Adam(A.parameters(), lr=1e-4)
-    eng = A2CEngine(A, R, chain_shards=args.chain_shards)
+    eng = A2CEngine(A, R, chain_shards=args.chain_shards, chain_segments=args.chain_segments, chain_warmup=args.chain_warmup)
     dp = DataParallelA2C(eng, opt)
     B = args.batch
     S = L_CAP - 1
@@ -215,6 +219,19 @@ def main():
     eng.phase_events = None
     _lib.call("icrl_chain_check", ctypes.c_void_p(torch.cuda.current_stream().cuda_stream),
               ctypes.c_void_p(eng.sync_state.data_ptr()))
+    seg_layout = eng._seg                      # (pieces, value segment, reward segment, warm-up) or None = serial kernels
+    seg_ok = torch.tensor([1 if eng.segments_verified() else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(seg_ok, op=dist.ReduceOp.MIN)
+    if int(seg_ok.item()) == 0:
+        # some rank's warm-up check failed inside the timed loop: those steps are not the reference's numbers.
+        # Time the serial kernels instead (every rank takes this branch together).
+        eng.chain_segments = 1
+        eng.phase_events = []
+        ms_step, launches = timed(step_resident, args.steps, 1)
+        phases = {k: sum(v) / len(v) for k, v in eng.phase_times_ms().items()}
+        eng.phase_events = None
+        seg_layout = None
 
     # ---- leg 2: end to end through the public API from pinned host buffers
     e2e = None
@@ -233,8 +250,20 @@ def main():
 
     # ---- leg 3 (reported separately, never the headline): the same workload with 8 chain shards per rank
     sharded = None
-    if args.chain_shards == 1 and not args.no_sharded_leg and (hi - lo) % 8 == 0:
-        eng8 = A2CEngine(A, R, chain_shards=8)
+    serial_leg = None
+    if seg_layout is not None and not args.no_serial_leg:
+        eng1 = A2CEngine(A, R, chain_segments=1)
+        dp1 = DataParallelA2C(eng1, opt)
+        ms1, _ = timed(lambda: dp1.step(prep, global_rows=B, check=False), min(args.steps, 2), 1)
+        _lib.call("icrl_chain_check", ctypes.c_void_p(torch.cuda.current_stream().cuda_stream),
+                  ctypes.c_void_p(eng1.sync_state.data_ptr()))
+        serial_leg = {"value": B / (ms1 * 1e-3), "unit": "captions/s", "ms_per_step": ms1, "steps": min(args.steps, 2),
+                      "note": "the same step on the serial chain kernels (chain_segments=1): one CTA group walks the whole "
+                              "carried-state chain position by position"}
+        del eng1, dp1
+        eng._attach_grads()
+    if args.chain_shards == 1 and args.sharded_leg and (hi - lo) % 8 == 0:
+        eng8 = A2CEngine(A, R, chain_shards=8, chain_segments=1)
         dp8 = DataParallelA2C(eng8, opt)
         ms8, _ = timed(lambda: dp8.step(prep, global_rows=B, check=False), args.steps, 2)
         _lib.call("icrl_chain_check", ctypes.c_void_p(torch.cuda.current_stream().cuda_stream),
@@ -282,6 +311,12 @@ def main():
         kbytes, ksteps = Tv * (4 * H * 4 + 6 * H * 4 + 4) + Tr * (3 * H * 4 + H * 4 + 4), max(Tv, Tr)
         # profiles/r01_chain_fwd_ncu.md: dram read+write = 695.5 MB per launch at B=256 (linear in rows)
         ktraffic = 695.5e6 * Bl / 256.0
+    if seg_layout is not None:                 # lockstep pieces: one kernel step advances `pieces` chain positions
+        pieces, seg_v, seg_r, warm = seg_layout
+        if bwd_ms >= fwd_ms:
+            kname, ksteps = "chain_lstm_bwd_batched_kernel<%d> x 2 groups" % (pieces // 2), seg_v + warm
+        else:
+            kname, ksteps = "chains_fwd_fused_batched_kernel<%d>" % pieces, max(seg_v, seg_r) + warm
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -297,7 +332,8 @@ def main():
                 "traffic": ktraffic, "peak_source": "measured" if peaks else "fallback",
                 "ms_per_launch": kms, "serial_steps_per_launch": ksteps,
                 "ns_per_serial_step": kms * 1e6 / ksteps if ksteps else None,
-                "note": "serial batch-1 recurrence: latency bound, neither HBM nor tensor pipe is the limiter",
+                "note": "serial batch-1 recurrence: latency bound, neither HBM nor tensor pipe is the limiter"
+                        + ("" if seg_layout is None else "; %d pieces of the chain advance per kernel step" % seg_layout[0]),
                 "latency_floor": {"one_way_l2_store_to_poll_ns": 494, "all_to_all_512_words_64_ctas_ns": 782,
                                   "register_gemv_plus_pointwise_ns": 230,
                                   "source": "profiles/r01_xchg_bench.log, profiles/r01_chain_micro.log (microbenchmarks, "
@@ -310,12 +346,21 @@ def main():
                                "global batch %d, max_len %d, S=%d" % (B, L_CAP, S),
                    "global_batch": B, "local_batch": Bl, "parallelism": "dp%d" % world, "vocab": 1004,
                    "chain_shards_per_rank": args.chain_shards,
+                   "chain_segments": None if seg_layout is None else
+                   {"pieces": seg_layout[0], "value_segment": seg_layout[1], "reward_segment": seg_layout[2],
+                    "warmup": seg_layout[3], "tolerance": eng.chain_tol,
+                    "checked_max": dict(zip(("value_h", "value_c", "reward_h", "joint_dgates", "dh_take"),
+                                            eng.segment_stats["max_err"])),
+                    "fallbacks_to_serial": eng.segment_stats["fallbacks"],
+                    "steps_checked": eng.segment_stats["segmented_steps"]},
                    "l2_flush": "not needed: per-step working set (chain stash, GBs) >> 126 MB L2"},
         "clocks": clk, "gpu_launches": int(launches), "phases_ms": phases, "roofline": roofline,
         "roofline_decode": decode,
     }
     if e2e:
         out["e2e"] = e2e
+    if serial_leg:
+        out["serial_chain"] = serial_leg
     if sharded:
         out["sharded"] = sharded
     if world == 1 and not args.no_cpu_baseline:

@@ -44,6 +44,10 @@ SIGNATURES = {
     "icrl_build_stream_sharded": [P, I, I, I, I, I, P, P, P, P, LP],
     "icrl_chains_fwd_fused_sharded": [P, I, P, I, P, P, P, P, P, P, I, P, P, P, P, P, LP],
     "icrl_chain_lstm_bwd_sharded": [P, I, I, P, P, P, P, P, P, P, LP],
+    "icrl_chain_segment_len": [L, I, I],
+    "icrl_chain_segment_ws_floats": [],
+    "icrl_chains_fwd_fused_segmented": [P, I, I, P, I, P, P, P, P, P, P, I, P, P, P, P, P, P, LP],
+    "icrl_chain_lstm_bwd_segmented": [P, I, I, I, P, P, P, P, P, L, P, P, P, LP],
     "icrl_chain_set_profile": [P],
     "icrl_chain_sync_bytes": [],
     "icrl_chain_lstm_fwd": [P, P, I] + [P] * 10 + [LP],
@@ -63,7 +67,7 @@ SIGNATURES = {
     "icrl_a2c_loss_fwd_bwd": [P, I, I, P, P, P, F, P, P, P, P, LP],
 }
 _RESTYPES = {"icrl_last_error": c_char_p, "icrl_wgrad_tc_ws_bytes": c_size_t, "icrl_decode_weight_halves": c_size_t, "icrl_colsum_ws_floats": c_size_t, "icrl_stream_len": c_longlong,
-             "icrl_chain_sync_bytes": c_size_t}
+             "icrl_chain_sync_bytes": c_size_t, "icrl_chain_segment_len": c_longlong, "icrl_chain_segment_ws_floats": c_size_t}
 _NO_STATUS = set(_RESTYPES) | {"icrl_version"}
 
 

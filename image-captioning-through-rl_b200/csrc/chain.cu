@@ -438,6 +438,13 @@ struct ChainFwdBatchArgs {
   unsigned long long* xchg;   // [2][NB][H] tagged words, zeroed before launch
   int* abort_flag;
   long long* prof;            // debug: {exchange wait, GEMV + reduce, pointwise + publish} cycles of CTA 0 thread 0, T
+  // Time-segment mode (warm > 0): the NB "shards" are consecutive segments of ONE chain.  stride = segment length,
+  // T = stride + warm, so shard b runs positions [b*stride, (b+1)*stride + warm) of the shared stream / stash arrays.
+  // Shards b >= 1 start from zero state `warm` positions early and discard those steps (nothing is stored for them);
+  // the state they reach at the end of the warm-up goes to warm_state for the caller's check against the state
+  // shard b-1 computes at the same position.
+  int warm;
+  float* warm_state;          // [NB][2][H]: h, c of shard b after its warm-up (rows of shard 0 unused)
 };
 
 // (Tried and dropped for this exchange, both slower at NB = 8: a unit-major word layout [unit][NB], 393 -> 426 ms, and
@@ -464,7 +471,8 @@ __device__ void chain_fwd_batched_body(const ChainFwdBatchArgs& p, int cta, floa
   float* my_h = p.stash_h + (size_t)b * p.stride * H;
   float* my_c = p.stash_c ? p.stash_c + (size_t)b * p.stride * H : nullptr;
   float* my_g = p.stash_gates ? p.stash_gates + (size_t)b * p.stride * (4 * H) : nullptr;
-  if (sub == 0) {
+  const bool seg_tail = p.warm > 0 && b > 0;           // a later segment of one chain: its first `warm` steps are discarded
+  if (sub == 0 && !seg_tail) {
     my_h[unit] = 0.f;
     if (NG == 4 && my_c) my_c[unit] = 0.f;
   }
@@ -528,6 +536,8 @@ __device__ void chain_fwd_batched_body(const ChainFwdBatchArgs& p, int cta, floa
     for (int g = 0; g < NG; ++g) sum[g] = reduce_transposed<NB>(acc[g], lane);
     const long long c2 = prof ? clock64() : 0;
 
+    const bool live = !seg_tail || t >= p.warm;        // warm-up steps of a later segment leave no trace
+    const bool warm_end = seg_tail && t == p.warm - 1;
     float hnew;
     if constexpr (NG == 4) {
       const float i = act_sigmoid(sum[0] + xg[0]);
@@ -536,11 +546,14 @@ __device__ void chain_fwd_batched_body(const ChainFwdBatchArgs& p, int cta, floa
       const float o = act_sigmoid(sum[3 % NG] + xg[3 % NG]);
       c = f * c + i * g;
       hnew = o * act_tanh(c);
-      if (my_g && sub < 4) {
+      if (my_g && sub < 4 && live) {
         const float sel = sub == 0 ? i : (sub == 1 ? f : (sub == 2 ? g : o));
         my_g[(size_t)t * 4 * H + sub * H + unit] = sel;
       }
-      if (my_c && sub == 4 % GL) my_c[(size_t)(t + 1) * H + unit] = c;
+      if (sub == 4 % GL) {
+        if (my_c && live) my_c[(size_t)(t + 1) * H + unit] = c;
+        if (warm_end) p.warm_state[(size_t)(2 * b + 1) * H + unit] = c;
+      }
     } else {
       const float r = act_sigmoid(sum[0] + xg[0]);
       const float z = act_sigmoid(sum[1] + xg[1]);
@@ -549,7 +562,10 @@ __device__ void chain_fwd_batched_body(const ChainFwdBatchArgs& p, int cta, floa
     }
     hprev = hnew;
     if (sub == 6 % GL) st_tagged(p.xchg + ((size_t)buf * NB + b) * H + unit, hnew, (unsigned)(t + 1));
-    if (sub == 5 % GL) my_h[(size_t)(t + 1) * H + unit] = hnew;
+    if (sub == 5 % GL) {
+      if (live) my_h[(size_t)(t + 1) * H + unit] = hnew;
+      if (warm_end) p.warm_state[(size_t)(2 * b) * H + unit] = hnew;
+    }
 #pragma unroll
     for (int g = 0; g < NG; ++g) xg[g] = xg_n[g];
     if (prof) { const long long c3 = clock64(); prof_wait += c1 - c0; prof_gemv += c2 - c1; prof_rest += c3 - c2; }
@@ -581,6 +597,11 @@ struct ChainBwdBatchArgs {
   unsigned long long* xchg;   // [2][shards][H]
   int shards;                 // total shards = gridDim.x / CHAIN_CTAS * NB
   int* abort_flag;
+  // Time-segment mode (warm > 0; see ChainFwdBatchArgs): shard k runs positions (k+1)*stride + warm - 1 down to k*stride of
+  // ONE chain.  All but the last shard start `warm` positions late with dh = dc = 0 and discard those steps; the
+  // gate gradients of their last warm-up step go to warm_dg for the caller's check against the row the next shard writes.
+  int warm;
+  float* warm_dg;             // [shards][4H]
 };
 
 // Backward recurrence of NB shards per 64-CTA group (see chain_lstm_bwd_kernel for the single-chain scheme).
@@ -685,8 +706,10 @@ __global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_batched_kernel(Chai
       *reinterpret_cast<float2*>(sd + H) = d_f;
       *reinterpret_cast<float2*>(sd + 2 * H) = d_g;
       *reinterpret_cast<float2*>(sd + 3 * H) = d_o;
-      if (owner) {
-        float* out = p.dgates + ((size_t)(sb + v) * p.stride + t) * 4 * H + pu;
+      const bool live = p.warm == 0 || it >= p.warm || sb + v == p.shards - 1;
+      if (owner && (live || it == p.warm - 1)) {
+        float* out = live ? p.dgates + ((size_t)(sb + v) * p.stride + t) * 4 * H + pu
+                          : p.warm_dg + (size_t)(sb + v) * 4 * H + pu;
         *reinterpret_cast<float2*>(out) = d_i;
         *reinterpret_cast<float2*>(out + H) = d_f;
         *reinterpret_cast<float2*>(out + 2 * H) = d_g;
@@ -865,6 +888,54 @@ int coop_launch(const void* fn, int grid, void** args, cudaStream_t st) {
   return ICRL_OK;
 }
 
+
+// ---- time-segment checks.  err words are non-negative floats kept as a running maximum (integer atomicMax on the bit
+// pattern; a NaN difference has the largest pattern, so it trips the caller's threshold as well).
+__device__ __forceinline__ void err_max(float* slot, float v) { atomicMax(reinterpret_cast<int*>(slot), __float_as_int(fabsf(v))); }
+
+// Block k (k = 0..nb-2) compares the state segment k+1 reached after its warm-up with the state segment k computed at
+// the same position (stash row (k+1)*seg + warm).  err[0] = max |dh|, err[1] = max |dc|.
+__global__ void chain_warm_check_fwd_kernel(long long seg, int warm, const float* warm_state, const float* stash_h,
+                                            const float* stash_c, float* err) {
+  const int b = blockIdx.x + 1, u = threadIdx.x;
+  const size_t row = (size_t)b * seg + warm;
+  float dh = fabsf(warm_state[(size_t)(2 * b) * H + u] - stash_h[row * H + u]);
+  float dc = stash_c ? fabsf(warm_state[(size_t)(2 * b + 1) * H + u] - stash_c[row * H + u]) : 0.f;
+  // warp maximum first (NaN-propagating through the integer compare)
+  int ih = __float_as_int(dh), ic = __float_as_int(dc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ih = max(ih, __shfl_xor_sync(0xffffffffu, ih, o));
+    ic = max(ic, __shfl_xor_sync(0xffffffffu, ic, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(reinterpret_cast<int*>(err), ih);
+    if (stash_c) atomicMax(reinterpret_cast<int*>(err + 1), ic);
+  }
+}
+
+// Blocks 0..shards-2: gate gradients of segment k's last warm-up step against row (k+1)*seg written by segment k+1
+// (err[0] = max |difference|).  The remaining blocks reduce err[1] = max |dh_take| (the scale of the injected gradient).
+__global__ void chain_warm_check_bwd_kernel(int shards, long long seg, const float* warm_dg, const float* dgates,
+                                            const float* dh_take, long long n_take, float* err) {
+  int m = 0;
+  float* slot;
+  if ((int)blockIdx.x < shards - 1) {
+    const int k = blockIdx.x;
+    slot = err;
+    for (int i = threadIdx.x; i < 4 * H; i += blockDim.x)
+      m = max(m, __float_as_int(fabsf(warm_dg[(size_t)k * 4 * H + i] - dgates[((size_t)(k + 1) * seg) * 4 * H + i])));
+  } else {
+    slot = err + 1;
+    const long long nblk = gridDim.x - (shards - 1), blk = blockIdx.x - (shards - 1);
+    for (long long i = blk * blockDim.x + threadIdx.x; i < n_take; i += nblk * blockDim.x)
+      m = max(m, __float_as_int(fabsf(dh_take[i])));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(slot), m);
+}
+
 }  // namespace
 
 int icrl_chain_ctas() { return CHAIN_CTAS; }
@@ -980,51 +1051,79 @@ static int coop_launch_smem(const void* fn, int grid, void** args, size_t smem, 
   return ICRL_OK;
 }
 
+// warm == 0: `nb` independent row shards, v_T / r_T steps each, arrays of shard k at row k * (T + 1).
+// warm  > 0: `nb` time segments of ONE chain; v_T / r_T are the segment lengths, every segment runs T + warm steps on the
+// shared arrays (row stride T) and the end-of-warm-up states are checked into seg_err[0..2] (see ChainFwdBatchArgs).
 int icrl_chains_fwd_fused_batched_impl(cudaStream_t st, int nb, const int* v_stream, int v_T, const float* v_table,
                                        const float* v_w_hh, float* v_stash_h, float* v_stash_c, float* v_stash_gates,
                                        const int* r_stream, int r_T, const float* r_table, const float* r_w_hh,
-                                       const float* r_b_hn, float* r_stash_h, void* sync_state) {
+                                       const float* r_b_hn, float* r_stash_h, void* sync_state, int warm,
+                                       float* warm_state, float* seg_err) {
   ICRL_REQUIRE(nb == 2 || nb == 4 || nb == 8, "chain shards per launch must be 2, 4 or 8");
   ICRL_REQUIRE(r_T > 0, "empty chain");
+  ICRL_REQUIRE(warm == 0 || (warm_state && seg_err && r_T >= warm && (v_T == 0 || v_T >= warm)),
+               "time segments must be at least as long as their warm-up");
   ICRL_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(sync_state) + 64, 0, icrl_chain_sync_bytes_impl() - 64, st));
+  const int pad = warm > 0 ? 0 : 1;
   ChainFwdBatchArgs a, b;
-  a.stream = v_stream; a.T = v_T; a.stride = (long long)v_T + 1; a.table = v_table; a.w_hh = v_w_hh; a.b_hn = nullptr;
+  a.stream = v_stream; a.T = v_T + warm; a.stride = (long long)v_T + pad; a.table = v_table; a.w_hh = v_w_hh; a.b_hn = nullptr;
   a.stash_h = v_stash_h; a.stash_c = v_stash_c; a.stash_gates = v_stash_gates; a.xchg = sync_xchg(sync_state, 0);
-  a.abort_flag = sync_abort(sync_state); a.prof = g_chain_prof;
-  b.stream = r_stream; b.T = r_T; b.stride = (long long)r_T + 1; b.table = r_table; b.w_hh = r_w_hh; b.b_hn = r_b_hn;
+  a.abort_flag = sync_abort(sync_state); a.prof = g_chain_prof; a.warm = warm; a.warm_state = warm_state;
+  b.stream = r_stream; b.T = r_T + warm; b.stride = (long long)r_T + pad; b.table = r_table; b.w_hh = r_w_hh; b.b_hn = r_b_hn;
   b.stash_h = r_stash_h; b.stash_c = nullptr; b.stash_gates = nullptr; b.xchg = sync_xchg(sync_state, 1);
   b.abort_flag = sync_abort(sync_state); b.prof = g_chain_prof ? g_chain_prof + 4 : nullptr;
+  b.warm = warm; b.warm_state = warm_state ? warm_state + (size_t)2 * NB_MAX * H : nullptr;
   const size_t smem = (size_t)2 * nb * H * sizeof(float);
   if (v_T > 0) {
     void* args[] = {&a, &b};
     const void* fn = nb == 2 ? (const void*)chains_fwd_fused_batched_kernel<2>
                              : (nb == 4 ? (const void*)chains_fwd_fused_batched_kernel<4> : (const void*)chains_fwd_fused_batched_kernel<8>);
-    return coop_launch_smem(fn, 2 * CHAIN_CTAS, args, smem, st);
+    const int rc = coop_launch_smem(fn, 2 * CHAIN_CTAS, args, smem, st);
+    if (rc != ICRL_OK) return rc;
+  } else {
+    void* args[] = {&b};
+    const void* fn = nb == 2 ? (const void*)chain_gru_fwd_batched_kernel<2>
+                             : (nb == 4 ? (const void*)chain_gru_fwd_batched_kernel<4> : (const void*)chain_gru_fwd_batched_kernel<8>);
+    const int rc = coop_launch_smem(fn, CHAIN_CTAS, args, smem, st);
+    if (rc != ICRL_OK) return rc;
   }
-  void* args[] = {&b};
-  const void* fn = nb == 2 ? (const void*)chain_gru_fwd_batched_kernel<2>
-                           : (nb == 4 ? (const void*)chain_gru_fwd_batched_kernel<4> : (const void*)chain_gru_fwd_batched_kernel<8>);
-  return coop_launch_smem(fn, CHAIN_CTAS, args, smem, st);
+  if (warm > 0) {
+    if (v_T > 0)
+      chain_warm_check_fwd_kernel<<<nb - 1, H, 0, st>>>(v_T, warm, a.warm_state, v_stash_h, v_stash_c, seg_err);
+    chain_warm_check_fwd_kernel<<<nb - 1, H, 0, st>>>(r_T, warm, b.warm_state, r_stash_h, nullptr, seg_err + 2);
+    ICRL_CUDA(cudaGetLastError());
+  }
+  return ICRL_OK;
 }
 
 // shards = 2, 4 or 8 total; they are split over two 64-CTA groups (1, 2 or 4 shards per group).
+// warm > 0: time segments of one chain (T = segment length, arrays shared with row stride T); the warm-up check goes to
+// seg_err[3] (max |gate-gradient difference| at the segment joints) and seg_err[4] (max |dh_take|, n_take floats).
 int icrl_chain_lstm_bwd_batched_impl(cudaStream_t st, int shards, int T, const float* w_hh, const float* stash_gates,
                                      const float* stash_c, const int* take, const float* dh_take, float* dgates,
-                                     void* sync_state) {
+                                     void* sync_state, int warm, float* warm_dg, long long n_take, float* seg_err) {
   ICRL_REQUIRE(shards == 2 || shards == 4 || shards == 8, "chain shards must be 2, 4 or 8");
   ICRL_REQUIRE(T > 0, "empty chain");
+  ICRL_REQUIRE(warm == 0 || (warm_dg && seg_err && T >= warm), "time segments must be at least as long as their warm-up");
   ICRL_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(sync_state) + 64, 0, icrl_chain_sync_bytes_impl() - 64, st));
-  const long long stride = (long long)T + 1;
-  for (int k = 0; k < shards; ++k)                      // padding row T of every shard (feeds the weight-gradient GEMM)
-    ICRL_CUDA(cudaMemsetAsync(dgates + ((size_t)k * stride + T) * 4 * H, 0, 4 * H * sizeof(float), st));
+  const long long stride = (long long)T + (warm > 0 ? 0 : 1);
+  if (warm == 0)
+    for (int k = 0; k < shards; ++k)                    // padding row T of every shard (feeds the weight-gradient GEMM)
+      ICRL_CUDA(cudaMemsetAsync(dgates + ((size_t)k * stride + T) * 4 * H, 0, 4 * H * sizeof(float), st));
   ChainBwdBatchArgs a;
-  a.T = T; a.stride = stride; a.w_hh = w_hh; a.stash_gates = stash_gates; a.stash_c = stash_c; a.take = take;
+  a.T = T + warm; a.stride = stride; a.w_hh = w_hh; a.stash_gates = stash_gates; a.stash_c = stash_c; a.take = take;
   a.dh_take = dh_take; a.dgates = dgates; a.xchg = sync_xchg(sync_state, 2); a.shards = shards;
-  a.abort_flag = sync_abort(sync_state);
+  a.abort_flag = sync_abort(sync_state); a.warm = warm; a.warm_dg = warm_dg;
   void* args[] = {&a};
   const int nb = shards / 2;
   const size_t smem = (size_t)2 * nb * 4 * H * sizeof(float);
   const void* fn = nb == 1 ? (const void*)chain_lstm_bwd_batched_kernel<1>
                            : (nb == 2 ? (const void*)chain_lstm_bwd_batched_kernel<2> : (const void*)chain_lstm_bwd_batched_kernel<4>);
-  return coop_launch_smem(fn, 2 * CHAIN_CTAS, args, smem, st);
+  const int rc = coop_launch_smem(fn, 2 * CHAIN_CTAS, args, smem, st);
+  if (rc != ICRL_OK) return rc;
+  if (warm > 0) {
+    chain_warm_check_bwd_kernel<<<shards - 1 + 64, 256, 0, st>>>(shards, T, warm_dg, dgates, dh_take, n_take, seg_err + 3);
+    ICRL_CUDA(cudaGetLastError());
+  }
+  return ICRL_OK;
 }

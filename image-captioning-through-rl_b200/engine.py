@@ -73,7 +73,8 @@ def plan_rollout(captions, level=None):
 class A2CEngine:
     DECODE_MODES = ("fused", "tc", "simt")
 
-    def __init__(self, a2c_network, reward_network, use_tc=None, decode="fused", chain_shards=1, wgrad="tc"):
+    def __init__(self, a2c_network, reward_network, use_tc=None, decode="fused", chain_shards=1, wgrad="tc",
+                 chain_segments=8, chain_warmup=512, chain_tol=1e-5):
         self.policy = a2c_network.policy_network
         self.value = a2c_network.value_network
         self.reward = reward_network
@@ -117,7 +118,26 @@ class A2CEngine:
         if chain_shards not in (1, 2, 4, 8):
             raise ValueError("chain_shards must be 1, 2, 4 or 8")
         self.chain_shards = int(chain_shards)
+        # chain_segments = K > 1 keeps the reference's ONE carried-state chain but advances K consecutive pieces of it in
+        # lockstep: piece k >= 1 starts from zero state `chain_warmup` positions early and throws those steps away.  A
+        # gated recurrence forgets its initial state, so the piece then carries the single chain's state up to float
+        # rounding.  That is verified on every step (state at the end of each warm-up vs the state the previous piece
+        # computes at the same position; gate gradients at the joints for the backward recurrence); a step whose check
+        # exceeds chain_tol is re-run on the serial kernels and the warm-up is lengthened.  Chains too short for K
+        # pieces of >= 2 warm-ups use fewer pieces or the serial kernels.  chain_segments = 1: always serial.
+        if chain_segments not in (1, 2, 4, 8):
+            raise ValueError("chain_segments must be 1, 2, 4 or 8")
+        self.chain_segments = 1 if self.chain_shards > 1 else int(chain_segments)
+        self.chain_warmup = int(chain_warmup)
+        self.chain_tol = float(chain_tol)
+        if self.chain_warmup < 1:
+            raise ValueError("chain_warmup must be positive")
+        self.segment_stats = {"steps": 0, "segmented_steps": 0, "fallbacks": 0, "max_err": [0.0] * 5}
+        self._seg = None                  # (K, seg_v, seg_r, warm) of the current step, None = serial kernels
+        self._seg_strikes = 0
+        self._seg_unverified = False
         with torch.cuda.device(dev):
+            self._seg_ws = torch.zeros(int(_lib.call("icrl_chain_segment_ws_floats")), dtype=torch.float32, device=dev)
             self.sync_state = torch.zeros(int(_lib.call("icrl_chain_sync_bytes")), dtype=torch.uint8, device=dev)
         self._check_params()
         self._bind_flat_grads()
@@ -300,7 +320,7 @@ class A2CEngine:
                   _p(tokcm), _p(tokens), _p(logp), _p(Hs), _p(Cs), _p(Gs), _p(logits), _p(gpre), self.launches.ref)
         return tokens, logp
 
-    def _streams(self, tokcm, B, p0, S):
+    def _streams(self, tokcm, B, p0, S, serial=False):
         st, L = self._stream, self.launches.ref
         K = self.chain_shards
         i32 = torch.int32
@@ -317,22 +337,54 @@ class A2CEngine:
             return Tv, Tr
         Tv = int(_lib.call("icrl_stream_len", B, p0, S, 0))
         Tr = int(_lib.call("icrl_stream_len", B, p0, S, 1))
-        v_stream, v_take, v_pos = self._buf("v_stream", Tv, i32), self._buf("v_take", Tv, i32), self._buf("v_pos", S * B, i32)
-        r_stream, r_pos = self._buf("r_stream", Tr, i32), self._buf("r_pos", S * B, i32)
+        self._seg = None if serial else self._pick_segments(Tv, Tr)
+        nv, nr = self._padded(Tv, 0), self._padded(Tr, 1)
+        v_stream, v_take, v_pos = self._buf("v_stream", nv, i32), self._buf("v_take", nv, i32), self._buf("v_pos", S * B, i32)
+        r_stream, r_pos = self._buf("r_stream", nr, i32), self._buf("r_pos", S * B, i32)
         _lib.call("icrl_build_stream", st, B, p0, S, 0, _p(tokcm), _p(v_stream), _p(v_take), _p(v_pos), L)
         _lib.call("icrl_build_stream", st, B, p0, S, 1, _p(tokcm), _p(r_stream), None, _p(r_pos), L)
+        if self._seg is not None:         # the last piece runs past the end of the chain: pad with token 0 / "no output"
+            v_stream[Tv:nv].zero_()
+            v_take[Tv:nv].fill_(-1)
+            r_stream[Tr:nr].zero_()
         return Tv, Tr
+
+    def _pick_segments(self, Tv, Tr):
+        """(K, seg_v, seg_r, warm) for chains of Tv / Tr positions, or None when they are too short."""
+        warm = self.chain_warmup
+        for K in (8, 4, 2):
+            if K > self.chain_segments:
+                continue
+            seg_r = int(_lib.call("icrl_chain_segment_len", Tr, K, warm))
+            seg_v = int(_lib.call("icrl_chain_segment_len", Tv, K, warm)) if Tv > 0 else 0
+            if seg_r > 0 and (Tv == 0 or seg_v > 0):
+                return (K, seg_v, seg_r, warm)
+        return None
+
+    def _padded(self, T, which):
+        """Positions the arrays of a chain must hold (which: 0 = value, 1 = reward)."""
+        if self._seg is None:
+            return T
+        K, seg_v, seg_r, warm = self._seg
+        return K * (seg_r if which else seg_v) + warm
 
     def _chains_forward(self, f, B, S, Tv, Tr, train):
         st, L, b = self._stream, self.launches.ref, self._bufs
         Vn, R = self.value, self.reward
         K = self.chain_shards
-        v_h = self._buf("v_stash_h", K * (Tv + 1) * H)
-        v_c = self._buf("v_stash_c", K * (Tv + 1) * H)
-        v_g = self._buf("v_stash_g", K * (Tv + 1) * 4 * H)
-        r_h = self._buf("r_stash_h", K * (Tr + 1) * H)
+        nv, nr = self._padded(Tv, 0), self._padded(Tr, 1)
+        v_h = self._buf("v_stash_h", K * (nv + 1) * H)
+        v_c = self._buf("v_stash_c", K * (nv + 1) * H)
+        v_g = self._buf("v_stash_g", K * (nv + 1) * 4 * H)
+        r_h = self._buf("r_stash_h", K * (nr + 1) * H)
         with self._phase("chains_fwd_fused"):
-          if K > 1:
+          if self._seg is not None:
+            Ks, seg_v, seg_r, warm = self._seg
+            _lib.call("icrl_chains_fwd_fused_segmented", st, Ks, warm, _p(b["v_stream"]), seg_v, _p(b["v_table"]),
+                  _p(Vn.valrnn.lstm.weight_hh_l0), _p(v_h), _p(v_c), _p(v_g), _p(b["r_stream"]), seg_r, _p(b["r_table"]),
+                  _p(R.rewrnn.gru.weight_hh_l0), _p(R.rewrnn.gru.bias_hh_l0[2 * H:]), _p(r_h), _p(self._seg_ws),
+                  _p(self.sync_state), L)
+          elif K > 1:
             _lib.call("icrl_chains_fwd_fused_sharded", st, K, _p(b["v_stream"]), Tv, _p(b["v_table"]),
                   _p(Vn.valrnn.lstm.weight_hh_l0), _p(v_h), _p(v_c), _p(v_g), _p(b["r_stream"]), Tr, _p(b["r_table"]),
                   _p(R.rewrnn.gru.weight_hh_l0), _p(R.rewrnn.gru.bias_hh_l0[2 * H:]), _p(r_h), _p(self.sync_state), L)
@@ -376,9 +428,14 @@ class A2CEngine:
                   _p(colsum_ws), L)
         # value chain BPTT (serial) and its parameter gradients (contractions over all T steps)
         K = self.chain_shards
-        dgates = self._buf("v_dgates", K * (Tv + 1) * 4 * H)
+        dgates = self._buf("v_dgates", K * (self._padded(Tv, 0) + 1) * 4 * H)
         with self._phase("chain_lstm_bwd"):
-          if K > 1:
+          if self._seg is not None:
+            Ks, seg_v, _, warm = self._seg
+            _lib.call("icrl_chain_lstm_bwd_segmented", st, Ks, warm, seg_v, _p(Vn.valrnn.lstm.weight_hh_l0),
+                  _p(b["v_stash_g"]), _p(b["v_stash_c"]), _p(b["v_take"]), _p(dh_take), SB, _p(dgates), _p(self._seg_ws),
+                  _p(self.sync_state), L)
+          elif K > 1:
             _lib.call("icrl_chain_lstm_bwd_sharded", st, K, Tv, _p(Vn.valrnn.lstm.weight_hh_l0), _p(b["v_stash_g"]),
                   _p(b["v_stash_c"]), _p(b["v_take"]), _p(dh_take), _p(dgates), _p(self.sync_state), L)
           else:
@@ -429,21 +486,64 @@ class A2CEngine:
                 self.pack_weights(reward="r_table" not in self._bufs)
             f, tokcm, u, fo, B = self._stage_inputs(prep, forced_tokens)
             tokens, logp = self._policy_forward(f, tokcm, u, fo, B, p0, S, greedy)
-            Tv, Tr = self._streams(tokcm, B, p0, S)
-            values, rewards = self._chains_forward(f, B, S, Tv, Tr, backward)
-            stats = torch.empty(3, dtype=torch.float32, device=self.device)
-            dv_sb = self._buf("dv_sb", S * B)
-            dlogp = self._buf("dlogp", S * B)
-            sum_dv = self._buf("sum_dv", 1)
-            inv = 1.0 / float((global_rows or B) * S)
-            _lib.call("icrl_a2c_loss_fwd_bwd", self._stream, B, S, _p(values), _p(rewards), _p(logp), inv, _p(stats),
-                      _p(dv_sb), _p(dlogp), _p(sum_dv), self.launches.ref)
-            if backward:
-                self._backward(f, tokcm, tokens, B, p0, S, Tv)
+            for serial in (False, True):
+                Tv, Tr = self._streams(tokcm, B, p0, S, serial=serial)
+                values, rewards = self._chains_forward(f, B, S, Tv, Tr, backward)
+                stats = torch.empty(3, dtype=torch.float32, device=self.device)
+                dv_sb = self._buf("dv_sb", S * B)
+                dlogp = self._buf("dlogp", S * B)
+                sum_dv = self._buf("sum_dv", 1)
+                inv = 1.0 / float((global_rows or B) * S)
+                _lib.call("icrl_a2c_loss_fwd_bwd", self._stream, B, S, _p(values), _p(rewards), _p(logp), inv, _p(stats),
+                          _p(dv_sb), _p(dlogp), _p(sum_dv), self.launches.ref)
+                if backward:
+                    self._backward(f, tokcm, tokens, B, p0, S, Tv)
+                self.segment_stats["steps"] += 1
+                if self._seg is None:
+                    break
+                self.segment_stats["segmented_steps"] += 1
+                if not check:
+                    self._seg_unverified = True       # the caller owes a segments_verified() before trusting the steps
+                    break
+                if self._segments_ok():
+                    break
             if check:
                 _lib.call("icrl_chain_check", self._stream, _p(self.sync_state))
         return StepResult(tokens=tokens, logp=logp, values=values, rewards=rewards, stats=stats, p0=p0, S=S, B=B,
                           Tv=Tv, Tr=Tr)
+
+    def _segments_ok(self):
+        """Read (and re-arm) the warm-up checks of the segmented chain launches since the last call (synchronises).
+        False = some segment had not converged onto the single chain within chain_tol: the caller re-runs serially;
+        the warm-up is lengthened for the next steps, and after three failures in a row segments are switched off."""
+        e = self._seg_ws[:5].tolist()
+        self._seg_ws[:5].zero_()
+        self._seg_unverified = False
+        st = self.segment_stats
+        st["max_err"] = [max(a, b) if b == b else float("nan") for a, b in zip(st["max_err"], e)]
+        tol = self.chain_tol
+        ok = e[0] <= tol and e[1] <= tol and e[2] <= tol and e[3] <= tol * max(e[4], 1e-30)
+        if ok:
+            self._seg_strikes = 0
+            return True
+        import warnings
+        st["fallbacks"] += 1
+        self._seg_strikes += 1
+        self.chain_warmup *= 4
+        if self._seg_strikes >= 3:
+            self.chain_segments = 1
+        warnings.warn("chain segments did not converge onto the single chain within %g after the warm-up (|dh| %.3g, |dc| "
+                      "%.3g, reward |dh| %.3g, joint gate gradients %.3g of %.3g): re-running on the serial kernels; %s"
+                      % (tol, e[0], e[1], e[2], e[3], e[4],
+                         "segments are now off" if self.chain_segments == 1 else "warm-up is now %d" % self.chain_warmup))
+        return False
+
+    def segments_verified(self):
+        """For callers that ran step(check=False): True when every segmented launch since the last check passed."""
+        if not self._seg_unverified:
+            return True
+        with torch.cuda.device(self.device):
+            return self._segments_ok()
 
     def get_rewards(self, features, captions):
         """GetRewards on whole captions from zero state (trainers.py:108-121): (B,1) tensor."""
@@ -455,11 +555,23 @@ class A2CEngine:
             f, tokcm, _, _, _ = self._stage_inputs(self.prepare(features, caps, plan=(Lc, 0)), None)
             st, L, b, R = self._stream, self.launches.ref, self._bufs, self.reward
             T = int(_lib.call("icrl_stream_len", B, Lc, 1, 0))
-            r_stream, r_pos = self._buf("r_stream", T, torch.int32), self._buf("r_pos", B, torch.int32)
-            _lib.call("icrl_build_stream", st, B, Lc, 1, 0, _p(tokcm), _p(r_stream), None, _p(r_pos), L)
-            r_h = self._buf("r_stash_h", (T + 1) * H)
-            _lib.call("icrl_chain_gru_fwd", st, _p(r_stream), T, _p(b["r_table"]), _p(R.rewrnn.gru.weight_hh_l0),
-                      _p(R.rewrnn.gru.bias_hh_l0[2 * H:]), None, _p(r_h), None, _p(self.sync_state), None, L)
+            for serial in (False, True):
+                self._seg = None if serial else self._pick_segments(0, T)
+                n = self._padded(T, 1)
+                r_stream, r_pos = self._buf("r_stream", n, torch.int32), self._buf("r_pos", B, torch.int32)
+                _lib.call("icrl_build_stream", st, B, Lc, 1, 0, _p(tokcm), _p(r_stream), None, _p(r_pos), L)
+                r_h = self._buf("r_stash_h", (n + 1) * H)
+                if self._seg is not None:
+                    Ks, _, seg_r, warm = self._seg
+                    r_stream[T:n].zero_()
+                    _lib.call("icrl_chains_fwd_fused_segmented", st, Ks, warm, None, 0, None, None, None, None, None,
+                              _p(r_stream), seg_r, _p(b["r_table"]), _p(R.rewrnn.gru.weight_hh_l0),
+                              _p(R.rewrnn.gru.bias_hh_l0[2 * H:]), _p(r_h), _p(self._seg_ws), _p(self.sync_state), L)
+                else:
+                    _lib.call("icrl_chain_gru_fwd", st, _p(r_stream), T, _p(b["r_table"]), _p(R.rewrnn.gru.weight_hh_l0),
+                              _p(R.rewrnn.gru.bias_hh_l0[2 * H:]), None, _p(r_h), None, _p(self.sync_state), None, L)
+                if self._seg is None or self._segments_ok():
+                    break
             r_take_h = self._buf("r_take_h", B * H)
             _lib.call("icrl_gather_rows", st, B, _p(r_h), _p(r_pos), 1, _p(r_take_h), L)
             se, ve = self._buf("r_se", B * H), self._buf("r_ve", B * H)

@@ -203,6 +203,31 @@ int icrl_chains_fwd_fused_sharded(void* stream, int shards, const int* v_stream,
 int icrl_chain_lstm_bwd_sharded(void* stream, int shards, int T, const float* W_hh, const float* stash_gates,
                                 const float* stash_c, const int* take, const float* dh_take, float* dgates,
                                 void* sync_state, int* launches);
+/* ---- chain segments (new; the reference has no equivalent).  ONE carried-state chain (the reference's semantics,
+ *      models.py:133-140 / :225-231) cut into `segments` (2, 4 or 8) consecutive pieces of `seg` positions that advance in
+ *      lockstep like the chain shards above.  Segment k >= 1 does not wait for the state of segment k-1: it starts from
+ *      zero state `warm` positions early and discards those steps.  An LSTM / GRU whose gates forget contracts the
+ *      difference of two states step by step, so after the warm-up the segment carries the state of the single chain
+ *      up to float rounding -- which is CHECKED, not assumed: the state reached at the end of every warm-up is compared
+ *      with the state the previous segment computes at the same position, and the backward recurrence (segment k starts
+ *      `warm` positions late with zero dh, dc) compares the gate gradients at the joints.  The caller reads
+ *      segment_ws[0..4] = {max |dh| value chain, max |dc| value chain, max |dh| reward chain, max |d dgates| at the
+ *      joints, max |dh_take|} (running maxima; zero them to re-arm) and, if they exceed its tolerance, re-runs the
+ *      serial entry points on the same buffers (the array layout IS the single-chain layout).
+ *      Sizes: seg = icrl_chain_segment_len(T, segments, warm) (0 = chain too short for this many segments: needs
+ *      seg >= 2*warm); streams hold segments*seg + warm tokens (tail padded with token 0), take the same number of
+ *      entries (tail -1), stash_h / stash_c segments*seg + warm + 1 rows, stash_gates / dgates segments*seg + warm rows.
+ *      v_seg = 0 runs the reward chain only.  segment_ws: icrl_chain_segment_ws_floats() floats. */
+long long icrl_chain_segment_len(long long T, int segments, int warm);
+size_t icrl_chain_segment_ws_floats(void);
+int icrl_chains_fwd_fused_segmented(void* stream, int segments, int warm, const int* v_stream, int v_seg,
+                                    const float* v_table, const float* v_W_hh, float* v_stash_h, float* v_stash_c,
+                                    float* v_stash_gates, const int* r_stream, int r_seg, const float* r_table,
+                                    const float* r_W_hh, const float* r_b_hn, float* r_stash_h, float* segment_ws,
+                                    void* sync_state, int* launches);
+int icrl_chain_lstm_bwd_segmented(void* stream, int segments, int warm, int seg, const float* W_hh,
+                                  const float* stash_gates, const float* stash_c, const int* take, const float* dh_take,
+                                  long long take_rows, float* dgates, float* segment_ws, void* sync_state, int* launches);
 /* Debug aid: when buf != NULL (8 device int64), CTA 0 / thread 0 of the sharded forward chains accumulates its cycles per
  * phase {exchange wait, GEMV + reduce, pointwise + publish, T}: [0..3] value LSTM, [4..7] reward GRU. */
 int icrl_chain_set_profile(void* buf);

@@ -689,3 +689,108 @@ def test_config4_full_size_properties():
     toks = r["tokens"].clone()
     rs = eng.step(f[1024:1536], c[1024:1536], uniforms=np.ascontiguousarray(u[:, 1024:1536]), backward=False)
     assert torch.equal(rs["tokens"], toks[1024:1536])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# chain segments: the single carried-state chain advanced as K pieces with a discarded, verified warm-up
+
+def _seg_engines(seed, segments, warm, tol=1e-5):
+    from icrl_b200.engine import A2CEngine
+    A, R, w = make_nets(seed)
+    return A2CEngine(A, R, chain_segments=1), A2CEngine(A, R, chain_segments=segments, chain_warmup=warm, chain_tol=tol), A
+
+
+@pytest.mark.parametrize("name", ["a2c_b32_l9", "curr_b24_l20_lv6"])
+def test_chain_segments_vs_reference_golden(name):
+    """The unmodified reference's numbers (one carried-state chain over the whole batch) reproduced by 8
+    lockstep pieces of that chain with a 32-position warm-up: same tolerances as the serial kernels."""
+    from icrl_b200.engine import A2CEngine
+    g, seed, f, c, u, level = load_case(name)
+    A, R, w = make_nets(seed)
+    eng = A2CEngine(A, R, chain_warmup=32)
+    res = eng.step(f, c, uniforms=u, level=level)
+    assert eng.segment_stats["segmented_steps"] == 1 and eng.segment_stats["fallbacks"] == 0, eng.segment_stats
+    _compare_forward(res, g, name + "_segments")
+    _record(name + "_segments", grad_worst=check_grads_vs_golden(named_grads(A), g, GTOL),
+            warm_h=eng.segment_stats["max_err"][0], warm_c=eng.segment_stats["max_err"][1],
+            warm_rh=eng.segment_stats["max_err"][2], warm_dg=eng.segment_stats["max_err"][3],
+            dh_take_max=eng.segment_stats["max_err"][4])
+
+
+@pytest.mark.parametrize("segments,B,L,level", [(8, 64, 10, None), (4, 48, 8, None), (2, 40, 6, None), (8, 96, 14, 5)])
+def test_chain_segments_equal_the_serial_chain(segments, B, L, level):
+    """Segmented and serial kernels on the same inputs: identical tokens, values / rewards within 2e-6, gradients within
+    2e-5 of the bucket's largest entry; the verification words stay at float-rounding level."""
+    seed = 131 + segments
+    e1, ek, A = _seg_engines(seed, segments, 32)
+    f, c = synth.make_inputs(seed, B, L)
+    S = (L - 1) if level is None else level
+    u = synth.make_uniforms(seed, S, B)
+    r1 = e1.step(f, c, uniforms=u, level=level)
+    v1, w1, g1 = r1["values"].clone(), r1["rewards"].clone(), e1.flat_grad.clone()
+    assert e1.segment_stats["segmented_steps"] == 0
+    rk = ek.step(f, c, uniforms=u, level=level)
+    assert ek._seg is not None and ek._seg[0] == segments, ek._seg
+    assert ek.segment_stats["fallbacks"] == 0, ek.segment_stats
+    assert torch.equal(rk["tokens"], r1["tokens"])
+    ev, er = float((rk["values"] - v1).abs().max()), float((rk["rewards"] - w1).abs().max())
+    eg = float((ek.flat_grad - g1).abs().max() / g1.abs().max())
+    _record("chain_segments_%d" % segments, values=ev, rewards=er, grad_rel=eg, warm_h=ek.segment_stats["max_err"][0],
+            warm_dg_rel=ek.segment_stats["max_err"][3] / max(ek.segment_stats["max_err"][4], 1e-30))
+    assert ev <= TOL and er <= TOL and eg <= GTOL, (ev, er, eg)
+    assert abs(rk.loss - r1.loss) <= TOL
+
+
+def test_chain_segments_fall_back_to_the_serial_kernels():
+    """A warm-up too short to forget the initial state (4 positions) must be caught by the check: the step is re-run on
+    the serial kernels (bit-identical to a serial engine), the warm-up is lengthened, and a warning is raised."""
+    seed, B, L = 141, 64, 10
+    e1, ek, A = _seg_engines(seed, 8, 4)
+    f, c = synth.make_inputs(seed, B, L)
+    u = synth.make_uniforms(seed, L - 1, B)
+    r1 = e1.step(f, c, uniforms=u)
+    v1, w1, g1 = r1["values"].clone(), r1["rewards"].clone(), e1.flat_grad.clone()
+    with pytest.warns(UserWarning, match="chain segments did not converge"):
+        rk = ek.step(f, c, uniforms=u)
+    assert ek.segment_stats["fallbacks"] == 1 and ek.chain_warmup == 16
+    assert torch.equal(rk["values"], v1) and torch.equal(rk["rewards"], w1)
+    assert float((ek.flat_grad - g1).abs().max() / g1.abs().max()) <= 1e-6      # atomics in the table scatter reorder sums
+    # unverified steps (check=False) are reported by segments_verified()
+    ek.chain_warmup = 4
+    ek.step(f, c, uniforms=u, check=False)
+    with pytest.warns(UserWarning):
+        assert ek.segments_verified() is False
+    assert ek.segments_verified() is True
+
+
+def test_get_rewards_segments_equal_the_serial_chain():
+    from icrl_b200.engine import A2CEngine
+    seed, B, L = 151, 256, 12
+    A, R, w = make_nets(seed)
+    f, c = synth.make_inputs(seed, B, L)
+    r1 = A2CEngine(A, R, chain_segments=1).get_rewards(f, c)
+    ek = A2CEngine(A, R, chain_warmup=48)
+    rk = ek.get_rewards(f, c)
+    assert ek._seg is not None and ek._seg[0] == 8 and ek.segment_stats["fallbacks"] == 0
+    assert float((rk - r1).abs().max()) <= TOL
+
+
+def test_config4_segments_full_size():
+    """BASELINE config 4 at full single-GPU size with the default engine (8 pieces, 512-position warm-up): the check
+    passes, and values / rewards / gradients agree with the serial chain at the tolerances of the golden tests."""
+    from icrl_b200.engine import A2CEngine
+    seed, B, L = 97, 4096, 20
+    A, R, w = make_nets(seed)
+    f, c = synth.make_inputs(seed, B, L)
+    u = synth.make_uniforms(seed, L - 1, B)
+    ek = A2CEngine(A, R)
+    rk = ek.step(f, c, uniforms=u)
+    assert ek.segment_stats["segmented_steps"] == 1 and ek.segment_stats["fallbacks"] == 0, ek.segment_stats
+    vk, wk, gk = rk["values"].clone(), rk["rewards"].clone(), ek.flat_grad.clone()
+    e1 = A2CEngine(A, R, chain_segments=1)
+    r1 = e1.step(f, c, uniforms=u)
+    assert torch.equal(rk["tokens"], r1["tokens"])
+    ev, er = float((vk - r1["values"]).abs().max()), float((wk - r1["rewards"]).abs().max())
+    eg = float((gk - e1.flat_grad).abs().max() / e1.flat_grad.abs().max())
+    _record("config4_segments", values=ev, rewards=er, grad_rel=eg, **{"err%d" % i: e for i, e in enumerate(ek.segment_stats["max_err"])})
+    assert ev <= TOL and er <= TOL and eg <= GTOL, (ev, er, eg)
