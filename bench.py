@@ -59,7 +59,7 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stamps, self.proc = index, [], [], None
 
     def start(self):
         try:
@@ -74,11 +74,22 @@ class ClockSampler:
             p = [x.strip() for x in line.split(",")]
             if len(p) >= 9 and p[0] == str(self.index):
                 self.rows.append(p)
+                self.stamps.append(time.time())
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples taken inside [t0, t1] (the timed region).  nvidia-smi needs ~0.5 s to start, so the sampler is
+        started before the warm-up steps; if the timed region is shorter than one sampling period the samples of the
+        warm-up steps (the same kernels, the same load) are used and `window` says so."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
+        window = "timed region"
+        if t0 is not None:
+            inside = [r for r, ts in zip(self.rows, self.stamps) if t0 <= ts <= t1 + 0.05]
+            if inside:
+                self.rows = inside
+            else:
+                window = "warm-up + timed region (timed region shorter than the 200 ms sampling period)"
         sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
         reasons = set()
         for r in self.rows:
@@ -87,7 +98,7 @@ class ClockSampler:
                     reasons.add(name)
         mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(self.rows), "window": window}
 
 
 def workload(batch):
@@ -208,13 +219,14 @@ def main():
     def step_resident():
         dp.step(prep, global_rows=B, check=False)
 
+    clocks.start()
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
     eng.phase_events = []
-    clocks.start()
+    t_wall0 = time.time()
     ms_step, launches = timed(step_resident, args.steps, 0)
-    clk = clocks.stop()
+    clk = clocks.stop(t_wall0, time.time())
     phases = {k: sum(v) / len(v) for k, v in eng.phase_times_ms().items()}
     eng.phase_events = None
     _lib.call("icrl_chain_check", ctypes.c_void_p(torch.cuda.current_stream().cuda_stream),
