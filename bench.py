@@ -43,9 +43,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=256, help="rows of the workload timed on the host cores")
     ap.add_argument("--chain-shards", type=int, default=1, choices=[1, 2, 4, 8],
                     help="value/reward recurrences per rank (1 = the reference's single carried-state chain)")
-    ap.add_argument("--chain-segments", type=int, default=8, choices=[1, 2, 4, 8],
+    ap.add_argument("--chain-segments", type=int, default=16, choices=[1, 2, 4, 8, 16, 24, 32],
                     help="lockstep pieces of the single carried-state chain (verified warm-up; 1 = serial kernels only)")
-    ap.add_argument("--chain-warmup", type=int, default=512, help="warm-up positions of every chain piece")
+    ap.add_argument("--chain-warmup", type=int, default=256, help="warm-up positions of every chain piece")
     ap.add_argument("--sharded-leg", action="store_true", help="also time 8 zero-state row shards per rank")
     ap.add_argument("--no-serial-leg", action="store_true", help="skip the serial-kernel leg (chain_segments = 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -326,9 +326,9 @@ def main():
     if seg_layout is not None:                 # lockstep pieces: one kernel step advances `pieces` chain positions
         pieces, seg_v, seg_r, warm = seg_layout
         if bwd_ms >= fwd_ms:
-            kname, ksteps = "chain_lstm_bwd_batched_kernel<%d> x 2 groups" % (pieces // 2), seg_v + warm
+            kname, ksteps = "chain_lstm_bwd_batched_kernel<4, 1> x 2 groups", seg_v * pieces // min(pieces, 8) + warm
         else:
-            kname, ksteps = "chains_fwd_fused_batched_kernel<%d>" % pieces, max(seg_v, seg_r) + warm
+            kname, ksteps = "chains_fwd_fused_batched_kernel<%d, %d>" % (min(pieces, 8), max(pieces // 8, 1)), max(seg_v, seg_r) + warm
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

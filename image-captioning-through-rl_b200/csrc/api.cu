@@ -341,7 +341,7 @@ long long icrl_chain_segment_len(long long T, int segments, int warm) {
   return seg >= 2ll * warm ? seg : 0;
 }
 
-size_t icrl_chain_segment_ws_floats(void) { return 8 + 2 * 8 * 2 * 512 + 8 * 4 * 512; }
+size_t icrl_chain_segment_ws_floats(void) { return 8 + 2 * 32 * 2 * 512 + 16 * 4 * 512; }
 
 int icrl_chains_fwd_fused_segmented(void* stream, int segments, int warm, const int* v_stream, int v_seg,
                                     const float* v_table, const float* v_W_hh, float* v_stash_h, float* v_stash_c,
@@ -363,7 +363,7 @@ int icrl_chain_lstm_bwd_segmented(void* stream, int segments, int warm, int seg,
                                   long long take_rows, float* dgates, float* segment_ws, void* sync_state, int* launches) {
   ICRL_REQUIRE(warm >= 1 && segment_ws, "segmented chains need a warm-up length and the segment workspace");
   TRY(icrl_chain_lstm_bwd_batched_impl(S_(stream), segments, seg, W_hh, stash_gates, stash_c, take, dh_take, dgates,
-                                       sync_state, warm, segment_ws + 8 + 2 * 8 * 2 * 512, take_rows * 512, segment_ws));
+                                       sync_state, warm, segment_ws + 8 + 2 * 32 * 2 * 512, take_rows * 512, segment_ws));
   bump(launches, 2);
   return ICRL_OK;
 }

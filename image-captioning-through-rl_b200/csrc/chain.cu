@@ -128,14 +128,18 @@ __device__ __forceinline__ float reduce_transposed(float (&v)[NB], int lane) {
 // Batched form: all NV polls are in flight before the first tag is examined (one L2 round trip for the whole
 // batch instead of one per vector); only words that had not arrived yet are polled again.
 template <int NV>
-__device__ __forceinline__ bool fetch_exchange_all(const unsigned long long* buf, unsigned tag, float* sm,
-                                                   volatile int* abort_flag) {
-  unsigned long long a[NV], b[NV];
+__device__ __forceinline__ void exchange_issue(const unsigned long long* buf, unsigned long long (&a)[NV],
+                                               unsigned long long (&b)[NV]) {
 #pragma unroll
   for (int v = 0; v < NV; ++v) ld_tagged2(buf + (v * THREADS + threadIdx.x) * 2, a[v], b[v]);
-  // Poll in ROUNDS: every word that has not arrived is re-read in the same round (one L2 round trip per round).
-  // Re-polling word by word costs one round trip per word, because the first sample of every later word was
-  // taken before the data existed: measured 1,705 / 2,593 / 5,574 cycles of wait at NV = 2 / 4 / 8.
+}
+// Poll in ROUNDS: every word that has not arrived is re-read in the same round (one L2 round trip per round).
+// Re-polling word by word costs one round trip per word, because the first sample of every later word was
+// taken before the data existed: measured 1,705 / 2,593 / 5,574 cycles of wait at NV = 2 / 4 / 8.
+template <int NV>
+__device__ __forceinline__ bool exchange_complete(const unsigned long long* buf, unsigned tag, float* sm,
+                                                  volatile int* abort_flag, unsigned long long (&a)[NV],
+                                                  unsigned long long (&b)[NV]) {
   unsigned pending = (1u << NV) - 1u, spins = 0;
   bool ok = true;
   while (true) {
@@ -153,6 +157,13 @@ __device__ __forceinline__ bool fetch_exchange_all(const unsigned long long* buf
     reinterpret_cast<float2*>(sm)[v * THREADS + threadIdx.x] =
         make_float2(__uint_as_float((unsigned)a[v]), __uint_as_float((unsigned)b[v]));
   return ok;
+}
+template <int NV>
+__device__ __forceinline__ bool fetch_exchange_all(const unsigned long long* buf, unsigned tag, float* sm,
+                                                   volatile int* abort_flag) {
+  unsigned long long a[NV], b[NV];
+  exchange_issue<NV>(buf, a, b);
+  return exchange_complete<NV>(buf, tag, sm, abort_flag, a, b);
 }
 
 template <int NG>   // 4 = LSTM (i,f,g,o), 3 = GRU (r,z,n)
@@ -423,7 +434,7 @@ __global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_kernel(ChainBwdArgs
 // All per-step arrays of a shard use the same row stride (T + 1): stream [NB][stride], stash_h / stash_c
 // [NB][stride][H], stash_gates / dgates [NB][stride][4H] (row T unused / zero), take [NB][stride].
 
-constexpr int NB_MAX = 8;
+constexpr int NB_MAX = 32;        // shards per forward launch (4 chunks of 8): exchange areas and check buffers are sized for it
 
 struct ChainFwdBatchArgs {
   const int* stream;          // [NB][stride]
@@ -450,12 +461,15 @@ struct ChainFwdBatchArgs {
 // (Tried and dropped for this exchange, both slower at NB = 8: a unit-major word layout [unit][NB], 393 -> 426 ms, and
 // plain data + one release flag per unit polled with acquire loads, 393 -> 508 ms: the release store waits for the
 // warp's stash writes.)
-template <int NG, int NB>
-__device__ void chain_fwd_batched_body(const ChainFwdBatchArgs& p, int cta, float* sh_h /* [2][NB][H] */) {
+// NCH > 1: the NB * NCH shards are walked as NCH chunks of NB per step.  Chunk q publishes its hidden vectors, then the
+// CTA computes the other chunks before it polls for chunk q's next vectors: the exchange round trip through L2 (the wait
+// that bounds a single chunk) is covered by the other chunks' arithmetic.  Shard index = q * NB + lane group.
+template <int NG, int NB, int NCH>
+__device__ void chain_fwd_batched_body(const ChainFwdBatchArgs& p, int cta, float* sh_h /* [NCH][2][NB][H] */) {
   constexpr int GL = 32 / NB;                          // lanes per shard group after the transposed reduction
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit = cta * UNITS + warp;
-  const int b = lane / GL, sub = lane % GL;            // this lane's shard for the pointwise stage
+  const int b = lane / GL, sub = lane % GL;            // this lane's shard (within a chunk) for the pointwise stage
 
   float w[NG][16];
 #pragma unroll
@@ -466,123 +480,143 @@ __device__ void chain_fwd_batched_body(const ChainFwdBatchArgs& p, int cta, floa
       w[g][4 * j + 0] = t.x; w[g][4 * j + 1] = t.y; w[g][4 * j + 2] = t.z; w[g][4 * j + 3] = t.w;
     }
   const float bhn = (NG == 3) ? p.b_hn[unit] : 0.f;
-  float c = 0.f, hprev = 0.f;
-  const int* my_stream = p.stream + (size_t)b * p.stride;
-  float* my_h = p.stash_h + (size_t)b * p.stride * H;
-  float* my_c = p.stash_c ? p.stash_c + (size_t)b * p.stride * H : nullptr;
-  float* my_g = p.stash_gates ? p.stash_gates + (size_t)b * p.stride * (4 * H) : nullptr;
-  const bool seg_tail = p.warm > 0 && b > 0;           // a later segment of one chain: its first `warm` steps are discarded
-  if (sub == 0 && !seg_tail) {
-    my_h[unit] = 0.f;
-    if (NG == 4 && my_c) my_c[unit] = 0.f;
-  }
-  for (int i = threadIdx.x; i < NB * H; i += THREADS) sh_h[i] = 0.f;      // step-0 vectors: zero state
-
-  int tok_next = p.T > 1 ? my_stream[1] : 0;
-  float xg[NG];
-  {
+  float c[NCH], hprev[NCH], xg[NCH][NG];
+  int tok_next[NCH];
+#pragma unroll
+  for (int q = 0; q < NCH; ++q) {
+    const int bg = q * NB + b;
+    const int* my_stream = p.stream + (size_t)bg * p.stride;
+    c[q] = 0.f; hprev[q] = 0.f;
+    if (sub == 0 && !(p.warm > 0 && bg > 0)) {         // (later segments of one chain store nothing before their warm-up ends)
+      p.stash_h[(size_t)bg * p.stride * H + unit] = 0.f;
+      if (NG == 4 && p.stash_c) p.stash_c[(size_t)bg * p.stride * H + unit] = 0.f;
+    }
+    tok_next[q] = p.T > 1 ? my_stream[1] : 0;
     const int tok0 = my_stream[0];
 #pragma unroll
-    for (int g = 0; g < NG; ++g) xg[g] = p.table[(size_t)tok0 * (NG * H) + g * H + unit];
+    for (int g = 0; g < NG; ++g) xg[q][g] = p.table[(size_t)tok0 * (NG * H) + g * H + unit];
   }
+  for (int i = threadIdx.x; i < NCH * 2 * NB * H; i += THREADS) sh_h[i] = 0.f;      // step-0 vectors: zero state
 
   long long prof_wait = 0, prof_gemv = 0, prof_rest = 0;
   const bool prof = p.prof != nullptr && cta == 0 && threadIdx.x == 0;
+  unsigned long long pre_a[NB], pre_b[NB];             // polled exchange words (tag, value) of the chunk about to run
   for (int t = 0; t < p.T; ++t) {
-    const long long c0 = prof ? clock64() : 0;
     const int buf = t & 1;
-    float* hb = sh_h + buf * NB * H;
-    bool ok = true;
-    if (t > 0) ok = fetch_exchange_all<NB>(p.xchg + (size_t)((t - 1) & 1) * NB * H, (unsigned)t, hb, p.abort_flag);
-    if (__syncthreads_or(!ok)) {
-      if (threadIdx.x == 0) atomicExch(p.abort_flag, 1);
-      return;
-    }
-    const long long c1 = prof ? clock64() : 0;
-    float xg_n[NG];
-    {
-      const int tk = tok_next;
-      if (t + 1 < p.T) {
+    // (unrolled on purpose: with `#pragma unroll 1` the per-chunk state moves to thread-local memory and the two-chunk
+    // kernel measured 121.6 ms instead of 110.0 ms at B = 2048)
 #pragma unroll
-        for (int g = 0; g < NG; ++g) xg_n[g] = p.table[(size_t)tk * (NG * H) + g * H + unit];
-      } else {
-#pragma unroll
-        for (int g = 0; g < NG; ++g) xg_n[g] = 0.f;
+    for (int q = 0; q < NCH; ++q) {
+      const long long c0 = prof ? clock64() : 0;
+      const int bg = q * NB + b;
+      const bool seg_tail = p.warm > 0 && bg > 0;      // a later segment of one chain: its first `warm` steps are discarded
+      const int* my_stream = p.stream + (size_t)bg * p.stride;
+      unsigned long long* xq = p.xchg + (size_t)q * (2 * NB * H);
+      float* hb = sh_h + (size_t)(q * 2 + buf) * NB * H;
+      bool ok = true;
+      if (t > 0) {
+        const unsigned long long* src = xq + (size_t)((t - 1) & 1) * NB * H;
+        if (NCH == 1) exchange_issue<NB>(src, pre_a, pre_b);          // (chunked: already in flight, see below)
+        ok = exchange_complete<NB>(src, (unsigned)t, hb, p.abort_flag, pre_a, pre_b);
       }
-      tok_next = (t + 2 < p.T) ? my_stream[t + 2] : 0;
-    }
-    // batch-NB GEMV: NG rows x 512 against NB hidden vectors, weights in registers
-    float acc[NG][NB];
+      if (__syncthreads_or(!ok)) {
+        if (threadIdx.x == 0) atomicExch(p.abort_flag, 1);
+        return;
+      }
+      if (NCH > 1) {
+        // first poll of the NEXT chunk's vectors (published one chunk ago) rides under this chunk's arithmetic, so
+        // an exchange that has arrived costs no L2 round trip on the critical path
+        const int qn = (q + 1) % NCH, tn = q + 1 < NCH ? t : t + 1;
+        if (tn > 0 && tn < p.T)
+          exchange_issue<NB>(p.xchg + (size_t)qn * (2 * NB * H) + (size_t)((tn - 1) & 1) * NB * H, pre_a, pre_b);
+      }
+      const long long c1 = prof ? clock64() : 0;
+      float xg_n[NG];
+      {
+        const int tk = tok_next[q];
+        if (t + 1 < p.T) {
 #pragma unroll
-    for (int g = 0; g < NG; ++g)
+          for (int g = 0; g < NG; ++g) xg_n[g] = p.table[(size_t)tk * (NG * H) + g * H + unit];
+        } else {
 #pragma unroll
-      for (int v = 0; v < NB; ++v) acc[g][v] = 0.f;
+          for (int g = 0; g < NG; ++g) xg_n[g] = 0.f;
+        }
+        tok_next[q] = (t + 2 < p.T) ? my_stream[t + 2] : 0;
+      }
+      // batch-NB GEMV: NG rows x 512 against NB hidden vectors, weights in registers
+      float acc[NG][NB];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+      for (int g = 0; g < NG; ++g)
 #pragma unroll
-      for (int v = 0; v < NB; ++v) {
-        const float4 hv = *reinterpret_cast<const float4*>(&hb[v * H + 128 * j + 4 * lane]);
+        for (int v = 0; v < NB; ++v) acc[g][v] = 0.f;
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          acc[g][v] = fmaf(w[g][4 * j + 0], hv.x, acc[g][v]);
-          acc[g][v] = fmaf(w[g][4 * j + 1], hv.y, acc[g][v]);
-          acc[g][v] = fmaf(w[g][4 * j + 2], hv.z, acc[g][v]);
-          acc[g][v] = fmaf(w[g][4 * j + 3], hv.w, acc[g][v]);
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int v = 0; v < NB; ++v) {
+          const float4 hv = *reinterpret_cast<const float4*>(&hb[v * H + 128 * j + 4 * lane]);
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            acc[g][v] = fmaf(w[g][4 * j + 0], hv.x, acc[g][v]);
+            acc[g][v] = fmaf(w[g][4 * j + 1], hv.y, acc[g][v]);
+            acc[g][v] = fmaf(w[g][4 * j + 2], hv.z, acc[g][v]);
+            acc[g][v] = fmaf(w[g][4 * j + 3], hv.w, acc[g][v]);
+          }
         }
       }
-    }
-    float sum[NG];
+      float sum[NG];
 #pragma unroll
-    for (int g = 0; g < NG; ++g) sum[g] = reduce_transposed<NB>(acc[g], lane);
-    const long long c2 = prof ? clock64() : 0;
+      for (int g = 0; g < NG; ++g) sum[g] = reduce_transposed<NB>(acc[g], lane);
+      const long long c2 = prof ? clock64() : 0;
 
-    const bool live = !seg_tail || t >= p.warm;        // warm-up steps of a later segment leave no trace
-    const bool warm_end = seg_tail && t == p.warm - 1;
-    float hnew;
-    if constexpr (NG == 4) {
-      const float i = act_sigmoid(sum[0] + xg[0]);
-      const float f = act_sigmoid(sum[1] + xg[1]);
-      const float g = act_tanh(sum[2] + xg[2]);
-      const float o = act_sigmoid(sum[3 % NG] + xg[3 % NG]);
-      c = f * c + i * g;
-      hnew = o * act_tanh(c);
-      if (my_g && sub < 4 && live) {
-        const float sel = sub == 0 ? i : (sub == 1 ? f : (sub == 2 ? g : o));
-        my_g[(size_t)t * 4 * H + sub * H + unit] = sel;
+      const bool live = !seg_tail || t >= p.warm;      // warm-up steps of a later segment leave no trace
+      const bool warm_end = seg_tail && t == p.warm - 1;
+      const size_t row = (size_t)bg * p.stride + t;    // this shard's row of the per-step arrays
+      float hnew;
+      if constexpr (NG == 4) {
+        const float i = act_sigmoid(sum[0] + xg[q][0]);
+        const float f = act_sigmoid(sum[1] + xg[q][1]);
+        const float g = act_tanh(sum[2] + xg[q][2]);
+        const float o = act_sigmoid(sum[3 % NG] + xg[q][3 % NG]);
+        c[q] = f * c[q] + i * g;
+        hnew = o * act_tanh(c[q]);
+        if (p.stash_gates && sub < 4 && live) {
+          const float sel = sub == 0 ? i : (sub == 1 ? f : (sub == 2 ? g : o));
+          p.stash_gates[row * 4 * H + sub * H + unit] = sel;
+        }
+        if (sub == 4 % GL) {
+          if (p.stash_c && live) p.stash_c[(row + 1) * H + unit] = c[q];
+          if (warm_end) p.warm_state[(size_t)(2 * bg + 1) * H + unit] = c[q];
+        }
+      } else {
+        const float r = act_sigmoid(sum[0] + xg[q][0]);
+        const float z = act_sigmoid(sum[1] + xg[q][1]);
+        const float n = act_tanh(xg[q][2] + r * (sum[2] + bhn));
+        hnew = (1.f - z) * n + z * hprev[q];
       }
-      if (sub == 4 % GL) {
-        if (my_c && live) my_c[(size_t)(t + 1) * H + unit] = c;
-        if (warm_end) p.warm_state[(size_t)(2 * b + 1) * H + unit] = c;
+      hprev[q] = hnew;
+      if (sub == 6 % GL) st_tagged(xq + ((size_t)buf * NB + b) * H + unit, hnew, (unsigned)(t + 1));
+      if (sub == 5 % GL) {
+        if (live) p.stash_h[(row + 1) * H + unit] = hnew;
+        if (warm_end) p.warm_state[(size_t)(2 * bg) * H + unit] = hnew;
       }
-    } else {
-      const float r = act_sigmoid(sum[0] + xg[0]);
-      const float z = act_sigmoid(sum[1] + xg[1]);
-      const float n = act_tanh(xg[2] + r * (sum[2] + bhn));
-      hnew = (1.f - z) * n + z * hprev;
-    }
-    hprev = hnew;
-    if (sub == 6 % GL) st_tagged(p.xchg + ((size_t)buf * NB + b) * H + unit, hnew, (unsigned)(t + 1));
-    if (sub == 5 % GL) {
-      if (live) my_h[(size_t)(t + 1) * H + unit] = hnew;
-      if (warm_end) p.warm_state[(size_t)(2 * b) * H + unit] = hnew;
-    }
 #pragma unroll
-    for (int g = 0; g < NG; ++g) xg[g] = xg_n[g];
-    if (prof) { const long long c3 = clock64(); prof_wait += c1 - c0; prof_gemv += c2 - c1; prof_rest += c3 - c2; }
+      for (int g = 0; g < NG; ++g) xg[q][g] = xg_n[g];
+      if (prof) { const long long c3 = clock64(); prof_wait += c1 - c0; prof_gemv += c2 - c1; prof_rest += c3 - c2; }
+    }
   }
   if (prof) { p.prof[0] = prof_wait; p.prof[1] = prof_gemv; p.prof[2] = prof_rest; p.prof[3] = p.T; }
 }
 
-template <int NB>
+template <int NB, int NCH>
 __global__ void __launch_bounds__(THREADS, 1) chains_fwd_fused_batched_kernel(ChainFwdBatchArgs lstm, ChainFwdBatchArgs gru) {
   extern __shared__ __align__(16) float sh_dyn[];
-  if (blockIdx.x < CHAIN_CTAS) chain_fwd_batched_body<4, NB>(lstm, blockIdx.x, sh_dyn);
-  else chain_fwd_batched_body<3, NB>(gru, blockIdx.x - CHAIN_CTAS, sh_dyn);
+  if (blockIdx.x < CHAIN_CTAS) chain_fwd_batched_body<4, NB, NCH>(lstm, blockIdx.x, sh_dyn);
+  else chain_fwd_batched_body<3, NB, NCH>(gru, blockIdx.x - CHAIN_CTAS, sh_dyn);
 }
-template <int NB>
+template <int NB, int NCH>
 __global__ void __launch_bounds__(THREADS, 1) chain_gru_fwd_batched_kernel(ChainFwdBatchArgs gru) {
   extern __shared__ __align__(16) float sh_dyn[];
-  chain_fwd_batched_body<3, NB>(gru, blockIdx.x, sh_dyn);
+  chain_fwd_batched_body<3, NB, NCH>(gru, blockIdx.x, sh_dyn);
 }
 
 struct ChainBwdBatchArgs {
@@ -602,19 +636,25 @@ struct ChainBwdBatchArgs {
   // gate gradients of their last warm-up step go to warm_dg for the caller's check against the row the next shard writes.
   int warm;
   float* warm_dg;             // [shards][4H]
+  long long* prof;            // debug: cycles of CTA 0 thread 0 {coefficients + requests, poll wait, gate gradients + stores,
+                              // barrier, contraction + reduce, barrier + publish}, then T
 };
 
 // Backward recurrence of NB shards per 64-CTA group (see chain_lstm_bwd_kernel for the single-chain scheme).
-template <int NB>
+// NCH > 1: every 64-CTA group walks NB * NCH shards as NCH chunks of NB per step (shard = (group * NCH + q) * NB + v).
+// A chunk publishes its dh vectors and the group works on the other chunks before it needs them back, and both the
+// stash rows and the first poll of the next chunk are requested one chunk ahead, so neither the L2 exchange nor the
+// stash reads sit on the critical path.
+template <int NB, int NCH, bool PROF>
 __global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_batched_kernel(ChainBwdBatchArgs p) {
   extern __shared__ __align__(16) float sh_dyn[];      // [2][NB][4H]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int group = blockIdx.x / CHAIN_CTAS, cta = blockIdx.x % CHAIN_CTAS;
-  const int sb = group * NB;                           // first shard of this group
+  const int sb0 = group * NCH * NB;                    // first shard of this group
   const int unit = cta * UNITS + warp;
   const int pu = 2 * threadIdx.x;
   const bool owner = (pu >= cta * UNITS) && (pu < cta * UNITS + UNITS);
-  const int myb = (lane >> 3) < NB ? (lane >> 3) : 0;  // shard whose dh lane 8*myb publishes
+  const int myb = (lane >> 3) < NB ? (lane >> 3) : 0;  // shard (within a chunk) whose dh lane 8*myb publishes
 
   // contraction split over the warps as in chain_lstm_bwd_kernel: wl[i][k] = W_hh[256w + 8 lane + k][8 cta + i]
   __shared__ float sh_part[UNITS][NB * UNITS];         // [warp][shard * 8 + unit]
@@ -627,10 +667,11 @@ __global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_batched_kernel(Chai
     wl[4][k] = x1.x; wl[5][k] = x1.y; wl[6][k] = x1.z; wl[7][k] = x1.w;
   }
 
-  float2 dc[NB], gi[NB], gf[NB], gg[NB], go[NB], cc[NB], cp[NB], dh[NB];
-  auto load_step = [&](int v, int t, float2& a_i, float2& a_f, float2& a_g, float2& a_o, float2& a_cc, float2& a_cp) {
-    const float* ga = p.stash_gates + ((size_t)(sb + v) * p.stride + t) * 4 * H + pu;
-    const float* ca = p.stash_c + ((size_t)(sb + v) * p.stride + t) * H + pu;
+  float2 dc[NCH][NB], gi[NB], gf[NB], gg[NB], go[NB], cc[NB], cp[NB];
+  int tk_prev[NCH];
+  auto load_step = [&](int shard, int t, float2& a_i, float2& a_f, float2& a_g, float2& a_o, float2& a_cc, float2& a_cp) {
+    const float* ga = p.stash_gates + ((size_t)shard * p.stride + t) * 4 * H + pu;
+    const float* ca = p.stash_c + ((size_t)shard * p.stride + t) * H + pu;
     a_i = *reinterpret_cast<const float2*>(ga);
     a_f = *reinterpret_cast<const float2*>(ga + H);
     a_g = *reinterpret_cast<const float2*>(ga + 2 * H);
@@ -639,112 +680,152 @@ __global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_batched_kernel(Chai
     a_cp = *reinterpret_cast<const float2*>(ca);
   };
 #pragma unroll
-  for (int v = 0; v < NB; ++v) {
-    dc[v] = make_float2(0.f, 0.f);
-    load_step(v, p.T - 1, gi[v], gf[v], gg[v], go[v], cc[v], cp[v]);
-    dh[v] = make_float2(0.f, 0.f);
-    const int tk = p.take[(size_t)(sb + v) * p.stride + p.T - 1];
-    if (tk >= 0) dh[v] = *reinterpret_cast<const float2*>(p.dh_take + (size_t)tk * H + pu);
+  for (int q = 0; q < NCH; ++q) {
+#pragma unroll
+    for (int v = 0; v < NB; ++v) dc[q][v] = make_float2(0.f, 0.f);
+    tk_prev[q] = p.T > 1 ? p.take[(size_t)(sb0 + q * NB + myb) * p.stride + p.T - 2] : -1;
   }
-  const int* my_take = p.take + (size_t)(sb + myb) * p.stride;
-  int tk_prev = p.T > 1 ? my_take[p.T - 2] : -1;
+#pragma unroll
+  for (int v = 0; v < NB; ++v) load_step(sb0 + v, p.T - 1, gi[v], gf[v], gg[v], go[v], cc[v], cp[v]);
+  unsigned long long pa[NB], pb[NB];                   // polled dh words of the chunk about to run
+  const bool prof = PROF && blockIdx.x == 0 && threadIdx.x == 0;       // PROF: the cycle-split build of the kernel
+  long long pr[PROF ? 6 : 1] = {};
 
   for (int it = 0; it < p.T; ++it) {
     const int t = p.T - 1 - it;
-    const int buf = it & 1;
-    float* dgb = sh_dyn + buf * NB * 4 * H;
-    bool ok = true;
-    unsigned long long pa[NB], pb[NB];
-    const unsigned long long* src = p.xchg + ((size_t)((it - 1) & 1) * p.shards + sb) * H + pu;
-    if (it > 0) {
 #pragma unroll
-      for (int v = 0; v < NB; ++v) ld_tagged2(src + (size_t)v * H, pa[v], pb[v]);
-    }
-    // coefficients that do not depend on dh
-    float2 kc[NB], ko[NB], ki[NB], kf[NB], kg[NB], fgate[NB];
+    for (int q = 0; q < NCH; ++q) {
+      const long long k0 = prof ? clock64() : 0;
+      const int sb = sb0 + q * NB;                     // first shard of this chunk
+      const int buf = (NCH == 1 ? it : it * NCH + q) & 1;
+      float* dgb = sh_dyn + buf * NB * 4 * H;
+      bool ok = true;
+      const unsigned long long* src = p.xchg + ((size_t)((it - 1) & 1) * p.shards + sb) * H + pu;
+      if (NCH == 1 && it > 0) {
 #pragma unroll
-    for (int v = 0; v < NB; ++v) {
-      const float tcx = act_tanh(cc[v].x), tcy = act_tanh(cc[v].y);
-      kc[v] = make_float2(go[v].x * (1.f - tcx * tcx), go[v].y * (1.f - tcy * tcy));
-      ko[v] = make_float2(tcx * go[v].x * (1.f - go[v].x), tcy * go[v].y * (1.f - go[v].y));
-      ki[v] = make_float2(gg[v].x * gi[v].x * (1.f - gi[v].x), gg[v].y * gi[v].y * (1.f - gi[v].y));
-      kf[v] = make_float2(cp[v].x * gf[v].x * (1.f - gf[v].x), cp[v].y * gf[v].y * (1.f - gf[v].y));
-      kg[v] = make_float2(gi[v].x * (1.f - gg[v].x * gg[v].x), gi[v].y * (1.f - gg[v].y * gg[v].y));
-      fgate[v] = gf[v];
-    }
-    const float inj = tk_prev >= 0 ? p.dh_take[(size_t)tk_prev * H + unit] : 0.f;
-    if (t > 0) {
-#pragma unroll
-      for (int v = 0; v < NB; ++v) load_step(v, t - 1, gi[v], gf[v], gg[v], go[v], cc[v], cp[v]);
-    }
-    tk_prev = t > 1 ? my_take[t - 2] : -1;
-
-    if (it > 0) {
-      unsigned pending = (1u << NB) - 1u, spins = 0;       // rounds: all missing words are re-read together
-      while (true) {
-#pragma unroll
-        for (int v = 0; v < NB; ++v)
-          if ((pending >> v & 1u) && (unsigned)(pa[v] >> 32) == (unsigned)it && (unsigned)(pb[v] >> 32) == (unsigned)it)
-            pending &= ~(1u << v);
-        if (pending == 0) break;
-        if (++spins >= SPIN_LIMIT || ((spins & 1023u) == 0 && *(volatile int*)p.abort_flag != 0)) { ok = false; break; }
-#pragma unroll
-        for (int v = 0; v < NB; ++v)
-          if (pending >> v & 1u) ld_tagged2(src + (size_t)v * H, pa[v], pb[v]);
+        for (int v = 0; v < NB; ++v) ld_tagged2(src + (size_t)v * H, pa[v], pb[v]);
       }
-#pragma unroll
-      for (int v = 0; v < NB; ++v) dh[v] = make_float2(__uint_as_float((unsigned)pa[v]), __uint_as_float((unsigned)pb[v]));
-    }
-#pragma unroll
-    for (int v = 0; v < NB; ++v) {
-      const float dctx = dc[v].x + dh[v].x * kc[v].x, dcty = dc[v].y + dh[v].y * kc[v].y;
-      dc[v] = make_float2(dctx * fgate[v].x, dcty * fgate[v].y);
-      const float2 d_i = make_float2(dctx * ki[v].x, dcty * ki[v].y), d_f = make_float2(dctx * kf[v].x, dcty * kf[v].y);
-      const float2 d_g = make_float2(dctx * kg[v].x, dcty * kg[v].y), d_o = make_float2(dh[v].x * ko[v].x, dh[v].y * ko[v].y);
-      float* sd = dgb + v * 4 * H + pu;
-      *reinterpret_cast<float2*>(sd) = d_i;
-      *reinterpret_cast<float2*>(sd + H) = d_f;
-      *reinterpret_cast<float2*>(sd + 2 * H) = d_g;
-      *reinterpret_cast<float2*>(sd + 3 * H) = d_o;
-      const bool live = p.warm == 0 || it >= p.warm || sb + v == p.shards - 1;
-      if (owner && (live || it == p.warm - 1)) {
-        float* out = live ? p.dgates + ((size_t)(sb + v) * p.stride + t) * 4 * H + pu
-                          : p.warm_dg + (size_t)(sb + v) * 4 * H + pu;
-        *reinterpret_cast<float2*>(out) = d_i;
-        *reinterpret_cast<float2*>(out + H) = d_f;
-        *reinterpret_cast<float2*>(out + 2 * H) = d_g;
-        *reinterpret_cast<float2*>(out + 3 * H) = d_o;
-      }
-    }
-    if (__syncthreads_or(!ok)) {
-      if (threadIdx.x == 0) atomicExch(p.abort_flag, 1);
-      return;
-    }
-    if (t > 0) {
-      float part[NB * UNITS];
+      // coefficients that do not depend on dh
+      float2 kc[NB], ko[NB], ki[NB], kf[NB], kg[NB], fgate[NB], dh[NB];
 #pragma unroll
       for (int v = 0; v < NB; ++v) {
-        const float4 d0 = *reinterpret_cast<const float4*>(&dgb[v * 4 * H + 256 * warp + 8 * lane]);
-        const float4 d1 = *reinterpret_cast<const float4*>(&dgb[v * 4 * H + 256 * warp + 8 * lane + 4]);
+        const float tcx = act_tanh(cc[v].x), tcy = act_tanh(cc[v].y);
+        kc[v] = make_float2(go[v].x * (1.f - tcx * tcx), go[v].y * (1.f - tcy * tcy));
+        ko[v] = make_float2(tcx * go[v].x * (1.f - go[v].x), tcy * go[v].y * (1.f - go[v].y));
+        ki[v] = make_float2(gg[v].x * gi[v].x * (1.f - gi[v].x), gg[v].y * gi[v].y * (1.f - gi[v].y));
+        kf[v] = make_float2(cp[v].x * gf[v].x * (1.f - gf[v].x), cp[v].y * gf[v].y * (1.f - gf[v].y));
+        kg[v] = make_float2(gi[v].x * (1.f - gg[v].x * gg[v].x), gi[v].y * (1.f - gg[v].y * gg[v].y));
+        fgate[v] = gf[v];
+      }
+      const float inj = tk_prev[q] >= 0 ? p.dh_take[(size_t)tk_prev[q] * H + unit] : 0.f;
+      tk_prev[q] = t > 1 ? p.take[(size_t)(sb + myb) * p.stride + t - 2] : -1;
+      const long long k1 = prof ? clock64() : 0;
+      if (it == 0) {                                   // the recurrence starts with the gradient injected at the last position
 #pragma unroll
-        for (int i = 0; i < UNITS; ++i) {
-          float a = wl[i][0] * d0.x;
-          a = fmaf(wl[i][1], d0.y, a); a = fmaf(wl[i][2], d0.z, a); a = fmaf(wl[i][3], d0.w, a);
-          a = fmaf(wl[i][4], d1.x, a); a = fmaf(wl[i][5], d1.y, a); a = fmaf(wl[i][6], d1.z, a); a = fmaf(wl[i][7], d1.w, a);
-          part[v * UNITS + i] = a;
+        for (int v = 0; v < NB; ++v) {
+          dh[v] = make_float2(0.f, 0.f);
+          const int tk = p.take[(size_t)(sb + v) * p.stride + p.T - 1];
+          if (tk >= 0) dh[v] = *reinterpret_cast<const float2*>(p.dh_take + (size_t)tk * H + pu);
+        }
+      } else {
+        unsigned pending = (1u << NB) - 1u, spins = 0;     // rounds: all missing words are re-read together
+        while (true) {
+#pragma unroll
+          for (int v = 0; v < NB; ++v)
+            if ((pending >> v & 1u) && (unsigned)(pa[v] >> 32) == (unsigned)it && (unsigned)(pb[v] >> 32) == (unsigned)it)
+              pending &= ~(1u << v);
+          if (pending == 0) break;
+          if (++spins >= SPIN_LIMIT || ((spins & 1023u) == 0 && *(volatile int*)p.abort_flag != 0)) { ok = false; break; }
+#pragma unroll
+          for (int v = 0; v < NB; ++v)
+            if (pending >> v & 1u) ld_tagged2(src + (size_t)v * H, pa[v], pb[v]);
+        }
+#pragma unroll
+        for (int v = 0; v < NB; ++v) dh[v] = make_float2(__uint_as_float((unsigned)pa[v]), __uint_as_float((unsigned)pb[v]));
+      }
+      const long long k2 = prof ? clock64() : 0;
+      // requests for the chunk that runs next: its stash rows and (chunked) the first poll of its dh words
+      {
+        const int qn = (q + 1) % NCH, itn = q + 1 < NCH ? it : it + 1;
+        if (itn < p.T) {
+#pragma unroll
+          for (int v = 0; v < NB; ++v)
+            load_step(sb0 + qn * NB + v, p.T - 1 - itn, gi[v], gf[v], gg[v], go[v], cc[v], cp[v]);
+          if (NCH > 1 && itn > 0) {
+            const unsigned long long* srcn = p.xchg + ((size_t)((itn - 1) & 1) * p.shards + sb0 + qn * NB) * H + pu;
+#pragma unroll
+            for (int v = 0; v < NB; ++v) ld_tagged2(srcn + (size_t)v * H, pa[v], pb[v]);
+          }
         }
       }
-      constexpr int R = NB * UNITS;                     // 8, 16 or 32 values: lane l ends with element l >> (5 - log2 R)
-      const float ps = reduce_transposed<R>(part, lane);
-      if ((lane & (32 / R - 1)) == 0) sh_part[warp][lane / (32 / R)] = ps;
-      __syncthreads();
-      if (lane < R) {
-        float r = sh_part[lane & 7][(lane >> 3) * UNITS + warp];     // lane 8v + w': warp w' partial of (shard v, unit `warp`)
-        r += __shfl_xor_sync((unsigned)((1ull << R) - 1), r, 1);
-        r += __shfl_xor_sync((unsigned)((1ull << R) - 1), r, 2);
-        r += __shfl_xor_sync((unsigned)((1ull << R) - 1), r, 4);
-        if ((lane & 7) == 0) st_tagged(p.xchg + ((size_t)buf * p.shards + sb + (lane >> 3)) * H + unit, r + inj, (unsigned)(it + 1));
+#pragma unroll
+      for (int v = 0; v < NB; ++v) {
+        const float dctx = dc[q][v].x + dh[v].x * kc[v].x, dcty = dc[q][v].y + dh[v].y * kc[v].y;
+        dc[q][v] = make_float2(dctx * fgate[v].x, dcty * fgate[v].y);
+        const float2 d_i = make_float2(dctx * ki[v].x, dcty * ki[v].y), d_f = make_float2(dctx * kf[v].x, dcty * kf[v].y);
+        const float2 d_g = make_float2(dctx * kg[v].x, dcty * kg[v].y), d_o = make_float2(dh[v].x * ko[v].x, dh[v].y * ko[v].y);
+        float* sd = dgb + v * 4 * H + pu;
+        *reinterpret_cast<float2*>(sd) = d_i;
+        *reinterpret_cast<float2*>(sd + H) = d_f;
+        *reinterpret_cast<float2*>(sd + 2 * H) = d_g;
+        *reinterpret_cast<float2*>(sd + 3 * H) = d_o;
+        const bool live = p.warm == 0 || it >= p.warm || sb + v == p.shards - 1;
+        if (owner && (live || it == p.warm - 1)) {
+          float* out = live ? p.dgates + ((size_t)(sb + v) * p.stride + t) * 4 * H + pu
+                            : p.warm_dg + (size_t)(sb + v) * 4 * H + pu;
+          *reinterpret_cast<float2*>(out) = d_i;
+          *reinterpret_cast<float2*>(out + H) = d_f;
+          *reinterpret_cast<float2*>(out + 2 * H) = d_g;
+          *reinterpret_cast<float2*>(out + 3 * H) = d_o;
+        }
       }
+      const long long k3 = prof ? clock64() : 0;
+      if (__syncthreads_or(!ok)) {
+        if (threadIdx.x == 0) atomicExch(p.abort_flag, 1);
+        return;
+      }
+      const long long k4 = prof ? clock64() : 0;
+      long long k5 = k4;
+      if (t > 0) {
+        float part[NB * UNITS];
+#pragma unroll
+        for (int v = 0; v < NB; ++v) {
+          const float4 d0 = *reinterpret_cast<const float4*>(&dgb[v * 4 * H + 256 * warp + 8 * lane]);
+          const float4 d1 = *reinterpret_cast<const float4*>(&dgb[v * 4 * H + 256 * warp + 8 * lane + 4]);
+#pragma unroll
+          for (int i = 0; i < UNITS; ++i) {
+            float a = wl[i][0] * d0.x;
+            a = fmaf(wl[i][1], d0.y, a); a = fmaf(wl[i][2], d0.z, a); a = fmaf(wl[i][3], d0.w, a);
+            a = fmaf(wl[i][4], d1.x, a); a = fmaf(wl[i][5], d1.y, a); a = fmaf(wl[i][6], d1.z, a); a = fmaf(wl[i][7], d1.w, a);
+            part[v * UNITS + i] = a;
+          }
+        }
+        constexpr int R = NB * UNITS;                   // 8, 16 or 32 values: lane l ends with element l >> (5 - log2 R)
+        const float ps = reduce_transposed<R>(part, lane);
+        if ((lane & (32 / R - 1)) == 0) sh_part[warp][lane / (32 / R)] = ps;
+        k5 = prof ? clock64() : 0;
+        __syncthreads();
+        if (lane < R) {
+          float r = sh_part[lane & 7][(lane >> 3) * UNITS + warp];   // lane 8v + w': warp w' partial of (shard v, unit `warp`)
+          r += __shfl_xor_sync((unsigned)((1ull << R) - 1), r, 1);
+          r += __shfl_xor_sync((unsigned)((1ull << R) - 1), r, 2);
+          r += __shfl_xor_sync((unsigned)((1ull << R) - 1), r, 4);
+          if ((lane & 7) == 0) st_tagged(p.xchg + ((size_t)(it & 1) * p.shards + sb + (lane >> 3)) * H + unit, r + inj, (unsigned)(it + 1));
+        }
+      }
+      if constexpr (PROF) {
+        if (prof) {
+          const long long k6 = clock64();
+          pr[0] += k1 - k0; pr[1] += k2 - k1; pr[2] += k3 - k2; pr[3] += k4 - k3; pr[4] += k5 - k4; pr[5] += k6 - k5;
+        }
+      }
+    }
+  }
+  if constexpr (PROF) {
+    if (prof) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) p.prof[i] = pr[i];
+      p.prof[6] = p.T;
     }
   }
 }
@@ -1038,7 +1119,7 @@ int icrl_chain_check_impl(cudaStream_t st, void* sync_state) {
 
 
 // ---- batched launchers (nb chain shards; see the kernels above)
-static long long* g_chain_prof = nullptr;      // icrl_chain_set_profile: 8 device int64 (LSTM then GRU shard kernels)
+static long long* g_chain_prof = nullptr;      // icrl_chain_set_profile: 16 device int64 (LSTM, GRU forward shard kernels [0..7]; backward [8..14])
 void icrl_chain_set_profile_impl(long long* buf) { g_chain_prof = buf; }
 static int coop_launch_smem(const void* fn, int grid, void** args, size_t smem, cudaStream_t st) {
   int dev = 0, sms = 0, per_sm = 0;
@@ -1059,7 +1140,8 @@ int icrl_chains_fwd_fused_batched_impl(cudaStream_t st, int nb, const int* v_str
                                        const int* r_stream, int r_T, const float* r_table, const float* r_w_hh,
                                        const float* r_b_hn, float* r_stash_h, void* sync_state, int warm,
                                        float* warm_state, float* seg_err) {
-  ICRL_REQUIRE(nb == 2 || nb == 4 || nb == 8, "chain shards per launch must be 2, 4 or 8");
+  ICRL_REQUIRE(nb == 2 || nb == 4 || nb == 8 || nb == 16 || nb == 24 || nb == 32,
+               "chain shards per launch must be 2, 4, 8, 16, 24 or 32");
   ICRL_REQUIRE(r_T > 0, "empty chain");
   ICRL_REQUIRE(warm == 0 || (warm_state && seg_err && r_T >= warm && (v_T == 0 || v_T >= warm)),
                "time segments must be at least as long as their warm-up");
@@ -1073,17 +1155,25 @@ int icrl_chains_fwd_fused_batched_impl(cudaStream_t st, int nb, const int* v_str
   b.stash_h = r_stash_h; b.stash_c = nullptr; b.stash_gates = nullptr; b.xchg = sync_xchg(sync_state, 1);
   b.abort_flag = sync_abort(sync_state); b.prof = g_chain_prof ? g_chain_prof + 4 : nullptr;
   b.warm = warm; b.warm_state = warm_state ? warm_state + (size_t)2 * NB_MAX * H : nullptr;
-  const size_t smem = (size_t)2 * nb * H * sizeof(float);
+  const size_t smem = (size_t)2 * nb * H * sizeof(float);      // [chunks][2][shards per chunk][H]
   if (v_T > 0) {
     void* args[] = {&a, &b};
-    const void* fn = nb == 2 ? (const void*)chains_fwd_fused_batched_kernel<2>
-                             : (nb == 4 ? (const void*)chains_fwd_fused_batched_kernel<4> : (const void*)chains_fwd_fused_batched_kernel<8>);
+    const void* fn = nb == 2 ? (const void*)chains_fwd_fused_batched_kernel<2, 1>
+                   : nb == 4 ? (const void*)chains_fwd_fused_batched_kernel<4, 1>
+                   : nb == 8 ? (const void*)chains_fwd_fused_batched_kernel<8, 1>
+                   : nb == 16 ? (const void*)chains_fwd_fused_batched_kernel<8, 2>
+                   : nb == 24 ? (const void*)chains_fwd_fused_batched_kernel<8, 3>
+                              : (const void*)chains_fwd_fused_batched_kernel<8, 4>;
     const int rc = coop_launch_smem(fn, 2 * CHAIN_CTAS, args, smem, st);
     if (rc != ICRL_OK) return rc;
   } else {
     void* args[] = {&b};
-    const void* fn = nb == 2 ? (const void*)chain_gru_fwd_batched_kernel<2>
-                             : (nb == 4 ? (const void*)chain_gru_fwd_batched_kernel<4> : (const void*)chain_gru_fwd_batched_kernel<8>);
+    const void* fn = nb == 2 ? (const void*)chain_gru_fwd_batched_kernel<2, 1>
+                   : nb == 4 ? (const void*)chain_gru_fwd_batched_kernel<4, 1>
+                   : nb == 8 ? (const void*)chain_gru_fwd_batched_kernel<8, 1>
+                   : nb == 16 ? (const void*)chain_gru_fwd_batched_kernel<8, 2>
+                   : nb == 24 ? (const void*)chain_gru_fwd_batched_kernel<8, 3>
+                              : (const void*)chain_gru_fwd_batched_kernel<8, 4>;
     const int rc = coop_launch_smem(fn, CHAIN_CTAS, args, smem, st);
     if (rc != ICRL_OK) return rc;
   }
@@ -1102,7 +1192,7 @@ int icrl_chains_fwd_fused_batched_impl(cudaStream_t st, int nb, const int* v_str
 int icrl_chain_lstm_bwd_batched_impl(cudaStream_t st, int shards, int T, const float* w_hh, const float* stash_gates,
                                      const float* stash_c, const int* take, const float* dh_take, float* dgates,
                                      void* sync_state, int warm, float* warm_dg, long long n_take, float* seg_err) {
-  ICRL_REQUIRE(shards == 2 || shards == 4 || shards == 8, "chain shards must be 2, 4 or 8");
+  ICRL_REQUIRE(shards == 2 || shards == 4 || shards == 8 || shards == 16, "chain shards must be 2, 4, 8 or 16");
   ICRL_REQUIRE(T > 0, "empty chain");
   ICRL_REQUIRE(warm == 0 || (warm_dg && seg_err && T >= warm), "time segments must be at least as long as their warm-up");
   ICRL_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(sync_state) + 64, 0, icrl_chain_sync_bytes_impl() - 64, st));
@@ -1114,11 +1204,17 @@ int icrl_chain_lstm_bwd_batched_impl(cudaStream_t st, int shards, int T, const f
   a.T = T + warm; a.stride = stride; a.w_hh = w_hh; a.stash_gates = stash_gates; a.stash_c = stash_c; a.take = take;
   a.dh_take = dh_take; a.dgates = dgates; a.xchg = sync_xchg(sync_state, 2); a.shards = shards;
   a.abort_flag = sync_abort(sync_state); a.warm = warm; a.warm_dg = warm_dg;
+  a.prof = g_chain_prof ? g_chain_prof + 8 : nullptr;
   void* args[] = {&a};
-  const int nb = shards / 2;
+  // two 64-CTA groups; 16 shards run as 2 chunks of 4 per group and kernel step
+  const int nb = shards == 16 ? 4 : shards / 2;
   const size_t smem = (size_t)2 * nb * 4 * H * sizeof(float);
-  const void* fn = nb == 1 ? (const void*)chain_lstm_bwd_batched_kernel<1>
-                           : (nb == 2 ? (const void*)chain_lstm_bwd_batched_kernel<2> : (const void*)chain_lstm_bwd_batched_kernel<4>);
+  const void* fn = shards == 2 ? (const void*)chain_lstm_bwd_batched_kernel<1, 1, false>
+                 : shards == 4 ? (const void*)chain_lstm_bwd_batched_kernel<2, 1, false>
+                 : shards == 8 ? (a.prof ? (const void*)chain_lstm_bwd_batched_kernel<4, 1, true>
+                                         : (const void*)chain_lstm_bwd_batched_kernel<4, 1, false>)
+                               : (a.prof ? (const void*)chain_lstm_bwd_batched_kernel<4, 2, true>
+                                         : (const void*)chain_lstm_bwd_batched_kernel<4, 2, false>);
   const int rc = coop_launch_smem(fn, 2 * CHAIN_CTAS, args, smem, st);
   if (rc != ICRL_OK) return rc;
   if (warm > 0) {

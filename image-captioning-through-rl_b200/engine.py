@@ -74,7 +74,7 @@ class A2CEngine:
     DECODE_MODES = ("fused", "tc", "simt")
 
     def __init__(self, a2c_network, reward_network, use_tc=None, decode="fused", chain_shards=1, wgrad="tc",
-                 chain_segments=8, chain_warmup=512, chain_tol=1e-5):
+                 chain_segments=16, chain_warmup=256, chain_tol=1e-5, chain_bwd_segments=None):
         self.policy = a2c_network.policy_network
         self.value = a2c_network.value_network
         self.reward = reward_network
@@ -125,8 +125,12 @@ class A2CEngine:
         # computes at the same position; gate gradients at the joints for the backward recurrence); a step whose check
         # exceeds chain_tol is re-run on the serial kernels and the warm-up is lengthened.  Chains too short for K
         # pieces of >= 2 warm-ups use fewer pieces or the serial kernels.  chain_segments = 1: always serial.
-        if chain_segments not in (1, 2, 4, 8):
-            raise ValueError("chain_segments must be 1, 2, 4 or 8")
+        # More than 8 pieces run as chunks of 8 inside a kernel step (16 / 24 / 32 = 2 / 3 / 4 chunks): a chunk's exchange
+        # round trip is covered by the arithmetic of the other chunks.  The backward recurrence uses at most 8 pieces
+        # (every 2nd / 3rd / 4th forward joint).
+        self.chain_bwd_segments = chain_bwd_segments
+        if chain_segments not in (1, 2, 4, 8, 16, 24, 32):
+            raise ValueError("chain_segments must be 1, 2, 4, 8, 16, 24 or 32")
         self.chain_segments = 1 if self.chain_shards > 1 else int(chain_segments)
         self.chain_warmup = int(chain_warmup)
         self.chain_tol = float(chain_tol)
@@ -352,7 +356,7 @@ class A2CEngine:
     def _pick_segments(self, Tv, Tr):
         """(K, seg_v, seg_r, warm) for chains of Tv / Tr positions, or None when they are too short."""
         warm = self.chain_warmup
-        for K in (8, 4, 2):
+        for K in (32, 24, 16, 8, 4, 2):
             if K > self.chain_segments:
                 continue
             seg_r = int(_lib.call("icrl_chain_segment_len", Tr, K, warm))
@@ -431,7 +435,13 @@ class A2CEngine:
         dgates = self._buf("v_dgates", K * (self._padded(Tv, 0) + 1) * 4 * H)
         with self._phase("chain_lstm_bwd"):
           if self._seg is not None:
-            Ks, seg_v, _, warm = self._seg
+            Kf, seg_v, _, warm = self._seg
+            # (16 backward pieces as 2 chunks of 4 per group measure the same as 8: that kernel is bound by its stash
+            # reads, not by the exchange, so the default stays at 8)
+            Ks = self.chain_bwd_segments or min(Kf, 8)
+            while Kf % Ks:
+                Ks //= 2
+            seg_v *= Kf // Ks                       # every (Kf/Ks)-th forward joint: same padded length
             _lib.call("icrl_chain_lstm_bwd_segmented", st, Ks, warm, seg_v, _p(Vn.valrnn.lstm.weight_hh_l0),
                   _p(b["v_stash_g"]), _p(b["v_stash_c"]), _p(b["v_take"]), _p(dh_take), SB, _p(dgates), _p(self._seg_ws),
                   _p(self.sync_state), L)

@@ -204,8 +204,10 @@ int icrl_chain_lstm_bwd_sharded(void* stream, int shards, int T, const float* W_
                                 const float* stash_c, const int* take, const float* dh_take, float* dgates,
                                 void* sync_state, int* launches);
 /* ---- chain segments (new; the reference has no equivalent).  ONE carried-state chain (the reference's semantics,
- *      models.py:133-140 / :225-231) cut into `segments` (2, 4 or 8) consecutive pieces of `seg` positions that advance in
- *      lockstep like the chain shards above.  Segment k >= 1 does not wait for the state of segment k-1: it starts from
+ *      models.py:133-140 / :225-231) cut into `segments` consecutive pieces of `seg` positions that advance in lockstep
+ *      like the chain shards above (forward: 2, 4, 8, or 16 / 24 / 32 walked as 2 / 3 / 4 chunks of 8 per kernel step so
+ *      that a chunk's exchange round trip is covered by the other chunks' arithmetic; backward: 2, 4 or 8 -- forward and
+ *      backward may differ as long as segments * seg is the same).  Segment k >= 1 does not wait for the state of segment k-1: it starts from
  *      zero state `warm` positions early and discards those steps.  An LSTM / GRU whose gates forget contracts the
  *      difference of two states step by step, so after the warm-up the segment carries the state of the single chain
  *      up to float rounding -- which is CHECKED, not assumed: the state reached at the end of every warm-up is compared
@@ -228,8 +230,10 @@ int icrl_chains_fwd_fused_segmented(void* stream, int segments, int warm, const 
 int icrl_chain_lstm_bwd_segmented(void* stream, int segments, int warm, int seg, const float* W_hh,
                                   const float* stash_gates, const float* stash_c, const int* take, const float* dh_take,
                                   long long take_rows, float* dgates, float* segment_ws, void* sync_state, int* launches);
-/* Debug aid: when buf != NULL (8 device int64), CTA 0 / thread 0 of the sharded forward chains accumulates its cycles per
- * phase {exchange wait, GEMV + reduce, pointwise + publish, T}: [0..3] value LSTM, [4..7] reward GRU. */
+/* Debug aid: when buf != NULL (16 device int64), CTA 0 / thread 0 of the sharded / segmented chain kernels accumulates its
+ * cycles per phase: [0..3] value LSTM forward {exchange wait, GEMV + reduce, pointwise + publish, T}, [4..7] reward GRU
+ * forward, [8..14] backward {coefficients + requests, poll wait, gate gradients + stores, barrier, contraction + reduce,
+ * barrier + publish, T} (the backward runs a separately compiled, instrumented build of the kernel). */
 int icrl_chain_set_profile(void* buf);
 /* synchronises `stream`; ICRL_ERR_WATCHDOG if any chain launch since the last check gave up waiting */
 int icrl_chain_check(void* stream, void* sync_state);

@@ -717,12 +717,14 @@ def test_chain_segments_vs_reference_golden(name):
             dh_take_max=eng.segment_stats["max_err"][4])
 
 
-@pytest.mark.parametrize("segments,B,L,level", [(8, 64, 10, None), (4, 48, 8, None), (2, 40, 6, None), (8, 96, 14, 5)])
+@pytest.mark.parametrize("segments,B,L,level", [(8, 64, 10, None), (4, 64, 8, None), (2, 48, 7, None), (8, 96, 14, 5),
+                                                (16, 96, 14, 5), (24, 128, 12, None), (32, 160, 12, None)])
 def test_chain_segments_equal_the_serial_chain(segments, B, L, level):
     """Segmented and serial kernels on the same inputs: identical tokens, values / rewards within 2e-6, gradients within
-    2e-5 of the bucket's largest entry; the verification words stay at float-rounding level."""
+    2e-5 of the bucket's largest entry; the verification words stay at float-rounding level.  (Warm-up 160: with a
+    64-position warm-up the reward GRU of seed 163 is still 1.5e-3 away and the engine -- correctly -- falls back.)"""
     seed = 131 + segments
-    e1, ek, A = _seg_engines(seed, segments, 64)
+    e1, ek, A = _seg_engines(seed, segments, 160)
     f, c = synth.make_inputs(seed, B, L)
     S = (L - 1) if level is None else level
     u = synth.make_uniforms(seed, S, B)
@@ -765,18 +767,18 @@ def test_chain_segments_fall_back_to_the_serial_kernels():
 
 def test_get_rewards_segments_equal_the_serial_chain():
     from icrl_b200.engine import A2CEngine
-    seed, B, L = 151, 256, 12
+    seed, B, L = 151, 512, 12
     A, R, w = make_nets(seed)
     f, c = synth.make_inputs(seed, B, L)
     r1 = A2CEngine(A, R, chain_segments=1).get_rewards(f, c)
-    ek = A2CEngine(A, R, chain_warmup=64)
+    ek = A2CEngine(A, R, chain_warmup=160)
     rk = ek.get_rewards(f, c)
-    assert ek._seg is not None and ek._seg[0] == 8 and ek.segment_stats["fallbacks"] == 0
+    assert ek._seg is not None and ek._seg[0] == 16 and ek.segment_stats["fallbacks"] == 0
     assert float((rk - r1).abs().max()) <= TOL
 
 
 def test_config4_segments_full_size():
-    """BASELINE config 4 at full single-GPU size with the default engine (8 pieces, 512-position warm-up): the check
+    """BASELINE config 4 at full single-GPU size with the default engine (16 pieces, 256-position warm-up): the check
     passes, and values / rewards / gradients agree with the serial chain at the tolerances of the golden tests."""
     from icrl_b200.engine import A2CEngine
     seed, B, L = 97, 4096, 20
