@@ -1207,14 +1207,16 @@ int icrl_chain_lstm_bwd_batched_impl(cudaStream_t st, int shards, int T, const f
   a.prof = g_chain_prof ? g_chain_prof + 8 : nullptr;
   void* args[] = {&a};
   // two 64-CTA groups; 16 shards run as 2 chunks of 4 per group and kernel step
+  // (measured at B = 2048: 8 shards as 4 x 1 chunk 113.8 ms, 2 x 2 chunks 162.7 ms; 16 shards as 4 x 2 chunks 113.3 ms,
+  // 2 x 4 chunks 166.1 ms -- a chunk costs about 1.0 us + 0.32 us per shard, so small chunks lose)
   const int nb = shards == 16 ? 4 : shards / 2;
-  const size_t smem = (size_t)2 * nb * 4 * H * sizeof(float);
   const void* fn = shards == 2 ? (const void*)chain_lstm_bwd_batched_kernel<1, 1, false>
                  : shards == 4 ? (const void*)chain_lstm_bwd_batched_kernel<2, 1, false>
                  : shards == 8 ? (a.prof ? (const void*)chain_lstm_bwd_batched_kernel<4, 1, true>
                                          : (const void*)chain_lstm_bwd_batched_kernel<4, 1, false>)
                                : (a.prof ? (const void*)chain_lstm_bwd_batched_kernel<4, 2, true>
                                          : (const void*)chain_lstm_bwd_batched_kernel<4, 2, false>);
+  const size_t smem = (size_t)2 * nb * 4 * H * sizeof(float);
   const int rc = coop_launch_smem(fn, 2 * CHAIN_CTAS, args, smem, st);
   if (rc != ICRL_OK) return rc;
   if (warm > 0) {
