@@ -36,13 +36,14 @@ def timed(fn, reps=3, warm=1):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     return float(ms)
 
-for shards in (1, 8):
-    eng = A2CEngine(A, R, chain_shards=shards)
+for mode, kw in (("serial_chain", dict(chain_segments=1)), ("chain_segments", dict()), ("chain_shards_8", dict(chain_shards=8))):
+    eng = A2CEngine(A, R, **kw)
     dp = DataParallelA2C(eng, opt)
-    if shards == 1:                       # every rank runs it: timed() contains collectives
+    if mode != "chain_shards_8":          # every rank runs it: timed() contains collectives
         f, c = synth.make_inputs(200, 8192, 20)
         ms = timed(lambda: eng.get_rewards(f, c))
-        out["config2_rewards_b8192"] = {"ms": ms, "captions_per_s": 8192 / (ms * 1e-3), "serial_gru_steps": 8192 * 20}
+        out["config2_rewards_b8192_" + mode] = {"ms": ms, "captions_per_s": 8192 / (ms * 1e-3), "serial_gru_steps": 8192 * 20,
+                                                "pieces": eng._seg[0] if eng._seg else 1, "fallbacks": eng.segment_stats["fallbacks"]}
     Bl, L = 1024, 20
     f, c = synth.make_inputs(300 + rank, Bl, L)
     per_level = {}
@@ -50,9 +51,10 @@ for shards in (1, 8):
         u = synth.make_uniforms(400 + rank + level, level, Bl)
         prep = eng.prepare(f, c, u, level=level)
         ms = timed(lambda: dp.step(prep, global_rows=Bl * world, check=False))
-        per_level[str(level)] = {"ms": ms, "captions_per_s": Bl * world / (ms * 1e-3)}
+        per_level[str(level)] = {"ms": ms, "captions_per_s": Bl * world / (ms * 1e-3), "pieces": eng._seg[0] if eng._seg else 1,
+                                 "verified": bool(eng.segments_verified())}
     tot = sum(v["ms"] for v in per_level.values())
-    out["config4_curriculum_chain_shards_%d" % shards] = {"per_level": per_level, "aggregate_captions_per_s": 6 * Bl * world / (tot * 1e-3)}
+    out["config4_curriculum_" + mode] = {"per_level": per_level, "aggregate_captions_per_s": 6 * Bl * world / (tot * 1e-3)}
 if rank == 0:
     print(json.dumps(out))
 if world > 1:
