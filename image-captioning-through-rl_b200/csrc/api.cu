@@ -341,7 +341,7 @@ long long icrl_chain_segment_len(long long T, int segments, int warm) {
   return seg >= 2ll * warm ? seg : 0;
 }
 
-size_t icrl_chain_segment_ws_floats(void) { return 8 + 2 * 32 * 2 * 512 + 16 * 4 * 512; }
+size_t icrl_chain_segment_ws_floats(void) { return 8 + 2 * 32 * 2 * 512 + 32 * 4 * 512; }
 
 int icrl_chains_fwd_fused_segmented(void* stream, int segments, int warm, const int* v_stream, int v_seg,
                                     const float* v_table, const float* v_W_hh, float* v_stash_h, float* v_stash_c,

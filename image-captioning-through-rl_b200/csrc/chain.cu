@@ -831,6 +831,176 @@ __global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_batched_kernel(Chai
 }
 
 
+// Eight shards per 64-CTA group in ONE chunk.  A backward step costs about 1.0 us of fixed work (poll round trip, two
+// barriers, butterfly, publish) plus 0.32 us per shard, so eight shards per step amortise the fixed part twice as well as
+// four (B = 2048: 113.8 -> 95.9 ms per launch).  The per-shard register state does not fit eight times, so the
+// gate-gradient stage runs as two halves of four that share one set of stash registers: half 0 of a step is requested
+// during the previous step, half 1 at the top of the step (it lands under the poll wait and half 0's arithmetic).  All
+// eight dh vectors are polled together at the top.  (A generalisation to quarters with per-quarter polls -- 8 or 16
+// shards per group -- measured 107.5 / 117.8 ms: every quarter then waits for its own L2 round trip.)
+__global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_batched8_kernel(ChainBwdBatchArgs p) {
+  constexpr int NB = 8, HB = 4;
+  extern __shared__ __align__(16) float sh_dyn[];      // [NB][4H] gate gradients of the current step
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = blockIdx.x / CHAIN_CTAS, cta = blockIdx.x % CHAIN_CTAS;
+  const int sb = group * NB;                           // first shard of this group
+  const int unit = cta * UNITS + warp;
+  const int pu = 2 * threadIdx.x;
+  const bool owner = (pu >= cta * UNITS) && (pu < cta * UNITS + UNITS);
+  const int myb = lane >> 3;                           // shard (within a half) whose dh lane 8*myb publishes
+
+  __shared__ float sh_part[2][UNITS][HB * UNITS];      // [half][warp][shard * 8 + unit]
+  float wl[UNITS][8];                                  // wl[i][k] = W_hh[256w + 8 lane + k][8 cta + i]
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float* src = p.w_hh + (size_t)(256 * warp + 8 * lane + k) * H + cta * UNITS;
+    const float4 x0 = *reinterpret_cast<const float4*>(src), x1 = *reinterpret_cast<const float4*>(src + 4);
+    wl[0][k] = x0.x; wl[1][k] = x0.y; wl[2][k] = x0.z; wl[3][k] = x0.w;
+    wl[4][k] = x1.x; wl[5][k] = x1.y; wl[6][k] = x1.z; wl[7][k] = x1.w;
+  }
+
+  float2 dc[NB], gi[HB], gf[HB], gg[HB], go[HB], cc[HB], cp[HB];
+  auto load_half = [&](int half, int t) {
+#pragma unroll
+    for (int v = 0; v < HB; ++v) {
+      const float* ga = p.stash_gates + ((size_t)(sb + half * HB + v) * p.stride + t) * 4 * H + pu;
+      const float* ca = p.stash_c + ((size_t)(sb + half * HB + v) * p.stride + t) * H + pu;
+      gi[v] = *reinterpret_cast<const float2*>(ga);
+      gf[v] = *reinterpret_cast<const float2*>(ga + H);
+      gg[v] = *reinterpret_cast<const float2*>(ga + 2 * H);
+      go[v] = *reinterpret_cast<const float2*>(ga + 3 * H);
+      cc[v] = *reinterpret_cast<const float2*>(ca + H);
+      cp[v] = *reinterpret_cast<const float2*>(ca);
+    }
+  };
+  float2 kc[HB], ko[HB], ki[HB], kf[HB], kg[HB], fgate[HB];
+  auto coefficients = [&]() {                          // everything of the gate gradients that does not depend on dh
+#pragma unroll
+    for (int v = 0; v < HB; ++v) {
+      const float tcx = act_tanh(cc[v].x), tcy = act_tanh(cc[v].y);
+      kc[v] = make_float2(go[v].x * (1.f - tcx * tcx), go[v].y * (1.f - tcy * tcy));
+      ko[v] = make_float2(tcx * go[v].x * (1.f - go[v].x), tcy * go[v].y * (1.f - go[v].y));
+      ki[v] = make_float2(gg[v].x * gi[v].x * (1.f - gi[v].x), gg[v].y * gi[v].y * (1.f - gi[v].y));
+      kf[v] = make_float2(cp[v].x * gf[v].x * (1.f - gf[v].x), cp[v].y * gf[v].y * (1.f - gf[v].y));
+      kg[v] = make_float2(gi[v].x * (1.f - gg[v].x * gg[v].x), gi[v].y * (1.f - gg[v].y * gg[v].y));
+      fgate[v] = gf[v];
+    }
+  };
+#pragma unroll
+  for (int v = 0; v < NB; ++v) dc[v] = make_float2(0.f, 0.f);
+  int tk_prev[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) tk_prev[h] = p.T > 1 ? p.take[(size_t)(sb + h * HB + myb) * p.stride + p.T - 2] : -1;
+  load_half(0, p.T - 1);
+
+  for (int it = 0; it < p.T; ++it) {
+    const int t = p.T - 1 - it;
+    bool ok = true;
+    unsigned long long pa[NB], pb[NB];
+    const unsigned long long* src = p.xchg + ((size_t)((it - 1) & 1) * p.shards + sb) * H + pu;
+    if (it > 0) {
+#pragma unroll
+      for (int v = 0; v < NB; ++v) ld_tagged2(src + (size_t)v * H, pa[v], pb[v]);
+    }
+    coefficients();                                    // half 0 (its rows were requested during the previous step)
+    load_half(1, t);
+    float inj[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      inj[h] = tk_prev[h] >= 0 ? p.dh_take[(size_t)tk_prev[h] * H + unit] : 0.f;
+      tk_prev[h] = t > 1 ? p.take[(size_t)(sb + h * HB + myb) * p.stride + t - 2] : -1;
+    }
+    float2 dh[NB];
+    if (it == 0) {                                     // the recurrence starts with the gradient injected at the last position
+#pragma unroll
+      for (int v = 0; v < NB; ++v) {
+        dh[v] = make_float2(0.f, 0.f);
+        const int tk = p.take[(size_t)(sb + v) * p.stride + p.T - 1];
+        if (tk >= 0) dh[v] = *reinterpret_cast<const float2*>(p.dh_take + (size_t)tk * H + pu);
+      }
+    } else {
+      unsigned pending = (1u << NB) - 1u, spins = 0;   // rounds: all missing words are re-read together
+      while (true) {
+#pragma unroll
+        for (int v = 0; v < NB; ++v)
+          if ((pending >> v & 1u) && (unsigned)(pa[v] >> 32) == (unsigned)it && (unsigned)(pb[v] >> 32) == (unsigned)it)
+            pending &= ~(1u << v);
+        if (pending == 0) break;
+        if (++spins >= SPIN_LIMIT || ((spins & 1023u) == 0 && *(volatile int*)p.abort_flag != 0)) { ok = false; break; }
+#pragma unroll
+        for (int v = 0; v < NB; ++v)
+          if (pending >> v & 1u) ld_tagged2(src + (size_t)v * H, pa[v], pb[v]);
+      }
+#pragma unroll
+      for (int v = 0; v < NB; ++v) dh[v] = make_float2(__uint_as_float((unsigned)pa[v]), __uint_as_float((unsigned)pb[v]));
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      if (half == 1) {
+        coefficients();                                // half 1 (requested at the top of this step)
+        if (t > 0) load_half(0, t - 1);                // half 0 of the next step
+      }
+#pragma unroll
+      for (int v = 0; v < HB; ++v) {
+        const int s = half * HB + v;                   // shard within the group
+        const float dctx = dc[s].x + dh[s].x * kc[v].x, dcty = dc[s].y + dh[s].y * kc[v].y;
+        dc[s] = make_float2(dctx * fgate[v].x, dcty * fgate[v].y);
+        const float2 d_i = make_float2(dctx * ki[v].x, dcty * ki[v].y), d_f = make_float2(dctx * kf[v].x, dcty * kf[v].y);
+        const float2 d_g = make_float2(dctx * kg[v].x, dcty * kg[v].y), d_o = make_float2(dh[s].x * ko[v].x, dh[s].y * ko[v].y);
+        float* sd = sh_dyn + s * 4 * H + pu;
+        *reinterpret_cast<float2*>(sd) = d_i;
+        *reinterpret_cast<float2*>(sd + H) = d_f;
+        *reinterpret_cast<float2*>(sd + 2 * H) = d_g;
+        *reinterpret_cast<float2*>(sd + 3 * H) = d_o;
+        const bool live = p.warm == 0 || it >= p.warm || sb + s == p.shards - 1;
+        if (owner && (live || it == p.warm - 1)) {
+          float* out = live ? p.dgates + ((size_t)(sb + s) * p.stride + t) * 4 * H + pu
+                            : p.warm_dg + (size_t)(sb + s) * 4 * H + pu;
+          *reinterpret_cast<float2*>(out) = d_i;
+          *reinterpret_cast<float2*>(out + H) = d_f;
+          *reinterpret_cast<float2*>(out + 2 * H) = d_g;
+          *reinterpret_cast<float2*>(out + 3 * H) = d_o;
+        }
+      }
+    }
+    if (__syncthreads_or(!ok)) {
+      if (threadIdx.x == 0) atomicExch(p.abort_flag, 1);
+      return;
+    }
+    if (t > 0) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float part[HB * UNITS];
+#pragma unroll
+        for (int v = 0; v < HB; ++v) {
+          const float* dg = sh_dyn + (half * HB + v) * 4 * H + 256 * warp + 8 * lane;
+          const float4 d0 = *reinterpret_cast<const float4*>(dg);
+          const float4 d1 = *reinterpret_cast<const float4*>(dg + 4);
+#pragma unroll
+          for (int i = 0; i < UNITS; ++i) {
+            float a = wl[i][0] * d0.x;
+            a = fmaf(wl[i][1], d0.y, a); a = fmaf(wl[i][2], d0.z, a); a = fmaf(wl[i][3], d0.w, a);
+            a = fmaf(wl[i][4], d1.x, a); a = fmaf(wl[i][5], d1.y, a); a = fmaf(wl[i][6], d1.z, a); a = fmaf(wl[i][7], d1.w, a);
+            part[v * UNITS + i] = a;
+          }
+        }
+        sh_part[half][warp][lane] = reduce_transposed<HB * UNITS>(part, lane);     // 32 values: lane l ends with element l
+      }
+      __syncthreads();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float r = sh_part[half][lane & 7][(lane >> 3) * UNITS + warp];   // lane 8v + w': warp w' partial of (shard v, unit `warp`)
+        r += __shfl_xor_sync(0xffffffffu, r, 1);
+        r += __shfl_xor_sync(0xffffffffu, r, 2);
+        r += __shfl_xor_sync(0xffffffffu, r, 4);
+        if ((lane & 7) == 0)
+          st_tagged(p.xchg + ((size_t)(it & 1) * p.shards + sb + half * HB + (lane >> 3)) * H + unit, r + inj[half], (unsigned)(it + 1));
+      }
+    }
+  }
+}
+
+
 struct ChainGruBwdArgs {
   int T;
   const float* w_hh;          // [3H][H]
@@ -1206,17 +1376,16 @@ int icrl_chain_lstm_bwd_batched_impl(cudaStream_t st, int shards, int T, const f
   a.abort_flag = sync_abort(sync_state); a.warm = warm; a.warm_dg = warm_dg;
   a.prof = g_chain_prof ? g_chain_prof + 8 : nullptr;
   void* args[] = {&a};
-  // two 64-CTA groups; 16 shards run as 2 chunks of 4 per group and kernel step
-  // (measured at B = 2048: 8 shards as 4 x 1 chunk 113.8 ms, 2 x 2 chunks 162.7 ms; 16 shards as 4 x 2 chunks 113.3 ms,
-  // 2 x 4 chunks 166.1 ms -- a chunk costs about 1.0 us + 0.32 us per shard, so small chunks lose)
-  const int nb = shards == 16 ? 4 : shards / 2;
+  // two 64-CTA groups of shards / 2 shards each.  Measured at B = 2048 (ms per launch): 8 shards as 4 per group 113.8;
+  // 16 shards as 8 per group in one chunk (chain_lstm_bwd_batched8_kernel) 95.9, as 2 chunks of 4 113.3; chunks of 2
+  // (8 shards as 2 x 2: 162.7, 16 as 4 x 2: 166.1) lose -- a chunk costs about 1.0 us + 0.32 us per shard.
+  const int nb = shards / 2;
   const void* fn = shards == 2 ? (const void*)chain_lstm_bwd_batched_kernel<1, 1, false>
                  : shards == 4 ? (const void*)chain_lstm_bwd_batched_kernel<2, 1, false>
                  : shards == 8 ? (a.prof ? (const void*)chain_lstm_bwd_batched_kernel<4, 1, true>
                                          : (const void*)chain_lstm_bwd_batched_kernel<4, 1, false>)
-                               : (a.prof ? (const void*)chain_lstm_bwd_batched_kernel<4, 2, true>
-                                         : (const void*)chain_lstm_bwd_batched_kernel<4, 2, false>);
-  const size_t smem = (size_t)2 * nb * 4 * H * sizeof(float);
+                               : (const void*)chain_lstm_bwd_batched8_kernel;
+  const size_t smem = (size_t)(shards == 16 ? 1 : 2) * nb * 4 * H * sizeof(float);
   const int rc = coop_launch_smem(fn, 2 * CHAIN_CTAS, args, smem, st);
   if (rc != ICRL_OK) return rc;
   if (warm > 0) {

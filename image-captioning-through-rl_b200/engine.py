@@ -436,9 +436,8 @@ class A2CEngine:
         with self._phase("chain_lstm_bwd"):
           if self._seg is not None:
             Kf, seg_v, _, warm = self._seg
-            # (16 backward pieces as 2 chunks of 4 per group measure the same as 8: that kernel is bound by its stash
-            # reads, not by the exchange, so the default stays at 8)
-            Ks = self.chain_bwd_segments or min(Kf, 8)
+            # backward pieces: 16 (8 per CTA group in one kernel step) when the forward has 16 or 32, else at most 8
+            Ks = self.chain_bwd_segments or (16 if Kf in (16, 32) else min(Kf, 8))
             while Kf % Ks:
                 Ks //= 2
             seg_v *= Kf // Ks                       # every (Kf/Ks)-th forward joint: same padded length
