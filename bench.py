@@ -326,7 +326,9 @@ def main():
     if seg_layout is not None:                 # lockstep pieces: one kernel step advances `pieces` chain positions
         pieces, seg_v, seg_r, warm = seg_layout
         if bwd_ms >= fwd_ms:
-            kname, ksteps = "chain_lstm_bwd_batched_kernel<4, 1> x 2 groups", seg_v * pieces // min(pieces, 8) + warm
+            bp = 16 if pieces in (16, 32) else min(pieces, 8)              # backward pieces (engine._backward)
+            kname = "chain_lstm_bwd_batched8_kernel x 2 groups" if bp == 16 else "chain_lstm_bwd_batched_kernel<%d, 1> x 2 groups" % (bp // 2)
+            ksteps = seg_v * pieces // bp + warm
         else:
             kname, ksteps = "chains_fwd_fused_batched_kernel<%d, %d>" % (min(pieces, 8), max(pieces // 8, 1)), max(seg_v, seg_r) + warm
     peaks = {}
