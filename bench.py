@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=256, help="rows of the workload timed on the host cores")
     ap.add_argument("--chain-shards", type=int, default=1, choices=[1, 2, 4, 8],
                     help="value/reward recurrences per rank (1 = the reference's single carried-state chain)")
-    ap.add_argument("--chain-segments", type=int, default=16, choices=[1, 2, 4, 8, 16, 24, 32],
+    ap.add_argument("--chain-segments", type=int, default=32, choices=[1, 2, 4, 8, 16, 32],
                     help="lockstep pieces of the single carried-state chain (verified warm-up; 1 = serial kernels only)")
     ap.add_argument("--chain-warmup", type=int, default=256, help="warm-up positions of every chain piece")
     ap.add_argument("--sharded-leg", action="store_true", help="also time 8 zero-state row shards per rank")
@@ -330,7 +330,8 @@ def main():
             kname = "chain_lstm_bwd_batched8_kernel x 2 groups" if bp == 16 else "chain_lstm_bwd_batched_kernel<%d, 1> x 2 groups" % (bp // 2)
             ksteps = seg_v * pieces // bp + warm
         else:
-            kname, ksteps = "chains_fwd_fused_batched_kernel<%d, %d>" % (min(pieces, 8), max(pieces // 8, 1)), max(seg_v, seg_r) + warm
+            kname = "chains_fwd_fused_batched_kernel<%d, %d>" % ((16, 2) if pieces == 32 else (min(pieces, 8), max(pieces // 8, 1)))
+            ksteps = max(seg_v, seg_r) + warm
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

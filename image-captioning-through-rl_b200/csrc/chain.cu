@@ -461,7 +461,7 @@ struct ChainFwdBatchArgs {
 // (Tried and dropped for this exchange, both slower at NB = 8: a unit-major word layout [unit][NB], 393 -> 426 ms, and
 // plain data + one release flag per unit polled with acquire loads, 393 -> 508 ms: the release store waits for the
 // warp's stash writes.)
-// NCH > 1: the NB * NCH shards are walked as NCH chunks of NB per step.  Chunk q publishes its hidden vectors, then the
+// NCH > 1 (built: 2 chunks of 8 or of 16): the NB * NCH shards are walked as NCH chunks of NB per step.  Chunk q publishes its hidden vectors, then the
 // CTA computes the other chunks before it polls for chunk q's next vectors: the exchange round trip through L2 (the wait
 // that bounds a single chunk) is covered by the other chunks' arithmetic.  Shard index = q * NB + lane group.
 template <int NG, int NB, int NCH>
@@ -579,9 +579,13 @@ __device__ void chain_fwd_batched_body(const ChainFwdBatchArgs& p, int cta, floa
         const float o = act_sigmoid(sum[3 % NG] + xg[q][3 % NG]);
         c[q] = f * c[q] + i * g;
         hnew = o * act_tanh(c[q]);
-        if (p.stash_gates && sub < 4 && live) {
-          const float sel = sub == 0 ? i : (sub == 1 ? f : (sub == 2 ? g : o));
-          p.stash_gates[row * 4 * H + sub * H + unit] = sel;
+        if (p.stash_gates && live) {                   // the GL lanes of a shard share the four stores
+          if constexpr (GL >= 4) {
+            if (sub < 4) p.stash_gates[row * 4 * H + sub * H + unit] = sub == 0 ? i : (sub == 1 ? f : (sub == 2 ? g : o));
+          } else {
+            p.stash_gates[row * 4 * H + sub * H + unit] = sub == 0 ? i : f;
+            p.stash_gates[row * 4 * H + (2 + sub) * H + unit] = sub == 0 ? g : o;
+          }
         }
         if (sub == 4 % GL) {
           if (p.stash_c && live) p.stash_c[(row + 1) * H + unit] = c[q];
@@ -1310,8 +1314,7 @@ int icrl_chains_fwd_fused_batched_impl(cudaStream_t st, int nb, const int* v_str
                                        const int* r_stream, int r_T, const float* r_table, const float* r_w_hh,
                                        const float* r_b_hn, float* r_stash_h, void* sync_state, int warm,
                                        float* warm_state, float* seg_err) {
-  ICRL_REQUIRE(nb == 2 || nb == 4 || nb == 8 || nb == 16 || nb == 24 || nb == 32,
-               "chain shards per launch must be 2, 4, 8, 16, 24 or 32");
+  ICRL_REQUIRE(nb == 2 || nb == 4 || nb == 8 || nb == 16 || nb == 32, "chain shards per launch must be 2, 4, 8, 16 or 32");
   ICRL_REQUIRE(r_T > 0, "empty chain");
   ICRL_REQUIRE(warm == 0 || (warm_state && seg_err && r_T >= warm && (v_T == 0 || v_T >= warm)),
                "time segments must be at least as long as their warm-up");
@@ -1326,14 +1329,15 @@ int icrl_chains_fwd_fused_batched_impl(cudaStream_t st, int nb, const int* v_str
   b.abort_flag = sync_abort(sync_state); b.prof = g_chain_prof ? g_chain_prof + 4 : nullptr;
   b.warm = warm; b.warm_state = warm_state ? warm_state + (size_t)2 * NB_MAX * H : nullptr;
   const size_t smem = (size_t)2 * nb * H * sizeof(float);      // [chunks][2][shards per chunk][H]
+  // 16 shards = 2 chunks of 8, 32 shards = 2 chunks of 16 (measured at B = 2048, ms per launch: 8 shards 146.5; 16 as
+  // 2 x 8 108.5; 24 as 3 x 8 107.0; 32 as 4 x 8 104.1, as 2 x 16 94.8)
   if (v_T > 0) {
     void* args[] = {&a, &b};
     const void* fn = nb == 2 ? (const void*)chains_fwd_fused_batched_kernel<2, 1>
                    : nb == 4 ? (const void*)chains_fwd_fused_batched_kernel<4, 1>
                    : nb == 8 ? (const void*)chains_fwd_fused_batched_kernel<8, 1>
                    : nb == 16 ? (const void*)chains_fwd_fused_batched_kernel<8, 2>
-                   : nb == 24 ? (const void*)chains_fwd_fused_batched_kernel<8, 3>
-                              : (const void*)chains_fwd_fused_batched_kernel<8, 4>;
+                              : (const void*)chains_fwd_fused_batched_kernel<16, 2>;
     const int rc = coop_launch_smem(fn, 2 * CHAIN_CTAS, args, smem, st);
     if (rc != ICRL_OK) return rc;
   } else {
@@ -1342,8 +1346,7 @@ int icrl_chains_fwd_fused_batched_impl(cudaStream_t st, int nb, const int* v_str
                    : nb == 4 ? (const void*)chain_gru_fwd_batched_kernel<4, 1>
                    : nb == 8 ? (const void*)chain_gru_fwd_batched_kernel<8, 1>
                    : nb == 16 ? (const void*)chain_gru_fwd_batched_kernel<8, 2>
-                   : nb == 24 ? (const void*)chain_gru_fwd_batched_kernel<8, 3>
-                              : (const void*)chain_gru_fwd_batched_kernel<8, 4>;
+                              : (const void*)chain_gru_fwd_batched_kernel<16, 2>;
     const int rc = coop_launch_smem(fn, CHAIN_CTAS, args, smem, st);
     if (rc != ICRL_OK) return rc;
   }

@@ -74,7 +74,7 @@ class A2CEngine:
     DECODE_MODES = ("fused", "tc", "simt")
 
     def __init__(self, a2c_network, reward_network, use_tc=None, decode="fused", chain_shards=1, wgrad="tc",
-                 chain_segments=16, chain_warmup=256, chain_tol=1e-5, chain_bwd_segments=None):
+                 chain_segments=32, chain_warmup=256, chain_tol=1e-5, chain_bwd_segments=None):
         self.policy = a2c_network.policy_network
         self.value = a2c_network.value_network
         self.reward = reward_network
@@ -125,9 +125,11 @@ class A2CEngine:
         # computes at the same position; gate gradients at the joints for the backward recurrence); a step whose check
         # exceeds chain_tol is re-run on the serial kernels and the warm-up is lengthened.  Chains too short for K
         # pieces of >= 2 warm-ups use fewer pieces or the serial kernels.  chain_segments = 1: always serial.
-        # More than 8 pieces run as chunks of 8 inside a kernel step (16 / 24 / 32 = 2 / 3 / 4 chunks): a chunk's exchange
-        # round trip is covered by the arithmetic of the other chunks.  The backward recurrence uses at most 8 pieces
-        # (every 2nd / 3rd / 4th forward joint).
+        # More than 8 pieces run as two chunks inside a kernel step (16 = 2 x 8, 32 = 2 x 16): a chunk's exchange round
+        # trip is covered by the arithmetic of the other chunk.  The backward recurrence uses at most 16 pieces (8 per
+        # CTA group; every 2nd forward joint when the forward has 32).
+        if chain_segments not in (1, 2, 4, 8, 16, 32):
+            raise ValueError("chain_segments must be 1, 2, 4, 8, 16 or 32")
         self.chain_bwd_segments = chain_bwd_segments
         if chain_segments not in (1, 2, 4, 8, 16, 24, 32):
             raise ValueError("chain_segments must be 1, 2, 4, 8, 16, 24 or 32")
@@ -356,7 +358,7 @@ class A2CEngine:
     def _pick_segments(self, Tv, Tr):
         """(K, seg_v, seg_r, warm) for chains of Tv / Tr positions, or None when they are too short."""
         warm = self.chain_warmup
-        for K in (32, 24, 16, 8, 4, 2):
+        for K in (32, 16, 8, 4, 2):
             if K > self.chain_segments:
                 continue
             seg_r = int(_lib.call("icrl_chain_segment_len", Tr, K, warm))

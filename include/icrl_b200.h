@@ -205,9 +205,9 @@ int icrl_chain_lstm_bwd_sharded(void* stream, int shards, int T, const float* W_
                                 void* sync_state, int* launches);
 /* ---- chain segments (new; the reference has no equivalent).  ONE carried-state chain (the reference's semantics,
  *      models.py:133-140 / :225-231) cut into `segments` consecutive pieces of `seg` positions that advance in lockstep
- *      like the chain shards above (forward: 2, 4, 8, or 16 / 24 / 32 walked as 2 / 3 / 4 chunks of 8 per kernel step so
- *      that a chunk's exchange round trip is covered by the other chunks' arithmetic; backward: 2, 4 or 8 -- forward and
- *      backward may differ as long as segments * seg is the same).  Segment k >= 1 does not wait for the state of segment k-1: it starts from
+ *      like the chain shards above (forward: 2, 4, 8, or 16 / 32 walked as 2 chunks of 8 / 16 per kernel step so that a
+ *      chunk's exchange round trip is covered by the other chunk's arithmetic; backward: 2, 4, 8, or 16 = 8 per CTA group
+ *      in one kernel step -- forward and backward may differ as long as segments * seg is the same).  Segment k >= 1 does not wait for the state of segment k-1: it starts from
  *      zero state `warm` positions early and discards those steps.  An LSTM / GRU whose gates forget contracts the
  *      difference of two states step by step, so after the warm-up the segment carries the state of the single chain
  *      up to float rounding -- which is CHECKED, not assumed: the state reached at the end of every warm-up is compared

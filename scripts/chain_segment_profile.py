@@ -8,7 +8,7 @@ from icrl_b200 import _lib, synth
 from icrl_b200.engine import A2CEngine
 from bench import make_nets
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-for K, Kb in ((8, 8), (16, 16), (24, 8), (32, 16)):
+for K, Kb in ((8, 8), (16, 8), (32, 8)):
     A, R = make_nets(0, "cuda:0")
     eng = A2CEngine(A, R, chain_segments=K, chain_bwd_segments=Kb)
     f, c = synth.make_inputs(100, B, 20)

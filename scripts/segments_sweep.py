@@ -15,7 +15,7 @@ import bench  # noqa: E402
 from icrl_b200.engine import A2CEngine  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
-cfgs = [tuple(int(x) for x in c.split(":")) for c in sys.argv[2:]] or [(8, 512), (16, 512, 8), (16, 512, 16), (24, 512, 8), (32, 512, 16)]
+cfgs = [tuple(int(x) for x in c.split(":")) for c in sys.argv[2:]] or [(8, 256), (16, 256), (32, 256)]
 dev = "cuda:0"
 torch.cuda.set_device(0)
 A, R = bench.make_nets(0, dev)
