@@ -231,7 +231,7 @@ def main():
     eng.phase_events = None
     _lib.call("icrl_chain_check", ctypes.c_void_p(torch.cuda.current_stream().cuda_stream),
               ctypes.c_void_p(eng.sync_state.data_ptr()))
-    seg_layout = eng._seg                      # (pieces, value segment, reward segment, warm-up) or None = serial kernels
+    seg_layout = eng.segment_layout                      # (pieces, value segment, reward segment, warm-up) or None = serial kernels
     seg_ok = torch.tensor([1 if eng.segments_verified() else 0], device=dev)
     if world > 1:
         dist.all_reduce(seg_ok, op=dist.ReduceOp.MIN)

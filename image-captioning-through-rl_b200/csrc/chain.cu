@@ -1149,13 +1149,17 @@ int coop_launch(const void* fn, int grid, void** args, cudaStream_t st) {
 __device__ __forceinline__ void err_max(float* slot, float v) { atomicMax(reinterpret_cast<int*>(slot), __float_as_int(fabsf(v))); }
 
 // Block k (k = 0..nb-2) compares the state segment k+1 reached after its warm-up with the state segment k computed at
-// the same position (stash row (k+1)*seg + warm).  err[0] = max |dh|, err[1] = max |dc|.
+// the same position (stash row (k+1)*seg + warm).  err[0] = max |dh|, err[1] = max |dc| / max(1, |c|).
 __global__ void chain_warm_check_fwd_kernel(long long seg, int warm, const float* warm_state, const float* stash_h,
                                             const float* stash_c, float* err) {
   const int b = blockIdx.x + 1, u = threadIdx.x;
   const size_t row = (size_t)b * seg + warm;
   float dh = fabsf(warm_state[(size_t)(2 * b) * H + u] - stash_h[row * H + u]);
-  float dc = stash_c ? fabsf(warm_state[(size_t)(2 * b + 1) * H + u] - stash_c[row * H + u]) : 0.f;
+  float dc = 0.f;                                      // the cell state is unbounded: error relative to max(1, |c|)
+  if (stash_c) {
+    const float ct = stash_c[row * H + u];
+    dc = fabsf(warm_state[(size_t)(2 * b + 1) * H + u] - ct) / fmaxf(1.f, fabsf(ct));
+  }
   // warp maximum first (NaN-propagating through the integer compare)
   int ih = __float_as_int(dh), ic = __float_as_int(dc);
 #pragma unroll

@@ -7,7 +7,9 @@ kernels behind ``include/icrl_b200.h``.  There is no CPU fallback.
 Single-pass formulation (verified against the unmodified reference):
   policy   one incremental LSTM pass with sampling (instead of re-running the prefix every step)
   value    ONE serial LSTM chain over the column-major token stream, h taken at the last B
-           positions of each step block; head evaluated in collapsed form
+           positions of each step block; head evaluated in collapsed form.  By default the chain
+           is advanced as up to 32 consecutive pieces in lockstep, each with a discarded warm-up
+           that is verified against the previous piece on every step (chain segments)
   reward   ONE serial GRU chain, semantic/visual embeds batched over all steps, fused cosine
   loss     advantage = values - rewards, gradient seeds for both networks
   backward policy BPTT (batched GEMMs + S serial cell steps), value-chain BPTT kernel, weight
@@ -130,9 +132,10 @@ class A2CEngine:
         # CTA group; every 2nd forward joint when the forward has 32).
         if chain_segments not in (1, 2, 4, 8, 16, 32):
             raise ValueError("chain_segments must be 1, 2, 4, 8, 16 or 32")
+        # chain_bwd_segments: backward pieces (None = 16 when the forward has 16 or 32, else min(forward, 8)); experiments.
+        if chain_bwd_segments not in (None, 2, 4, 8, 16):
+            raise ValueError("chain_bwd_segments must be None, 2, 4, 8 or 16")
         self.chain_bwd_segments = chain_bwd_segments
-        if chain_segments not in (1, 2, 4, 8, 16, 24, 32):
-            raise ValueError("chain_segments must be 1, 2, 4, 8, 16, 24 or 32")
         self.chain_segments = 1 if self.chain_shards > 1 else int(chain_segments)
         self.chain_warmup = int(chain_warmup)
         self.chain_tol = float(chain_tol)
@@ -548,6 +551,12 @@ class A2CEngine:
                       % (tol, e[0], e[1], e[2], e[3], e[4],
                          "segments are now off" if self.chain_segments == 1 else "warm-up is now %d" % self.chain_warmup))
         return False
+
+    @property
+    def segment_layout(self):
+        """(pieces, value-chain piece length, reward-chain piece length, warm-up) of the last step, or None when it ran on
+        the serial kernels (chain too short, chain_segments = 1, or a failed warm-up check)."""
+        return self._seg
 
     def segments_verified(self):
         """For callers that ran step(check=False): True when every segmented launch since the last check passed."""

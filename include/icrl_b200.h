@@ -213,7 +213,7 @@ int icrl_chain_lstm_bwd_sharded(void* stream, int shards, int T, const float* W_
  *      up to float rounding -- which is CHECKED, not assumed: the state reached at the end of every warm-up is compared
  *      with the state the previous segment computes at the same position, and the backward recurrence (segment k starts
  *      `warm` positions late with zero dh, dc) compares the gate gradients at the joints.  The caller reads
- *      segment_ws[0..4] = {max |dh| value chain, max |dc| value chain, max |dh| reward chain, max |d dgates| at the
+ *      segment_ws[0..4] = {max |dh| value chain, max |dc| / max(1, |c|) value chain, max |dh| reward chain, max |d dgates| at the
  *      joints, max |dh_take|} (running maxima; zero them to re-arm) and, if they exceed its tolerance, re-runs the
  *      serial entry points on the same buffers (the array layout IS the single-chain layout).
  *      Sizes: seg = icrl_chain_segment_len(T, segments, warm) (0 = chain too short for this many segments: needs

@@ -43,7 +43,7 @@ for mode, kw in (("serial_chain", dict(chain_segments=1)), ("chain_segments", di
         f, c = synth.make_inputs(200, 8192, 20)
         ms = timed(lambda: eng.get_rewards(f, c))
         out["config2_rewards_b8192_" + mode] = {"ms": ms, "captions_per_s": 8192 / (ms * 1e-3), "serial_gru_steps": 8192 * 20,
-                                                "pieces": eng._seg[0] if eng._seg else 1, "fallbacks": eng.segment_stats["fallbacks"]}
+                                                "pieces": eng.segment_layout[0] if eng.segment_layout else 1, "fallbacks": eng.segment_stats["fallbacks"]}
     Bl, L = 1024, 20
     f, c = synth.make_inputs(300 + rank, Bl, L)
     per_level = {}
@@ -51,7 +51,7 @@ for mode, kw in (("serial_chain", dict(chain_segments=1)), ("chain_segments", di
         u = synth.make_uniforms(400 + rank + level, level, Bl)
         prep = eng.prepare(f, c, u, level=level)
         ms = timed(lambda: dp.step(prep, global_rows=Bl * world, check=False))
-        per_level[str(level)] = {"ms": ms, "captions_per_s": Bl * world / (ms * 1e-3), "pieces": eng._seg[0] if eng._seg else 1,
+        per_level[str(level)] = {"ms": ms, "captions_per_s": Bl * world / (ms * 1e-3), "pieces": eng.segment_layout[0] if eng.segment_layout else 1,
                                  "verified": bool(eng.segments_verified())}
     tot = sum(v["ms"] for v in per_level.values())
     out["config4_curriculum_" + mode] = {"per_level": per_level, "aggregate_captions_per_s": 6 * Bl * world / (tot * 1e-3)}

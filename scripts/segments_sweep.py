@@ -46,5 +46,5 @@ for cfg in cfgs:
     ok = eng.segments_verified()
     print("pieces %2d (backward %s) warm-up %4d: %.1f ms/step  %.0f captions/s  fwd %.1f bwd %.1f | vs serial: values %.1e rewards %.1e "
           "grads %.1e | verified %s fallbacks %d layout %s" % (K, Kb, warm, e0.elapsed_time(e1_) / 3, B / (e0.elapsed_time(e1_) / 3e3),
-          ph.get("chains_fwd_fused", 0), ph.get("chain_lstm_bwd", 0), ev, er, eg, ok, eng.segment_stats["fallbacks"], eng._seg), flush=True)
+          ph.get("chains_fwd_fused", 0), ph.get("chain_lstm_bwd", 0), ev, er, eg, ok, eng.segment_stats["fallbacks"], eng.segment_layout), flush=True)
     del eng

@@ -732,7 +732,7 @@ def test_chain_segments_equal_the_serial_chain(segments, B, L, level):
     v1, w1, g1 = r1["values"].clone(), r1["rewards"].clone(), e1.flat_grad.clone()
     assert e1.segment_stats["segmented_steps"] == 0
     rk = ek.step(f, c, uniforms=u, level=level)
-    assert ek._seg is not None and ek._seg[0] == segments, ek._seg
+    assert ek.segment_layout is not None and ek.segment_layout[0] == segments, ek.segment_layout
     assert ek.segment_stats["fallbacks"] == 0, ek.segment_stats
     assert torch.equal(rk["tokens"], r1["tokens"])
     ev, er = float((rk["values"] - v1).abs().max()), float((rk["rewards"] - w1).abs().max())
@@ -773,7 +773,7 @@ def test_get_rewards_segments_equal_the_serial_chain():
     r1 = A2CEngine(A, R, chain_segments=1).get_rewards(f, c)
     ek = A2CEngine(A, R, chain_warmup=160)
     rk = ek.get_rewards(f, c)
-    assert ek._seg is not None and ek._seg[0] == 16 and ek.segment_stats["fallbacks"] == 0
+    assert ek.segment_layout is not None and ek.segment_layout[0] == 16 and ek.segment_stats["fallbacks"] == 0
     assert float((rk - r1).abs().max()) <= TOL
 
 
