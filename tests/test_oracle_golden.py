@@ -107,3 +107,67 @@ def test_dp_shard_oracle_is_sum_of_shards(golden_dir):
     assert np.array_equal(np.concatenate([h["tokens"] for h in halves]), full["tokens"])
     k = "policy_network.linear2vocab.bias"
     assert halves[0]["grads"][k].shape == full["grads"][k].shape
+
+
+def test_chain_segment_formulation_on_cpu():
+    """The chain-segment formulation of DESIGN 4.1, restated with the oracle's cells on the CPU: cut ONE carried-state
+    LSTM chain into K pieces, let every later piece start from zero state `warm` positions early (forward) and every
+    earlier piece start its backward recurrence `warm` positions late with zero dh / dc (backward), discard the warm-up
+    steps -- hidden states and gate-table gradients must equal the serial chain's to float rounding.  Same geometry as
+    the kernels: piece k covers positions [k*seg, (k+1)*seg + warm), seg = ceil((T - warm) / K)."""
+    torch.manual_seed(0)
+    w = synth.make_weights(7)["value"]
+    E, w_ih, w_hh = w["valrnn.caption_embedding.weight"], w["valrnn.lstm.weight_ih_l0"], w["valrnn.lstm.weight_hh_l0"]
+    bias = w["valrnn.lstm.bias_ih_l0"] + w["valrnn.lstm.bias_hh_l0"]
+    T, K, warm = 700, 4, 64
+    seg = (T - warm + K - 1) // K
+    rs = np.random.RandomState(5)
+    stream = torch.from_numpy(rs.randint(0, synth.VOCAB, T))
+    inject = torch.zeros(T, single_pass.HID)
+    take = rs.rand(T) < 0.3                                    # positions whose hidden state feeds the loss
+    inject[torch.from_numpy(take)] = torch.from_numpy(rs.standard_normal((int(take.sum()), single_pass.HID)).astype(np.float32)) * 1e-3
+
+    def run(lo, hi, h, c, xg):
+        hs = []
+        for t in range(lo, hi):
+            h, c = single_pass.lstm_cell(xg[t - lo], h, c, w_hh)
+            hs.append(h)
+        return torch.stack(hs), h, c
+
+    zero = torch.zeros(single_pass.HID)
+    xg_all = (E[stream] @ w_ih.t() + bias).detach()
+    # serial chain with autograd
+    xg = xg_all.clone().requires_grad_(True)
+    hs, _, _ = run(0, T, zero, zero, xg)
+    (hs * inject).sum().backward()
+    h_serial, g_serial = hs.detach(), xg.grad.clone()
+
+    h_seg, g_seg = torch.zeros_like(h_serial), torch.zeros_like(g_serial)
+    for k in range(K):
+        lo, hi = k * seg, min((k + 1) * seg + warm, T)
+        # forward: later pieces start from ZERO state and discard their first `warm` steps
+        with torch.no_grad():
+            hk, _, _ = run(lo, hi, zero, zero, xg_all[lo:hi])
+        live = lo + (warm if k > 0 else 0)
+        h_seg[live:hi] = hk[live - lo:]
+        # backward: the piece runs [lo, hi) from the TRUE state at lo (the stash) and its recurrence starts at hi - 1
+        # with zero dh / dc, i.e. nothing flows in from positions >= hi; the gradients of its last `warm` positions
+        # are discarded unless it is the last piece
+        h0 = h_serial[lo - 1] if lo > 0 else zero
+        with torch.no_grad():
+            c0 = zero
+            if lo > 0:
+                _, _, c0 = run(0, lo, zero, zero, xg_all[:lo])
+        xk = xg_all[lo:hi].clone().requires_grad_(True)
+        hk, _, _ = run(lo, hi, h0, c0, xk)
+        (hk * inject[lo:hi]).sum().backward()
+        keep_hi = hi if k == K - 1 else (k + 1) * seg
+        g_seg[lo:keep_hi] = xk.grad[:keep_hi - lo]
+    assert float((h_seg - h_serial).abs().max()) <= 1e-6
+    scale = float(g_serial.abs().max())
+    assert float((g_seg - g_serial).abs().max()) <= 1e-5 * scale
+    # and a warm-up that is too short IS visible (what the run-time check is for)
+    with torch.no_grad():
+        lo = seg
+        hk, _, _ = run(lo, lo + 4, zero, zero, xg_all[lo:lo + 4])
+    assert float((hk[-1] - h_serial[lo + 3]).abs().max()) > 1e-3
