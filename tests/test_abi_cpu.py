@@ -149,3 +149,23 @@ def test_chain_segment_geometry(lib):
                     assert Kb * (seg * (K // Kb)) == K * seg
     assert seglen(100, 1, 16) == 0 and seglen(16, 2, 16) == 0 and seglen(1000, 2, 0) == 0
     assert int(lib.call("icrl_chain_segment_ws_floats")) >= 8 + 2 * 32 * 2 * 512
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) prints ONE JSON line with the keys of
+    the bench contract; it times oracle/ref_port on the host cores and needs no GPU."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-sample", "4"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "A2C train captions/sec" and d["unit"] == "captions/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"] and "model" not in d["config"]
