@@ -18,6 +18,11 @@
 //     compute dh_{t-1}[u].
 //   * every spin is bounded (watchdog) and checks a global abort word, so a scheduling failure
 //     returns ICRL_ERR_WATCHDOG instead of hanging the GPU.
+//   * batched kernels (second half of the file): the same CTAs advance several recurrences in lockstep, sharing the
+//     register-resident weights and one exchange round trip -- either independent row shards from zero state
+//     ("chain shards", the numbers of K data-parallel ranks) or consecutive pieces of the ONE chain that start from zero
+//     state a warm-up early, discard those steps and are checked against the previous piece ("chain segments", the
+//     engine's default: the single chain's numbers to float rounding at 5-6x its speed).
 #include <cooperative_groups.h>
 #include "common.cuh"
 
@@ -434,7 +439,7 @@ __global__ void __launch_bounds__(THREADS, 1) chain_lstm_bwd_kernel(ChainBwdArgs
 // All per-step arrays of a shard use the same row stride (T + 1): stream [NB][stride], stash_h / stash_c
 // [NB][stride][H], stash_gates / dgates [NB][stride][4H] (row T unused / zero), take [NB][stride].
 
-constexpr int NB_MAX = 32;        // shards per forward launch (4 chunks of 8): exchange areas and check buffers are sized for it
+constexpr int NB_MAX = 32;        // shards per forward launch (2 chunks of 16): exchange areas and check buffers are sized for it
 
 struct ChainFwdBatchArgs {
   const int* stream;          // [NB][stride]
@@ -446,7 +451,7 @@ struct ChainFwdBatchArgs {
   float* stash_h;             // [NB][stride][H]; row 0 = 0, row t+1 = h_t
   float* stash_c;             // LSTM: [NB][stride][H] or null
   float* stash_gates;         // LSTM: [NB][stride][4H] or null
-  unsigned long long* xchg;   // [2][NB][H] tagged words, zeroed before launch
+  unsigned long long* xchg;   // [chunks][2][NB][H] tagged words, zeroed before launch
   int* abort_flag;
   long long* prof;            // debug: {exchange wait, GEMV + reduce, pointwise + publish} cycles of CTA 0 thread 0, T
   // Time-segment mode (warm > 0): the NB "shards" are consecutive segments of ONE chain.  stride = segment length,
@@ -461,8 +466,8 @@ struct ChainFwdBatchArgs {
 // (Tried and dropped for this exchange, both slower at NB = 8: a unit-major word layout [unit][NB], 393 -> 426 ms, and
 // plain data + one release flag per unit polled with acquire loads, 393 -> 508 ms: the release store waits for the
 // warp's stash writes.)
-// NCH > 1 (built: 2 chunks of 8 or of 16): the NB * NCH shards are walked as NCH chunks of NB per step.  Chunk q publishes its hidden vectors, then the
-// CTA computes the other chunks before it polls for chunk q's next vectors: the exchange round trip through L2 (the wait
+// NCH > 1 (built: 2 chunks of 8 or of 16): the NB * NCH shards are walked as NCH chunks of NB per step.  Chunk q
+// publishes its hidden vectors, then the CTA computes the other chunks before it polls for chunk q's next vectors: the exchange round trip through L2 (the wait
 // that bounds a single chunk) is covered by the other chunks' arithmetic.  Shard index = q * NB + lane group.
 template <int NG, int NB, int NCH>
 __device__ void chain_fwd_batched_body(const ChainFwdBatchArgs& p, int cta, float* sh_h /* [NCH][2][NB][H] */) {
