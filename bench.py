@@ -353,6 +353,19 @@ def main():
                                   "register_gemv_plus_pointwise_ns": 230,
                                   "source": "profiles/r01_xchg_bench.log, profiles/r01_chain_micro.log (microbenchmarks, "
                                             "not measured in this run)"}}
+    try:
+        # What bounds this kernel is FP32 issue on the CUDA cores, so the same launch is also put against
+        # that roof: multiply-adds of the recurrent GEMVs (forward: 4*512*512 per value position + 3*512*512 per reward
+        # position; backward: the 2048 x 512 contraction per value position) over SMs x 128 lanes x 2 x the sampled SM clock.
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+        mhz = float(clk.get("sm_mhz") or 1965.0)
+        macs = Tv * 4.0 * H * H if kname.startswith("chain_lstm_bwd") else Tv * 4.0 * H * H + Tr * 3.0 * H * H
+        peak32 = sms * 128 * 2 * mhz * 1e6 / 1e12
+        ach32 = 2.0 * macs / (kms * 1e-3) / 1e12 if kms > 0 else 0.0
+        roofline["fp32"] = {"achieved": ach32, "peak": peak32, "unit": "TFLOP/s", "frac": ach32 / peak32,
+                            "peak_source": "nominal: %d SMs x 128 FP32 lanes x 2 x %.0f MHz" % (sms, mhz)}
+    except Exception as exc:                                   # a side figure must never cost the bench line
+        roofline["fp32"] = {"error": str(exc)}
     out = {
         "metric": "A2C train captions/sec", "value": B / (ms_step * 1e-3), "unit": "captions/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
