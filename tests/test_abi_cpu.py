@@ -169,3 +169,31 @@ def test_bench_reference_arm_json_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_bench_clock_sampler_window():
+    """bench.ClockSampler.stop(t0, t1): samples inside the timed region are used; when the region is shorter than one
+    sampling period the warm-up samples (same kernels, same load) are used and the window says so; throttle reasons are
+    collected from the rows that are used."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+
+    class _Proc:
+        def terminate(self):
+            pass
+
+    def sampler(rows, stamps):
+        s = bench.ClockSampler(0)
+        s.proc, s.rows, s.stamps = _Proc(), list(rows), list(stamps)
+        return s
+
+    idle = ["0", "1200", "1965", "300", "0x0", "Not Active", "Not Active", "Not Active", "Not Active"]
+    busy = ["0", "1965", "1965", "900", "0x4", "Not Active", "Not Active", "Not Active", "Active"]
+    out = sampler([idle, busy, busy, busy], [10.0, 10.2, 10.4, 10.6]).stop(10.1, 10.5)
+    assert out["samples"] == 2 and out["sm_mhz"] == 1965.0 and out["window"] == "timed region"
+    assert out["reasons"] == ["sw_power_cap"] and out["sm_max_mhz"] == 1965.0
+    out = sampler([busy, busy], [10.0, 10.2]).stop(10.25, 10.30)              # timed region between two samples
+    assert out["samples"] == 2 and out["window"].startswith("warm-up")
+    assert bench.ClockSampler(0).stop()["reasons"] == ["nvidia-smi unavailable"]
