@@ -197,3 +197,27 @@ def test_bench_clock_sampler_window():
     out = sampler([busy, busy], [10.0, 10.2]).stop(10.25, 10.30)              # timed region between two samples
     assert out["samples"] == 2 and out["window"].startswith("warm-up")
     assert bench.ClockSampler(0).stop()["reasons"] == ["nvidia-smi unavailable"]
+
+
+def test_stream_length_and_take_positions_match_the_oracle(lib):
+    """icrl_stream_len (host arithmetic of the C ABI) against the oracle's stream builder for random shapes: the value
+    chain holds B * sum_s (p0 + s) positions, the reward chain one more column per block, and the take positions are
+    the last B positions of every block (models.py:168-169, 254-255: one RNN call per column, state carried)."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import single_pass
+
+    @settings(max_examples=40, deadline=None)
+    @given(B=st.integers(1, 9), p0=st.integers(1, 6), S=st.integers(1, 7), extra=st.integers(0, 1))
+    def check(B, p0, S, extra):
+        tokens = np.arange(B * (p0 + S + 1), dtype=np.int64).reshape(B, p0 + S + 1)
+        stream, take = single_pass.stream_tokens(tokens, p0, S, extra)
+        assert int(lib.call("icrl_stream_len", B, p0, S, extra)) == len(stream) == B * sum(p0 + s + extra for s in range(S))
+        off = 0
+        for s in range(S):
+            off += (p0 + s + extra) * B
+            assert list(take[s]) == list(range(off - B, off))
+            # block s is the column-major prefix of length p0 + s + extra
+            blk = stream[off - (p0 + s + extra) * B: off].reshape(p0 + s + extra, B)
+            assert np.array_equal(blk, tokens[:, :p0 + s + extra].T)
+
+    check()
