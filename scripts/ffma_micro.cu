@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(TH, 1) gemv_kernel(const float* __restrict__ w
 #pragma unroll 1
   for (int it = 0; it < iters; ++it) {
     asm volatile("" ::: "memory");                  // the hidden vectors change every step in the real kernel: reload them
-    if constexpr (VARIANT == 0 || VARIANT == 3) {
+    if constexpr (VARIANT == 0) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -46,6 +46,18 @@ __global__ void __launch_bounds__(TH, 1) gemv_kernel(const float* __restrict__ w
             acc[g][v] = fmaf(w[g][4 * j + 2], hv.z, acc[g][v]);
             acc[g][v] = fmaf(w[g][4 * j + 3], hv.w, acc[g][v]);
           }
+        }
+    } else if constexpr (VARIANT == 3) {               // same count, but neighbouring FMAs never share an operand register
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int v = 0; v < NB; ++v) {
+          const float4 hv = *reinterpret_cast<const float4*>(&hb[v * H + 128 * j + 4 * lane]);
+          const float ha[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int g = 0; g < NG; ++g) acc[g][v] = fmaf(w[g][4 * j + ((k + g) & 3)], ha[(k + g) & 3], acc[g][v]);
         }
     } else if constexpr (VARIANT == 1) {
 #pragma unroll
@@ -87,15 +99,6 @@ __global__ void __launch_bounds__(TH, 1) gemv_kernel(const float* __restrict__ w
               asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[g][v]), "=f"(acc[g][v + 1]) : "l"(d));
             }
         }
-    }
-    if constexpr (VARIANT == 3) {                      // break the reuse: rotate the weights so no operand repeats
-#pragma unroll
-      for (int g = 0; g < NG; ++g) {
-        const float t = w[g][0];
-#pragma unroll
-        for (int k = 0; k + 1 < KW; ++k) w[g][k] = w[g][k + 1];
-        w[g][KW - 1] = t;
-      }
     }
   }
   const long long t1 = clock64();
