@@ -368,6 +368,36 @@ int icrl_chain_lstm_bwd_segmented(void* stream, int segments, int warm, int seg,
   return ICRL_OK;
 }
 
+int icrl_chain_tc_max_pieces(void) { return icrl_chain_tc_max_pieces_impl(); }
+size_t icrl_chain_tc_weight_halves(int kind) { return icrl_chain_tc_weight_halves_impl(kind); }
+size_t icrl_chain_tc_ws_bytes(int pieces) { return icrl_chain_tc_ws_bytes_impl(pieces); }
+size_t icrl_chain_tc_cp_floats(int pieces) { return icrl_chain_tc_cp_floats_impl(pieces); }
+int icrl_chain_tc_set_profile(void* buf) { icrl_chain_tc_set_profile_impl(reinterpret_cast<long long*>(buf)); return ICRL_OK; }
+
+int icrl_pack_chain_tc_weights(void* stream, int kind, const float* W_hh, void* packed, int* launches) {
+  TRY(icrl_pack_chain_tc_weights_impl(S_(stream), kind, W_hh, packed));
+  bump(launches, 1);
+  return ICRL_OK;
+}
+
+int icrl_chain_tc_fwd(void* stream, int kind, int pieces, long long seg, int warm, const int* tok_stream,
+                      const float* table, const void* packed, const float* b_hn, float* stash_h, float* stash_c,
+                      float* stash_gates, void* ws, float* cp_state, float* err, int* launches) {
+  TRY(icrl_chain_tc_fwd_impl(S_(stream), kind, pieces, seg, warm, tok_stream, table, packed, b_hn, stash_h, stash_c,
+                             stash_gates, ws, cp_state, err));
+  bump(launches, 2);                       // the persistent cluster kernel + the joint check
+  return ICRL_OK;
+}
+
+int icrl_chain_tc_lstm_bwd(void* stream, int pieces, long long seg, int warm, const void* packed,
+                           const float* stash_gates, const float* stash_c, const int* take, const float* dh_take,
+                           long long take_rows, float* dgates, void* ws, float* cp_state, float* err, int* launches) {
+  TRY(icrl_chain_tc_lstm_bwd_impl(S_(stream), pieces, seg, warm, packed, stash_gates, stash_c, take, dh_take, take_rows,
+                                  dgates, ws, cp_state, err));
+  bump(launches, 3);                       // |dh_take| maximum, the persistent cluster kernel, the joint check
+  return ICRL_OK;
+}
+
 int icrl_chain_set_profile(void* buf) { icrl_chain_set_profile_impl(reinterpret_cast<long long*>(buf)); return ICRL_OK; }
 
 size_t icrl_chain_sync_bytes(void) { return icrl_chain_sync_bytes_impl(); }

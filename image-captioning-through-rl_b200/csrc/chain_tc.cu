@@ -1,0 +1,909 @@
+// Chain pieces on tcgen05 (sm_100a): the value-LSTM / reward-GRU batch-as-time recurrences of the reference
+// (models.py:130-135, 223-228: seq = B, batch = 1, hidden state carried across calls; trainers.py:479 for the backward)
+// advanced as HUNDREDS of lockstep pieces of the ONE carried-state chain.
+//
+// Why this is a GEMM.  chain.cu walks the chain position by position (latency floor ~1.3 us per position) or as <= 32
+// lockstep pieces on CUDA cores.  With P pieces in lockstep, one kernel step is  H_prev [P x 512] . W_hh^T [512 x G]
+// (G = 2048 LSTM, 1536 GRU) followed by the pointwise cell update -- exactly the shape decode.cu already runs on
+// tcgen05 with the policy's batch rows in the M dimension.  Here the M rows are PIECES of one chain: piece k covers
+// stream positions [k*seg, (k+1)*seg + warm); pieces k >= 1 start from zero state, discard their first `warm` positions
+// (nothing is stored for them) and by then carry the single chain's state to float rounding because the gated
+// recurrence contracts state differences.  That is CHECKED on every launch, never assumed: the state each piece
+// reaches at the end of (and half-way through) its warm-up is compared with the state the preceding pieces stored at
+// the same positions (chain_tc_check_*), and the engine re-runs with a longer warm-up when the check fails.
+//
+// Decomposition (forward).  A cluster of 8 CTAs owns 128 pieces for the whole launch and never talks to another
+// cluster.  CTA r owns hidden units [64r, 64r+64): NG*64 gate columns (W_hh rows permuted at pack time), i.e. the
+// N-slice of the step GEMM; K = 512.  Per step: TMA ring (4 stages of 32-wide K blocks; the A tile = fp16 split of
+// h_{t-1} of the 128 pieces is fetched in 16-row slices and multicast to the whole cluster, the B tile = this CTA's
+// W_hh slice comes from L2) -> tcgen05.mma (M=128, N=NG*64; three products hi*hi -> main accumulator, hi*lo' + lo'*hi
+// -> correction accumulator, f32 in tensor memory: fp32-grade, see decode.cu) -> epilogue warps: gate-table rows of
+// the consumed tokens and the carried c (LSTM) / h (GRU) gathered into a swizzled shared-memory tile with cp.async,
+// cell update thread-per-row, coalesced stores of the backward stash (live positions only), of the carried state and
+// of the fp16 split of h_t for the next step -> cluster barrier.
+//
+// Backward (LSTM).  Mirrored: piece k walks positions (k+1)*seg + warm - 1 down to k*seg, pieces other than the last
+// start with dh = dc = 0 and discard the gate gradients of their first `warm` steps (injections at take positions inside
+// the window are applied).  Step GEMM: dh_{t-1} [P x 512] = dgates_t [P x 2048] . W_hh [2048 x 512]: CTA r produces the
+// 64 hidden units it owns (N = 64, K = 2048; A = fp16 split of the gate gradients of all 8 CTAs, exchanged through
+// L2 and TMA-multicast; B = W_hh^T slice).  Gate gradients span many orders of magnitude, so the exchanged copy is
+// scaled by a power of two derived from max |dL/dh_take| (fp16 keeps 22 bits down to 2^-18 of that maximum; overflow
+// is detected and reported).  The fp32 gate gradients of live positions go to `dgates` for the parameter-gradient
+// contractions exactly as the serial kernel writes them.
+#include "tc_ptx.cuh"
+#include "internal.h"
+
+using namespace icrl_tc;
+
+namespace {
+
+constexpr int H = ICRL_H;
+constexpr int CL = 8;                       // CTAs per cluster
+constexpr int BM = 128;                     // pieces per cluster (MMA M)
+constexpr int UN = H / CL;                  // 64 hidden units per CTA
+constexpr int BK = 32, UMMA_K = 16;         // 64-byte K rows (SWIZZLE_64B)
+constexpr int A_TILE = BM * BK * 2;         // 8 KB
+constexpr int A_SLICE_ROWS = BM / CL;       // 16 rows fetched (and multicast) per CTA
+constexpr int A_SLICE = A_SLICE_ROWS * BK * 2;
+constexpr int EPI_WARPS = 8, EPI_WARP0 = 4;
+constexpr int THREADS = 32 * (EPI_WARP0 + EPI_WARPS);      // 384
+constexpr float LO_INV = 1.f / 2048.f;
+constexpr int CORR = 256;                   // forward: TMEM column of the correction accumulator
+
+// ------------------------------------------------------------------------------------------------ forward
+constexpr int F_STAGES = 4, F_KB = H / BK;  // 16 K blocks per step
+template <int NG> struct FwdCfg {
+  static constexpr int GN = NG * UN;                        // 256 / 192 gate columns per CTA
+  static constexpr int B_TILE = GN * BK * 2;                // 16 / 12 KB
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;     // 48 / 40 KB
+  static constexpr int NARR = NG == 4 ? 6 : 4;              // staging arrays of [32 rows][32 units] f32 per epilogue warp
+  static constexpr int GST_WARP = NARR * 4096;
+  static constexpr int SMEM = F_STAGES * STAGE + 256 + 1024;
+  static_assert(EPI_WARPS * GST_WARP <= F_STAGES * STAGE, "epilogue staging lives inside the (idle) TMA ring");
+};
+
+struct FwdArgs {
+  int P, Ppad, steps, warm, cp_half;
+  long long seg;
+  const int* stream;       // [P*seg + warm]
+  const float* table;      // [V][NG*512]
+  const float* b_hn;       // GRU: [512]
+  float* stash_h;          // [(P*seg + warm + 1)][512]; row 0 = zeros (set by the launcher)
+  float* stash_c;          // LSTM
+  float* stash_g;          // LSTM: [P*seg + warm][2048] activated i,f,g,o (nullable)
+  float* state;            // [Ppad][512] carried c (LSTM) / h (GRU), zeroed by the launcher
+  __half* hparts;          // [2 buffers][2 parts][Ppad][512]; buffer 0 zeroed by the launcher
+  float* wstate;           // [2 checkpoints][P][2][512]: (h, c) of piece k after step cp_half (0) / warm-1 (1)
+  long long* prof;         // optional: cycle sums of CTA 0's first epilogue warp {acc wait, gather, cell, store, barrier}, steps
+};
+
+template <int NG>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
+chain_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_w, const FwdArgs p) {
+  using C = FwdCfg<NG>;
+  constexpr int GN = C::GN, B_TILE = C::B_TILE, STAGE = C::STAGE, STAGES = F_STAGES;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + STAGES * STAGE);
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * STAGES + 2);
+  const unsigned bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[STAGES]);
+  const unsigned bar_acc_full = smem_u32(&bars[2 * STAGES]), bar_acc_empty = smem_u32(&bars[2 * STAGES + 1]);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned rank = cluster_rank();
+  const int m0 = (blockIdx.x / CL) * BM;
+  const int P = p.P, Ppad = p.Ppad, steps = p.steps;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
+    mbar_init(bar_acc_full, 1);
+    mbar_init(bar_acc_empty, EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_h) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = *tmem_slot;
+  cluster_arrive();                      // every CTA's mbarriers are initialised before anyone multicasts into them
+  cluster_wait();
+
+  if (warp == 2 || warp == 3) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    for (int j = 0; j < steps; ++j) { cluster_arrive(); cluster_wait(); }
+  } else if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    unsigned it = 0;
+    for (int j = 0; j < steps; ++j) {
+      if (lane == 0) {
+        const int arow = ((j & 1) * 2) * Ppad + m0;
+        for (int kb = 0; kb < F_KB; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(bar_empty + 8 * s, ((it / STAGES) & 1u) ^ 1u);
+          const unsigned full = bar_full + 8 * s;
+          mbar_expect_tx(full, 2 * A_TILE + 2 * B_TILE);
+          const unsigned base = smem_u32(smem + s * STAGE);
+          tma_load_2d_mcast(base + rank * A_SLICE, &map_h, kb * BK, arow + (int)rank * A_SLICE_ROWS, full, 0xFF);
+          tma_load_2d_mcast(base + A_TILE + rank * A_SLICE, &map_h, kb * BK, arow + Ppad + (int)rank * A_SLICE_ROWS, full, 0xFF);
+          tma_load_3d(base + 2 * A_TILE, &map_w, kb * BK, (int)rank * GN, 0, full);      // hi at +0, lo' at +B_TILE
+        }
+      }
+      __syncwarp();
+      cluster_arrive();
+      cluster_wait();                    // h_j of all 8 CTAs is in global memory
+      if (lane == 0) fence_proxy_async();
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loops, elect.sync)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    unsigned it = 0;
+    for (int j = 0; j < steps; ++j) {
+      if (j > 0) mbar_wait(bar_acc_empty, (unsigned)(j - 1) & 1u);        // previous epilogue drained TMEM
+      tc_fence_after();
+      for (int kb = 0; kb < F_KB; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(bar_full + 8 * s, (it / STAGES) & 1u);
+        tc_fence_after();
+        const unsigned base = smem_u32(smem + s * STAGE);
+        const unsigned long long dA0 = smem_desc_sw64(base), dA1 = smem_desc_sw64(base + A_TILE);
+        const unsigned long long dB0 = smem_desc_sw64(base + 2 * A_TILE), dB1 = smem_desc_sw64(base + 2 * A_TILE + B_TILE);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {                          // +2 = 32 bytes (16 fp16 along K) in 16-byte units
+            tc_mma(tmem_base, dA0 + 2 * k, dB0 + 2 * k, idesc_f16_m128(GN), (kb | k) != 0);          // hi  * hi  -> main
+            tc_mma(tmem_base + CORR, dA0 + 2 * k, dB1 + 2 * k, idesc_f16_m128(GN), (kb | k) != 0);   // hi  * lo' -> correction
+            tc_mma(tmem_base + CORR, dA1 + 2 * k, dB0 + 2 * k, idesc_f16_m128(GN), 1u);              // lo' * hi  -> correction
+          }
+          tc_commit_mcast(bar_empty + 8 * s, 0xFF);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) tc_commit(bar_acc_full);
+      __syncwarp();
+      cluster_arrive();
+      cluster_wait();
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int ew = warp - EPI_WARP0;
+    const int q = warp & 3;                    // TMEM lane quarter this warp may read
+    const int ch = ew >> 2;                    // unit half
+    const int k_own = m0 + 32 * q + lane;      // this thread's piece (row of the cluster tile)
+    const bool valid = k_own < P;
+    const unsigned tq = tmem_base + ((unsigned)(32 * q) << 16);
+    unsigned char* gst = smem + ew * C::GST_WARP;
+    const int ucol0 = (int)rank * UN + 32 * ch;
+    const long long seg = p.seg;
+    int tok = valid ? p.stream[(long long)k_own * seg] : 0;
+    const bool prof = p.prof != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0;
+    long long pr[5] = {0, 0, 0, 0, 0};
+
+    for (int j = 0; j < steps; ++j) {
+      const long long t0 = prof ? clock64() : 0;
+      const int tok_n = (valid && j + 1 < steps) ? p.stream[(long long)k_own * seg + j + 1] : 0;
+      mbar_wait(bar_acc_full, (unsigned)j & 1u);
+      tc_fence_after();
+      const long long t1 = prof ? clock64() : 0;
+      // (L) gate-table rows of the consumed tokens (arrays 0..NG-1) and the carried state (array NG) -> staging,
+      //     8 lanes per row; element (row, 16-byte chunk c) lives at row*128 + ((c ^ (row & 7)) << 4).
+      {
+        const int c4 = lane & 7;
+#pragma unroll
+        for (int i8 = 0; i8 < 8; ++i8) {
+          const int r = i8 * 4 + (lane >> 3);
+          const int tokr = __shfl_sync(0xffffffffu, tok, r);
+          const int kr = m0 + 32 * q + r;
+          if (kr < P) {
+            const unsigned dst = smem_u32(gst) + (unsigned)(r * 128 + ((c4 ^ (r & 7)) << 4));
+            const float* tsrc = p.table + (size_t)tokr * (NG * H) + ucol0 + c4 * 4;
+#pragma unroll
+            for (int a = 0; a < NG; ++a) cp_async16(dst + a * 4096, tsrc + a * H);
+            cp_async16(dst + NG * 4096, p.state + (size_t)kr * H + ucol0 + c4 * 4);
+          }
+        }
+        cp_async_wait_all();
+        __syncwarp();
+      }
+      const long long t2 = prof ? clock64() : 0;
+      // (C) cell update, one row per lane, in place on the staging tile
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        float acc[NG][8], cor[NG][8];
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+          tmem_ld8x2(tq + (unsigned)(g * UN + 32 * ch + 8 * c8), tq + (unsigned)(CORR + g * UN + 32 * ch + 8 * c8), acc[g], cor[g]);
+        unsigned char* e0 = gst + lane * 128 + (((2 * c8) ^ (lane & 7)) << 4);
+        unsigned char* e1 = gst + lane * 128 + (((2 * c8 + 1) ^ (lane & 7)) << 4);
+        float tin[NG + 1][8];
+#pragma unroll
+        for (int a = 0; a < NG + 1; ++a) {
+          const float4 u0 = *reinterpret_cast<const float4*>(e0 + a * 4096);
+          const float4 u1 = *reinterpret_cast<const float4*>(e1 + a * 4096);
+          tin[a][0] = u0.x; tin[a][1] = u0.y; tin[a][2] = u0.z; tin[a][3] = u0.w;
+          tin[a][4] = u1.x; tin[a][5] = u1.y; tin[a][6] = u1.z; tin[a][7] = u1.w;
+        }
+        if constexpr (NG == 4) {
+          float gi[8], gf[8], gg[8], go[8], cn[8], hn[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            gi[i] = sigmoidf_sfu(fmaf(cor[0][i], LO_INV, acc[0][i]) + tin[0][i]);
+            gf[i] = sigmoidf_sfu(fmaf(cor[1][i], LO_INV, acc[1][i]) + tin[1][i]);
+            gg[i] = tanhf_sfu(fmaf(cor[2][i], LO_INV, acc[2][i]) + tin[2][i]);
+            go[i] = sigmoidf_sfu(fmaf(cor[3 % NG][i], LO_INV, acc[3 % NG][i]) + tin[3 % NG][i]);
+            cn[i] = gf[i] * tin[NG][i] + gi[i] * gg[i];
+            hn[i] = go[i] * tanhf_sfu(cn[i]);
+          }
+          *reinterpret_cast<float4*>(e0) = make_float4(gi[0], gi[1], gi[2], gi[3]);
+          *reinterpret_cast<float4*>(e1) = make_float4(gi[4], gi[5], gi[6], gi[7]);
+          *reinterpret_cast<float4*>(e0 + 4096) = make_float4(gf[0], gf[1], gf[2], gf[3]);
+          *reinterpret_cast<float4*>(e1 + 4096) = make_float4(gf[4], gf[5], gf[6], gf[7]);
+          *reinterpret_cast<float4*>(e0 + 2 * 4096) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+          *reinterpret_cast<float4*>(e1 + 2 * 4096) = make_float4(gg[4], gg[5], gg[6], gg[7]);
+          *reinterpret_cast<float4*>(e0 + 3 * 4096) = make_float4(go[0], go[1], go[2], go[3]);
+          *reinterpret_cast<float4*>(e1 + 3 * 4096) = make_float4(go[4], go[5], go[6], go[7]);
+          *reinterpret_cast<float4*>(e0 + 4 * 4096) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+          *reinterpret_cast<float4*>(e1 + 4 * 4096) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+          *reinterpret_cast<float4*>(e0 + (C::NARR - 1) * 4096) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+          *reinterpret_cast<float4*>(e1 + (C::NARR - 1) * 4096) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+        } else {
+          // GRU (gate order r, z, n): n = tanh(x_n + r * (W_hn h + b_hn)), h' = (1 - z) n + z h   (models.py:215)
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.b_hn + ucol0 + 8 * c8));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.b_hn + ucol0 + 8 * c8 + 4));
+          const float bh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          float hn[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float r = sigmoidf_sfu(fmaf(cor[0][i], LO_INV, acc[0][i]) + tin[0][i]);
+            const float z = sigmoidf_sfu(fmaf(cor[1][i], LO_INV, acc[1][i]) + tin[1][i]);
+            const float n = tanhf_sfu(tin[2][i] + r * (fmaf(cor[2][i], LO_INV, acc[2][i]) + bh[i]));
+            hn[i] = (1.f - z) * n + z * tin[NG][i];
+          }
+          *reinterpret_cast<float4*>(e0 + NG * 4096) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+          *reinterpret_cast<float4*>(e1 + NG * 4096) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+        }
+      }
+      __syncwarp();
+      const long long t3 = prof ? clock64() : 0;
+      // (S) coalesced stores, 8 lanes per row: backward stash (live positions), carried state, checkpoints, fp16 split of h
+      {
+        const int c4 = lane & 7;
+        const bool cp_full = j == p.warm - 1, cp_half = j == p.cp_half;
+#pragma unroll
+        for (int i8 = 0; i8 < 8; ++i8) {
+          const int r = i8 * 4 + (lane >> 3);
+          const int kr = m0 + 32 * q + r;
+          if (kr < P) {
+            const unsigned char* e = gst + r * 128 + ((c4 ^ (r & 7)) << 4);
+            const size_t pos = (size_t)kr * seg + j;
+            const bool live = kr == 0 || j >= p.warm;
+            const int uc = ucol0 + c4 * 4;
+            const float4 h4 = *reinterpret_cast<const float4*>(e + (C::NARR - 1) * 4096);
+            if constexpr (NG == 4) {
+              const float4 cn4 = *reinterpret_cast<const float4*>(e + 4 * 4096);
+              *reinterpret_cast<float4*>(p.state + (size_t)kr * H + uc) = cn4;
+              if (live) {
+                if (p.stash_g) {
+                  float* gs = p.stash_g + pos * (4 * H) + uc;
+#pragma unroll
+                  for (int a = 0; a < 4; ++a) *reinterpret_cast<float4*>(gs + a * H) = *reinterpret_cast<const float4*>(e + a * 4096);
+                }
+                *reinterpret_cast<float4*>(p.stash_c + (pos + 1) * H + uc) = cn4;
+              }
+              if (kr >= 1 && (cp_full || cp_half))
+                *reinterpret_cast<float4*>(p.wstate + ((size_t)((cp_full ? 1 : 0) * P + kr) * 2 + 1) * H + uc) = cn4;
+            } else {
+              *reinterpret_cast<float4*>(p.state + (size_t)kr * H + uc) = h4;
+            }
+            if (live) *reinterpret_cast<float4*>(p.stash_h + (pos + 1) * H + uc) = h4;
+            if (kr >= 1 && (cp_full || cp_half))
+              *reinterpret_cast<float4*>(p.wstate + ((size_t)((cp_full ? 1 : 0) * P + kr) * 2) * H + uc) = h4;
+            uint2 hi, lo;
+            split4_f16(h4, hi, lo);
+            __half* hp = p.hparts + ((size_t)(((j + 1) & 1) * 2) * Ppad + kr) * H + uc;
+            *reinterpret_cast<uint2*>(hp) = hi;
+            *reinterpret_cast<uint2*>(hp + (size_t)Ppad * H) = lo;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty);
+      const long long t4 = prof ? clock64() : 0;
+      __threadfence();
+      fence_proxy_async();                     // generic-proxy writes of the h split -> visible to the peers' TMA loads
+      __syncwarp();
+      cluster_arrive();
+      cluster_wait();
+      tok = tok_n;
+      if (prof) { const long long t5 = clock64(); pr[0] += t1 - t0; pr[1] += t2 - t1; pr[2] += t3 - t2; pr[3] += t4 - t3; pr[4] += t5 - t4; }
+    }
+    if (prof) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) p.prof[i] = pr[i];
+      p.prof[5] = steps;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_arrive();                          // nobody leaves while a peer may still multicast into its shared memory
+  cluster_wait();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward (LSTM)
+constexpr int B_STAGES = 8, B_KB = 4 * H / BK;              // 64 K blocks per step (K = 2048 gate gradients)
+constexpr int BB_TILE = UN * BK * 2;                        // 4 KB: this CTA's 64 output units x 32 K
+constexpr int B_STAGE = 2 * A_TILE + 2 * BB_TILE;           // 24 KB
+constexpr int B_NARR = 7, B_GST_WARP = B_NARR * 2048;       // staging arrays of [32 rows][16 units] f32 (two unit passes per step)
+constexpr int B_SMEM = B_STAGES * B_STAGE + 256 + 1024;
+constexpr int B_TMEM_COLS = 128, B_CORR = 64;
+static_assert(EPI_WARPS * B_GST_WARP <= B_STAGES * B_STAGE, "epilogue staging lives inside the (idle) TMA ring");
+
+struct BwdArgs {
+  int P, Ppad, steps, warm, cp_half;
+  long long seg;
+  const float* stash_g;    // [P*seg + warm][2048] activated i,f,g,o
+  const float* stash_c;    // [P*seg + warm + 1][512]
+  const int* take;         // [P*seg + warm] row of dh_take injected at the position, or -1
+  const float* dh_take;    // [take_rows][512]
+  float* dgates;           // [P*seg + warm][2048] pre-activation gate gradients of the live positions
+  __half* dgx;             // [2 buffers][2 parts][Ppad][2048] scaled fp16 split of the gate gradients (exchange)
+  const float* dh_max;     // device word: max |dh_take| (scale of the recurrence)
+  float* bstate;           // [2 checkpoints][2 sides][P][2][512] (dh, dc) at the joints
+  float* overflow;         // device word: set to 1 when a scaled gate gradient left the fp16 range
+  long long* prof;
+};
+
+// power-of-two scale S with max|dh_take| * S in [8, 16): fp16 then holds 22 bits of every gate gradient down to
+// 2^-18 of that maximum and has 2^12 of headroom above it.
+__device__ __forceinline__ float bwd_scale(float m) {
+  if (!(m > 0.f) || !isfinite(m)) return 1.f;
+  int ex;
+  frexpf(m, &ex);                              // m = f * 2^ex, f in [0.5, 1)
+  ex = 4 - ex;
+  ex = ex > 100 ? 100 : (ex < -100 ? -100 : ex);
+  return ldexpf(1.f, ex);
+}
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
+chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_constant__ CUtensorMap map_w, const BwdArgs p) {
+  constexpr int STAGES = B_STAGES, STAGE = B_STAGE;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + STAGES * STAGE);
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * STAGES + 2);
+  const unsigned bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[STAGES]);
+  const unsigned bar_acc_full = smem_u32(&bars[2 * STAGES]), bar_acc_empty = smem_u32(&bars[2 * STAGES + 1]);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned rank = cluster_rank();
+  const int m0 = (blockIdx.x / CL) * BM;
+  const int P = p.P, Ppad = p.Ppad, steps = p.steps;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
+    mbar_init(bar_acc_full, 1);
+    mbar_init(bar_acc_empty, EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dg) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(B_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = *tmem_slot;
+  cluster_arrive();
+  cluster_wait();
+
+  if (warp == 2 || warp == 3) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    for (int it = 0; it < steps; ++it) { cluster_arrive(); cluster_wait(); }
+  } else if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (no GEMM before the first step)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    unsigned n = 0;
+    for (int it = 0; it < steps; ++it) {
+      if (it > 0 && lane == 0) {
+        const int arow = ((it & 1) * 2) * Ppad + m0;
+        for (int kb = 0; kb < B_KB; ++kb, ++n) {
+          const int s = n % STAGES;
+          mbar_wait(bar_empty + 8 * s, ((n / STAGES) & 1u) ^ 1u);
+          const unsigned full = bar_full + 8 * s;
+          mbar_expect_tx(full, 2 * A_TILE + 2 * BB_TILE);
+          const unsigned base = smem_u32(smem + s * STAGE);
+          tma_load_2d_mcast(base + rank * A_SLICE, &map_dg, kb * BK, arow + (int)rank * A_SLICE_ROWS, full, 0xFF);
+          tma_load_2d_mcast(base + A_TILE + rank * A_SLICE, &map_dg, kb * BK, arow + Ppad + (int)rank * A_SLICE_ROWS, full, 0xFF);
+          tma_load_3d(base + 2 * A_TILE, &map_w, kb * BK, (int)rank * UN, 0, full);       // hi at +0, lo' at +BB_TILE
+        }
+      }
+      __syncwarp();
+      cluster_arrive();
+      cluster_wait();                    // the gate gradients of this step (all 8 CTAs) are in global memory
+      if (lane == 0) fence_proxy_async();
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    unsigned n = 0;
+    for (int it = 0; it < steps; ++it) {
+      if (it > 0) {
+        mbar_wait(bar_acc_empty, (unsigned)(it - 1) & 1u);
+        tc_fence_after();
+        for (int kb = 0; kb < B_KB; ++kb, ++n) {
+          const int s = n % STAGES;
+          mbar_wait(bar_full + 8 * s, (n / STAGES) & 1u);
+          tc_fence_after();
+          const unsigned base = smem_u32(smem + s * STAGE);
+          const unsigned long long dA0 = smem_desc_sw64(base), dA1 = smem_desc_sw64(base + A_TILE);
+          const unsigned long long dB0 = smem_desc_sw64(base + 2 * A_TILE), dB1 = smem_desc_sw64(base + 2 * A_TILE + BB_TILE);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              tc_mma(tmem_base, dA0 + 2 * k, dB0 + 2 * k, idesc_f16_m128(UN), (kb | k) != 0);
+              tc_mma(tmem_base + B_CORR, dA0 + 2 * k, dB1 + 2 * k, idesc_f16_m128(UN), (kb | k) != 0);
+              tc_mma(tmem_base + B_CORR, dA1 + 2 * k, dB0 + 2 * k, idesc_f16_m128(UN), 1u);
+            }
+            tc_commit_mcast(bar_empty + 8 * s, 0xFF);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) tc_commit(bar_acc_full);
+      }
+      __syncwarp();
+      cluster_arrive();
+      cluster_wait();
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int ew = warp - EPI_WARP0;
+    const int q = warp & 3;
+    const int ch = ew >> 2;
+    const int k_own = m0 + 32 * q + lane;
+    const bool valid = k_own < P;
+    const unsigned tq = tmem_base + ((unsigned)(32 * q) << 16);
+    unsigned char* gst = smem + ew * B_GST_WARP;
+    const long long seg = p.seg;
+    const float S = bwd_scale(*p.dh_max), invS = 1.f / S;
+    float dc[2][2][8];                         // carried dL/dc of this thread's piece: [unit pass][8-unit group][unit]
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dc[a][b][i] = 0.f;
+    float ovf = 0.f;
+    int tk = valid ? p.take[(long long)k_own * seg + steps - 1] : -1;
+    const bool prof = p.prof != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0;
+    long long pr[5] = {0, 0, 0, 0, 0};
+    const int half_ref_it = steps - 1 - (p.warm - 1 - p.cp_half);      // reference side of the half-way checkpoint
+
+    for (int it = 0; it < steps; ++it) {
+      const long long t0 = prof ? clock64() : 0;
+      const int t = steps - 1 - it;
+      const int tk_n = (valid && t > 0) ? p.take[(long long)k_own * seg + t - 1] : -1;
+      if (it > 0) {
+        mbar_wait(bar_acc_full, (unsigned)(it - 1) & 1u);
+        tc_fence_after();
+      }
+      const long long t1 = prof ? clock64() : 0;
+      const bool w_full = it == p.warm - 1, w_half = it == p.cp_half;            // warm-up side records (pieces < P-1)
+      const bool r_full = it == steps - 1, r_half = p.cp_half >= 0 && it == half_ref_it;   // reference side (pieces >= 1)
+      long long tg = 0, tc = 0, ts = 0;
+#pragma unroll
+      for (int ps = 0; ps < 2; ++ps) {
+        const long long u0 = prof ? clock64() : 0;
+        const int ucolp = (int)rank * UN + 32 * ch + 16 * ps;
+        // (L) stash of this position: activated gates (arrays 0..3), c_t (4), c_{t-1} (5), injected dL/dh (6);
+        //     4 lanes per row; element (row, 16-byte chunk c) lives at row*64 + ((c ^ ((row >> 1) & 3)) << 4).
+        {
+          const int c4 = lane & 3;
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const int r = i4 * 8 + (lane >> 2);
+            const int tkr = __shfl_sync(0xffffffffu, tk, r);
+            const int kr = m0 + 32 * q + r;
+            if (kr < P) {
+              const size_t pos = (size_t)kr * seg + t;
+              const unsigned dst = smem_u32(gst) + (unsigned)(r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4));
+              const float* gsrc = p.stash_g + pos * (4 * H) + ucolp + c4 * 4;
+#pragma unroll
+              for (int a = 0; a < 4; ++a) cp_async16(dst + a * 2048, gsrc + a * H);
+              cp_async16(dst + 4 * 2048, p.stash_c + (pos + 1) * H + ucolp + c4 * 4);
+              cp_async16(dst + 5 * 2048, p.stash_c + pos * H + ucolp + c4 * 4);
+              if (tkr >= 0) cp_async16(dst + 6 * 2048, p.dh_take + (size_t)tkr * H + ucolp + c4 * 4);
+              else *reinterpret_cast<float4*>(gst + 6 * 2048 + r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          cp_async_wait_all();
+          __syncwarp();
+        }
+        const long long u1 = prof ? clock64() : 0;
+        // (C) gate gradients, one row per lane, in place on the staging tile
+#pragma unroll
+        for (int c8 = 0; c8 < 2; ++c8) {
+          float rec[8], cor[8];
+          if (it > 0) {
+            tmem_ld8x2(tq + (unsigned)(32 * ch + 16 * ps + 8 * c8), tq + (unsigned)(B_CORR + 32 * ch + 16 * ps + 8 * c8), rec, cor);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { rec[i] = 0.f; cor[i] = 0.f; }
+          }
+          unsigned char* e0 = gst + lane * 64 + (((2 * c8) ^ ((lane >> 1) & 3)) << 4);
+          unsigned char* e1 = gst + lane * 64 + (((2 * c8 + 1) ^ ((lane >> 1) & 3)) << 4);
+          float tin[B_NARR][8];
+#pragma unroll
+          for (int a = 0; a < B_NARR; ++a) {
+            const float4 v0 = *reinterpret_cast<const float4*>(e0 + a * 2048);
+            const float4 v1 = *reinterpret_cast<const float4*>(e1 + a * 2048);
+            tin[a][0] = v0.x; tin[a][1] = v0.y; tin[a][2] = v0.z; tin[a][3] = v0.w;
+            tin[a][4] = v1.x; tin[a][5] = v1.y; tin[a][6] = v1.z; tin[a][7] = v1.w;
+          }
+          float d_i[8], d_f[8], d_g[8], d_o[8], dhv[8], dci[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float gi = tin[0][i], gf = tin[1][i], gg = tin[2][i], go = tin[3][i], cc = tin[4][i], cp = tin[5][i];
+            const float dh = fmaf(cor[i], LO_INV, rec[i]) * invS + tin[6][i];
+            const float tcv = tanhf_sfu(cc);
+            const float dct = dc[ps][c8][i] + dh * (go * (1.f - tcv * tcv));
+            dhv[i] = dh;
+            dci[i] = dc[ps][c8][i];
+            d_o[i] = dh * (tcv * go * (1.f - go));
+            d_i[i] = dct * (gg * gi * (1.f - gi));
+            d_f[i] = dct * (cp * gf * (1.f - gf));
+            d_g[i] = dct * (gi * (1.f - gg * gg));
+            dc[ps][c8][i] = dct * gf;
+            ovf = fmaxf(ovf, fmaxf(fmaxf(fabsf(d_i[i]), fabsf(d_f[i])), fmaxf(fabsf(d_g[i]), fabsf(d_o[i]))));
+          }
+          *reinterpret_cast<float4*>(e0) = make_float4(d_i[0], d_i[1], d_i[2], d_i[3]);
+          *reinterpret_cast<float4*>(e1) = make_float4(d_i[4], d_i[5], d_i[6], d_i[7]);
+          *reinterpret_cast<float4*>(e0 + 2048) = make_float4(d_f[0], d_f[1], d_f[2], d_f[3]);
+          *reinterpret_cast<float4*>(e1 + 2048) = make_float4(d_f[4], d_f[5], d_f[6], d_f[7]);
+          *reinterpret_cast<float4*>(e0 + 2 * 2048) = make_float4(d_g[0], d_g[1], d_g[2], d_g[3]);
+          *reinterpret_cast<float4*>(e1 + 2 * 2048) = make_float4(d_g[4], d_g[5], d_g[6], d_g[7]);
+          *reinterpret_cast<float4*>(e0 + 3 * 2048) = make_float4(d_o[0], d_o[1], d_o[2], d_o[3]);
+          *reinterpret_cast<float4*>(e1 + 3 * 2048) = make_float4(d_o[4], d_o[5], d_o[6], d_o[7]);
+          *reinterpret_cast<float4*>(e0 + 4 * 2048) = make_float4(dhv[0], dhv[1], dhv[2], dhv[3]);
+          *reinterpret_cast<float4*>(e1 + 4 * 2048) = make_float4(dhv[4], dhv[5], dhv[6], dhv[7]);
+          *reinterpret_cast<float4*>(e0 + 5 * 2048) = make_float4(dci[0], dci[1], dci[2], dci[3]);
+          *reinterpret_cast<float4*>(e1 + 5 * 2048) = make_float4(dci[4], dci[5], dci[6], dci[7]);
+        }
+        __syncwarp();
+        const long long u2 = prof ? clock64() : 0;
+        // (S) coalesced stores, 4 lanes per row
+        {
+          const int c4 = lane & 3;
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const int r = i4 * 8 + (lane >> 2);
+            const int kr = m0 + 32 * q + r;
+            if (kr < P) {
+              const size_t pos = (size_t)kr * seg + t;
+              const unsigned char* e = gst + r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4);
+              const bool live = kr == P - 1 || it >= p.warm;
+              const int uc = ucolp + c4 * 4;
+              __half* xp = p.dgx + ((size_t)((((it + 1) & 1) * 2) * Ppad + kr)) * (4 * H) + uc;
+#pragma unroll
+              for (int a = 0; a < 4; ++a) {
+                const float4 d = *reinterpret_cast<const float4*>(e + a * 2048);
+                if (live) *reinterpret_cast<float4*>(p.dgates + pos * (4 * H) + a * H + uc) = d;
+                uint2 hi, lo;
+                split4_f16(make_float4(d.x * S, d.y * S, d.z * S, d.w * S), hi, lo);
+                *reinterpret_cast<uint2*>(xp + a * H) = hi;
+                *reinterpret_cast<uint2*>(xp + (size_t)Ppad * (4 * H) + a * H) = lo;
+              }
+              const float4 dh4 = *reinterpret_cast<const float4*>(e + 4 * 2048);
+              const float4 dc4 = *reinterpret_cast<const float4*>(e + 5 * 2048);
+              if (kr < P - 1 && (w_full || w_half)) {
+                float* b = p.bstate + ((size_t)(((w_full ? 1 : 0) * 2 + 0) * P + kr) * 2) * H + uc;
+                *reinterpret_cast<float4*>(b) = dh4;
+                *reinterpret_cast<float4*>(b + H) = dc4;
+              }
+              if (kr >= 1 && (r_full || r_half)) {
+                float* b = p.bstate + ((size_t)(((r_full ? 1 : 0) * 2 + 1) * P + kr) * 2) * H + uc;
+                *reinterpret_cast<float4*>(b) = dh4;
+                *reinterpret_cast<float4*>(b + H) = dc4;
+              }
+            }
+          }
+        }
+        __syncwarp();                          // the next pass overwrites the staging tile
+        if (prof) { const long long u3 = clock64(); tg += u1 - u0; tc += u2 - u1; ts += u3 - u2; }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty);
+      const long long t4 = prof ? clock64() : 0;
+      __threadfence();
+      fence_proxy_async();
+      __syncwarp();
+      cluster_arrive();
+      cluster_wait();
+      tk = tk_n;
+      if (prof) { const long long t5 = clock64(); pr[0] += t1 - t0; pr[1] += tg; pr[2] += tc; pr[3] += ts; pr[4] += t5 - t4; }
+    }
+    if (valid && !(ovf * S < 30000.f)) *p.overflow = 1.f;       // also catches NaN
+    if (prof) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) p.prof[i] = pr[i];
+      p.prof[5] = steps;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_arrive();
+  cluster_wait();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(B_TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ packing / checks
+// LSTM / GRU forward operand: [2 parts][NG*512][512], row (r*GN + g*64 + jj) = W_hh row (g*512 + r*64 + jj).
+// LSTM backward operand:      [2 parts][512][2048],   row n (hidden unit), column k (gate row): W_hh[k][n].
+__global__ void pack_chain_tc_kernel(int NG, const float* __restrict__ W_hh, __half* __restrict__ fwd, __half* __restrict__ bwd) {
+  const long long n_f = (long long)NG * H * H;
+  const long long total = n_f + (bwd ? n_f : 0);
+  const int GN = NG * UN;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float v;
+    __half *hi, *lo;
+    if (i < n_f) {
+      const int prow = (int)(i / H), k = (int)(i % H);
+      const int r = prow / GN, g = (prow % GN) / UN, jj = prow % UN;
+      v = W_hh[(size_t)(g * H + r * UN + jj) * H + k];
+      hi = fwd + i;
+      lo = fwd + n_f + i;
+    } else {
+      const long long e = i - n_f;
+      const int n = (int)(e / (NG * H)), k = (int)(e % (NG * H));
+      v = W_hh[(size_t)k * H + n];
+      hi = bwd + e;
+      lo = bwd + n_f + e;
+    }
+    const __half h = __float2half_rn(v);
+    *hi = h;
+    *lo = __float2half_rn((v - __half2float(h)) * 2048.f);
+  }
+}
+
+// integer max of the bit pattern: non-negative floats order like their patterns, a NaN has the largest one
+__device__ __forceinline__ void err_max_bits(float* slot, int bits) { atomicMax(reinterpret_cast<int*>(slot), bits); }
+
+// Block (k-1, cp): state piece k reached after step cp_half (cp = 0) / warm-1 (cp = 1) against the stash row the
+// preceding pieces wrote for the same position.  err[0] = max |dh| (full), err[1] = max |dc| / max(1, |c|) (full),
+// err[2], err[3] = the same half-way through the warm-up.
+__global__ void chain_tc_check_fwd_kernel(int P, long long seg, int warm, int cp_half, const float* wstate,
+                                          const float* stash_h, const float* stash_c, float* err) {
+  const int k = blockIdx.x + 1, cp = blockIdx.y, u = threadIdx.x;
+  const int j = cp ? warm - 1 : cp_half;
+  if (j < 0) return;
+  const size_t row = (size_t)k * seg + j + 1;
+  const float* w = wstate + ((size_t)(cp * P + k) * 2) * H;
+  int ih = __float_as_int(fabsf(w[u] - stash_h[row * H + u])), ic = 0;
+  if (stash_c) {
+    const float ct = stash_c[row * H + u];
+    ic = __float_as_int(fabsf(w[H + u] - ct) / fmaxf(1.f, fabsf(ct)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ih = max(ih, __shfl_xor_sync(0xffffffffu, ih, o));
+    ic = max(ic, __shfl_xor_sync(0xffffffffu, ic, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    err_max_bits(err + (cp ? 0 : 2), ih);
+    if (stash_c) err_max_bits(err + (cp ? 1 : 3), ic);
+  }
+}
+
+// Block (k, cp): (dh, dc) piece k carried at the joint (cp = 1: position (k+1)*seg, its last warm-up step; cp = 0:
+// half-way through the warm-up) against what piece k+1 computed at the same position, relative to max |dh_take|.
+// err[0] = dh (full), err[1] = dc (full), err[2], err[3] = half-way; err[4] = max |dh_take| (read only).
+__global__ void chain_tc_check_bwd_kernel(int P, int cp_half, const float* bstate, float* err) {
+  const int k = blockIdx.x, cp = blockIdx.y, u = threadIdx.x;
+  if (cp == 0 && cp_half < 0) return;
+  const float m = err[4];
+  const float inv = m > 0.f ? 1.f / m : 1.f;
+  const float* a = bstate + ((size_t)((cp * 2 + 0) * P + k) * 2) * H;
+  const float* b = bstate + ((size_t)((cp * 2 + 1) * P + k + 1) * 2) * H;
+  int ih = __float_as_int(fabsf(a[u] - b[u]) * inv), ic = __float_as_int(fabsf(a[H + u] - b[H + u]) * inv);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ih = max(ih, __shfl_xor_sync(0xffffffffu, ih, o));
+    ic = max(ic, __shfl_xor_sync(0xffffffffu, ic, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    err_max_bits(err + (cp ? 0 : 2), ih);
+    err_max_bits(err + (cp ? 1 : 3), ic);
+  }
+}
+
+__global__ void absmax_kernel(long long n, const float* __restrict__ x, float* out) {
+  int m = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = max(m, __float_as_int(fabsf(x[i])));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) err_max_bits(out, m);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult qres;
+    void* q = nullptr;
+    ICRL_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qres));
+    ICRL_REQUIRE(q && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled unavailable");
+    fn = reinterpret_cast<EncodeTiledFn>(q);
+  }
+  *out = fn;
+  return ICRL_OK;
+}
+
+// fp16 [rows][cols] row-major, box {32, box_rows}, 64B swizzle
+int make_map_2d(CUtensorMap* map, const void* ptr, long long cols, long long rows, int box_rows) {
+  EncodeTiledFn fn;
+  int rc = encode_fn(&fn);
+  if (rc) return rc;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    icrl_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %lld, cols %lld)", (int)r, rows, cols);
+    return ICRL_ERR_CUDA;
+  }
+  return ICRL_OK;
+}
+
+// fp16 [2 parts][rows][cols], box {32, box_rows, 2}
+int make_map_3d(CUtensorMap* map, const void* ptr, long long cols, long long rows, int box_rows) {
+  EncodeTiledFn fn;
+  int rc = encode_fn(&fn);
+  if (rc) return rc;
+  const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
+  const cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * cols * 2};
+  const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 2};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    icrl_set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult %d (rows %lld, cols %lld)", (int)r, rows, cols);
+    return ICRL_ERR_CUDA;
+  }
+  return ICRL_OK;
+}
+
+int cp_half_of(int warm) { return warm >= 8 ? warm / 2 - 1 : -1; }
+
+}  // namespace
+
+static long long* g_chain_tc_prof = nullptr;      // icrl_chain_tc_set_profile: 16 device int64 (forward [0..5], backward [8..13])
+void icrl_chain_tc_set_profile_impl(long long* buf) { g_chain_tc_prof = buf; }
+
+// Co-resident clusters of 8 CTAs x 128 pieces (a cluster cannot span GPCs: 15-16 clusters on a B200).
+int icrl_chain_tc_max_pieces_impl() {
+  static int cached = 0;
+  if (cached) return cached;
+  int n = 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CL * 64);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = FwdCfg<4>::SMEM;
+  cudaLaunchAttribute at;
+  at.id = cudaLaunchAttributeClusterDimension;
+  at.val.clusterDim.x = CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaFuncSetAttribute(chain_tc_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<4>::SMEM);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, (void*)chain_tc_fwd_kernel<4>, &cfg);
+  if (e != cudaSuccess || n < 1) { cudaGetLastError(); n = 12; }
+  cached = n * BM;
+  return cached;
+}
+
+size_t icrl_chain_tc_weight_halves_impl(int kind) { return kind == 0 ? (size_t)4 * 4 * H * H : (size_t)2 * 3 * H * H; }
+
+int icrl_pack_chain_tc_weights_impl(cudaStream_t st, int kind, const float* W_hh, void* packed) {
+  ICRL_REQUIRE(kind == 0 || kind == 1, "kind: 0 = LSTM, 1 = GRU");
+  __half* fwd = reinterpret_cast<__half*>(packed);
+  const int NG = kind == 0 ? 4 : 3;
+  __half* bwd = kind == 0 ? fwd + (size_t)2 * NG * H * H : nullptr;
+  pack_chain_tc_kernel<<<148 * 4, 256, 0, st>>>(NG, W_hh, fwd, bwd);
+  ICRL_LAUNCH_CHECK();
+  return ICRL_OK;
+}
+
+static int pad_pieces(int P) { return icrl_cdiv(P, BM) * BM; }
+
+// one launch's scratch: the backward exchange buffer is the largest user (fp16 [2][2][Ppad][2048])
+size_t icrl_chain_tc_ws_bytes_impl(int pieces) { return (size_t)4 * pad_pieces(pieces) * 4 * H * sizeof(__half); }
+size_t icrl_chain_tc_cp_floats_impl(int pieces) { return (size_t)2 * 2 * pieces * 2 * H; }
+
+int icrl_chain_tc_fwd_impl(cudaStream_t st, int kind, int P, long long seg, int warm, const int* stream,
+                           const float* table, const void* packed, const float* b_hn, float* stash_h, float* stash_c,
+                           float* stash_g, void* ws, float* cp_state, float* err) {
+  ICRL_REQUIRE(kind == 0 || kind == 1, "kind: 0 = LSTM, 1 = GRU");
+  ICRL_REQUIRE(P >= 2 && seg >= 1 && warm >= 1, "chain pieces need P >= 2, seg >= 1, warm >= 1");
+  ICRL_REQUIRE((long long)P * seg + warm < (1ll << 31), "token stream longer than 2^31");
+  ICRL_REQUIRE(stream && table && packed && stash_h && ws && cp_state && err, "null argument");
+  ICRL_REQUIRE(kind == 1 ? b_hn != nullptr : stash_c != nullptr, "LSTM needs stash_c, GRU needs b_hn");
+  const int Ppad = pad_pieces(P);
+  __half* hparts = reinterpret_cast<__half*>(ws);
+  float* state = reinterpret_cast<float*>(hparts + (size_t)4 * Ppad * H);
+  ICRL_CUDA(cudaMemsetAsync(hparts, 0, (size_t)4 * Ppad * H * sizeof(__half) + (size_t)Ppad * H * sizeof(float), st));
+  ICRL_CUDA(cudaMemsetAsync(stash_h, 0, H * sizeof(float), st));
+  if (stash_c) ICRL_CUDA(cudaMemsetAsync(stash_c, 0, H * sizeof(float), st));
+  FwdArgs a;
+  a.P = P; a.Ppad = Ppad; a.steps = (int)(seg + warm); a.warm = warm; a.cp_half = cp_half_of(warm); a.seg = seg;
+  a.stream = stream; a.table = table; a.b_hn = b_hn; a.stash_h = stash_h; a.stash_c = stash_c; a.stash_g = stash_g;
+  a.state = state; a.hparts = hparts; a.wstate = cp_state; a.prof = g_chain_tc_prof;
+  CUtensorMap mh, mw;
+  int rc;
+  if ((rc = make_map_2d(&mh, hparts, H, (long long)4 * Ppad, A_SLICE_ROWS))) return rc;
+  const int grid = CL * (Ppad / BM);
+  if (kind == 0) {
+    if ((rc = make_map_3d(&mw, packed, H, 4 * H, FwdCfg<4>::GN))) return rc;
+    ICRL_CUDA(cudaFuncSetAttribute(chain_tc_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<4>::SMEM));
+    chain_tc_fwd_kernel<4><<<dim3(grid), dim3(THREADS), FwdCfg<4>::SMEM, st>>>(mh, mw, a);
+  } else {
+    if ((rc = make_map_3d(&mw, packed, H, 3 * H, FwdCfg<3>::GN))) return rc;
+    ICRL_CUDA(cudaFuncSetAttribute(chain_tc_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<3>::SMEM));
+    chain_tc_fwd_kernel<3><<<dim3(grid), dim3(THREADS), FwdCfg<3>::SMEM, st>>>(mh, mw, a);
+  }
+  ICRL_LAUNCH_CHECK();
+  chain_tc_check_fwd_kernel<<<dim3(P - 1, 2), H, 0, st>>>(P, seg, warm, a.cp_half, cp_state, stash_h, kind == 0 ? stash_c : nullptr, err);
+  ICRL_LAUNCH_CHECK();
+  return ICRL_OK;
+}
+
+int icrl_chain_tc_lstm_bwd_impl(cudaStream_t st, int P, long long seg, int warm, const void* packed,
+                                const float* stash_g, const float* stash_c, const int* take, const float* dh_take,
+                                long long take_rows, float* dgates, void* ws, float* cp_state, float* err) {
+  ICRL_REQUIRE(P >= 2 && seg >= 1 && warm >= 1, "chain pieces need P >= 2, seg >= 1, warm >= 1");
+  ICRL_REQUIRE(packed && stash_g && stash_c && take && dh_take && dgates && ws && cp_state && err, "null argument");
+  const int Ppad = pad_pieces(P);
+  __half* dgx = reinterpret_cast<__half*>(ws);
+  const __half* whhT = reinterpret_cast<const __half*>(packed) + (size_t)2 * 4 * H * H;
+  // err[4] = max |dh_take| (scale of the recurrence), err[5] = overflow flag
+  ICRL_CUDA(cudaMemsetAsync(err + 4, 0, 2 * sizeof(float), st));
+  absmax_kernel<<<148 * 2, 256, 0, st>>>(take_rows * H, dh_take, err + 4);
+  ICRL_LAUNCH_CHECK();
+  BwdArgs a;
+  a.P = P; a.Ppad = Ppad; a.steps = (int)(seg + warm); a.warm = warm; a.cp_half = cp_half_of(warm); a.seg = seg;
+  a.stash_g = stash_g; a.stash_c = stash_c; a.take = take; a.dh_take = dh_take; a.dgates = dgates; a.dgx = dgx;
+  a.dh_max = err + 4; a.bstate = cp_state; a.overflow = err + 5; a.prof = g_chain_tc_prof ? g_chain_tc_prof + 8 : nullptr;
+  CUtensorMap mg, mw;
+  int rc;
+  if ((rc = make_map_2d(&mg, dgx, 4 * H, (long long)4 * Ppad, A_SLICE_ROWS))) return rc;
+  if ((rc = make_map_3d(&mw, whhT, 4 * H, H, UN))) return rc;
+  ICRL_CUDA(cudaFuncSetAttribute(chain_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+  chain_tc_bwd_kernel<<<dim3(CL * (Ppad / BM)), dim3(THREADS), B_SMEM, st>>>(mg, mw, a);
+  ICRL_LAUNCH_CHECK();
+  chain_tc_check_bwd_kernel<<<dim3(P - 1, 2), H, 0, st>>>(P, a.cp_half, cp_state, err);
+  ICRL_LAUNCH_CHECK();
+  return ICRL_OK;
+}

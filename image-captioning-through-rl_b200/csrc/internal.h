@@ -81,3 +81,17 @@ int icrl_wgrad_tc_impl(cudaStream_t st, int M, int N, long long T, const float* 
                        float* C, int ldc, void* ws, size_t ws_bytes, int splits);
 int icrl_adam_flat_impl(cudaStream_t st, long long n, float* p, const float* g, float* m, float* v, float lr, float b1,
                         float b2, float eps, int step);
+
+// chain_tc.cu: chain pieces on tcgen05
+void icrl_chain_tc_set_profile_impl(long long* buf);
+int icrl_chain_tc_max_pieces_impl();
+size_t icrl_chain_tc_weight_halves_impl(int kind);
+int icrl_pack_chain_tc_weights_impl(cudaStream_t st, int kind, const float* W_hh, void* packed);
+size_t icrl_chain_tc_ws_bytes_impl(int pieces);
+size_t icrl_chain_tc_cp_floats_impl(int pieces);
+int icrl_chain_tc_fwd_impl(cudaStream_t st, int kind, int P, long long seg, int warm, const int* stream,
+                           const float* table, const void* packed, const float* b_hn, float* stash_h, float* stash_c,
+                           float* stash_g, void* ws, float* cp_state, float* err);
+int icrl_chain_tc_lstm_bwd_impl(cudaStream_t st, int P, long long seg, int warm, const void* packed,
+                                const float* stash_g, const float* stash_c, const int* take, const float* dh_take,
+                                long long take_rows, float* dgates, void* ws, float* cp_state, float* err);

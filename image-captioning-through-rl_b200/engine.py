@@ -34,7 +34,11 @@ def _p(t):
 class StepResult(dict):
     """Device tensors of one minibatch; ``loss`` / ``mean_reward`` / ``mean_adv`` sync lazily."""
 
+    host_stats = None       # (loss, mean reward, mean advantage) when the step's check already brought them to the host
+
     def _stat(self, i):
+        if self.host_stats is not None:
+            return float(self.host_stats[i])
         return float(self["stats"][i].item())
 
     @property
@@ -75,8 +79,11 @@ def plan_rollout(captions, level=None):
 class A2CEngine:
     DECODE_MODES = ("fused", "tc", "simt")
 
+    CHAIN_ENGINES = ("tc", "simt")
+
     def __init__(self, a2c_network, reward_network, use_tc=None, decode="fused", chain_shards=1, wgrad="tc",
-                 chain_segments=32, chain_warmup=256, chain_tol=1e-5, chain_bwd_segments=None):
+                 chain_segments=32, chain_warmup=256, chain_tol=1e-5, chain_bwd_segments=None, chain_engine="tc",
+                 chain_pieces=None, chain_adapt=True, chain_warmup_min=32):
         self.policy = a2c_network.policy_network
         self.value = a2c_network.value_network
         self.reward = reward_network
@@ -141,13 +148,37 @@ class A2CEngine:
         self.chain_tol = float(chain_tol)
         if self.chain_warmup < 1:
             raise ValueError("chain_warmup must be positive")
-        self.segment_stats = {"steps": 0, "segmented_steps": 0, "fallbacks": 0, "max_err": [0.0] * 5}
+        # chain_engine: "tc" (default) = chain pieces on tcgen05 (chain_tc.cu): hundreds of lockstep pieces, 128 per cluster of
+        # 8 CTAs, one kernel step = H_prev [pieces x 512] . W_hh^T on the tensor cores.  The warm-up is sized PER CHAIN
+        # (value LSTM forward + backward, reward GRU) from the contraction rate measured on every step (errors half-way
+        # through and at the end of the warm-up): it grows before the check can fail and shrinks again after
+        # `_SHRINK_AFTER` clean steps; a failed check re-runs the chains with a longer warm-up, and only a chain that
+        # cannot be cut at all runs on the serial kernels.  "simt" = the CUDA-core segment kernels of chain.cu
+        # (chain_segments pieces, fixed warm-up, serial re-run on failure).  chain_segments = 1 forces the serial kernels.
+        if chain_engine not in self.CHAIN_ENGINES:
+            raise ValueError("chain_engine must be one of %s" % (self.CHAIN_ENGINES,))
+        self.chain_engine = chain_engine
+        self.chain_pieces = None if chain_pieces is None else int(chain_pieces)
+        if self.chain_pieces is not None and self.chain_pieces < 2:
+            raise ValueError("chain_pieces must be at least 2")
+        self.chain_adapt = bool(chain_adapt)
+        self.chain_warmup_min = int(chain_warmup_min)
+        self.warm = {"v": self.chain_warmup, "r": self.chain_warmup}      # current warm-up per chain (tc engine)
+        self._clean = {"v": 0, "r": 0}
+        self._tc = None                   # {"v": (P, seg, warm) | None, "r": (P, seg, warm)} of the current step
+        self.segment_stats = {"steps": 0, "segmented_steps": 0, "fallbacks": 0, "reruns": 0, "max_err": [0.0] * 5,
+                              "tc_max_err": [0.0] * 16, "warm_history": []}
         self._seg = None                  # (K, seg_v, seg_r, warm) of the current step, None = serial kernels
         self._seg_strikes = 0
         self._seg_unverified = False
         with torch.cuda.device(dev):
             self._seg_ws = torch.zeros(int(_lib.call("icrl_chain_segment_ws_floats")), dtype=torch.float32, device=dev)
             self.sync_state = torch.zeros(int(_lib.call("icrl_chain_sync_bytes")), dtype=torch.uint8, device=dev)
+            # [0:3] loss, mean reward, mean advantage; [4:20] joint-check words of the tc chain launches (value forward
+            # 4..7, reward forward 8..11, value backward 12..17): read together in ONE device-to-host copy per step
+            self._stat_err = torch.zeros(20, dtype=torch.float32, device=dev)
+        self._tc_err = self._stat_err[4:]
+        self._reward_versions = None
         self._check_params()
         self._bind_flat_grads()
 
@@ -246,8 +277,22 @@ class A2CEngine:
             n = int(_lib.call("icrl_decode_weight_halves"))
             _lib.call("icrl_pack_decode_weights", st, V, _p(P.lstm.weight_hh_l0), _p(P.linear2vocab.weight),
                       _p(self._buf("p_decode_pk", n, torch.float16)), L)
-        if reward:
+        if self._use_tc_chains():
+            n = int(_lib.call("icrl_chain_tc_weight_halves", 0))
+            _lib.call("icrl_pack_chain_tc_weights", st, 0, _p(Vn.valrnn.lstm.weight_hh_l0),
+                      _p(self._buf("v_chain_pk", n, torch.float16)), L)
+        if reward or self._reward_changed():
             self.pack_reward()
+
+    def _use_tc_chains(self):
+        return self.chain_engine == "tc" and self.chain_segments > 1 and self.chain_shards == 1
+
+    def _reward_changed(self):
+        """The reward network is frozen during A2C training (trainers.py:372-373) and its derived operands are packed once;
+        an in-place change of its parameters (load_state_dict, more reward pretraining on the same object) is noticed
+        through the tensors' version counters."""
+        v = tuple(p._version for p in self.reward.parameters()) + tuple(p.data_ptr() for p in self.reward.parameters())
+        return v != self._reward_versions
 
     def _pack_policy_tc(self):
         """3-part bf16 splits of the two decode-step weight matrices (tensor-core operands)."""
@@ -262,6 +307,11 @@ class A2CEngine:
         _lib.call("icrl_pack_gate_table", self._stream, V, 3 * H, 2 * H, R.rewrnn.caption_embedding.weight.shape[1], _p(R.rewrnn.caption_embedding.weight),
                   _p(R.rewrnn.gru.weight_ih_l0), _p(R.rewrnn.gru.bias_ih_l0), _p(R.rewrnn.gru.bias_hh_l0),
                   _p(self._buf("r_table", V * 3 * H)), self.launches.ref)
+        if self._use_tc_chains():
+            n = int(_lib.call("icrl_chain_tc_weight_halves", 1))
+            _lib.call("icrl_pack_chain_tc_weights", self._stream, 1, _p(R.rewrnn.gru.weight_hh_l0),
+                      _p(self._buf("r_chain_pk", n, torch.float16)), self.launches.ref)
+        self._reward_versions = tuple(p._version for p in R.parameters()) + tuple(p.data_ptr() for p in R.parameters())
 
     def _gemm(self, ta, tb, M, N, K, A, lda, B, ldb, C, ldc, bias=None, beta=0.0):
         _lib.call("icrl_gemm_f32", self._stream, ta, tb, M, N, K, _p(A), lda, _p(B), ldb, _p(C), ldc, _p(bias),
@@ -346,13 +396,18 @@ class A2CEngine:
             return Tv, Tr
         Tv = int(_lib.call("icrl_stream_len", B, p0, S, 0))
         Tr = int(_lib.call("icrl_stream_len", B, p0, S, 1))
-        self._seg = None if serial else self._pick_segments(Tv, Tr)
+        self._seg, self._tc = None, None
+        if not serial:
+            if self._use_tc_chains():
+                self._tc = self._pick_pieces(Tv, Tr)
+            elif self.chain_segments > 1:
+                self._seg = self._pick_segments(Tv, Tr)
         nv, nr = self._padded(Tv, 0), self._padded(Tr, 1)
         v_stream, v_take, v_pos = self._buf("v_stream", nv, i32), self._buf("v_take", nv, i32), self._buf("v_pos", S * B, i32)
         r_stream, r_pos = self._buf("r_stream", nr, i32), self._buf("r_pos", S * B, i32)
         _lib.call("icrl_build_stream", st, B, p0, S, 0, _p(tokcm), _p(v_stream), _p(v_take), _p(v_pos), L)
         _lib.call("icrl_build_stream", st, B, p0, S, 1, _p(tokcm), _p(r_stream), None, _p(r_pos), L)
-        if self._seg is not None:         # the last piece runs past the end of the chain: pad with token 0 / "no output"
+        if self._seg is not None or self._tc is not None:   # the last piece runs past the end of the chain: pad with token 0 / "no output"
             v_stream[Tv:nv].zero_()
             v_take[Tv:nv].fill_(-1)
             r_stream[Tr:nr].zero_()
@@ -370,12 +425,43 @@ class A2CEngine:
                 return (K, seg_v, seg_r, warm)
         return None
 
+    def _pieces_for(self, T, warm):
+        """(P, seg) for a chain of T positions cut into tcgen05 pieces with a `warm`-position warm-up, or None when it is
+        too short.  As many pieces as are co-resident (whole clusters of 128 once there is more than one), each at least
+        max(warm / 4, 8) live positions long: the wall time of a launch is seg + warm kernel steps."""
+        pmax = self.chain_pieces or int(_lib.call("icrl_chain_tc_max_pieces"))
+        min_seg = max(warm // 4, 8)
+        if T <= warm + 2 * min_seg:
+            return None
+        P = min(pmax, (T - warm) // min_seg)
+        if P > 128 and self.chain_pieces is None:
+            P -= P % 128
+        if P < 2:
+            return None
+        return P, -(-(T - warm) // P)
+
+    def _pick_pieces(self, Tv, Tr):
+        r = self._pieces_for(Tr, self.warm["r"])
+        v = self._pieces_for(Tv, self.warm["v"]) if Tv > 0 else None
+        if r is None or (Tv > 0 and v is None):
+            return None
+        return {"v": None if v is None else (v[0], v[1], self.warm["v"]), "r": (r[0], r[1], self.warm["r"])}
+
     def _padded(self, T, which):
         """Positions the arrays of a chain must hold (which: 0 = value, 1 = reward)."""
+        if self._tc is not None:
+            lay = self._tc["r" if which else "v"]
+            return T if lay is None else lay[0] * lay[1] + lay[2]
         if self._seg is None:
             return T
         K, seg_v, seg_r, warm = self._seg
         return K * (seg_r if which else seg_v) + warm
+
+    def _tc_scratch(self, key, P):
+        """(ws, cp_state) of a tc chain launch; the tensors stay referenced by the engine."""
+        ws = self._buf("tc_ws_" + key, (int(_lib.call("icrl_chain_tc_ws_bytes", P)) + 3) // 4)
+        cp = self._buf("tc_cp_" + key, int(_lib.call("icrl_chain_tc_cp_floats", P)))
+        return ws, cp
 
     def _chains_forward(self, f, B, S, Tv, Tr, train):
         st, L, b = self._stream, self.launches.ref, self._bufs
@@ -387,7 +473,16 @@ class A2CEngine:
         v_g = self._buf("v_stash_g", K * (nv + 1) * 4 * H)
         r_h = self._buf("r_stash_h", K * (nr + 1) * H)
         with self._phase("chains_fwd_fused"):
-          if self._seg is not None:
+          if self._tc is not None:
+            Pv, seg_v, warm_v = self._tc["v"]
+            Pr, seg_r, warm_r = self._tc["r"]
+            ws, cp = self._tc_scratch("v", Pv)
+            _lib.call("icrl_chain_tc_fwd", st, 0, Pv, seg_v, warm_v, _p(b["v_stream"]), _p(b["v_table"]), _p(b["v_chain_pk"]),
+                      None, _p(v_h), _p(v_c), _p(v_g), _p(ws), _p(cp), _p(self._tc_err[0:]), L)
+            ws, cp = self._tc_scratch("r", Pr)
+            _lib.call("icrl_chain_tc_fwd", st, 1, Pr, seg_r, warm_r, _p(b["r_stream"]), _p(b["r_table"]), _p(b["r_chain_pk"]),
+                      _p(R.rewrnn.gru.bias_hh_l0[2 * H:]), _p(r_h), None, None, _p(ws), _p(cp), _p(self._tc_err[4:]), L)
+          elif self._seg is not None:
             Ks, seg_v, seg_r, warm = self._seg
             _lib.call("icrl_chains_fwd_fused_segmented", st, Ks, warm, _p(b["v_stream"]), seg_v, _p(b["v_table"]),
                   _p(Vn.valrnn.lstm.weight_hh_l0), _p(v_h), _p(v_c), _p(v_g), _p(b["r_stream"]), seg_r, _p(b["r_table"]),
@@ -439,7 +534,13 @@ class A2CEngine:
         K = self.chain_shards
         dgates = self._buf("v_dgates", K * (self._padded(Tv, 0) + 1) * 4 * H)
         with self._phase("chain_lstm_bwd"):
-          if self._seg is not None:
+          if self._tc is not None:
+            Pv, seg_v, warm_v = self._tc["v"]
+            ws, _ = self._tc_scratch("v", Pv)
+            cp = self._buf("tc_cp_b", int(_lib.call("icrl_chain_tc_cp_floats", Pv)))
+            _lib.call("icrl_chain_tc_lstm_bwd", st, Pv, seg_v, warm_v, _p(b["v_chain_pk"]), _p(b["v_stash_g"]), _p(b["v_stash_c"]),
+                      _p(b["v_take"]), _p(dh_take), SB, _p(dgates), _p(ws), _p(cp), _p(self._tc_err[8:]), L)
+          elif self._seg is not None:
             Kf, seg_v, _, warm = self._seg
             # backward pieces: 16 (8 per CTA group in one kernel step) when the forward has 16 or 32, else at most 8
             Ks = self.chain_bwd_segments or (16 if Kf in (16, 32) else min(Kf, 8))
@@ -500,31 +601,110 @@ class A2CEngine:
                 self.pack_weights(reward="r_table" not in self._bufs)
             f, tokcm, u, fo, B = self._stage_inputs(prep, forced_tokens)
             tokens, logp = self._policy_forward(f, tokcm, u, fo, B, p0, S, greedy)
-            for serial in (False, True):
+            dv_sb = self._buf("dv_sb", S * B)
+            dlogp = self._buf("dlogp", S * B)
+            sum_dv = self._buf("sum_dv", 1)
+            inv = 1.0 / float((global_rows or B) * S)
+
+            def run_chains(serial):
                 Tv, Tr = self._streams(tokcm, B, p0, S, serial=serial)
                 values, rewards = self._chains_forward(f, B, S, Tv, Tr, backward)
-                stats = torch.empty(3, dtype=torch.float32, device=self.device)
-                dv_sb = self._buf("dv_sb", S * B)
-                dlogp = self._buf("dlogp", S * B)
-                sum_dv = self._buf("sum_dv", 1)
-                inv = 1.0 / float((global_rows or B) * S)
-                _lib.call("icrl_a2c_loss_fwd_bwd", self._stream, B, S, _p(values), _p(rewards), _p(logp), inv, _p(stats),
+                _lib.call("icrl_a2c_loss_fwd_bwd", self._stream, B, S, _p(values), _p(rewards), _p(logp), inv, _p(self._stat_err),
                           _p(dv_sb), _p(dlogp), _p(sum_dv), self.launches.ref)
                 if backward:
                     self._backward(f, tokcm, tokens, B, p0, S, Tv)
                 self.segment_stats["steps"] += 1
-                if self._seg is None:
+                return Tv, Tr, values, rewards
+
+            # Attempts 0 .. _TC_ATTEMPTS-1 run the chains cut into pieces; a failed joint check lengthens the warm-up and
+            # tries again (tc engine) or goes straight to the serial kernels (simt engine); the last attempt is always
+            # the serial kernels, the guaranteed floor.  Gradients are overwritten, not accumulated, by a re-run.
+            host, serial = None, False
+            for attempt in range(self._TC_ATTEMPTS + 1):
+                serial = serial or attempt == self._TC_ATTEMPTS
+                Tv, Tr, values, rewards = run_chains(serial)
+                if self._seg is None and self._tc is None:
                     break
                 self.segment_stats["segmented_steps"] += 1
                 if not check:
                     self._seg_unverified = True       # the caller owes a segments_verified() before trusting the steps
                     break
-                if self._segments_ok():
+                if self._tc is not None:
+                    ok, host = self._tc_ok()
+                    if not ok:
+                        host = None
+                        serial = self._tc_force_serial or attempt + 1 == self._TC_ATTEMPTS
+                        if serial:
+                            self.segment_stats["fallbacks"] += 1
+                else:
+                    ok = self._segments_ok()
+                    serial = True
+                if ok:
                     break
-            if check:
+            stats = self._stat_err[:3].clone()
+            if check and self._tc is None:
                 _lib.call("icrl_chain_check", self._stream, _p(self.sync_state))
-        return StepResult(tokens=tokens, logp=logp, values=values, rewards=rewards, stats=stats, p0=p0, S=S, B=B,
-                          Tv=Tv, Tr=Tr)
+        res = StepResult(tokens=tokens, logp=logp, values=values, rewards=rewards, stats=stats, p0=p0, S=S, B=B,
+                         Tv=Tv, Tr=Tr)
+        if host is not None:
+            res.host_stats = host[:3]
+        return res
+
+    _TC_ATTEMPTS = 3
+    _SHRINK_AFTER = 8
+    _tc_force_serial = False
+
+    def _adapt_warm(self, key, e_half, e_full):
+        """Size the next warm-up of chain `key` from the joint errors half-way through / at the end of this one.
+        Returns False when the step failed its check (e_full above chain_tol, or not a number)."""
+        tol = self.chain_tol
+        target = tol / 4.0
+        warm = self.warm[key]
+        failed = not (e_full <= tol)
+        if failed or (self.chain_adapt and not (e_full <= target)):
+            need = 2.0 * warm
+            if e_half > e_full > 0.0 and np.isfinite(e_half):
+                rate = np.log(e_half / e_full) / float(warm - warm // 2)         # nats forgotten per position
+                need = warm + np.log(e_full / (target / 4.0)) / rate
+            new = min(max(need, (1.5 if failed else 1.25) * warm), 4.0 * warm)
+            self.warm[key] = int(-(-int(np.ceil(new)) // 32) * 32)
+            self._clean[key] = 0
+        elif self.chain_adapt and warm >= 8 and e_half <= target:
+            self._clean[key] += 1
+            if self._clean[key] >= self._SHRINK_AFTER and warm > self.chain_warmup_min:
+                self.warm[key] = max(self.chain_warmup_min, int(-(-int(0.75 * warm) // 32) * 32))
+                self._clean[key] = 0
+        else:
+            self._clean[key] = 0
+        if self.warm[key] != warm:
+            self.segment_stats["warm_history"].append((self.segment_stats["steps"], key, warm, self.warm[key]))
+        return not failed
+
+    def _tc_ok(self):
+        """Joint checks of the tc chain launches of this step, read together with the three step statistics in ONE
+        device-to-host copy (synchronises), and re-armed.  Returns (ok, host words)."""
+        host = self._stat_err.tolist()
+        self._tc_err.zero_()
+        self._seg_unverified = False
+        e = host[4:]
+        st = self.segment_stats
+        st["tc_max_err"] = [max(a, b) if b == b else float("nan") for a, b in zip(st["tc_max_err"], e)]
+        v_full, v_half = max(e[0], e[1], e[8], e[9]), max(e[2], e[3], e[10], e[11])
+        if any(x != x for x in e[0:4] + e[8:12]):
+            v_full = float("nan")
+        self._tc_force_serial = e[13] != 0.0          # the fp16 exchange of the backward recurrence overflowed
+        ok_v = self._adapt_warm("v", v_half, v_full) if self._tc["v"] is not None else True
+        ok_r = self._adapt_warm("r", e[6], e[4])
+        ok = ok_v and ok_r and not self._tc_force_serial
+        if not ok:
+            import warnings
+            st["reruns"] += 1
+            warnings.warn("chain segments did not converge onto the single chain within %g after the warm-up (value chain "
+                          "forward |dh| %.3g |dc| %.3g, backward %.3g %.3g; reward chain |dh| %.3g%s): re-running with "
+                          "warm-ups %d / %d" % (self.chain_tol, e[0], e[1], e[8], e[9], e[4],
+                                                "; gate gradients overflowed the fp16 exchange" if self._tc_force_serial else "",
+                                                self.warm["v"], self.warm["r"]))
+        return ok, host
 
     def _segments_ok(self):
         """Read (and re-arm) the warm-up checks of the segmented chain launches since the last call (synchronises).
@@ -556,13 +736,24 @@ class A2CEngine:
     def segment_layout(self):
         """(pieces, value-chain piece length, reward-chain piece length, warm-up) of the last step, or None when it ran on
         the serial kernels (chain too short, chain_segments = 1, or a failed warm-up check)."""
+        if self._tc is not None:
+            v, r = self._tc["v"], self._tc["r"]
+            return (r[0] if v is None else v[0], 0 if v is None else v[1], r[1], max(r[2], 0 if v is None else v[2]))
         return self._seg
+
+    @property
+    def piece_layout(self):
+        """{"v": (pieces, positions per piece, warm-up) | None, "r": (...)} of the last step on the tcgen05 chain kernels,
+        or None."""
+        return self._tc
 
     def segments_verified(self):
         """For callers that ran step(check=False): True when every segmented launch since the last check passed."""
         if not self._seg_unverified:
             return True
         with torch.cuda.device(self.device):
+            if self._tc is not None:
+                return self._tc_ok()[0]
             return self._segments_ok()
 
     def get_rewards(self, features, captions):
@@ -570,27 +761,48 @@ class A2CEngine:
         caps = np.asarray(captions)
         B, Lc = caps.shape
         with torch.cuda.device(self.device):
-            if "r_table" not in self._bufs:
+            if "r_table" not in self._bufs or self._reward_changed():
                 self.pack_reward()
             f, tokcm, _, _, _ = self._stage_inputs(self.prepare(features, caps, plan=(Lc, 0)), None)
             st, L, b, R = self._stream, self.launches.ref, self._bufs, self.reward
             T = int(_lib.call("icrl_stream_len", B, Lc, 1, 0))
-            for serial in (False, True):
-                self._seg = None if serial else self._pick_segments(0, T)
+            serial = False
+            for attempt in range(self._TC_ATTEMPTS + 1):
+                serial = serial or attempt == self._TC_ATTEMPTS
+                self._seg, self._tc = None, None
+                if not serial:
+                    if self._use_tc_chains():
+                        self._tc = self._pick_pieces(0, T)
+                    elif self.chain_segments > 1:
+                        self._seg = self._pick_segments(0, T)
                 n = self._padded(T, 1)
                 r_stream, r_pos = self._buf("r_stream", n, torch.int32), self._buf("r_pos", B, torch.int32)
                 _lib.call("icrl_build_stream", st, B, Lc, 1, 0, _p(tokcm), _p(r_stream), None, _p(r_pos), L)
                 r_h = self._buf("r_stash_h", (n + 1) * H)
-                if self._seg is not None:
+                if self._tc is not None:
+                    Pr, seg_r, warm_r = self._tc["r"]
+                    r_stream[T:n].zero_()
+                    ws, cp = self._tc_scratch("r", Pr)
+                    _lib.call("icrl_chain_tc_fwd", st, 1, Pr, seg_r, warm_r, _p(r_stream), _p(b["r_table"]), _p(b["r_chain_pk"]),
+                              _p(R.rewrnn.gru.bias_hh_l0[2 * H:]), _p(r_h), None, None, _p(ws), _p(cp), _p(self._tc_err[4:]), L)
+                    ok, _ = self._tc_ok()
+                    if ok:
+                        break
+                    serial = attempt + 1 == self._TC_ATTEMPTS
+                    if serial:
+                        self.segment_stats["fallbacks"] += 1
+                elif self._seg is not None:
                     Ks, _, seg_r, warm = self._seg
                     r_stream[T:n].zero_()
                     _lib.call("icrl_chains_fwd_fused_segmented", st, Ks, warm, None, 0, None, None, None, None, None,
                               _p(r_stream), seg_r, _p(b["r_table"]), _p(R.rewrnn.gru.weight_hh_l0),
                               _p(R.rewrnn.gru.bias_hh_l0[2 * H:]), _p(r_h), _p(self._seg_ws), _p(self.sync_state), L)
+                    if self._segments_ok():
+                        break
+                    serial = True
                 else:
                     _lib.call("icrl_chain_gru_fwd", st, _p(r_stream), T, _p(b["r_table"]), _p(R.rewrnn.gru.weight_hh_l0),
                               _p(R.rewrnn.gru.bias_hh_l0[2 * H:]), None, _p(r_h), None, _p(self.sync_state), None, L)
-                if self._seg is None or self._segments_ok():
                     break
             r_take_h = self._buf("r_take_h", B * H)
             _lib.call("icrl_gather_rows", st, B, _p(r_h), _p(r_pos), 1, _p(r_take_h), L)

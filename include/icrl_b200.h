@@ -230,6 +230,38 @@ int icrl_chains_fwd_fused_segmented(void* stream, int segments, int warm, const 
 int icrl_chain_lstm_bwd_segmented(void* stream, int segments, int warm, int seg, const float* W_hh,
                                   const float* stash_gates, const float* stash_c, const int* take, const float* dh_take,
                                   long long take_rows, float* dgates, float* segment_ws, void* sync_state, int* launches);
+/* ---- chain pieces on tcgen05 (chain_tc.cu; the default engine).  The same ONE carried-state chain
+ *      (models.py:130-135 value LSTM, :223-228 reward GRU; backward of trainers.py:479) advanced as `pieces` lockstep
+ *      pieces, 128 per cluster of 8 CTAs: one kernel step is the contraction H_prev [pieces x 512] . W_hh^T on the
+ *      tensor cores (fp16 hi/lo' split, three products, f32 accumulation in tensor memory: fp32-grade) with the cell
+ *      update in its epilogue.  Piece k covers positions [k*seg, (k+1)*seg + warm) of the stream; pieces k >= 1 start
+ *      from zero state and discard their first `warm` positions; the backward recurrence is mirrored (piece k walks
+ *      (k+1)*seg + warm - 1 down to k*seg; all but the last start with dh = dc = 0 and discard `warm` steps).
+ *      Array sizes are those of the chain segments above with segments = pieces (streams / take pieces*seg + warm
+ *      entries padded with token 0 / -1; stash_h, stash_c one row more; row 0 is zeroed by the call); any pieces >= 2,
+ *      seg >= 1 is accepted.  CHECKED, not assumed: after every launch err[] holds running maxima (zero to re-arm) of
+ *      the state differences at the joints -- forward err[0] = max |dh| and err[1] = max |dc| / max(1, |c|) at the end
+ *      of the warm-up, err[2], err[3] the same half-way through it (the slope gives the contraction rate the caller
+ *      sizes the next warm-up with); backward err[0..3] = |d(dh)|, |d(dc)| at the joints (end / half-way) relative to
+ *      err[4] = max |dh_take|, err[5] = 1 when a scaled gate gradient left the fp16 range of the exchange.
+ *      kind: 0 = LSTM (stash_c, stash_gates = activated i,f,g,o), 1 = GRU (b_hn [512]; stash_c, stash_gates NULL).
+ *      packed: icrl_pack_chain_tc_weights (icrl_chain_tc_weight_halves(kind) fp16 values; after every optimizer step).
+ *      ws: icrl_chain_tc_ws_bytes(pieces) bytes of scratch per launch; cp_state: icrl_chain_tc_cp_floats(pieces)
+ *      floats (joint checkpoints).  icrl_chain_tc_max_pieces(): pieces that are co-resident on the device. */
+int icrl_chain_tc_max_pieces(void);
+size_t icrl_chain_tc_weight_halves(int kind);
+size_t icrl_chain_tc_ws_bytes(int pieces);
+size_t icrl_chain_tc_cp_floats(int pieces);
+int icrl_pack_chain_tc_weights(void* stream, int kind, const float* W_hh, void* packed, int* launches);
+int icrl_chain_tc_fwd(void* stream, int kind, int pieces, long long seg, int warm, const int* tok_stream,
+                      const float* table, const void* packed, const float* b_hn, float* stash_h, float* stash_c,
+                      float* stash_gates, void* ws, float* cp_state, float* err, int* launches);
+int icrl_chain_tc_lstm_bwd(void* stream, int pieces, long long seg, int warm, const void* packed,
+                           const float* stash_gates, const float* stash_c, const int* take, const float* dh_take,
+                           long long take_rows, float* dgates, void* ws, float* cp_state, float* err, int* launches);
+/* Debug aid: buf != NULL (16 device int64): cycle sums of cluster 0 / CTA 0's first epilogue warp, forward [0..5] =
+ * {accumulator wait, gather, cell update, stores, cluster barrier, steps}, backward [8..13] likewise. */
+int icrl_chain_tc_set_profile(void* buf);
 /* Debug aid: when buf != NULL (16 device int64), CTA 0 / thread 0 of the sharded / segmented chain kernels accumulates its
  * cycles per phase: [0..3] value LSTM forward {exchange wait, GEMV + reduce, pointwise + publish, T}, [4..7] reward GRU
  * forward, [8..14] backward {coefficients + requests, poll wait, gate gradients + stores, barrier, contraction + reduce,
