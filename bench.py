@@ -36,21 +36,30 @@ H, L_CAP = 512, 20
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="global batch (captions per step)")
-    ap.add_argument("--cpu-sample", type=int, default=256, help="rows of the workload timed on the host cores")
+    ap.add_argument("--cpu-sample", type=int, default=256, help="rows of the workload per sampled step on the host cores")
     ap.add_argument("--chain-shards", type=int, default=1, choices=[1, 2, 4, 8],
                     help="value/reward recurrences per rank (1 = the reference's single carried-state chain)")
+    ap.add_argument("--chain-engine", default="tc", choices=["tc", "simt"],
+                    help="tc = chain pieces on tcgen05 (chain_tc.cu, default); simt = CUDA-core segment kernels (chain.cu)")
+    ap.add_argument("--chain-pieces", type=int, default=None, help="tc: cap on the lockstep pieces (default: co-resident clusters x 128)")
     ap.add_argument("--chain-segments", type=int, default=32, choices=[1, 2, 4, 8, 16, 32],
-                    help="lockstep pieces of the single carried-state chain (verified warm-up; 1 = serial kernels only)")
-    ap.add_argument("--chain-warmup", type=int, default=256, help="warm-up positions of every chain piece")
+                    help="simt: lockstep pieces of the single carried-state chain (1 = serial kernels only, either engine)")
+    ap.add_argument("--chain-warmup", type=int, default=256, help="first warm-up of every chain piece (the tc engine adapts it)")
+    ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam instead of the flat fused Adam kernel")
     ap.add_argument("--sharded-leg", action="store_true", help="also time 8 zero-state row shards per rank")
     ap.add_argument("--no-serial-leg", action="store_true", help="skip the serial-kernel leg (chain_segments = 1)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config 3 (reward throughput) and config 5 (curriculum) objects")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
+
+
+WORKLOAD = ("configs[3]: full A2C training step (rollout+reward+value+loss+backward+allreduce+Adam), "
+            "global batch %d, max_len %d, S=%d")
 
 
 class ClockSampler:
@@ -123,42 +132,97 @@ def make_nets(seed, dev):
     return M.AdvantageActorCriticNetwork(V, P).to(dev), R.to(dev)
 
 
-def cpu_reference(batch_sample, steps, warmup):
-    """The reference algorithm as executed (oracle/ref_port: per-step prefix re-runs, batch-as-time RNN
-    calls, numpy sampling, autograd backward, Adam) on the host cores; returns (captions/s, cores, s/step)."""
+def cpu_reference(rows_per_step, warm_rows=64):
+    """The reference algorithm as executed (oracle/ref_port: per-step prefix re-runs, batch-as-time RNN calls, numpy
+    sampling, autograd backward, Adam) on all host cores.  `rows_per_step` lists the rows of each timed step (leading
+    rows of the bench workload); one un-timed step of `warm_rows` rows comes first (thread pool, allocator, Adam state).
+    Returns (captions/s over the timed steps, cores, [seconds per step])."""
     from oracle import ref_port        # the one place bench.py executes oracle/: the CPU reference being timed
     from icrl_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     nets = ref_port.Nets(synth.make_weights(0))
     opt = torch.optim.Adam([p for _, p in nets.named_trainable()], lr=1e-4)
-    f, c, u = workload(batch_sample)
+    f, c, u = workload(max(list(rows_per_step) + [warm_rows]))
     times = []
-    for i in range(warmup + steps):
+    for i, rows in enumerate([warm_rows] + list(rows_per_step)):
         t0 = time.perf_counter()
-        ref_port.a2c_minibatch(nets, f, c, u)
+        ref_port.a2c_minibatch(nets, f[:rows], c[:rows], np.ascontiguousarray(u[:, :rows]))
         opt.step()
-        if i >= warmup:
+        if i > 0:
             times.append(time.perf_counter() - t0)
-    dt = sum(times) / len(times)
-    return batch_sample / dt, torch.get_num_threads(), dt
+    return sum(rows_per_step) / sum(times), torch.get_num_threads(), times
 
 
 def main_reference(args, rank):
+    """Reference arm: rank 0 alone times the reference's CPU implementation of the path on the box's host cores.  The
+    first timed step is the FULL workload (every row of the global batch: one carried-state chain over all of them, as
+    the reference runs it); the remaining steps are bounded samples (--cpu-sample leading rows; the cost is linear in
+    rows) so that the run ends within minutes; value = rows processed / time over all timed steps."""
     if rank != 0:
         return
-    B = min(args.cpu_sample, args.batch)
-    cps, cores, dt = cpu_reference(B, args.steps, args.warmup)
-    sample = "%d of %d captions per step (cost is linear in rows: serial RNN chains), L=%d, %d steps" % (
-        B, args.batch, L_CAP, args.steps)
+    sample = min(args.cpu_sample, args.batch)
+    n_sample = max(0, min(args.steps, 20) - 1)
+    rows = [args.batch] + [sample] * n_sample
+    cps, cores, times = cpu_reference(rows)
+    desc = ("step 1: all %d captions of the workload (%.1f s); %d further steps of the first %d captions each (%.2f s "
+            "mean); 1 un-timed warm-up step of 64 captions; value = captions processed / time over the timed steps" % (
+                args.batch, times[0], n_sample, sample, (sum(times[1:]) / n_sample) if n_sample else 0.0))
     print(json.dumps({
         "impl": "reference", "metric": "A2C train captions/sec", "value": cps, "unit": "captions/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": times[0] * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[3]: full A2C training step, global batch %d, max_len %d" % (args.batch, L_CAP)},
-        "cpu_baseline": {"value": cps, "unit": "captions/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD % (args.batch, L_CAP, L_CAP - 1), "global_batch": args.batch,
+                   "steps_timed": len(rows), "full_size_step_s": times[0]},
+        "cpu_baseline": {"value": cps, "unit": "captions/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": cps, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the chain kernels from `ncu --set full` captures of THIS command
+# (profiles/r02_chain_tc_ncu.md); keyed by (kernel, local batch).  A configuration that was not captured reports null.
+NCU_TRAFFIC = {}
+
+
+def roofline_of(phases, Bl, lay, peaks, clk):
+    """Roofline of the dominant kernel of the step (the longest chain launch): tensor pipe.  `achieved` counts the
+    ALGORITHMIC flops of the recurrent products once (2 x 512 x G per chain position, G = 2048 LSTM / 1536 GRU; the input
+    half of the gates is the packed table): SURVEY 8(d) per-caption figures minus the tabled half.  The kernels execute
+    3x that (fp16 hi/lo' split, fp32-grade) on the warm-up positions as well."""
+    Tv, Tr = Bl * 190, Bl * 209
+    fwd_ms, bwd_ms = phases.get("chains_fwd_fused", 0.0), phases.get("chain_lstm_bwd", 0.0)
+    peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: the kernel is timed inside a long step)" if peaks else "fallback"
+    if lay is None:
+        return {"kernel": "serial chain kernels (chain.cu)", "bound": "latency", "achieved": None, "peak": peak, "unit": "TFLOP/s",
+                "frac": None, "traffic": None, "note": "chains too short to cut or chain_segments=1: latency-bound serial walk"}
+    (Pv, seg_v, warm_v), (Pr, seg_r, warm_r) = lay["v"], lay["r"]
+    if bwd_ms >= fwd_ms:
+        kname, kms = "chain_tc_bwd_kernel", bwd_ms
+        alg = Tv * 2.0 * 2048 * 512
+        executed = 3.0 * Pv * (seg_v + warm_v) * 2.0 * 2048 * 512
+        steps = seg_v + warm_v
+        hbm_bytes = Tv * (6 * H * 4 + 4 * H * 4 + 4)          # stash read (gates, c_t, c_{t-1}) + dgates write + take
+    else:
+        kname, kms = "chain_tc_fwd_kernel<4> + chain_tc_fwd_kernel<3> (value LSTM, reward GRU; two launches)", fwd_ms
+        alg = Tv * 2.0 * 512 * 2048 + Tr * 2.0 * 512 * 1536
+        executed = 3.0 * (Pv * (seg_v + warm_v) * 2.0 * 512 * 2048 + Pr * (seg_r + warm_r) * 2.0 * 512 * 1536)
+        steps = seg_v + warm_v + seg_r + warm_r
+        hbm_bytes = Tv * (4 * H * 4 + 6 * H * 4 + 4) + Tr * (3 * H * 4 + H * 4 + 4)     # table row + stash (+ token)
+    ach = alg / (kms * 1e-3) / 1e12 if kms > 0 else 0.0
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_ach = hbm_bytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+    return {"kernel": kname, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "traffic": NCU_TRAFFIC.get((kname.split(" ")[0], Bl)), "peak_source": src, "ms_per_launch": kms,
+            "executed_tflops": executed / (kms * 1e-3) / 1e12 if kms > 0 else 0.0,
+            "frac_executed": executed / (kms * 1e-3) / 1e12 / peak if kms > 0 else 0.0,
+            "kernel_steps_per_launch": steps, "us_per_kernel_step": kms * 1e3 / steps if steps else None,
+            "pieces": {"value": Pv, "reward": Pr}, "warmup": {"value": warm_v, "reward": warm_r},
+            "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                    "note": "algorithmic stash / table bytes of the same launch against the measured copy bandwidth"},
+            "note": "one kernel step = [pieces x 512] . W_hh^T on tcgen05 (M = 128 pieces per cluster of 8 CTAs) + cell "
+                    "update; `achieved` = algorithmic recurrent flops of the live chain positions, counted once; "
+                    "`executed` = x3 (fp16 hi/lo' split) including the discarded warm-up positions and padded rows"}
 
 
 def main():
@@ -171,17 +235,19 @@ def main():
 
     import ctypes
     import torch.distributed as dist
-    from icrl_b200 import _lib
+    from icrl_b200 import _lib, synth
     from icrl_b200.dp import DataParallelA2C, shard_bounds
     from icrl_b200.engine import A2CEngine
+    from icrl_b200.optim import FlatAdam
 
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
     A, R = make_nets(0, dev)
-    opt = torch.optim.Adam(A.parameters(), lr=1e-4)
-    eng = A2CEngine(A, R, chain_shards=args.chain_shards, chain_segments=args.chain_segments, chain_warmup=args.chain_warmup)
+    eng = A2CEngine(A, R, chain_shards=args.chain_shards, chain_segments=args.chain_segments, chain_warmup=args.chain_warmup,
+                    chain_engine=args.chain_engine, chain_pieces=args.chain_pieces)
+    opt = torch.optim.Adam(A.parameters(), lr=1e-4) if args.torch_adam else FlatAdam(eng, lr=1e-4)
     dp = DataParallelA2C(eng, opt)
     B = args.batch
     S = L_CAP - 1
@@ -194,6 +260,12 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def all_min(flag):
+        t = torch.tensor([1 if flag else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return int(t.item()) == 1
 
     def timed(run_step, steps, warmup):
         for _ in range(warmup):
@@ -211,41 +283,57 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) / steps, (eng.launches.value - l0) // steps
 
-    # ---- leg 1: minibatch resident in HBM
+    def seg_counters():
+        st = eng.segment_stats
+        return {"fallbacks_to_serial": st["fallbacks"], "warmup_reruns": st["reruns"], "steps": st["steps"]}
+
+    def seg_delta(c0):
+        c1 = seg_counters()
+        return {k: c1[k] - c0[k] for k in c0}
+
+    # ---- warm-up: W (>= 3) steps, then up to 16 more checked steps while the engine is still re-sizing its chain warm-ups
+    # (every step verified; the warm-up of each chain follows the measured contraction rate, engine._adapt_warm)
     prep = eng.prepare(fl, cl, ul, plan=plan)
     clocks = ClockSampler(local)
-    eng.phase_events = None
-
-    def step_resident():
-        dp.step(prep, global_rows=B, check=False)
-
     clocks.start()
+    n_warm = 0
     for _ in range(max(args.warmup, 3)):
-        step_resident()
+        dp.step(prep, global_rows=B)
+        n_warm += 1
+    for _ in range(16):
+        settled = len(eng.segment_stats["warm_history"]) == 0 or \
+            eng.segment_stats["warm_history"][-1][0] + 3 < eng.segment_stats["steps"]
+        if all_min(settled):
+            break
+        dp.step(prep, global_rows=B)
+        n_warm += 1
     barrier()
+
+    # ---- leg 1: minibatch resident in HBM.  The steps run unchecked (no host read inside the timed region) and are
+    # verified together afterwards (the joint-check words are running maxima); a failure re-times with a check per step.
+    c0 = seg_counters()
     eng.phase_events = []
     t_wall0 = time.time()
-    ms_step, launches = timed(step_resident, args.steps, 0)
+    ms_step, launches = timed(lambda: dp.step(prep, global_rows=B, check=False), args.steps, 0)
     clk = clocks.stop(t_wall0, time.time())
     phases = {k: sum(v) / len(v) for k, v in eng.phase_times_ms().items()}
     eng.phase_events = None
-    _lib.call("icrl_chain_check", ctypes.c_void_p(torch.cuda.current_stream().cuda_stream),
-              ctypes.c_void_p(eng.sync_state.data_ptr()))
-    seg_layout = eng.segment_layout                      # (pieces, value segment, reward segment, warm-up) or None = serial kernels
-    seg_ok = torch.tensor([1 if eng.segments_verified() else 0], device=dev)
-    if world > 1:
-        dist.all_reduce(seg_ok, op=dist.ReduceOp.MIN)
-    if int(seg_ok.item()) == 0:
-        # some rank's warm-up check failed inside the timed loop: those steps are not the reference's numbers.
-        # Time the serial kernels instead (every rank takes this branch together).
-        eng.chain_segments = 1
+    lay = eng.piece_layout if args.chain_engine == "tc" else None
+    seg_layout = eng.segment_layout
+    value_checked_per_step = False
+    if not all_min(eng.segments_verified()):
+        # some rank's joint check failed inside the unchecked loop: those steps are not the reference's numbers.
+        # Time again with every step checked (re-runs with longer warm-ups included); every rank takes this branch.
+        value_checked_per_step = True
         eng.phase_events = []
-        ms_step, launches = timed(step_resident, args.steps, 1)
+        ms_step, launches = timed(lambda: dp.step(prep, global_rows=B), args.steps, 2)
         phases = {k: sum(v) / len(v) for k, v in eng.phase_times_ms().items()}
         eng.phase_events = None
-        seg_layout = None
+        lay = eng.piece_layout if args.chain_engine == "tc" else None
+        seg_layout = eng.segment_layout
+    value_seg = seg_delta(c0)
 
-    # ---- leg 2: end to end through the public API from pinned host buffers
+    # ---- leg 2: end to end through the public API from pinned host buffers, every step checked, loss read on the host
     e2e = None
     if not args.no_e2e:
         fh = torch.from_numpy(fl).pin_memory()
@@ -254,29 +342,31 @@ def main():
 
         def step_e2e():
             res = dp.step(fh, cl, uh, global_rows=B, plan=plan)
-            sink.append(res.loss)                     # D2H read of the step's result
+            sink.append(res.loss)                     # D2H read of the step's result (rides the joint-check read)
 
+        c0 = seg_counters()
         ms_e2e, _ = timed(step_e2e, args.steps, 1)
-        e2e = {"value": B / (ms_e2e * 1e-3), "unit": "captions/s",
-               "h2d_bytes_per_step": int(fl.nbytes + (hi - lo) * 4 + ul.nbytes), "d2h_bytes_per_step": 8}
+        e2e = {"value": B / (ms_e2e * 1e-3), "unit": "captions/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": int(fl.nbytes + (hi - lo) * 4 + ul.nbytes), "d2h_bytes_per_step": 80,
+               "chain_checks": seg_delta(c0)}
 
-    # ---- leg 3 (reported separately, never the headline): the same workload with 8 chain shards per rank
+    # ---- leg 3 (reported separately, never the headline): the serial chain kernels; 8 zero-state shards per rank
     sharded = None
     serial_leg = None
     if seg_layout is not None and not args.no_serial_leg:
         eng1 = A2CEngine(A, R, chain_segments=1)
-        dp1 = DataParallelA2C(eng1, opt)
+        dp1 = DataParallelA2C(eng1, None)
         ms1, _ = timed(lambda: dp1.step(prep, global_rows=B, check=False), min(args.steps, 2), 1)
         _lib.call("icrl_chain_check", ctypes.c_void_p(torch.cuda.current_stream().cuda_stream),
                   ctypes.c_void_p(eng1.sync_state.data_ptr()))
         serial_leg = {"value": B / (ms1 * 1e-3), "unit": "captions/s", "ms_per_step": ms1, "steps": min(args.steps, 2),
-                      "note": "the same step on the serial chain kernels (chain_segments=1): one CTA group walks the whole "
-                              "carried-state chain position by position"}
+                      "note": "the same step (without Adam) on the serial chain kernels (chain_segments=1): one CTA group walks "
+                              "the whole carried-state chain position by position"}
         del eng1, dp1
         eng._attach_grads()
     if args.chain_shards == 1 and args.sharded_leg and (hi - lo) % 8 == 0:
         eng8 = A2CEngine(A, R, chain_shards=8, chain_segments=1)
-        dp8 = DataParallelA2C(eng8, opt)
+        dp8 = DataParallelA2C(eng8, None)
         ms8, _ = timed(lambda: dp8.step(prep, global_rows=B, check=False), args.steps, 2)
         _lib.call("icrl_chain_check", ctypes.c_void_p(torch.cuda.current_stream().cuda_stream),
                   ctypes.c_void_p(eng8.sync_state.data_ptr()))
@@ -287,100 +377,103 @@ def main():
         del eng8, dp8
         eng._attach_grads()
 
+    # ---- BASELINE configs 3 and 5 in the same run (side objects, not the headline)
+    reward_tp, curriculum = None, None
+    if not args.no_extras:
+        # config 3: RewardNetwork embedding-cosine reward throughput, 8192 captions x 20 tokens, one GPU (rank 0)
+        if rank == 0:
+            f3, c3 = synth.make_inputs(103, 8192, L_CAP)
+            for _ in range(2):
+                eng.get_rewards(f3, c3)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            e0.record()
+            for _ in range(reps):
+                eng.get_rewards(f3, c3)
+            e1.record()
+            torch.cuda.synchronize()
+            ms3 = e0.elapsed_time(e1) / reps
+            reward_tp = {"workload": "configs[2]: GetRewards on 8192 captions x %d tokens from zero state (163,840 serial GRU "
+                                     "positions), one GPU, host inputs" % L_CAP,
+                         "value": 8192 / (ms3 * 1e-3), "unit": "captions/s", "ms_per_call": ms3, "n_gpus": 1,
+                         "pieces": None if eng.piece_layout is None else eng.piece_layout["r"][0],
+                         "warmup": None if eng.piece_layout is None else eng.piece_layout["r"][2]}
+        # config 5: curriculum A2C (partial-prefix rollouts), global batch 8192 sharded over the run's ranks
+        B5 = 8192
+        f5, c5 = synth.make_inputs(105, B5, L_CAP)
+        lo5, hi5 = shard_bounds(B5, rank, world)
+        levels = {}
+        tot_ms = 0.0
+        for level in (3, 6, 9, 12, 15, 16):
+            p0 = L_CAP - level
+            u5 = np.ascontiguousarray(synth.make_uniforms(105 + level, level, B5)[:, lo5:hi5])
+            prep5 = eng.prepare(f5[lo5:hi5], c5[lo5:hi5], u5, plan=(p0, level))
+            c0 = seg_counters()
+            ms5, _ = timed(lambda: dp.step(prep5, global_rows=B5), 2, 2)
+            levels[str(level)] = {"p0": p0, "S": level, "ms_per_step": ms5, "captions_per_s": B5 / (ms5 * 1e-3),
+                                  "chain_checks": seg_delta(c0)}
+            tot_ms += ms5
+        curriculum = {"workload": "configs[4]: curriculum A2C step (ground-truth prefix of L - level columns, `level` sampled "
+                                  "steps), global batch %d over %d GPU(s), levels 3..16, every step checked" % (B5, world),
+                      "global_batch": B5, "local_batch": hi5 - lo5, "n_gpus": world, "levels": levels,
+                      "aggregate_captions_per_s": 6 * B5 / (tot_ms * 1e-3), "unit": "captions/s"}
+        eng.prepare(fl, cl, ul, plan=plan)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- tensor-pipe figure of the persistent decode kernel (policy_decode_kernel: all S steps in one launch).
-    # Timed live as the policy_fwd phase (h0 GEMM + h split + the decode kernel; the kernel is >95 % of it).
-    decode = None
-    try:
-        Bl_ = hi - lo
-        us = phases.get("policy_fwd", 0.0) * 1e3
-        n_cell = S                                    # p0 = 1: S cell steps, each followed by a vocab projection
-        alg = Bl_ * (n_cell * 2.0 * 2048 * 512 + S * 2.0 * 1004 * 512)
-        rows_pad = ((Bl_ + 127) // 128) * 128
-        executed = 3.0 * rows_pad * (n_cell * 2.0 * 2048 * 512 + S * 2.0 * 1024 * 512)
-        decode = {"kernel": "policy_decode_kernel (gate GEMM + cell update + vocab GEMM + softmax + sampling, all %d steps)" % S,
-                  "bound": "tensor", "achieved": alg / us / 1e6, "executed_tflops": executed / us / 1e6, "unit": "TFLOP/s",
-                  "us_per_launch": us, "rows": Bl_, "mma_passes": 3,
-                  "note": "achieved counts the algorithmic 2MNK of the recurrent gate GEMM and the vocab GEMM once; the "
-                          "tensor pipe executes 3x that (2-part fp16 split) on rows padded to 128 and V padded to 1024; "
-                          "ncu sm__pipe_tensor_cycles_active of this kernel: profiles/"}
-    except Exception as exc:                                   # never let the side measurement kill the bench line
-        decode = {"error": str(exc)}
-
-    # ---- roofline of the dominant kernel (serial chains: latency bound -- see DESIGN.md)
-    Bl = hi - lo
-    Tv, Tr = Bl * 190, Bl * 209
-    fwd_ms, bwd_ms = phases.get("chains_fwd_fused", 0.0), phases.get("chain_lstm_bwd", 0.0)
-    ktraffic = None
-    if bwd_ms >= fwd_ms:
-        kname, kms, kbytes, ksteps = "chain_lstm_bwd_kernel", bwd_ms, Tv * (6 * H * 4 + 4 + 4 * H * 4), Tv
-    else:
-        kname, kms = "chains_fwd_fused_kernel", fwd_ms
-        kbytes, ksteps = Tv * (4 * H * 4 + 6 * H * 4 + 4) + Tr * (3 * H * 4 + H * 4 + 4), max(Tv, Tr)
-        # profiles/r01_chain_fwd_ncu.md: dram read+write = 695.5 MB per launch at B=256 (linear in rows)
-        ktraffic = 695.5e6 * Bl / 256.0
-    if seg_layout is not None:                 # lockstep pieces: one kernel step advances `pieces` chain positions
-        pieces, seg_v, seg_r, warm = seg_layout
-        if bwd_ms >= fwd_ms:
-            bp = 16 if pieces in (16, 32) else min(pieces, 8)              # backward pieces (engine._backward)
-            kname = "chain_lstm_bwd_batched8_kernel x 2 groups" if bp == 16 else "chain_lstm_bwd_batched_kernel<%d, 1> x 2 groups" % (bp // 2)
-            ksteps = seg_v * pieces // bp + warm
-        else:
-            kname = "chains_fwd_fused_batched_kernel<%d, %d>" % ((16, 2) if pieces == 32 else (min(pieces, 8), max(pieces // 8, 1)))
-            ksteps = max(seg_v, seg_r) + warm
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    if decode and "achieved" in decode:
-        tp = float(peaks.get("bf16_tflops", 1590.0))
-        decode.update(peak=tp, frac=decode["achieved"] / tp, frac_executed=decode["executed_tflops"] / tp,
-                      peak_source="measured" if peaks else "fallback")
-    ach = kbytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
-    roofline = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": ktraffic, "peak_source": "measured" if peaks else "fallback",
-                "ms_per_launch": kms, "serial_steps_per_launch": ksteps,
-                "ns_per_serial_step": kms * 1e6 / ksteps if ksteps else None,
-                "note": "serial batch-1 recurrence: latency bound, neither HBM nor tensor pipe is the limiter"
-                        + ("" if seg_layout is None else "; %d pieces of the chain advance per kernel step" % seg_layout[0]),
-                "latency_floor": {"one_way_l2_store_to_poll_ns": 494, "all_to_all_512_words_64_ctas_ns": 782,
-                                  "register_gemv_plus_pointwise_ns": 230,
-                                  "source": "profiles/r01_xchg_bench.log, profiles/r01_chain_micro.log (microbenchmarks, "
-                                            "not measured in this run)"}}
+    # ---- tensor-pipe figure of the persistent decode kernel (policy_decode_kernel: all S steps in one launch).
+    # Timed live as the policy_fwd phase (h0 GEMM + h split + the decode kernel; the kernel is >95 % of it).
+    Bl = hi - lo
+    decode = None
     try:
-        # What bounds this kernel is FP32 issue on the CUDA cores, so the same launch is also put against
-        # that roof: multiply-adds of the recurrent GEMVs (forward: 4*512*512 per value position + 3*512*512 per reward
-        # position; backward: the 2048 x 512 contraction per value position) over SMs x 128 lanes x 2 x the sampled SM clock.
-        sms = torch.cuda.get_device_properties(local).multi_processor_count
-        mhz = float(clk.get("sm_mhz") or 1965.0)
-        macs = Tv * 4.0 * H * H if kname.startswith("chain_lstm_bwd") else Tv * 4.0 * H * H + Tr * 3.0 * H * H
-        peak32 = sms * 128 * 2 * mhz * 1e6 / 1e12
-        ach32 = 2.0 * macs / (kms * 1e-3) / 1e12 if kms > 0 else 0.0
-        roofline["fp32"] = {"achieved": ach32, "peak": peak32, "unit": "TFLOP/s", "frac": ach32 / peak32,
-                            "peak_source": "nominal: %d SMs x 128 FP32 lanes x 2 x %.0f MHz" % (sms, mhz)}
-    except Exception as exc:                                   # a side figure must never cost the bench line
-        roofline["fp32"] = {"error": str(exc)}
+        us = phases.get("policy_fwd", 0.0) * 1e3
+        alg = Bl * (S * 2.0 * 2048 * 512 + S * 2.0 * 1004 * 512)
+        rows_pad = ((Bl + 127) // 128) * 128
+        executed = 3.0 * rows_pad * (S * 2.0 * 2048 * 512 + S * 2.0 * 1024 * 512)
+        tp = float(peaks.get("bf16_tflops", 1590.0))
+        decode = {"kernel": "policy_decode_kernel (gate GEMM + cell update + vocab GEMM + softmax + sampling, all %d steps)" % S,
+                  "bound": "tensor", "achieved": alg / us / 1e6, "executed_tflops": executed / us / 1e6, "unit": "TFLOP/s",
+                  "us_per_launch": us, "rows": Bl, "mma_passes": 3, "peak": tp, "frac": alg / us / 1e6 / tp,
+                  "frac_executed": executed / us / 1e6 / tp, "peak_source": "measured" if peaks else "fallback",
+                  "note": "achieved counts the algorithmic 2MNK of the recurrent gate GEMM and the vocab GEMM once; the "
+                          "tensor pipe executes 3x that (2-part fp16 split) on rows padded to 128 and V padded to 1024"}
+    except Exception as exc:                                   # never let the side measurement kill the bench line
+        decode = {"error": str(exc)}
+    try:
+        roofline = roofline_of(phases, Bl, lay, peaks, clk)
+    except Exception as exc:
+        roofline = {"error": str(exc)}
+
+    st = eng.segment_stats
+    chain_cfg = None
+    if lay is not None:
+        chain_cfg = {"engine": "tc", "pieces": {"value": lay["v"][0], "reward": lay["r"][0]},
+                     "positions_per_piece": {"value": lay["v"][1], "reward": lay["r"][1]},
+                     "warmup": {"value": lay["v"][2], "reward": lay["r"][2]}, "tolerance": eng.chain_tol,
+                     "checked_max": dict(zip(("value_h", "value_c", "value_h_half", "value_c_half", "reward_h", "-", "reward_h_half",
+                                              "--", "bwd_dh", "bwd_dc", "bwd_dh_half", "bwd_dc_half", "dh_take_max", "fp16_overflow"),
+                                             st["tc_max_err"][:14])),
+                     "warmup_history": st["warm_history"][-12:], "value_leg": dict(value_seg, checked_per_step=value_checked_per_step)}
+    elif seg_layout is not None:
+        chain_cfg = {"engine": "simt", "pieces": seg_layout[0], "value_segment": seg_layout[1], "reward_segment": seg_layout[2],
+                     "warmup": seg_layout[3], "tolerance": eng.chain_tol, "value_leg": value_seg}
     out = {
         "metric": "A2C train captions/sec", "value": B / (ms_step * 1e-3), "unit": "captions/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[3]: full A2C training step (rollout+reward+value+loss+backward+allreduce+Adam), "
-                               "global batch %d, max_len %d, S=%d" % (B, L_CAP, S),
+        "config": {"workload": WORKLOAD % (B, L_CAP, S),
                    "global_batch": B, "local_batch": Bl, "parallelism": "dp%d" % world, "vocab": 1004,
-                   "chain_shards_per_rank": args.chain_shards,
-                   "chain_segments": None if seg_layout is None else
-                   {"pieces": seg_layout[0], "value_segment": seg_layout[1], "reward_segment": seg_layout[2],
-                    "warmup": seg_layout[3], "tolerance": eng.chain_tol,
-                    "checked_max": dict(zip(("value_h", "value_c", "reward_h", "joint_dgates", "dh_take"),
-                                            eng.segment_stats["max_err"])),
-                    "fallbacks_to_serial": eng.segment_stats["fallbacks"],
-                    "steps_checked": eng.segment_stats["segmented_steps"]},
+                   "optimizer": "torch.optim.Adam" if args.torch_adam else "FlatAdam (one kernel over the flat bucket)",
+                   "chain_shards_per_rank": args.chain_shards, "chain_segments": chain_cfg,
                    "l2_flush": "not needed: per-step working set (chain stash, GBs) >> 126 MB L2"},
         "clocks": clk, "gpu_launches": int(launches), "phases_ms": phases, "roofline": roofline,
         "roofline_decode": decode,
@@ -391,11 +484,17 @@ def main():
         out["serial_chain"] = serial_leg
     if sharded:
         out["sharded"] = sharded
+    if reward_tp:
+        out["reward_throughput"] = reward_tp
+    if curriculum:
+        out["curriculum"] = curriculum
     if world == 1 and not args.no_cpu_baseline:
         Bs = min(args.cpu_sample, B)
-        cps, cores, dt = cpu_reference(Bs, 1, 0)
+        cps, cores, times = cpu_reference([Bs])
         out["cpu_baseline"] = {"value": cps, "unit": "captions/s", "cores": cores, "kind": "port",
-                               "sample": "1 step of %d of the %d captions (%.1f s); reference cost is linear in rows" % (Bs, B, dt)}
+                               "sample": "1 timed step of the first %d of the %d captions (%.1f s) after an un-timed 64-caption "
+                                         "step; the reference's cost is linear in rows (serial RNN chains); the reference arm "
+                                         "(--impl reference) times all %d rows" % (Bs, B, times[0], B)}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -43,12 +43,27 @@ class DataParallelA2C:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
 
+    def _global_rows(self, features_local, captions_local):
+        local = getattr(features_local, "B", None)              # a Prepared minibatch knows its rows
+        if local is None:
+            local = len(captions_local) if captions_local is not None else len(features_local)
+        if self.world == 1:
+            return int(local)
+        dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
+        n = torch.tensor([int(local)], dtype=torch.int64, device=dev)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM, group=self.group)
+        return int(n.item())
+
     def step(self, features_local, captions_local=None, uniforms_local=None, global_rows=None, level=None,
              plan=None, **kw):
         """One global minibatch; every rank passes its own row shard.  Returns the local StepResult
         whose 'stats' now hold the GLOBAL loss / mean reward / mean advantage."""
         if plan is None and captions_local is not None:
             plan = global_plan(captions_local, level, self.group)
+        if global_rows is None:
+            # the loss is a mean over the GLOBAL batch (trainers.py:472-475): every rank must scale its gradient seeds by
+            # 1 / (B_global * S), so the row count is agreed on before the step (one 8-byte all-reduce)
+            global_rows = self._global_rows(features_local, captions_local)
         res = self.engine.step(features_local, captions_local, uniforms=uniforms_local, global_rows=global_rows,
                                level=level, plan=plan, **kw)
         if res is None:

@@ -165,6 +165,7 @@ class A2CEngine:
         self.chain_warmup_min = int(chain_warmup_min)
         self.warm = {"v": self.chain_warmup, "r": self.chain_warmup}      # current warm-up per chain (tc engine)
         self._clean = {"v": 0, "r": 0}
+        self._hold = {"v": 0, "r": 0}
         self._tc = None                   # {"v": (P, seg, warm) | None, "r": (P, seg, warm)} of the current step
         self.segment_stats = {"steps": 0, "segmented_steps": 0, "fallbacks": 0, "reruns": 0, "max_err": [0.0] * 5,
                               "tc_max_err": [0.0] * 16, "warm_history": []}
@@ -651,16 +652,23 @@ class A2CEngine:
         return res
 
     _TC_ATTEMPTS = 3
-    _SHRINK_AFTER = 8
+    _SHRINK_AFTER = 2
+    _HOLD_AFTER_GROWTH = 64
     _tc_force_serial = False
 
     def _adapt_warm(self, key, e_half, e_full):
         """Size the next warm-up of chain `key` from the joint errors half-way through / at the end of this one.
-        Returns False when the step failed its check (e_full above chain_tol, or not a number)."""
+        The two errors give the contraction rate of the recurrence under the current weights: the warm-up GROWS as soon
+        as the end-of-warm-up error passes chain_tol / 4 (before the check can fail; by the measured rate, at least
+        x1.25, at most x4), and SHRINKS to 5/8 once the half-way error alone has been below that target on
+        _SHRINK_AFTER consecutive steps (the new end point then lies beyond a point already measured clean); after a
+        growth it is held for _HOLD_AFTER_GROWTH steps.  Returns False when the step failed its check (end-of-warm-up
+        error above chain_tol, or not a number)."""
         tol = self.chain_tol
         target = tol / 4.0
         warm = self.warm[key]
         failed = not (e_full <= tol)
+        self._hold[key] = max(0, self._hold[key] - 1)
         if failed or (self.chain_adapt and not (e_full <= target)):
             need = 2.0 * warm
             if e_half > e_full > 0.0 and np.isfinite(e_half):
@@ -669,10 +677,11 @@ class A2CEngine:
             new = min(max(need, (1.5 if failed else 1.25) * warm), 4.0 * warm)
             self.warm[key] = int(-(-int(np.ceil(new)) // 32) * 32)
             self._clean[key] = 0
-        elif self.chain_adapt and warm >= 8 and e_half <= target:
+            self._hold[key] = self._HOLD_AFTER_GROWTH
+        elif self.chain_adapt and warm >= 8 and e_half <= target and self._hold[key] == 0:
             self._clean[key] += 1
             if self._clean[key] >= self._SHRINK_AFTER and warm > self.chain_warmup_min:
-                self.warm[key] = max(self.chain_warmup_min, int(-(-int(0.75 * warm) // 32) * 32))
+                self.warm[key] = max(self.chain_warmup_min, int(-(-int(0.625 * warm) // 32) * 32))
                 self._clean[key] = 0
         else:
             self._clean[key] = 0

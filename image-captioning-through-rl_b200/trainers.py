@@ -450,7 +450,13 @@ def train_a2c_network(train_data, save_paths, network_paths, plot_dir, bidirecti
     reward_network.train(False)
     a2c_network = AdvantageActorCriticNetwork(nets["value_network"], nets["policy_network"]).to(device)
     a2c_network.train(True)
-    optimizer = optim.Adam(a2c_network.parameters(), lr=0.0001)
+    if bidirectional:
+        optimizer = optim.Adam(a2c_network.parameters(), lr=0.0001)          # module route: torch's own Adam (trainers.py:378)
+    else:
+        # fused route: the same Adam(lr=1e-4) as ONE kernel over the flat gradient bucket the engine fills (optim.FlatAdam;
+        # torch's update operation by operation, <= 2e-7 from torch.optim.Adam over 3 steps)
+        from .optim import FlatAdam
+        optimizer = FlatAdam(_engine_for(a2c_network, reward_network), lr=0.0001)
     paths = [save_paths["model_path"], network_paths["a2c_network"]]
     if curriculum is None:
         a2c_network = a2c_training(train_data, a2c_network, reward_network, optimizer, plot_dir, paths, batch_size, epochs)

@@ -46,7 +46,11 @@ def _worker(rank, world, port, out):
     dp = DataParallelA2C(eng, opt)
     plan = global_plan(caps[lo:hi][:, :6] if rank == 0 else caps[lo:hi], None)
     res = dp.step(feats[lo:hi], caps[lo:hi], None, global_rows=10)
-    out[rank] = (plan, eng.flat_grad.clone(), res["stats"].clone(), eng.param.detach().clone())
+    first = (plan, eng.flat_grad.clone(), res["stats"].clone(), eng.param.detach().clone())
+    # default path: global_rows=None must be resolved to the GLOBAL row count (sum over ranks), not the local shard
+    eng2 = _FakeEngine(16)
+    res2 = DataParallelA2C(eng2, None).step(feats[lo:hi], caps[lo:hi], None)
+    out[rank] = first + (eng2.flat_grad.clone(), res2["stats"].clone())
     dist.destroy_process_group()
 
 
@@ -62,7 +66,9 @@ def test_two_rank_allreduce_matches_single_process():
     feats = torch.from_numpy(rs.standard_normal((10, 16)).astype(np.float32))
     expect = feats.sum(dim=0) / (10 * 8)
     for r in (0, 1):
-        plan, grad, stats, param = out[r]
+        plan, grad, stats, param, grad_default, stats_default = out[r]
+        assert torch.allclose(grad_default, expect, atol=1e-6)  # global_rows=None: same normalisation as the explicit call
+        assert torch.allclose(stats_default, stats, atol=1e-6)
         assert plan == (1, 8)                                   # caplen from the GLOBAL batch
         assert torch.allclose(grad, expect, atol=1e-6)
         assert torch.allclose(param, -expect, atol=1e-6)        # identical SGD step on both ranks

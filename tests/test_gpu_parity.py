@@ -692,39 +692,41 @@ def test_config4_full_size_properties():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# chain segments: the single carried-state chain advanced as K pieces with a discarded, verified warm-up
+# chain pieces: the single carried-state chain advanced as lockstep pieces with a discarded, verified warm-up.
+# Default engine = chain_tc.cu (hundreds of pieces on tcgen05); chain_engine="simt" = the CUDA-core kernels of chain.cu.
 
-def _seg_engines(seed, segments, warm, tol=1e-5):
+def _seg_engines(seed, segments, warm, tol=1e-5, engine="simt", **kw):
     from icrl_b200.engine import A2CEngine
     A, R, w = make_nets(seed)
-    return A2CEngine(A, R, chain_segments=1), A2CEngine(A, R, chain_segments=segments, chain_warmup=warm, chain_tol=tol), A
+    return (A2CEngine(A, R, chain_segments=1),
+            A2CEngine(A, R, chain_segments=segments, chain_warmup=warm, chain_tol=tol, chain_engine=engine, **kw), A)
 
 
-@pytest.mark.parametrize("name", ["a2c_b32_l9", "curr_b24_l20_lv6"])
-def test_chain_segments_vs_reference_golden(name):
-    """The unmodified reference's numbers (one carried-state chain over the whole batch) reproduced by 8
-    lockstep pieces of that chain with a 64-position warm-up: same tolerances as the serial kernels."""
+@pytest.mark.parametrize("name", ["a2c_b32_l9", "curr_b24_l20_lv6", "a2c_b256_l20"])
+def test_chain_pieces_vs_reference_golden(name):
+    """The unmodified reference's numbers (one carried-state chain over the whole batch) reproduced by the default
+    engine: the chains cut into tcgen05 pieces (a 64-position first warm-up, lengthened by the joint check where a
+    chain needs more): same tolerances as the serial kernels, no fall-back to them."""
     from icrl_b200.engine import A2CEngine
     g, seed, f, c, u, level = load_case(name)
     A, R, w = make_nets(seed)
     eng = A2CEngine(A, R, chain_warmup=64)
     res = eng.step(f, c, uniforms=u, level=level)
-    assert eng.segment_stats["segmented_steps"] == 1 and eng.segment_stats["fallbacks"] == 0, eng.segment_stats
-    _compare_forward(res, g, name + "_segments")
-    _record(name + "_segments", grad_worst=check_grads_vs_golden(named_grads(A), g, GTOL),
-            warm_h=eng.segment_stats["max_err"][0], warm_c=eng.segment_stats["max_err"][1],
-            warm_rh=eng.segment_stats["max_err"][2], warm_dg=eng.segment_stats["max_err"][3],
-            dh_take_max=eng.segment_stats["max_err"][4])
+    st = eng.segment_stats
+    assert eng.piece_layout is not None and st["segmented_steps"] >= 1 and st["fallbacks"] == 0, (eng.piece_layout, st)
+    _compare_forward(res, g, name + "_pieces")
+    _record(name + "_pieces", grad_worst=check_grads_vs_golden(named_grads(A), g, GTOL), reruns=st["reruns"],
+            pieces_v=eng.piece_layout["v"][0], warm_v=eng.piece_layout["v"][2], warm_r=eng.piece_layout["r"][2])
 
 
-@pytest.mark.parametrize("segments,B,L,level", [(8, 64, 10, None), (4, 64, 8, None), (2, 48, 7, None), (8, 96, 14, 5),
-                                                (16, 96, 14, 5), (32, 160, 12, None), (32, 256, 20, 7)])
-def test_chain_segments_equal_the_serial_chain(segments, B, L, level):
-    """Segmented and serial kernels on the same inputs: identical tokens, values / rewards within 2e-6, gradients within
-    2e-5 of the bucket's largest entry; the verification words stay at float-rounding level.  (Warm-up 160: with a
-    64-position warm-up the reward GRU of seed 163 is still 1.5e-3 away and the engine -- correctly -- falls back.)"""
-    seed = 131 + segments
-    e1, ek, A = _seg_engines(seed, segments, 160)
+@pytest.mark.parametrize("pieces,B,L,level,warm", [(None, 64, 10, None, 96), (7, 64, 8, None, 96), (2, 48, 7, None, 96),
+                                                    (130, 96, 14, 5, 160), (300, 512, 12, None, 160), (None, 256, 20, 7, 160)])
+def test_chain_pieces_equal_the_serial_chain(pieces, B, L, level, warm):
+    """tcgen05 pieces and serial kernels on the same inputs: identical tokens, values / rewards within 2e-6, gradients
+    within 2e-5 of the bucket's largest entry -- for piece counts that do not fill a cluster (7, 2), that straddle
+    clusters (130, 300) and for the automatic layout."""
+    seed = 131 + (pieces or 0)
+    e1, ek, A = _seg_engines(seed, 32, warm, engine="tc", chain_pieces=pieces)
     f, c = synth.make_inputs(seed, B, L)
     S = (L - 1) if level is None else level
     u = synth.make_uniforms(seed, S, B)
@@ -732,20 +734,208 @@ def test_chain_segments_equal_the_serial_chain(segments, B, L, level):
     v1, w1, g1 = r1["values"].clone(), r1["rewards"].clone(), e1.flat_grad.clone()
     assert e1.segment_stats["segmented_steps"] == 0
     rk = ek.step(f, c, uniforms=u, level=level)
+    st = ek.segment_stats
+    assert ek.piece_layout is not None and st["fallbacks"] == 0, (ek.piece_layout, st)
+    if pieces is not None:
+        assert ek.piece_layout["v"][0] <= pieces and ek.piece_layout["r"][0] <= pieces
+    assert torch.equal(rk["tokens"], r1["tokens"])
+    ev, er = float((rk["values"] - v1).abs().max()), float((rk["rewards"] - w1).abs().max())
+    eg = float((ek.flat_grad - g1).abs().max() / g1.abs().max())
+    _record("chain_pieces_%s_b%d" % (pieces, B), values=ev, rewards=er, grad_rel=eg, reruns=st["reruns"],
+            **{"err%d" % i: e for i, e in enumerate(st["tc_max_err"][:14])})
+    assert ev <= TOL and er <= TOL and eg <= GTOL, (ev, er, eg)
+    assert abs(rk.loss - r1.loss) <= TOL
+
+
+def test_chain_pieces_short_warmup_is_caught_and_rerun():
+    """A warm-up too short to forget the initial state (4 positions) must be caught by the joint check: the chains are
+    re-run with a longer warm-up (or, after three attempts, on the serial kernels) before anything leaves the engine,
+    a warning is raised, and the step comes out within the serial kernels' tolerances."""
+    seed, B, L = 141, 64, 10
+    e1, ek, A = _seg_engines(seed, 32, 4, engine="tc")
+    f, c = synth.make_inputs(seed, B, L)
+    u = synth.make_uniforms(seed, L - 1, B)
+    r1 = e1.step(f, c, uniforms=u)
+    v1, w1, g1 = r1["values"].clone(), r1["rewards"].clone(), e1.flat_grad.clone()
+    with pytest.warns(UserWarning, match="chain segments did not converge"):
+        rk = ek.step(f, c, uniforms=u)
+    assert ek.segment_stats["reruns"] >= 1 and ek.warm["v"] > 4 and ek.warm["r"] > 4
+    assert float((rk["values"] - v1).abs().max()) <= TOL and float((rk["rewards"] - w1).abs().max()) <= TOL
+    assert float((ek.flat_grad - g1).abs().max() / g1.abs().max()) <= GTOL
+    # unverified steps (check=False) are reported by segments_verified()
+    ek.warm = {"v": 4, "r": 4}
+    ek.step(f, c, uniforms=u, check=False)
+    with pytest.warns(UserWarning):
+        assert ek.segments_verified() is False
+    assert ek.segments_verified() is True
+
+
+def test_get_rewards_pieces_equal_the_serial_chain():
+    from icrl_b200.engine import A2CEngine
+    seed, B, L = 151, 512, 12
+    A, R, w = make_nets(seed)
+    f, c = synth.make_inputs(seed, B, L)
+    r1 = A2CEngine(A, R, chain_segments=1).get_rewards(f, c)
+    ek = A2CEngine(A, R, chain_warmup=160)
+    rk = ek.get_rewards(f, c)
+    assert ek.piece_layout is not None and ek.piece_layout["v"] is None and ek.segment_stats["fallbacks"] == 0
+    assert float((rk - r1).abs().max()) <= TOL
+
+
+def test_config4_pieces_full_size():
+    """BASELINE config 4 at full single-GPU size with the default engine: the joint checks pass without a serial
+    fall-back, and values / rewards / gradients agree with the serial chain at the tolerances of the golden tests."""
+    from icrl_b200.engine import A2CEngine
+    seed, B, L = 97, 4096, 20
+    A, R, w = make_nets(seed)
+    f, c = synth.make_inputs(seed, B, L)
+    u = synth.make_uniforms(seed, L - 1, B)
+    ek = A2CEngine(A, R)
+    rk = ek.step(f, c, uniforms=u)
+    assert ek.piece_layout is not None and ek.segment_stats["fallbacks"] == 0, ek.segment_stats
+    vk, wk, gk = rk["values"].clone(), rk["rewards"].clone(), ek.flat_grad.clone()
+    e1 = A2CEngine(A, R, chain_segments=1)
+    r1 = e1.step(f, c, uniforms=u)
+    assert torch.equal(rk["tokens"], r1["tokens"])
+    ev, er = float((vk - r1["values"]).abs().max()), float((wk - r1["rewards"]).abs().max())
+    eg = float((gk - e1.flat_grad).abs().max() / e1.flat_grad.abs().max())
+    _record("config4_pieces", values=ev, rewards=er, grad_rel=eg, pieces=ek.piece_layout["v"][0],
+            **{"err%d" % i: e for i, e in enumerate(ek.segment_stats["tc_max_err"][:14])})
+    assert ev <= TOL and er <= TOL and eg <= GTOL, (ev, er, eg)
+
+
+# ---- full-size parity against the CPU port of the reference computed on the GPU box (not against our own kernels)
+
+def test_full_step_b1024_vs_cpu_port():
+    """One complete A2C minibatch at B = 1024, L = 20 (config 4's per-rank size at 4 GPUs: 194,560 + 214,016 serial chain
+    positions) on the default engine against oracle/ref_port executing the reference's algorithm on the host cores:
+    token ids bit-exact, values / rewards / log-probs within 2e-6, loss within 2e-6, all 18 gradients within 2e-5 of
+    each tensor's largest entry."""
+    from icrl_b200.engine import A2CEngine
+    seed, B, L = 211, 1024, 20
+    A, R, w = make_nets(seed)
+    f, c = synth.make_inputs(seed, B, L)
+    u = synth.make_uniforms(seed, L - 1, B)
+    eng = A2CEngine(A, R)
+    res = eng.step(f, c, uniforms=u)
+    assert eng.piece_layout is not None and eng.segment_stats["fallbacks"] == 0, eng.segment_stats
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    ref = ref_port.a2c_minibatch(ref_port.Nets(w), f, c, u)
+    assert np.array_equal(res["tokens"].cpu().numpy(), ref["tokens"])
+    errs = {k: float(np.abs(res[k].cpu().numpy() - ref[k]).max()) for k in ("values", "rewards", "logp")}
+    errs["loss"] = abs(res.loss - ref["loss"])
+    grads = named_grads(A)
+    worst = 0.0
+    for k, gr in grads.items():
+        r = ref["grads"][k].numpy()
+        worst = max(worst, float(np.abs(gr - r).max()) / max(float(np.abs(r).max()), 1e-12))
+    _record("full_step_b1024_vs_port", grad_worst=worst, **errs)
+    assert all(v <= TOL for v in errs.values()), errs
+    assert worst <= GTOL, worst
+
+
+def test_get_rewards_config3_full_size_vs_cpu_port():
+    """BASELINE config 3 at full size (8192 captions x 20 tokens, one GetRewards from zero state = 163,840 serial GRU
+    positions) against the CPU port of the reference computed here: within 2e-6."""
+    from icrl_b200.engine import A2CEngine
+    seed, B, L = 223, 8192, 20
+    A, R, w = make_nets(seed)
+    f, c = synth.make_inputs(seed, B, L)
+    eng = A2CEngine(A, R)
+    got = eng.get_rewards(f, c).cpu().numpy()
+    assert eng.piece_layout is not None and eng.segment_stats["fallbacks"] == 0
+    ref = ref_port.get_rewards(ref_port.Nets(w), f, c)
+    err = float(np.abs(got - ref).max())
+    _record("rewards_b8192_vs_port", rewards=err, pieces=eng.piece_layout["r"][0], warm=eng.piece_layout["r"][2])
+    assert got.shape == (B, 1) and err <= TOL, err
+
+
+# ---- the warm-up survives training
+
+def test_pieces_survive_200_adam_steps():
+    """200 optimizer steps at B = 1024 on the default engine (the weights move, so does the forgetting length of the two
+    chains): the warm-up adapts (it may grow and shrink), no step falls back to the serial kernels, re-runs stay rare,
+    and the last step agrees with the serial kernels run on the same weights."""
+    from icrl_b200.engine import A2CEngine
+    from icrl_b200.optim import FlatAdam
+    seed, B, L = 307, 1024, 20
+    A, R, w = make_nets(seed)
+    eng = A2CEngine(A, R)
+    opt = FlatAdam(eng, lr=1e-4)
+    f, c = synth.make_inputs(seed, B, L)
+    for i in range(200):
+        res = eng.step(f, c, uniforms=synth.make_uniforms(seed + i, L - 1, B))
+        assert np.isfinite(res.loss)
+        opt.step()
+    st = eng.segment_stats
+    _record("pieces_200_steps", reruns=st["reruns"], fallbacks=st["fallbacks"], warm_v=eng.warm["v"], warm_r=eng.warm["r"],
+            changes=len(st["warm_history"]))
+    assert st["fallbacks"] == 0 and st["reruns"] <= 4, st
+    assert st["segmented_steps"] >= 200
+    u = synth.make_uniforms(seed + 999, L - 1, B)
+    rk = eng.step(f, c, uniforms=u)
+    gk = eng.flat_grad.clone()
+    e1 = A2CEngine(A, R, chain_segments=1)
+    r1 = e1.step(f, c, uniforms=u)
+    eng._attach_grads()
+    assert torch.equal(rk["tokens"], r1["tokens"])
+    assert float((rk["values"] - r1["values"]).abs().max()) <= TOL
+    assert float((rk["rewards"] - r1["rewards"]).abs().max()) <= TOL
+    assert float((gk - e1.flat_grad).abs().max() / e1.flat_grad.abs().max()) <= GTOL
+
+
+def test_slow_forgetting_weights_degrade_gracefully():
+    """Weights whose gates forget slowly (forget-gate bias of the value LSTM +4: c decays by ~0.98 per position; update
+    gate of the reward GRU pushed towards 'keep'): the joint check notices, the warm-up grows (or the step ends on the
+    serial kernels) and the numbers still match the serial chain -- slower, never wrong."""
+    from icrl_b200.engine import A2CEngine
+    seed, B, L = 311, 512, 12
+    A, R, w = make_nets(seed)
+    with torch.no_grad():
+        A.value_network.valrnn.lstm.bias_hh_l0[512:1024] += 4.0
+        R.rewrnn.gru.bias_hh_l0[512:1024] += 2.0
+    f, c = synth.make_inputs(seed, B, L)
+    u = synth.make_uniforms(seed, L - 1, B)
+    e1 = A2CEngine(A, R, chain_segments=1)
+    r1 = e1.step(f, c, uniforms=u)
+    v1, w1, g1 = r1["values"].clone(), r1["rewards"].clone(), e1.flat_grad.clone()
+    ek = A2CEngine(A, R, chain_warmup=64)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        rk = ek.step(f, c, uniforms=u)
+        first = dict(ek.segment_stats)
+        rk2 = ek.step(f, c, uniforms=u)               # the second step starts from the warm-up the first one learned
+    st = ek.segment_stats
+    _record("slow_forgetting", reruns=st["reruns"], fallbacks=st["fallbacks"], warm_v=ek.warm["v"], warm_r=ek.warm["r"])
+    assert first["reruns"] + first["fallbacks"] >= 1, "a 64-position warm-up cannot be enough for these weights"
+    assert max(ek.warm.values()) > 64
+    for r in (rk, rk2):
+        assert float((r["values"] - v1).abs().max()) <= TOL and float((r["rewards"] - w1).abs().max()) <= TOL
+    assert float((ek.flat_grad - g1).abs().max() / g1.abs().max()) <= GTOL
+
+
+# ---- legacy CUDA-core segment kernels (chain_engine="simt")
+
+@pytest.mark.parametrize("segments,B,L,level", [(8, 64, 10, None), (16, 96, 14, 5), (32, 256, 20, 7)])
+def test_chain_segments_simt_equal_the_serial_chain(segments, B, L, level):
+    seed = 131 + segments
+    e1, ek, A = _seg_engines(seed, segments, 160)
+    f, c = synth.make_inputs(seed, B, L)
+    S = (L - 1) if level is None else level
+    u = synth.make_uniforms(seed, S, B)
+    r1 = e1.step(f, c, uniforms=u, level=level)
+    v1, w1, g1 = r1["values"].clone(), r1["rewards"].clone(), e1.flat_grad.clone()
+    rk = ek.step(f, c, uniforms=u, level=level)
     assert ek.segment_layout is not None and ek.segment_layout[0] == segments, ek.segment_layout
     assert ek.segment_stats["fallbacks"] == 0, ek.segment_stats
     assert torch.equal(rk["tokens"], r1["tokens"])
     ev, er = float((rk["values"] - v1).abs().max()), float((rk["rewards"] - w1).abs().max())
     eg = float((ek.flat_grad - g1).abs().max() / g1.abs().max())
-    _record("chain_segments_%d" % segments, values=ev, rewards=er, grad_rel=eg, warm_h=ek.segment_stats["max_err"][0],
-            warm_dg_rel=ek.segment_stats["max_err"][3] / max(ek.segment_stats["max_err"][4], 1e-30))
     assert ev <= TOL and er <= TOL and eg <= GTOL, (ev, er, eg)
-    assert abs(rk.loss - r1.loss) <= TOL
 
 
-def test_chain_segments_fall_back_to_the_serial_kernels():
-    """A warm-up too short to forget the initial state (4 positions) must be caught by the check: the step is re-run on
-    the serial kernels (bit-identical to a serial engine), the warm-up is lengthened, and a warning is raised."""
+def test_chain_segments_simt_fall_back_to_the_serial_kernels():
     seed, B, L = 141, 64, 10
     e1, ek, A = _seg_engines(seed, 8, 4)
     f, c = synth.make_inputs(seed, B, L)
@@ -757,42 +947,3 @@ def test_chain_segments_fall_back_to_the_serial_kernels():
     assert ek.segment_stats["fallbacks"] == 1 and ek.chain_warmup == 16
     assert torch.equal(rk["values"], v1) and torch.equal(rk["rewards"], w1)
     assert float((ek.flat_grad - g1).abs().max() / g1.abs().max()) <= 1e-6      # atomics in the table scatter reorder sums
-    # unverified steps (check=False) are reported by segments_verified()
-    ek.chain_warmup = 4
-    ek.step(f, c, uniforms=u, check=False)
-    with pytest.warns(UserWarning):
-        assert ek.segments_verified() is False
-    assert ek.segments_verified() is True
-
-
-def test_get_rewards_segments_equal_the_serial_chain():
-    from icrl_b200.engine import A2CEngine
-    seed, B, L = 151, 512, 12
-    A, R, w = make_nets(seed)
-    f, c = synth.make_inputs(seed, B, L)
-    r1 = A2CEngine(A, R, chain_segments=1).get_rewards(f, c)
-    ek = A2CEngine(A, R, chain_warmup=160)
-    rk = ek.get_rewards(f, c)
-    assert ek.segment_layout is not None and ek.segment_layout[0] == 16 and ek.segment_stats["fallbacks"] == 0
-    assert float((rk - r1).abs().max()) <= TOL
-
-
-def test_config4_segments_full_size():
-    """BASELINE config 4 at full single-GPU size with the default engine (32 pieces, 256-position warm-up): the check
-    passes, and values / rewards / gradients agree with the serial chain at the tolerances of the golden tests."""
-    from icrl_b200.engine import A2CEngine
-    seed, B, L = 97, 4096, 20
-    A, R, w = make_nets(seed)
-    f, c = synth.make_inputs(seed, B, L)
-    u = synth.make_uniforms(seed, L - 1, B)
-    ek = A2CEngine(A, R)
-    rk = ek.step(f, c, uniforms=u)
-    assert ek.segment_stats["segmented_steps"] == 1 and ek.segment_stats["fallbacks"] == 0, ek.segment_stats
-    vk, wk, gk = rk["values"].clone(), rk["rewards"].clone(), ek.flat_grad.clone()
-    e1 = A2CEngine(A, R, chain_segments=1)
-    r1 = e1.step(f, c, uniforms=u)
-    assert torch.equal(rk["tokens"], r1["tokens"])
-    ev, er = float((vk - r1["values"]).abs().max()), float((wk - r1["rewards"]).abs().max())
-    eg = float((gk - e1.flat_grad).abs().max() / e1.flat_grad.abs().max())
-    _record("config4_segments", values=ev, rewards=er, grad_rel=eg, **{"err%d" % i: e for i, e in enumerate(ek.segment_stats["max_err"])})
-    assert ev <= TOL and er <= TOL and eg <= GTOL, (ev, er, eg)
