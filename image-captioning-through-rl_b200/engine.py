@@ -195,14 +195,16 @@ class A2CEngine:
     def _bind_flat_grads(self):
         """One flat fp32 bucket in a2c.parameters() order; every .grad is a view into it."""
         ps = [p for p in self._params() if p.requires_grad]
-        n = sum(p.numel() for p in ps)
-        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=self.device)
-        self._grad_views = []
-        off = 0
+        # every tensor starts on a 256-byte boundary of the bucket (the kernels read parameters and write gradients with
+        # 16-byte accesses; optim.FlatAdam lays the parameters out the same way): the padding floats stay zero
+        self._flat_offsets, off = [], 0
         for p in ps:
-            v = self.flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
-            self._grad_views.append((p, v))
+            self._flat_offsets.append(off)
+            off += -(-p.numel() // 64) * 64
+        self.flat_grad = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self._grad_views = []
+        for p, o in zip(ps, self._flat_offsets):
+            self._grad_views.append((p, self.flat_grad[o:o + p.numel()].view_as(p)))
         self._attach_grads()
 
     def _attach_grads(self):

@@ -18,13 +18,11 @@ class FlatAdam:
         ps = [p for p, _ in engine._grad_views]
         n = engine.flat_grad.numel()
         dev = engine.device
-        self.flat_param = torch.empty(n, dtype=torch.float32, device=dev)
-        off = 0
-        for p in ps:
+        self.flat_param = torch.zeros(n, dtype=torch.float32, device=dev)
+        for p, off in zip(ps, engine._flat_offsets):          # the bucket's layout: every tensor on a 256-byte boundary
             view = self.flat_param[off:off + p.numel()].view_as(p)
             view.copy_(p.data)
             p.data = view
-            off += p.numel()
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
 

@@ -670,6 +670,14 @@ def test_flat_adam_matches_torch():
             assert d <= 2e-7, (it, k, d)
             p2.data.copy_(p1.data)                  # keep both sides on the same trajectory
     assert A2.policy_network.linear2vocab.weight.data_ptr() >= o2.flat_param.data_ptr()      # parameters live in the flat buffer
+    # the kernels must run on parameters that live inside the flat buffer (16-byte accesses: every tensor, including
+    # the ones behind the 1-element linear2.bias, starts on a 256-byte boundary of the bucket)
+    assert all(p.data_ptr() % 256 == 0 for p in A2.parameters())
+    f, c = synth.make_inputs(seed + 7, B, L)
+    u = synth.make_uniforms(seed + 7, L - 1, B)
+    r1, r2 = e1.step(f, c, uniforms=u), e2.step(f, c, uniforms=u)
+    assert torch.equal(r1["tokens"], r2["tokens"]) and abs(r1.loss - r2.loss) <= TOL
+    assert float((e1.flat_grad - e2.flat_grad).abs().max() / e1.flat_grad.abs().max()) <= 1e-6
 
 
 def test_config4_full_size_properties():
