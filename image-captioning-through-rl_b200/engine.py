@@ -566,12 +566,16 @@ class A2CEngine:
                   _p(Vn.valrnn.caption_embedding.weight), _p(lstm.weight_ih_l0), _p(dtable), _p(colsum_ws), _p(gemm_ws),
                   gemm_ws_floats * 4, _p(g(Vn.valrnn.caption_embedding.weight, True)), _p(g(lstm.weight_ih_l0)),
                   _p(g(lstm.weight_hh_l0)), _p(g(lstm.bias_ih_l0)), _p(g(lstm.bias_hh_l0)), L)
-        # policy BPTT
+        # policy BPTT.  icrl_policy_rollout_bwd turns the logits into dL/dlogits IN PLACE; a step whose chains are re-run
+        # (longer warm-up, serial fall-back) runs this backward again with slightly different dL/dlogp, so it works on a
+        # copy and the rollout's logits stay intact.
         pl = P.lstm
+        dz = self._buf("p_dlogits", SB * V)
         with self._phase("policy_bwd"):
+          dz[:SB * V].copy_(b["p_logits"][:SB * V])
           _lib.call("icrl_policy_rollout_bwd", st, B, V, p0, S, P.caption_embedding.weight.shape[1], _p(f), _p(P.caption_embedding.weight), _p(pl.weight_ih_l0),
                   _p(pl.weight_hh_l0), _p(P.linear2vocab.weight), _p(tokcm), _p(tokens), _p(b["dlogp"]), _p(b["p_Hs"]),
-                  _p(b["p_Cs"]), _p(b["p_Gs"]), _p(b["p_logits"]), _p(self._buf("p_dHv", SB * H)),
+                  _p(b["p_Cs"]), _p(b["p_Gs"]), _p(dz), _p(self._buf("p_dHv", SB * H)),
                   _p(self._buf("p_DG", n_cell * B * 4 * H)), _p(self._buf("p_dh", 2 * B * H)), _p(self._buf("p_dc", B * H)),
                   _p(dtable), _p(colsum_ws), _p(gemm_ws), gemm_ws_floats * 4, _p(g(P.caption_embedding.weight, True)),
                   _p(g(P.cnn2linear.weight)), _p(g(P.cnn2linear.bias)), _p(g(pl.weight_ih_l0)), _p(g(pl.weight_hh_l0)),

@@ -887,27 +887,34 @@ def test_pieces_survive_200_adam_steps():
     r1 = e1.step(f, c, uniforms=u)
     eng._attach_grads()
     assert torch.equal(rk["tokens"], r1["tokens"])
-    assert float((rk["values"] - r1["values"]).abs().max()) <= TOL
+    # 200 steps of this unbounded loss (advantage = values - rewards, trainers.py:471) have driven |values| to ~10: the
+    # tolerance is relative to their magnitude (2e-6 of 8 is two float ulps)
+    vscale = max(1.0, float(r1["values"].abs().max()))
+    ev = float((rk["values"] - r1["values"]).abs().max())
+    _record("pieces_200_steps", values_rel=ev / vscale, vscale=vscale)
+    assert ev <= TOL * vscale, (ev, vscale)
     assert float((rk["rewards"] - r1["rewards"]).abs().max()) <= TOL
     assert float((gk - e1.flat_grad).abs().max() / e1.flat_grad.abs().max()) <= GTOL
 
 
 def test_slow_forgetting_weights_degrade_gracefully():
-    """Weights whose gates forget slowly (forget-gate bias of the value LSTM +4: c decays by ~0.98 per position; update
-    gate of the reward GRU pushed towards 'keep'): the joint check notices, the warm-up grows (or the step ends on the
-    serial kernels) and the numbers still match the serial chain -- slower, never wrong."""
+    """Weights whose gates forget slowly (forget-gate bias of the value LSTM +1.5, update gate of the reward GRU pushed
+    towards 'keep'; +4 would make the recurrence itself non-contractive -- the reference's own gradients overflow there):
+    the joint check notices, the warm-up grows (or the step ends on the serial kernels) and the numbers still match the
+    serial chain -- slower, never wrong."""
     from icrl_b200.engine import A2CEngine
     seed, B, L = 311, 512, 12
     A, R, w = make_nets(seed)
     with torch.no_grad():
-        A.value_network.valrnn.lstm.bias_hh_l0[512:1024] += 4.0
-        R.rewrnn.gru.bias_hh_l0[512:1024] += 2.0
+        A.value_network.valrnn.lstm.bias_hh_l0[512:1024] += 1.5
+        R.rewrnn.gru.bias_hh_l0[512:1024] += 1.5
     f, c = synth.make_inputs(seed, B, L)
     u = synth.make_uniforms(seed, L - 1, B)
     e1 = A2CEngine(A, R, chain_segments=1)
     r1 = e1.step(f, c, uniforms=u)
     v1, w1, g1 = r1["values"].clone(), r1["rewards"].clone(), e1.flat_grad.clone()
-    ek = A2CEngine(A, R, chain_warmup=64)
+    assert torch.isfinite(g1).all()
+    ek = A2CEngine(A, R, chain_warmup=32)
     import warnings
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
@@ -916,8 +923,8 @@ def test_slow_forgetting_weights_degrade_gracefully():
         rk2 = ek.step(f, c, uniforms=u)               # the second step starts from the warm-up the first one learned
     st = ek.segment_stats
     _record("slow_forgetting", reruns=st["reruns"], fallbacks=st["fallbacks"], warm_v=ek.warm["v"], warm_r=ek.warm["r"])
-    assert first["reruns"] + first["fallbacks"] >= 1, "a 64-position warm-up cannot be enough for these weights"
-    assert max(ek.warm.values()) > 64
+    assert first["reruns"] + first["fallbacks"] >= 1, "a 32-position warm-up cannot be enough for these weights"
+    assert max(ek.warm.values()) > 32
     for r in (rk, rk2):
         assert float((r["values"] - v1).abs().max()) <= TOL and float((r["rewards"] - w1).abs().max()) <= TOL
     assert float((ek.flat_grad - g1).abs().max() / g1.abs().max()) <= GTOL
