@@ -36,6 +36,8 @@ SIGNATURES = {
     "icrl_pack_value_head": [P, P, P, P, P, P, P, LP],
     "icrl_policy_rollout_fwd": [P, I, I, I, I, I] + [P] * 17 + [LP],
     "icrl_policy_rollout_bwd": [P, I, I, I, I, I] + [P] * 19 + [Z] + [P] * 9 + [LP],
+    "icrl_policy_rollout_bwd_tc": [P, I, I, I, I, I] + [P] * 19 + [Z] + [P] * 9 + [P, P, P, LP],
+    "icrl_policy_bptt_tc_ws_bytes": [I, I],
     "icrl_colsum_ws_floats": [L, I],
     "icrl_lstm_seq_fwd": [P, I, I] + [P] * 8 + [LP],
     "icrl_lstm_seq_bwd": [P, I, I, I, I] + [P] * 14 + [Z] + [P] * 6 + [LP],
@@ -56,6 +58,7 @@ SIGNATURES = {
     "icrl_chain_tc_fwd": [P, I, I, L, I] + [P] * 10 + [LP],
     "icrl_chain_tc_lstm_bwd": [P, I, L, I, P, P, P, P, P, L, P, P, P, P, LP],
     "icrl_chain_tc_set_profile": [P],
+    "icrl_chain_tc_set_bias": [F, F],
     "icrl_chain_set_profile": [P],
     "icrl_chain_sync_bytes": [],
     "icrl_chain_lstm_fwd": [P, P, I] + [P] * 10 + [LP],
@@ -76,7 +79,8 @@ SIGNATURES = {
 }
 _RESTYPES = {"icrl_last_error": c_char_p, "icrl_wgrad_tc_ws_bytes": c_size_t, "icrl_decode_weight_halves": c_size_t, "icrl_colsum_ws_floats": c_size_t, "icrl_stream_len": c_longlong,
              "icrl_chain_sync_bytes": c_size_t, "icrl_chain_segment_len": c_longlong, "icrl_chain_segment_ws_floats": c_size_t,
-             "icrl_chain_tc_weight_halves": c_size_t, "icrl_chain_tc_ws_bytes": c_size_t, "icrl_chain_tc_cp_floats": c_size_t}
+             "icrl_chain_tc_weight_halves": c_size_t, "icrl_chain_tc_ws_bytes": c_size_t, "icrl_chain_tc_cp_floats": c_size_t,
+             "icrl_policy_bptt_tc_ws_bytes": c_size_t}
 _NO_STATUS = set(_RESTYPES) | {"icrl_version", "icrl_chain_tc_max_pieces"}
 
 

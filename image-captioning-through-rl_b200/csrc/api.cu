@@ -229,13 +229,16 @@ int icrl_lstm_seq_bwd(void* stream, int B, int n, int V, int D, const int* tokcm
 
 size_t icrl_colsum_ws_floats(long long rows, int cols) { return (size_t)icrl_wcolsum_chunks(rows) * cols; }
 
-int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, int D, const float* features, const float* E,
+}  // extern "C"
+
+// tc_packed != NULL: the serial part (step 4) runs as ONE launch of the tcgen05 chain-backward kernel (chain_tc.cu).
+static int policy_rollout_bwd_common(void* stream, int B, int V, int p0, int S, int D, const float* features, const float* E,
                             const float* W_ih, const float* W_hh, const float* W_v, const int* tokcm,
                             const long long* tokens_out, const float* dlogp, const float* Hs, const float* Cs,
                             const float* Gs, float* logits, float* dHv, float* DG, float* dh, float* dc,
                             float* dtable, float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE,
                             float* dW_cnn, float* db_cnn, float* dW_ih, float* dW_hh, float* db_ih, float* db_hh,
-                            float* dW_v, float* db_v, int* launches) {
+                            float* dW_v, float* db_v, const void* tc_packed, void* tc_ws, float* tc_err, int* launches) {
   cudaStream_t st = S_(stream);
   const int n_cell = p0 - 1 + S;
   const size_t BH = (size_t)B * H;
@@ -256,16 +259,21 @@ int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, int D, co
   // 4. BPTT
   float* dh_cur = dh;
   float* dh_nxt = dh + BH;
-  ICRL_CUDA(cudaMemsetAsync(dh_cur, 0, BH * sizeof(float), st));
-  ICRL_CUDA(cudaMemsetAsync(dc, 0, BH * sizeof(float), st));
-  for (int j = n_cell - 1; j >= 0; --j) {
-    const int s = j - (p0 - 1);
-    float* dg = DG + (size_t)j * B * 4 * H;
-    TRY(icrl_lstm_pointwise_bwd(st, B, dh_cur, s >= 0 ? dHv + (size_t)s * BH : nullptr, dc,
-                                Gs + (size_t)j * B * 4 * H, Cs + j * BH, Cs + (j + 1) * BH, dg));
-    bump(launches, 1);
-    TRY(icrl_gemm_f32_impl(st, 0, 0, B, H, 4 * H, dg, 4 * H, W_hh, H, dh_nxt, H, nullptr, 0.f, gemm_ws, gemm_ws_bytes, launches));
-    float* t = dh_cur; dh_cur = dh_nxt; dh_nxt = t;
+  if (tc_packed) {
+    TRY(icrl_policy_bptt_tc_impl(st, B, n_cell, p0, tc_packed, Gs, Cs, dHv, DG, dh_cur, tc_ws, tc_err));
+    bump(launches, 3);                     // |dHv| maximum, the injection map, the persistent cluster kernel
+  } else {
+    ICRL_CUDA(cudaMemsetAsync(dh_cur, 0, BH * sizeof(float), st));
+    ICRL_CUDA(cudaMemsetAsync(dc, 0, BH * sizeof(float), st));
+    for (int j = n_cell - 1; j >= 0; --j) {
+      const int s = j - (p0 - 1);
+      float* dg = DG + (size_t)j * B * 4 * H;
+      TRY(icrl_lstm_pointwise_bwd(st, B, dh_cur, s >= 0 ? dHv + (size_t)s * BH : nullptr, dc,
+                                  Gs + (size_t)j * B * 4 * H, Cs + j * BH, Cs + (j + 1) * BH, dg));
+      bump(launches, 1);
+      TRY(icrl_gemm_f32_impl(st, 0, 0, B, H, 4 * H, dg, 4 * H, W_hh, H, dh_nxt, H, nullptr, 0.f, gemm_ws, gemm_ws_bytes, launches));
+      float* t = dh_cur; dh_cur = dh_nxt; dh_nxt = t;
+    }
   }
   // dh_cur = dL/dh0
   // 5. recurrent weight gradient: DG^T [2048 x nB] * H_prev [nB x 512]
@@ -292,6 +300,36 @@ int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, int D, co
   TRY(icrl_wcolsum(st, B, H, dh_cur, nullptr, 0, colsum_ws, db_cnn));
   bump(launches, 2);
   return ICRL_OK;
+}
+
+extern "C" {
+
+int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, int D, const float* features, const float* E,
+                            const float* W_ih, const float* W_hh, const float* W_v, const int* tokcm,
+                            const long long* tokens_out, const float* dlogp, const float* Hs, const float* Cs,
+                            const float* Gs, float* logits, float* dHv, float* DG, float* dh, float* dc,
+                            float* dtable, float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE,
+                            float* dW_cnn, float* db_cnn, float* dW_ih, float* dW_hh, float* db_ih, float* db_hh,
+                            float* dW_v, float* db_v, int* launches) {
+  return policy_rollout_bwd_common(stream, B, V, p0, S, D, features, E, W_ih, W_hh, W_v, tokcm, tokens_out, dlogp, Hs, Cs, Gs,
+                                   logits, dHv, DG, dh, dc, dtable, colsum_ws, gemm_ws, gemm_ws_bytes, dE, dW_cnn, db_cnn, dW_ih,
+                                   dW_hh, db_ih, db_hh, dW_v, db_v, nullptr, nullptr, nullptr, launches);
+}
+
+size_t icrl_policy_bptt_tc_ws_bytes(int B, int n_cell) { return icrl_policy_bptt_tc_ws_bytes_impl(B, n_cell); }
+
+int icrl_policy_rollout_bwd_tc(void* stream, int B, int V, int p0, int S, int D, const float* features, const float* E,
+                               const float* W_ih, const float* W_hh, const float* W_v, const int* tokcm,
+                               const long long* tokens_out, const float* dlogp, const float* Hs, const float* Cs,
+                               const float* Gs, float* logits, float* dHv, float* DG, float* dh, float* dc,
+                               float* dtable, float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE,
+                               float* dW_cnn, float* db_cnn, float* dW_ih, float* dW_hh, float* db_ih, float* db_hh,
+                               float* dW_v, float* db_v, const void* tc_packed, void* tc_ws, float* tc_err,
+                               int* launches) {
+  ICRL_REQUIRE(tc_packed && tc_ws && tc_err, "the tcgen05 BPTT needs the packed W_hh, its workspace and the error words");
+  return policy_rollout_bwd_common(stream, B, V, p0, S, D, features, E, W_ih, W_hh, W_v, tokcm, tokens_out, dlogp, Hs, Cs, Gs,
+                                   logits, dHv, DG, dh, dc, dtable, colsum_ws, gemm_ws, gemm_ws_bytes, dE, dW_cnn, db_cnn, dW_ih,
+                                   dW_hh, db_ih, db_hh, dW_v, db_v, tc_packed, tc_ws, tc_err, launches);
 }
 
 long long icrl_stream_len(int B, int p0, int S, int extra) {
@@ -372,6 +410,7 @@ int icrl_chain_tc_max_pieces(void) { return icrl_chain_tc_max_pieces_impl(); }
 size_t icrl_chain_tc_weight_halves(int kind) { return icrl_chain_tc_weight_halves_impl(kind); }
 size_t icrl_chain_tc_ws_bytes(int pieces) { return icrl_chain_tc_ws_bytes_impl(pieces); }
 size_t icrl_chain_tc_cp_floats(int pieces) { return icrl_chain_tc_cp_floats_impl(pieces); }
+int icrl_chain_tc_set_bias(float fwd, float bwd) { icrl_chain_tc_set_bias_impl(fwd, bwd); return ICRL_OK; }
 int icrl_chain_tc_set_profile(void* buf) { icrl_chain_tc_set_profile_impl(reinterpret_cast<long long*>(buf)); return ICRL_OK; }
 
 int icrl_pack_chain_tc_weights(void* stream, int kind, const float* W_hh, void* packed, int* launches) {

@@ -74,6 +74,7 @@ struct FwdArgs {
   float* state;            // [Ppad][512] carried c (LSTM) / h (GRU), zeroed by the launcher
   __half* hparts;          // [2 buffers][2 parts][Ppad][512]; buffer 0 zeroed by the launcher
   float* wstate;           // [2 checkpoints][P][2][512]: (h, c) of piece k after step cp_half (0) / warm-1 (1)
+  float main_gain;         // 1 + compensation of the tensor core's truncating accumulation (see g_tc_bias)
   long long* prof;         // optional: cycle sums of CTA 0's first epilogue warp {acc wait, gather, cell, store, barrier}, steps
 };
 
@@ -183,6 +184,7 @@ chain_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
     const int ucol0 = (int)rank * UN + 32 * ch;
     const long long seg = p.seg;
     int tok = valid ? p.stream[(long long)k_own * seg] : 0;
+    const float mg = p.main_gain;
     const bool prof = p.prof != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0;
     long long pr[5] = {0, 0, 0, 0, 0};
 
@@ -234,10 +236,10 @@ chain_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
           float gi[8], gf[8], gg[8], go[8], cn[8], hn[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            gi[i] = sigmoidf_sfu(fmaf(cor[0][i], LO_INV, acc[0][i]) + tin[0][i]);
-            gf[i] = sigmoidf_sfu(fmaf(cor[1][i], LO_INV, acc[1][i]) + tin[1][i]);
-            gg[i] = tanhf_sfu(fmaf(cor[2][i], LO_INV, acc[2][i]) + tin[2][i]);
-            go[i] = sigmoidf_sfu(fmaf(cor[3 % NG][i], LO_INV, acc[3 % NG][i]) + tin[3 % NG][i]);
+            gi[i] = sigmoidf_sfu(fmaf(cor[0][i], LO_INV, acc[0][i] * mg) + tin[0][i]);
+            gf[i] = sigmoidf_sfu(fmaf(cor[1][i], LO_INV, acc[1][i] * mg) + tin[1][i]);
+            gg[i] = tanhf_sfu(fmaf(cor[2][i], LO_INV, acc[2][i] * mg) + tin[2][i]);
+            go[i] = sigmoidf_sfu(fmaf(cor[3 % NG][i], LO_INV, acc[3 % NG][i] * mg) + tin[3 % NG][i]);
             cn[i] = gf[i] * tin[NG][i] + gi[i] * gg[i];
             hn[i] = go[i] * tanhf_sfu(cn[i]);
           }
@@ -261,9 +263,9 @@ chain_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
           float hn[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float r = sigmoidf_sfu(fmaf(cor[0][i], LO_INV, acc[0][i]) + tin[0][i]);
-            const float z = sigmoidf_sfu(fmaf(cor[1][i], LO_INV, acc[1][i]) + tin[1][i]);
-            const float n = tanhf_sfu(tin[2][i] + r * (fmaf(cor[2][i], LO_INV, acc[2][i]) + bh[i]));
+            const float r = sigmoidf_sfu(fmaf(cor[0][i], LO_INV, acc[0][i] * mg) + tin[0][i]);
+            const float z = sigmoidf_sfu(fmaf(cor[1][i], LO_INV, acc[1][i] * mg) + tin[1][i]);
+            const float n = tanhf_sfu(tin[2][i] + r * (fmaf(cor[2][i], LO_INV, acc[2][i] * mg) + bh[i]));
             hn[i] = (1.f - z) * n + z * tin[NG][i];
           }
           *reinterpret_cast<float4*>(e0 + NG * 4096) = make_float4(hn[0], hn[1], hn[2], hn[3]);
@@ -351,16 +353,21 @@ static_assert(EPI_WARPS * B_GST_WARP <= B_STAGES * B_STAGE, "epilogue staging li
 
 struct BwdArgs {
   int P, Ppad, steps, warm, cp_half;
-  long long seg;
-  const float* stash_g;    // [P*seg + warm][2048] activated i,f,g,o
-  const float* stash_c;    // [P*seg + warm + 1][512]
-  const int* take;         // [P*seg + warm] row of dh_take injected at the position, or -1
+  // Row of the per-position arrays that piece (= MMA row) k works on at local time t: k * stride_k + t * stride_t.
+  // Chain pieces: (seg, 1).  The policy's BPTT runs on the same kernel with the batch rows as "pieces", the cell steps
+  // as time and the rollout's [step][row] arrays: (1, B), warm = 0, no checkpoints, and dL/dh0 written at the end.
+  long long stride_k, stride_t;
+  const float* stash_g;    // [rows][2048] activated i,f,g,o
+  const float* stash_c;    // [rows + stride_t][512]: c after the cell of row r lives at row r + stride_t
+  const int* take;         // [rows] row of dh_take injected at the position, or -1
   const float* dh_take;    // [take_rows][512]
   float* dgates;           // [P*seg + warm][2048] pre-activation gate gradients of the live positions
   __half* dgx;             // [2 buffers][2 parts][Ppad][2048] scaled fp16 split of the gate gradients (exchange)
   const float* dh_max;     // device word: max |dh_take| (scale of the recurrence)
-  float* bstate;           // [2 checkpoints][2 sides][P][2][512] (dh, dc) at the joints
+  float* bstate;           // [2 checkpoints][2 sides][P][2][512] (dh, dc) at the joints (null: no checkpoints)
+  float* dh0_out;          // [P][512] dL/dh entering local time 0 (one more contraction after the last step), or null
   float* overflow;         // device word: set to 1 when a scaled gate gradient left the fp16 range
+  float main_gain;
   long long* prof;
 };
 
@@ -389,6 +396,7 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
   const unsigned rank = cluster_rank();
   const int m0 = (blockIdx.x / CL) * BM;
   const int P = p.P, Ppad = p.Ppad, steps = p.steps;
+  const int iters = steps + (p.dh0_out ? 1 : 0);       // one more contraction when dL/dh0 is wanted
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
@@ -411,12 +419,12 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
 
   if (warp == 2 || warp == 3) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    for (int it = 0; it < steps; ++it) { cluster_arrive(); cluster_wait(); }
+    for (int it = 0; it < iters; ++it) { cluster_arrive(); cluster_wait(); }
   } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (no GEMM before the first step)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     unsigned n = 0;
-    for (int it = 0; it < steps; ++it) {
+    for (int it = 0; it < iters; ++it) {
       if (it > 0 && lane == 0) {
         const int arow = ((it & 1) * 2) * Ppad + m0;
         for (int kb = 0; kb < B_KB; ++kb, ++n) {
@@ -440,7 +448,7 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
     // ------------------------------------------------------------------ MMA issuer
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     unsigned n = 0;
-    for (int it = 0; it < steps; ++it) {
+    for (int it = 0; it < iters; ++it) {
       if (it > 0) {
         mbar_wait(bar_acc_empty, (unsigned)(it - 1) & 1u);
         tc_fence_after();
@@ -478,8 +486,9 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
     const bool valid = k_own < P;
     const unsigned tq = tmem_base + ((unsigned)(32 * q) << 16);
     unsigned char* gst = smem + ew * B_GST_WARP;
-    const long long seg = p.seg;
+    const long long sk = p.stride_k, stt = p.stride_t;
     const float S = bwd_scale(*p.dh_max), invS = 1.f / S;
+    const float mg = p.main_gain;
     float dc[2][2][8];                         // carried dL/dc of this thread's piece: [unit pass][8-unit group][unit]
 #pragma unroll
     for (int a = 0; a < 2; ++a)
@@ -488,18 +497,52 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
 #pragma unroll
         for (int i = 0; i < 8; ++i) dc[a][b][i] = 0.f;
     float ovf = 0.f;
-    int tk = valid ? p.take[(long long)k_own * seg + steps - 1] : -1;
+    int tk = valid ? p.take[(long long)k_own * sk + (long long)(steps - 1) * stt] : -1;
     const bool prof = p.prof != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0;
     long long pr[5] = {0, 0, 0, 0, 0};
     const int half_ref_it = steps - 1 - (p.warm - 1 - p.cp_half);      // reference side of the half-way checkpoint
 
-    for (int it = 0; it < steps; ++it) {
+    for (int it = 0; it < iters; ++it) {
       const long long t0 = prof ? clock64() : 0;
       const int t = steps - 1 - it;
-      const int tk_n = (valid && t > 0) ? p.take[(long long)k_own * seg + t - 1] : -1;
+      const int tk_n = (valid && t > 0) ? p.take[(long long)k_own * sk + (long long)(t - 1) * stt] : -1;
       if (it > 0) {
         mbar_wait(bar_acc_full, (unsigned)(it - 1) & 1u);
         tc_fence_after();
+      }
+      if (it == steps) {
+        // the extra iteration: dL/dh entering local time 0 = the contraction of the last step's gate gradients
+#pragma unroll
+        for (int ps = 0; ps < 2; ++ps) {
+          const int ucolp = (int)rank * UN + 32 * ch + 16 * ps;
+#pragma unroll
+          for (int c8 = 0; c8 < 2; ++c8) {
+            float rec[8], cor[8];
+            tmem_ld8x2(tq + (unsigned)(32 * ch + 16 * ps + 8 * c8), tq + (unsigned)(B_CORR + 32 * ch + 16 * ps + 8 * c8), rec, cor);
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = fmaf(cor[i], LO_INV, rec[i] * mg) * invS;
+            *reinterpret_cast<float4*>(gst + lane * 64 + (((2 * c8) ^ ((lane >> 1) & 3)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(gst + lane * 64 + (((2 * c8 + 1) ^ ((lane >> 1) & 3)) << 4)) = make_float4(o[4], o[5], o[6], o[7]);
+          }
+          __syncwarp();
+          const int c4 = lane & 3;
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const int r = i4 * 8 + (lane >> 2);
+            const int kr = m0 + 32 * q + r;
+            if (kr < P)
+              *reinterpret_cast<float4*>(p.dh0_out + (size_t)kr * H + ucolp + c4 * 4) =
+                  *reinterpret_cast<const float4*>(gst + r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4));
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty);
+        cluster_arrive();
+        cluster_wait();
+        break;
       }
       const long long t1 = prof ? clock64() : 0;
       const bool w_full = it == p.warm - 1, w_half = it == p.cp_half;            // warm-up side records (pieces < P-1)
@@ -519,12 +562,12 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
             const int tkr = __shfl_sync(0xffffffffu, tk, r);
             const int kr = m0 + 32 * q + r;
             if (kr < P) {
-              const size_t pos = (size_t)kr * seg + t;
+              const size_t pos = (size_t)kr * sk + (size_t)t * stt;
               const unsigned dst = smem_u32(gst) + (unsigned)(r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4));
               const float* gsrc = p.stash_g + pos * (4 * H) + ucolp + c4 * 4;
 #pragma unroll
               for (int a = 0; a < 4; ++a) cp_async16(dst + a * 2048, gsrc + a * H);
-              cp_async16(dst + 4 * 2048, p.stash_c + (pos + 1) * H + ucolp + c4 * 4);
+              cp_async16(dst + 4 * 2048, p.stash_c + (pos + stt) * H + ucolp + c4 * 4);
               cp_async16(dst + 5 * 2048, p.stash_c + pos * H + ucolp + c4 * 4);
               if (tkr >= 0) cp_async16(dst + 6 * 2048, p.dh_take + (size_t)tkr * H + ucolp + c4 * 4);
               else *reinterpret_cast<float4*>(gst + 6 * 2048 + r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -558,7 +601,7 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float gi = tin[0][i], gf = tin[1][i], gg = tin[2][i], go = tin[3][i], cc = tin[4][i], cp = tin[5][i];
-            const float dh = fmaf(cor[i], LO_INV, rec[i]) * invS + tin[6][i];
+            const float dh = fmaf(cor[i], LO_INV, rec[i] * mg) * invS + tin[6][i];
             const float tcv = tanhf_sfu(cc);
             const float dct = dc[ps][c8][i] + dh * (go * (1.f - tcv * tcv));
             dhv[i] = dh;
@@ -593,7 +636,7 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
             const int r = i4 * 8 + (lane >> 2);
             const int kr = m0 + 32 * q + r;
             if (kr < P) {
-              const size_t pos = (size_t)kr * seg + t;
+              const size_t pos = (size_t)kr * sk + (size_t)t * stt;
               const unsigned char* e = gst + r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4);
               const bool live = kr == P - 1 || it >= p.warm;
               const int uc = ucolp + c4 * 4;
@@ -609,12 +652,12 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
               }
               const float4 dh4 = *reinterpret_cast<const float4*>(e + 4 * 2048);
               const float4 dc4 = *reinterpret_cast<const float4*>(e + 5 * 2048);
-              if (kr < P - 1 && (w_full || w_half)) {
+              if (p.bstate && kr < P - 1 && (w_full || w_half)) {
                 float* b = p.bstate + ((size_t)(((w_full ? 1 : 0) * 2 + 0) * P + kr) * 2) * H + uc;
                 *reinterpret_cast<float4*>(b) = dh4;
                 *reinterpret_cast<float4*>(b + H) = dc4;
               }
-              if (kr >= 1 && (r_full || r_half)) {
+              if (p.bstate && kr >= 1 && (r_full || r_half)) {
                 float* b = p.bstate + ((size_t)(((r_full ? 1 : 0) * 2 + 1) * P + kr) * 2) * H + uc;
                 *reinterpret_cast<float4*>(b) = dh4;
                 *reinterpret_cast<float4*>(b + H) = dc4;
@@ -801,6 +844,9 @@ int cp_half_of(int warm) { return warm >= 8 ? warm / 2 - 1 : -1; }
 
 }  // namespace
 
+// Debug knob (icrl_chain_tc_set_bias): relative compensation of the main accumulator, forward / backward.
+static float g_tc_bias[2] = {0.f, 0.f};
+void icrl_chain_tc_set_bias_impl(float fwd, float bwd) { g_tc_bias[0] = fwd; g_tc_bias[1] = bwd; }
 static long long* g_chain_tc_prof = nullptr;      // icrl_chain_tc_set_profile: 16 device int64 (forward [0..5], backward [8..13])
 void icrl_chain_tc_set_profile_impl(long long* buf) { g_chain_tc_prof = buf; }
 
@@ -860,7 +906,7 @@ int icrl_chain_tc_fwd_impl(cudaStream_t st, int kind, int P, long long seg, int 
   FwdArgs a;
   a.P = P; a.Ppad = Ppad; a.steps = (int)(seg + warm); a.warm = warm; a.cp_half = cp_half_of(warm); a.seg = seg;
   a.stream = stream; a.table = table; a.b_hn = b_hn; a.stash_h = stash_h; a.stash_c = stash_c; a.stash_g = stash_g;
-  a.state = state; a.hparts = hparts; a.wstate = cp_state; a.prof = g_chain_tc_prof;
+  a.state = state; a.hparts = hparts; a.wstate = cp_state; a.prof = g_chain_tc_prof; a.main_gain = 1.f + g_tc_bias[0];
   CUtensorMap mh, mw;
   int rc;
   if ((rc = make_map_2d(&mh, hparts, H, (long long)4 * Ppad, A_SLICE_ROWS))) return rc;
@@ -893,9 +939,11 @@ int icrl_chain_tc_lstm_bwd_impl(cudaStream_t st, int P, long long seg, int warm,
   absmax_kernel<<<148 * 2, 256, 0, st>>>(take_rows * H, dh_take, err + 4);
   ICRL_LAUNCH_CHECK();
   BwdArgs a;
-  a.P = P; a.Ppad = Ppad; a.steps = (int)(seg + warm); a.warm = warm; a.cp_half = cp_half_of(warm); a.seg = seg;
+  a.P = P; a.Ppad = Ppad; a.steps = (int)(seg + warm); a.warm = warm; a.cp_half = cp_half_of(warm);
+  a.stride_k = seg; a.stride_t = 1; a.dh0_out = nullptr;
   a.stash_g = stash_g; a.stash_c = stash_c; a.take = take; a.dh_take = dh_take; a.dgates = dgates; a.dgx = dgx;
   a.dh_max = err + 4; a.bstate = cp_state; a.overflow = err + 5; a.prof = g_chain_tc_prof ? g_chain_tc_prof + 8 : nullptr;
+  a.main_gain = 1.f + g_tc_bias[1];
   CUtensorMap mg, mw;
   int rc;
   if ((rc = make_map_2d(&mg, dgx, 4 * H, (long long)4 * Ppad, A_SLICE_ROWS))) return rc;
@@ -904,6 +952,55 @@ int icrl_chain_tc_lstm_bwd_impl(cudaStream_t st, int P, long long seg, int warm,
   chain_tc_bwd_kernel<<<dim3(CL * (Ppad / BM)), dim3(THREADS), B_SMEM, st>>>(mg, mw, a);
   ICRL_LAUNCH_CHECK();
   chain_tc_check_bwd_kernel<<<dim3(P - 1, 2), H, 0, st>>>(P, a.cp_half, cp_state, err);
+  ICRL_LAUNCH_CHECK();
+  return ICRL_OK;
+}
+
+// ---- the policy's BPTT on the same kernel (trainers.py:479 through PolicyNetwork's LSTM, models.py:80): rows of the batch in
+// the MMA M dimension, n_cell serial cell steps, the rollout's [step][row] stash, dL/dh injected at the sampled steps.
+namespace {
+__global__ void policy_take_kernel(int B, int n_cell, int p0, int* take) {
+  const long long n = (long long)B * n_cell;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / B), k = (int)(i % B);
+    take[i] = t >= p0 - 1 ? (t - (p0 - 1)) * B + k : -1;
+  }
+}
+}  // namespace
+
+size_t icrl_policy_bptt_tc_ws_bytes_impl(int B, int n_cell) {
+  return icrl_chain_tc_ws_bytes_impl(B) + (size_t)B * n_cell * sizeof(int) + 256;
+}
+
+// packed: icrl_pack_chain_tc_weights(kind 0) of the policy's W_hh.  Gs [n_cell][B][2048], Cs [(n_cell+1)][B][512],
+// dHv [S][B][512] (S = n_cell - p0 + 1), DG [n_cell][B][2048] out, dh0 [B][512] out, err: 8 floats (err[4] = max |dHv|,
+// err[5] = 1 on fp16 overflow of the exchange).
+int icrl_policy_bptt_tc_impl(cudaStream_t st, int B, int n_cell, int p0, const void* packed, const float* Gs,
+                             const float* Cs, const float* dHv, float* DG, float* dh0, void* ws, float* err) {
+  ICRL_REQUIRE(B >= 1 && n_cell >= 1 && p0 >= 1 && n_cell >= p0, "bad rollout shape");
+  ICRL_REQUIRE(packed && Gs && Cs && dHv && DG && dh0 && ws && err, "null argument");
+  const int Ppad = pad_pieces(B);
+  __half* dgx = reinterpret_cast<__half*>(ws);
+  int* take = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + ((icrl_chain_tc_ws_bytes_impl(B) + 255) / 256) * 256);
+  const __half* whhT = reinterpret_cast<const __half*>(packed) + (size_t)2 * 4 * H * H;
+  const int S = n_cell - p0 + 1;
+  ICRL_CUDA(cudaMemsetAsync(err + 4, 0, 2 * sizeof(float), st));
+  absmax_kernel<<<148 * 2, 256, 0, st>>>((long long)S * B * H, dHv, err + 4);
+  ICRL_LAUNCH_CHECK();
+  policy_take_kernel<<<148, 256, 0, st>>>(B, n_cell, p0, take);
+  ICRL_LAUNCH_CHECK();
+  BwdArgs a;
+  a.P = B; a.Ppad = Ppad; a.steps = n_cell; a.warm = 0; a.cp_half = -1;
+  a.stride_k = 1; a.stride_t = B; a.dh0_out = dh0;
+  a.stash_g = Gs; a.stash_c = Cs; a.take = take; a.dh_take = dHv; a.dgates = DG; a.dgx = dgx;
+  a.dh_max = err + 4; a.bstate = nullptr; a.overflow = err + 5; a.prof = nullptr;
+  a.main_gain = 1.f + g_tc_bias[1];
+  CUtensorMap mg, mw;
+  int rc;
+  if ((rc = make_map_2d(&mg, dgx, 4 * H, (long long)4 * Ppad, A_SLICE_ROWS))) return rc;
+  if ((rc = make_map_3d(&mw, whhT, 4 * H, H, UN))) return rc;
+  ICRL_CUDA(cudaFuncSetAttribute(chain_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+  chain_tc_bwd_kernel<<<dim3(CL * (Ppad / BM)), dim3(THREADS), B_SMEM, st>>>(mg, mw, a);
   ICRL_LAUNCH_CHECK();
   return ICRL_OK;
 }

@@ -84,6 +84,7 @@ int icrl_adam_flat_impl(cudaStream_t st, long long n, float* p, const float* g, 
 
 // chain_tc.cu: chain pieces on tcgen05
 void icrl_chain_tc_set_profile_impl(long long* buf);
+void icrl_chain_tc_set_bias_impl(float fwd, float bwd);
 int icrl_chain_tc_max_pieces_impl();
 size_t icrl_chain_tc_weight_halves_impl(int kind);
 int icrl_pack_chain_tc_weights_impl(cudaStream_t st, int kind, const float* W_hh, void* packed);
@@ -95,3 +96,6 @@ int icrl_chain_tc_fwd_impl(cudaStream_t st, int kind, int P, long long seg, int 
 int icrl_chain_tc_lstm_bwd_impl(cudaStream_t st, int P, long long seg, int warm, const void* packed,
                                 const float* stash_g, const float* stash_c, const int* take, const float* dh_take,
                                 long long take_rows, float* dgates, void* ws, float* cp_state, float* err);
+size_t icrl_policy_bptt_tc_ws_bytes_impl(int B, int n_cell);
+int icrl_policy_bptt_tc_impl(cudaStream_t st, int B, int n_cell, int p0, const void* packed, const float* Gs,
+                             const float* Cs, const float* dHv, float* DG, float* dh0, void* ws, float* err);

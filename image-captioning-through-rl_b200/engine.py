@@ -83,7 +83,7 @@ class A2CEngine:
 
     def __init__(self, a2c_network, reward_network, use_tc=None, decode="fused", chain_shards=1, wgrad="tc",
                  chain_segments=32, chain_warmup=256, chain_tol=1e-5, chain_bwd_segments=None, chain_engine="tc",
-                 chain_pieces=None, chain_adapt=True, chain_warmup_min=32):
+                 chain_pieces=None, chain_adapt=True, chain_warmup_min=32, policy_bptt="tc"):
         self.policy = a2c_network.policy_network
         self.value = a2c_network.value_network
         self.reward = reward_network
@@ -161,6 +161,11 @@ class A2CEngine:
         self.chain_pieces = None if chain_pieces is None else int(chain_pieces)
         if self.chain_pieces is not None and self.chain_pieces < 2:
             raise ValueError("chain_pieces must be at least 2")
+        # policy_bptt: "tc" = the policy's serial cell-backward steps on the tcgen05 chain-backward kernel (one launch),
+        # "simt" = one pointwise kernel + one fp32 CUDA-core GEMM per cell step
+        if policy_bptt not in ("tc", "simt"):
+            raise ValueError("policy_bptt must be 'tc' or 'simt'")
+        self.policy_bptt = policy_bptt
         self.chain_adapt = bool(chain_adapt)
         self.chain_warmup_min = int(chain_warmup_min)
         self.warm = {"v": self.chain_warmup, "r": self.chain_warmup}      # current warm-up per chain (tc engine)
@@ -177,8 +182,9 @@ class A2CEngine:
             self.sync_state = torch.zeros(int(_lib.call("icrl_chain_sync_bytes")), dtype=torch.uint8, device=dev)
             # [0:3] loss, mean reward, mean advantage; [4:20] joint-check words of the tc chain launches (value forward
             # 4..7, reward forward 8..11, value backward 12..17): read together in ONE device-to-host copy per step
-            self._stat_err = torch.zeros(20, dtype=torch.float32, device=dev)
-        self._tc_err = self._stat_err[4:]
+            # [20:28] words of the policy's tcgen05 BPTT ([24] max |dL/dh|, [25] fp16-exchange overflow flag)
+            self._stat_err = torch.zeros(28, dtype=torch.float32, device=dev)
+        self._tc_err = self._stat_err[4:20]
         self._reward_versions = None
         self._check_params()
         self._bind_flat_grads()
@@ -284,6 +290,10 @@ class A2CEngine:
             n = int(_lib.call("icrl_chain_tc_weight_halves", 0))
             _lib.call("icrl_pack_chain_tc_weights", st, 0, _p(Vn.valrnn.lstm.weight_hh_l0),
                       _p(self._buf("v_chain_pk", n, torch.float16)), L)
+        if self.policy_bptt == "tc":
+            n = int(_lib.call("icrl_chain_tc_weight_halves", 0))
+            _lib.call("icrl_pack_chain_tc_weights", st, 0, _p(P.lstm.weight_hh_l0),
+                      _p(self._buf("p_chain_pk", n, torch.float16)), L)
         if reward or self._reward_changed():
             self.pack_reward()
 
@@ -573,13 +583,19 @@ class A2CEngine:
         dz = self._buf("p_dlogits", SB * V)
         with self._phase("policy_bwd"):
           dz[:SB * V].copy_(b["p_logits"][:SB * V])
-          _lib.call("icrl_policy_rollout_bwd", st, B, V, p0, S, P.caption_embedding.weight.shape[1], _p(f), _p(P.caption_embedding.weight), _p(pl.weight_ih_l0),
+          args = [st, B, V, p0, S, P.caption_embedding.weight.shape[1], _p(f), _p(P.caption_embedding.weight), _p(pl.weight_ih_l0),
                   _p(pl.weight_hh_l0), _p(P.linear2vocab.weight), _p(tokcm), _p(tokens), _p(b["dlogp"]), _p(b["p_Hs"]),
                   _p(b["p_Cs"]), _p(b["p_Gs"]), _p(dz), _p(self._buf("p_dHv", SB * H)),
                   _p(self._buf("p_DG", n_cell * B * 4 * H)), _p(self._buf("p_dh", 2 * B * H)), _p(self._buf("p_dc", B * H)),
                   _p(dtable), _p(colsum_ws), _p(gemm_ws), gemm_ws_floats * 4, _p(g(P.caption_embedding.weight, True)),
                   _p(g(P.cnn2linear.weight)), _p(g(P.cnn2linear.bias)), _p(g(pl.weight_ih_l0)), _p(g(pl.weight_hh_l0)),
-                  _p(g(pl.bias_ih_l0)), _p(g(pl.bias_hh_l0)), _p(g(P.linear2vocab.weight)), _p(g(P.linear2vocab.bias)), L)
+                  _p(g(pl.bias_ih_l0)), _p(g(pl.bias_hh_l0)), _p(g(P.linear2vocab.weight)), _p(g(P.linear2vocab.bias))]
+          if self.policy_bptt == "tc":
+            # the n_cell serial cell-backward steps as ONE launch of the tcgen05 chain-backward kernel (rows = MMA rows)
+            ws = self._buf("p_bptt_ws", (int(_lib.call("icrl_policy_bptt_tc_ws_bytes", B, n_cell)) + 3) // 4)
+            _lib.call("icrl_policy_rollout_bwd_tc", *args, _p(b["p_chain_pk"]), _p(ws), _p(self._stat_err[20:]), L)
+          else:
+            _lib.call("icrl_policy_rollout_bwd", *args, L)
 
     # ------------------------------------------------------------------ public API
     def step(self, features, captions=None, uniforms=None, level=None, greedy=False, backward=True,

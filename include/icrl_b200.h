@@ -122,6 +122,20 @@ int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, int D, co
                             float* dtable, float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE,
                             float* dW_cnn, float* db_cnn, float* dW_ih, float* dW_hh, float* db_ih, float* db_hh,
                             float* dW_v, float* db_v, int* launches);
+/* The same backward with its serial part -- the n_cell cell-backward steps, one [B x 2048] . W_hh contraction each -- as ONE
+ * launch of the tcgen05 chain-backward kernel (chain_tc.cu: batch rows in the MMA M dimension, 128 per cluster of 8 CTAs).
+ * tc_packed: icrl_pack_chain_tc_weights(kind 0) of the policy's W_hh; tc_ws: icrl_policy_bptt_tc_ws_bytes(B, p0 - 1 + S)
+ * bytes; tc_err: 8 floats (tc_err[4] = max |dL/dh| injected, tc_err[5] = 1 when the fp16 exchange overflowed: re-run with
+ * icrl_policy_rollout_bwd). */
+size_t icrl_policy_bptt_tc_ws_bytes(int B, int n_cell);
+int icrl_policy_rollout_bwd_tc(void* stream, int B, int V, int p0, int S, int D, const float* features, const float* E,
+                               const float* W_ih, const float* W_hh, const float* W_v, const int* tokcm,
+                               const long long* tokens_out, const float* dlogp, const float* Hs, const float* Cs,
+                               const float* Gs, float* logits, float* dHv, float* DG, float* dh, float* dc,
+                               float* dtable, float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE,
+                               float* dW_cnn, float* db_cnn, float* dW_ih, float* dW_hh, float* db_ih, float* db_hh,
+                               float* dW_v, float* db_v, const void* tc_packed, void* tc_ws, float* tc_err,
+                               int* launches);
 size_t icrl_colsum_ws_floats(long long rows, int cols);
 /* ---- teacher-forced LSTM sequence, one direction (bidirectional policy variant, models.py:59-78; for the reverse
  *      direction the caller passes the token columns reversed).  Cell j consumes tokcm[j][:]; Hs/Cs [(n+1)][B][512]
@@ -262,6 +276,9 @@ int icrl_chain_tc_lstm_bwd(void* stream, int pieces, long long seg, int warm, co
 /* Debug aid: buf != NULL (16 device int64): cycle sums of cluster 0 / CTA 0's first epilogue warp, forward [0..5] =
  * {accumulator wait, gather, cell update, stores, cluster barrier, steps}, backward [8..13] likewise. */
 int icrl_chain_tc_set_profile(void* buf);
+/* Experiment knob: relative compensation (1 + x) applied to the main tensor-memory accumulator of the forward / backward
+ * chain kernels (the tensor core truncates on every accumulate).  Default 0, 0. */
+int icrl_chain_tc_set_bias(float fwd, float bwd);
 /* Debug aid: when buf != NULL (16 device int64), CTA 0 / thread 0 of the sharded / segmented chain kernels accumulates its
  * cycles per phase: [0..3] value LSTM forward {exchange wait, GEMV + reduce, pointwise + publish, T}, [4..7] reward GRU
  * forward, [8..14] backward {coefficients + requests, poll wait, gate gradients + stores, barrier, contraction + reduce,

@@ -158,8 +158,8 @@ def test_bench_reference_arm_json_contract():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--cpu-sample", "4"], capture_output=True, text=True, timeout=600, cwd=root)
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "0",
+                          "--cpu-sample", "4", "--batch", "16"], capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -169,6 +169,9 @@ def test_bench_reference_arm_json_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"] and "model" not in d["config"]
+    # the first timed step is the whole global batch (same workload string as the GPU arm), the rest bounded samples
+    assert d["config"]["workload"].startswith("configs[3]: full A2C training step") and "global batch 16" in d["config"]["workload"]
+    assert d["config"]["steps_timed"] == 2 and "all 16 captions" in d["cpu_baseline"]["sample"]
 
 
 def test_bench_clock_sampler_window():
