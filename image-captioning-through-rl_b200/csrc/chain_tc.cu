@@ -844,8 +844,16 @@ int cp_half_of(int warm) { return warm >= 8 ? warm / 2 - 1 : -1; }
 
 }  // namespace
 
-// Debug knob (icrl_chain_tc_set_bias): relative compensation of the main accumulator, forward / backward.
-static float g_tc_bias[2] = {0.f, 0.f};
+// Compensation of the tensor core's truncating accumulation.  tcgen05.mma truncates (round toward zero) each time it adds
+// into a tensor-memory accumulator: measured -1.5e-8 .. -1.8e-8 of the accumulator per MMA (scripts/tc_accuracy_probe.py,
+// scripts/debug_bias.py).  The main accumulator of a step sums K / 16 instructions, so its expected relative loss is
+// (K / 16) * 1.8e-8: 5.8e-7 forward (K = 512), 2.3e-6 backward (K = 2048) -- a SYSTEMATIC bias toward zero, unlike the
+// unbiased round-to-nearest of the fp32 FMA chains.  Uncompensated it leaves mean(h_tc - h_serial) * sign(h) = -3.3e-7
+// after 200 optimizer steps (values 1.1e-5 off at |v| ~ 8, gradients 4e-4 of max where the advantage cancels);
+// multiplying the main accumulator by 1 + that expectation zeroes the mean (-5e-8 .. +8e-8 between 4.8e-7 and 7.2e-7) and
+// leaves the random part (~1.6 ulp, below the 512-term FMA chain's own rounding noise).  icrl_chain_tc_set_bias
+// overrides the two factors (experiments).
+static float g_tc_bias[2] = {32 * 1.8e-8f, 128 * 1.8e-8f};
 void icrl_chain_tc_set_bias_impl(float fwd, float bwd) { g_tc_bias[0] = fwd; g_tc_bias[1] = bwd; }
 static long long* g_chain_tc_prof = nullptr;      // icrl_chain_tc_set_profile: 16 device int64 (forward [0..5], backward [8..13])
 void icrl_chain_tc_set_profile_impl(long long* buf) { g_chain_tc_prof = buf; }

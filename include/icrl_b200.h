@@ -277,7 +277,8 @@ int icrl_chain_tc_lstm_bwd(void* stream, int pieces, long long seg, int warm, co
  * {accumulator wait, gather, cell update, stores, cluster barrier, steps}, backward [8..13] likewise. */
 int icrl_chain_tc_set_profile(void* buf);
 /* Experiment knob: relative compensation (1 + x) applied to the main tensor-memory accumulator of the forward / backward
- * chain kernels (the tensor core truncates on every accumulate).  Default 0, 0. */
+ * chain kernels (the tensor core truncates on every accumulate).  Default 5.76e-7, 2.3e-6 = 1.8e-8 per
+ * accumulating MMA instruction. */
 int icrl_chain_tc_set_bias(float fwd, float bwd);
 /* Debug aid: when buf != NULL (16 device int64), CTA 0 / thread 0 of the sharded / segmented chain kernels accumulates its
  * cycles per phase: [0..3] value LSTM forward {exchange wait, GEMV + reduce, pointwise + publish, T}, [4..7] reward GRU
