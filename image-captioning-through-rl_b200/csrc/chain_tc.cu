@@ -236,10 +236,22 @@ chain_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
           float gi[8], gf[8], gg[8], go[8], cn[8], hn[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            gi[i] = sigmoidf_sfu(fmaf(cor[0][i], LO_INV, acc[0][i] * mg) + tin[0][i]);
-            gf[i] = sigmoidf_sfu(fmaf(cor[1][i], LO_INV, acc[1][i] * mg) + tin[1][i]);
-            gg[i] = tanhf_sfu(fmaf(cor[2][i], LO_INV, acc[2][i] * mg) + tin[2][i]);
-            go[i] = sigmoidf_sfu(fmaf(cor[3 % NG][i], LO_INV, acc[3 % NG][i] * mg) + tin[3 % NG][i]);
+            // sigmoid(x) = 1 / (1 + e^-x), tanh(x) = 1 - 2 / (1 + e^2x): the four denominators share ONE reciprocal
+            // (the cell phase is MUFU-bound: 10 -> 7 special-function operations per cell).  Arguments are clamped to
+            // +-20 (both functions are saturated to the last float bit there), so the product of the four
+            // denominators stays below 6e34.
+            const float xi = fminf(fmaxf(fmaf(cor[0][i], LO_INV, acc[0][i] * mg) + tin[0][i], -20.f), 20.f);
+            const float xf = fminf(fmaxf(fmaf(cor[1][i], LO_INV, acc[1][i] * mg) + tin[1][i], -20.f), 20.f);
+            const float xg = fminf(fmaxf(fmaf(cor[2][i], LO_INV, acc[2][i] * mg) + tin[2][i], -10.f), 10.f);
+            const float xo = fminf(fmaxf(fmaf(cor[3 % NG][i], LO_INV, acc[3 % NG][i] * mg) + tin[3 % NG][i], -20.f), 20.f);
+            const float di = 1.f + __expf(-xi), df = 1.f + __expf(-xf), dg = 1.f + __expf(2.f * xg), dz = 1.f + __expf(-xo);
+            const float pif = di * df, pgo = dg * dz;
+            const float r = __fdividef(1.f, pif * pgo);
+            const float rif = r * pgo, rgo = r * pif;            // 1 / (di df), 1 / (dg dz)
+            gi[i] = rif * df;
+            gf[i] = rif * di;
+            gg[i] = 1.f - 2.f * (rgo * dz);
+            go[i] = rgo * dg;
             cn[i] = gf[i] * tin[NG][i] + gi[i] * gg[i];
             hn[i] = go[i] * tanhf_sfu(cn[i]);
           }
@@ -274,7 +286,30 @@ chain_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
       }
       __syncwarp();
       const long long t3 = prof ? clock64() : 0;
-      // (S) coalesced stores, 8 lanes per row: backward stash (live positions), carried state, checkpoints, fp16 split of h
+      // (S1) what the next step needs: fp16 split of h (read by every CTA of the cluster through TMA) and the carried state
+      {
+        const int c4 = lane & 7;
+#pragma unroll
+        for (int i8 = 0; i8 < 8; ++i8) {
+          const int r = i8 * 4 + (lane >> 3);
+          const int kr = m0 + 32 * q + r;
+          if (kr < P) {
+            const unsigned char* e = gst + r * 128 + ((c4 ^ (r & 7)) << 4);
+            const int uc = ucol0 + c4 * 4;
+            const float4 h4 = *reinterpret_cast<const float4*>(e + (C::NARR - 1) * 4096);
+            uint2 hi, lo;
+            split4_f16(h4, hi, lo);
+            __half* hp = p.hparts + ((size_t)(((j + 1) & 1) * 2) * Ppad + kr) * H + uc;
+            *reinterpret_cast<uint2*>(hp) = hi;
+            *reinterpret_cast<uint2*>(hp + (size_t)Ppad * H) = lo;
+            if constexpr (NG == 4) *reinterpret_cast<float4*>(p.state + (size_t)kr * H + uc) = *reinterpret_cast<const float4*>(e + 4 * 4096);
+            else *reinterpret_cast<float4*>(p.state + (size_t)kr * H + uc) = h4;
+          }
+        }
+      }
+      __threadfence();                         // orders only the stores above: the stash stores below are not waited for
+      fence_proxy_async();                     // generic-proxy writes of the h split -> visible to the peers' TMA loads
+      // (S2) coalesced stores, 8 lanes per row: backward stash (live positions) and checkpoints
       {
         const int c4 = lane & 7;
         const bool cp_full = j == p.warm - 1, cp_half = j == p.cp_half;
@@ -290,7 +325,6 @@ chain_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
             const float4 h4 = *reinterpret_cast<const float4*>(e + (C::NARR - 1) * 4096);
             if constexpr (NG == 4) {
               const float4 cn4 = *reinterpret_cast<const float4*>(e + 4 * 4096);
-              *reinterpret_cast<float4*>(p.state + (size_t)kr * H + uc) = cn4;
               if (live) {
                 if (p.stash_g) {
                   float* gs = p.stash_g + pos * (4 * H) + uc;
@@ -301,17 +335,10 @@ chain_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
               }
               if (kr >= 1 && (cp_full || cp_half))
                 *reinterpret_cast<float4*>(p.wstate + ((size_t)((cp_full ? 1 : 0) * P + kr) * 2 + 1) * H + uc) = cn4;
-            } else {
-              *reinterpret_cast<float4*>(p.state + (size_t)kr * H + uc) = h4;
             }
             if (live) *reinterpret_cast<float4*>(p.stash_h + (pos + 1) * H + uc) = h4;
             if (kr >= 1 && (cp_full || cp_half))
               *reinterpret_cast<float4*>(p.wstate + ((size_t)((cp_full ? 1 : 0) * P + kr) * 2) * H + uc) = h4;
-            uint2 hi, lo;
-            split4_f16(h4, hi, lo);
-            __half* hp = p.hparts + ((size_t)(((j + 1) & 1) * 2) * Ppad + kr) * H + uc;
-            *reinterpret_cast<uint2*>(hp) = hi;
-            *reinterpret_cast<uint2*>(hp + (size_t)Ppad * H) = lo;
           }
         }
       }
@@ -319,10 +346,8 @@ chain_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty);
       const long long t4 = prof ? clock64() : 0;
-      __threadfence();
-      fence_proxy_async();                     // generic-proxy writes of the h split -> visible to the peers' TMA loads
       __syncwarp();
-      cluster_arrive();
+      cluster_arrive_relaxed();                // the h split was fenced above; the stash stores need no ordering
       cluster_wait();
       tok = tok_n;
       if (prof) { const long long t5 = clock64(); pr[0] += t1 - t0; pr[1] += t2 - t1; pr[2] += t3 - t2; pr[3] += t4 - t3; pr[4] += t5 - t4; }
@@ -628,7 +653,32 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
         }
         __syncwarp();
         const long long u2 = prof ? clock64() : 0;
-        // (S) coalesced stores, 4 lanes per row
+        // (S1) the scaled fp16 split of the gate gradients: the next step's A operand of every CTA of the cluster
+        {
+          const int c4 = lane & 3;
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const int r = i4 * 8 + (lane >> 2);
+            const int kr = m0 + 32 * q + r;
+            if (kr < P) {
+              const unsigned char* e = gst + r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4);
+              __half* xp = p.dgx + ((size_t)((((it + 1) & 1) * 2) * Ppad + kr)) * (4 * H) + ucolp + c4 * 4;
+#pragma unroll
+              for (int a = 0; a < 4; ++a) {
+                const float4 d = *reinterpret_cast<const float4*>(e + a * 2048);
+                uint2 hi, lo;
+                split4_f16(make_float4(d.x * S, d.y * S, d.z * S, d.w * S), hi, lo);
+                *reinterpret_cast<uint2*>(xp + a * H) = hi;
+                *reinterpret_cast<uint2*>(xp + (size_t)Ppad * (4 * H) + a * H) = lo;
+              }
+            }
+          }
+        }
+        if (ps == 1) {
+          __threadfence();                     // orders the exchange stores of both passes; what follows is not waited for
+          fence_proxy_async();
+        }
+        // (S2) fp32 gate gradients of the live positions (parameter-gradient contractions) and the joint checkpoints
         {
           const int c4 = lane & 3;
 #pragma unroll
@@ -640,15 +690,10 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
               const unsigned char* e = gst + r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4);
               const bool live = kr == P - 1 || it >= p.warm;
               const int uc = ucolp + c4 * 4;
-              __half* xp = p.dgx + ((size_t)((((it + 1) & 1) * 2) * Ppad + kr)) * (4 * H) + uc;
+              if (live) {
 #pragma unroll
-              for (int a = 0; a < 4; ++a) {
-                const float4 d = *reinterpret_cast<const float4*>(e + a * 2048);
-                if (live) *reinterpret_cast<float4*>(p.dgates + pos * (4 * H) + a * H + uc) = d;
-                uint2 hi, lo;
-                split4_f16(make_float4(d.x * S, d.y * S, d.z * S, d.w * S), hi, lo);
-                *reinterpret_cast<uint2*>(xp + a * H) = hi;
-                *reinterpret_cast<uint2*>(xp + (size_t)Ppad * (4 * H) + a * H) = lo;
+                for (int a = 0; a < 4; ++a)
+                  *reinterpret_cast<float4*>(p.dgates + pos * (4 * H) + a * H + uc) = *reinterpret_cast<const float4*>(e + a * 2048);
               }
               const float4 dh4 = *reinterpret_cast<const float4*>(e + 4 * 2048);
               const float4 dc4 = *reinterpret_cast<const float4*>(e + 5 * 2048);
@@ -672,10 +717,8 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty);
       const long long t4 = prof ? clock64() : 0;
-      __threadfence();
-      fence_proxy_async();
       __syncwarp();
-      cluster_arrive();
+      cluster_arrive_relaxed();
       cluster_wait();
       tk = tk_n;
       if (prof) { const long long t5 = clock64(); pr[0] += t1 - t0; pr[1] += tg; pr[2] += tc; pr[3] += ts; pr[4] += t5 - t4; }

@@ -88,6 +88,9 @@ __device__ __forceinline__ void tmem_ld8x2(unsigned ta, unsigned tb, float* a, f
 }
 
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// arrive without memory ordering: for callers that have fenced what the peers need themselves (a release arrive would also
+// wait for every other outstanding global store of the thread)
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ unsigned cluster_rank() {
