@@ -36,8 +36,9 @@ SIGNATURES = {
     "icrl_pack_value_head": [P, P, P, P, P, P, P, LP],
     "icrl_policy_rollout_fwd": [P, I, I, I, I, I] + [P] * 17 + [LP],
     "icrl_policy_rollout_bwd": [P, I, I, I, I, I] + [P] * 19 + [Z] + [P] * 9 + [LP],
-    "icrl_policy_rollout_bwd_tc": [P, I, I, I, I, I] + [P] * 19 + [Z] + [P] * 9 + [P, P, P, LP],
-    "icrl_policy_bptt_tc_ws_bytes": [I, I],
+    "icrl_policy_rollout_bwd_tc": [P, I, I, I, I, I] + [P] * 19 + [Z] + [P] * 9 + [P, P, P, I, LP],
+    "icrl_policy_bwd_tc_ws_bytes": [I, I, I],
+    "icrl_vocab_pad": [],
     "icrl_colsum_ws_floats": [L, I],
     "icrl_lstm_seq_fwd": [P, I, I] + [P] * 8 + [LP],
     "icrl_lstm_seq_bwd": [P, I, I, I, I] + [P] * 14 + [Z] + [P] * 6 + [LP],
@@ -80,8 +81,8 @@ SIGNATURES = {
 _RESTYPES = {"icrl_last_error": c_char_p, "icrl_wgrad_tc_ws_bytes": c_size_t, "icrl_decode_weight_halves": c_size_t, "icrl_colsum_ws_floats": c_size_t, "icrl_stream_len": c_longlong,
              "icrl_chain_sync_bytes": c_size_t, "icrl_chain_segment_len": c_longlong, "icrl_chain_segment_ws_floats": c_size_t,
              "icrl_chain_tc_weight_halves": c_size_t, "icrl_chain_tc_ws_bytes": c_size_t, "icrl_chain_tc_cp_floats": c_size_t,
-             "icrl_policy_bptt_tc_ws_bytes": c_size_t}
-_NO_STATUS = set(_RESTYPES) | {"icrl_version", "icrl_chain_tc_max_pieces"}
+             "icrl_policy_bwd_tc_ws_bytes": c_size_t}
+_NO_STATUS = set(_RESTYPES) | {"icrl_version", "icrl_chain_tc_max_pieces", "icrl_vocab_pad"}
 
 
 class IcrlError(RuntimeError):

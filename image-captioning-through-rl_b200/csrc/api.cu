@@ -238,24 +238,54 @@ static int policy_rollout_bwd_common(void* stream, int B, int V, int p0, int S, 
                             const float* Gs, float* logits, float* dHv, float* DG, float* dh, float* dc,
                             float* dtable, float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE,
                             float* dW_cnn, float* db_cnn, float* dW_ih, float* dW_hh, float* db_ih, float* db_hh,
-                            float* dW_v, float* db_v, const void* tc_packed, void* tc_ws, float* tc_err, int* launches) {
+                            float* dW_v, float* db_v, const void* tc_packed, void* tc_ws, float* tc_err, int ldz,
+                            int* launches) {
+  // ldz: row stride of `logits` / dL/dlogits.  tc path: ldz = ICRL_VPAD (1024) with zero padding columns, so that the two
+  // vocabulary-sized contractions run on tcgen05 as well (dW_v: K = S*B on wgrad_tc; dHv: bf16x3 GEMM with K = ldz).
   cudaStream_t st = S_(stream);
   const int n_cell = p0 - 1 + S;
   const size_t BH = (size_t)B * H;
   const int SB = S * B;
   // 1. dL/dlogits in place (log(softmax(z))[a] backward); dlogp == NULL: `logits` already holds dL/dlogits
   if (dlogp) {
-    TRY(icrl_softmax_bwd(st, B, S, V, logits, V, tokens_out, dlogp));
+    TRY(icrl_softmax_bwd(st, B, S, V, logits, ldz, tokens_out, dlogp));
     bump(launches, 1);
   }
   const float* dZ = logits;
   const float* Hsel = Hs + (size_t)p0 * BH;          // h after cell step p0-1+s, s = 0..S-1
-  // 2. vocab projection gradients
-  TRY(icrl_gemm_f32_impl(st, 1, 0, V, H, SB, dZ, V, Hsel, H, dW_v, H, nullptr, 0.f, gemm_ws, gemm_ws_bytes, launches));
-  TRY(icrl_wcolsum(st, SB, V, dZ, nullptr, 0, colsum_ws, db_v));
-  bump(launches, 2);
-  // 3. dL/dh from the vocab path, all steps at once
-  TRY(icrl_gemm_f32_impl(st, 0, 0, SB, H, V, dZ, V, W_v, H, dHv, H, nullptr, 0.f, nullptr, 0, launches));
+  const bool tc_vocab = tc_packed && ldz == ICRL_VPAD && V <= ICRL_VPAD &&
+                        gemm_ws_bytes >= icrl_wgrad_tc_ws_bytes_impl(ICRL_VPAD, H, SB, 2);
+  if (tc_vocab) {
+    char* w2 = reinterpret_cast<char*>(tc_ws) + ((icrl_policy_bptt_tc_ws_bytes_impl(B, n_cell) + 255) / 256) * 256;
+    void* zparts = w2;                                               // [3][SB][1024] bf16
+    void* wvT = w2 + (size_t)3 * SB * ICRL_VPAD * 2;                 // [3][512][1024] bf16
+    float* dWv_tmp = reinterpret_cast<float*>(reinterpret_cast<char*>(wvT) + (size_t)3 * H * ICRL_VPAD * 2);   // [1024][512]
+    float* dbv_tmp = dWv_tmp + (size_t)ICRL_VPAD * H;                // [1024]
+    // 2. vocab projection gradients: dW_v = dZ^T Hsel (K = S*B) on wgrad_tc, rows >= V of the padded result dropped
+    TRY(icrl_wgrad_tc_impl(st, ICRL_VPAD, H, SB, dZ, ldz, Hsel, H, dWv_tmp, H, gemm_ws, gemm_ws_bytes, 2));
+    ICRL_CUDA(cudaMemcpyAsync(dW_v, dWv_tmp, (size_t)V * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TRY(icrl_wcolsum(st, SB, ICRL_VPAD, dZ, nullptr, 0, colsum_ws, dbv_tmp));
+    ICRL_CUDA(cudaMemcpyAsync(db_v, dbv_tmp, (size_t)V * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    bump(launches, 7);
+    // 3. dL/dh from the vocab path, all steps at once: dHv = dZ W_v as a 3-part bf16 split product (fp32-grade)
+    TRY(icrl_split_bf16x3_impl(st, (long long)SB * ICRL_VPAD, dZ, zparts));
+    TRY(icrl_pack_transposed_bf16x3_impl(st, V, H, ICRL_VPAD, W_v, wvT));
+    TRY(icrl_gemm_bf16x3_impl(st, SB, H, ICRL_VPAD, zparts, wvT, dHv, H, nullptr));
+    bump(launches, 3);
+  } else {
+    // 2. vocab projection gradients
+    TRY(icrl_gemm_f32_impl(st, 1, 0, V, H, SB, dZ, ldz, Hsel, H, dW_v, H, nullptr, 0.f, gemm_ws, gemm_ws_bytes, launches));
+    if (ldz == V) {
+      TRY(icrl_wcolsum(st, SB, V, dZ, nullptr, 0, colsum_ws, db_v));
+    } else {
+      float* tmp = colsum_ws + (size_t)icrl_wcolsum_chunks(SB) * ldz;
+      TRY(icrl_wcolsum(st, SB, ldz, dZ, nullptr, 0, colsum_ws, tmp));
+      ICRL_CUDA(cudaMemcpyAsync(db_v, tmp, (size_t)V * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    bump(launches, 2);
+    // 3. dL/dh from the vocab path, all steps at once
+    TRY(icrl_gemm_f32_impl(st, 0, 0, SB, H, V, dZ, ldz, W_v, H, dHv, H, nullptr, 0.f, nullptr, 0, launches));
+  }
   // 4. BPTT
   float* dh_cur = dh;
   float* dh_nxt = dh + BH;
@@ -313,10 +343,15 @@ int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, int D, co
                             float* dW_v, float* db_v, int* launches) {
   return policy_rollout_bwd_common(stream, B, V, p0, S, D, features, E, W_ih, W_hh, W_v, tokcm, tokens_out, dlogp, Hs, Cs, Gs,
                                    logits, dHv, DG, dh, dc, dtable, colsum_ws, gemm_ws, gemm_ws_bytes, dE, dW_cnn, db_cnn, dW_ih,
-                                   dW_hh, db_ih, db_hh, dW_v, db_v, nullptr, nullptr, nullptr, launches);
+                                   dW_hh, db_ih, db_hh, dW_v, db_v, nullptr, nullptr, nullptr, V, launches);
 }
 
-size_t icrl_policy_bptt_tc_ws_bytes(int B, int n_cell) { return icrl_policy_bptt_tc_ws_bytes_impl(B, n_cell); }
+size_t icrl_policy_bwd_tc_ws_bytes(int B, int S, int n_cell) {
+  const size_t SB = (size_t)S * B;
+  return ((icrl_policy_bptt_tc_ws_bytes_impl(B, n_cell) + 255) / 256) * 256 + 3 * SB * ICRL_VPAD * 2 + (size_t)3 * H * ICRL_VPAD * 2 +
+         (size_t)ICRL_VPAD * H * 4 + ICRL_VPAD * 4 + 256;
+}
+int icrl_vocab_pad(void) { return ICRL_VPAD; }
 
 int icrl_policy_rollout_bwd_tc(void* stream, int B, int V, int p0, int S, int D, const float* features, const float* E,
                                const float* W_ih, const float* W_hh, const float* W_v, const int* tokcm,
@@ -324,12 +359,13 @@ int icrl_policy_rollout_bwd_tc(void* stream, int B, int V, int p0, int S, int D,
                                const float* Gs, float* logits, float* dHv, float* DG, float* dh, float* dc,
                                float* dtable, float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE,
                                float* dW_cnn, float* db_cnn, float* dW_ih, float* dW_hh, float* db_ih, float* db_hh,
-                               float* dW_v, float* db_v, const void* tc_packed, void* tc_ws, float* tc_err,
+                               float* dW_v, float* db_v, const void* tc_packed, void* tc_ws, float* tc_err, int ldz,
                                int* launches) {
   ICRL_REQUIRE(tc_packed && tc_ws && tc_err, "the tcgen05 BPTT needs the packed W_hh, its workspace and the error words");
+  ICRL_REQUIRE(ldz >= V, "row stride of the logits");
   return policy_rollout_bwd_common(stream, B, V, p0, S, D, features, E, W_ih, W_hh, W_v, tokcm, tokens_out, dlogp, Hs, Cs, Gs,
                                    logits, dHv, DG, dh, dc, dtable, colsum_ws, gemm_ws, gemm_ws_bytes, dE, dW_cnn, db_cnn, dW_ih,
-                                   dW_hh, db_ih, db_hh, dW_v, db_v, tc_packed, tc_ws, tc_err, launches);
+                                   dW_hh, db_ih, db_hh, dW_v, db_v, tc_packed, tc_ws, tc_err, ldz, launches);
 }
 
 long long icrl_stream_len(int B, int p0, int S, int extra) {

@@ -50,6 +50,23 @@ constexpr int THREADS = 32 * (EPI_WARP0 + EPI_WARPS);      // 384
 constexpr float LO_INV = 1.f / 2048.f;
 constexpr int CORR = 256;                   // forward: TMEM column of the correction accumulator
 
+// Publishing the per-step exchange (fp16 split of h / of the gate gradients, written with ordinary global stores) to the
+// TMA loads of the other CTAs of the cluster: fence.proxy.async (generic -> async proxy) on both sides of a cluster
+// barrier whose arrive is a RELEASE and whose wait is an ACQUIRE at cluster scope.  An extra __threadfence() (gpu-scope
+// fence, as decode.cu issues) costs ~2.5 K cycles per step and is not required by the memory model; build with
+// -DICRL_TC_GPU_FENCE=1 to restore it.
+#ifndef ICRL_TC_GPU_FENCE
+#define ICRL_TC_GPU_FENCE 0
+#endif
+__device__ __forceinline__ void publish_exchange() {
+#if ICRL_TC_GPU_FENCE
+  __threadfence();
+#endif
+  fence_proxy_async();
+  __syncwarp();
+  cluster_arrive();
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 constexpr int F_STAGES = 4, F_KB = H / BK;  // 16 K blocks per step
 template <int NG> struct FwdCfg {
@@ -307,8 +324,6 @@ chain_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
           }
         }
       }
-      __threadfence();                         // orders only the stores above: the stash stores below are not waited for
-      fence_proxy_async();                     // generic-proxy writes of the h split -> visible to the peers' TMA loads
       // (S2) coalesced stores, 8 lanes per row: backward stash (live positions) and checkpoints
       {
         const int c4 = lane & 7;
@@ -346,8 +361,7 @@ chain_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty);
       const long long t4 = prof ? clock64() : 0;
-      __syncwarp();
-      cluster_arrive_relaxed();                // the h split was fenced above; the stash stores need no ordering
+      publish_exchange();                      // the h split -> visible to the peers' TMA loads
       cluster_wait();
       tok = tok_n;
       if (prof) { const long long t5 = clock64(); pr[0] += t1 - t0; pr[1] += t2 - t1; pr[2] += t3 - t2; pr[3] += t4 - t3; pr[4] += t5 - t4; }
@@ -674,10 +688,6 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
             }
           }
         }
-        if (ps == 1) {
-          __threadfence();                     // orders the exchange stores of both passes; what follows is not waited for
-          fence_proxy_async();
-        }
         // (S2) fp32 gate gradients of the live positions (parameter-gradient contractions) and the joint checkpoints
         {
           const int c4 = lane & 3;
@@ -717,8 +727,7 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty);
       const long long t4 = prof ? clock64() : 0;
-      __syncwarp();
-      cluster_arrive_relaxed();
+      publish_exchange();
       cluster_wait();
       tk = tk_n;
       if (prof) { const long long t5 = clock64(); pr[0] += t1 - t0; pr[1] += tg; pr[2] += tc; pr[3] += ts; pr[4] += t5 - t4; }

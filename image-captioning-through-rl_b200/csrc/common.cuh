@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#define ICRL_VPAD 1024        // vocabulary padded to the tensor-core tile (V = 1004 in the reference's data)
 #define ICRL_H 512            // hidden / embedding / feature width (models.py:41,160,250)
 
 // error codes returned across the C ABI (include/icrl_b200.h)

@@ -235,6 +235,22 @@ __global__ void split_bf16x3_kernel(long long n, const float* __restrict__ x, __
   }
 }
 
+// W [rows][cols] fp32 -> parts [3][cols][Kp] bf16 of W^T, columns k >= rows zero (operand of C = A W for A [M][Kp])
+__global__ void pack_transposed_bf16x3_kernel(int rows, int cols, int Kp, const float* __restrict__ W,
+                                              __nv_bfloat16* __restrict__ parts) {
+  const long long n = (long long)cols * Kp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i / Kp), k = (int)(i % Kp);
+    const float v = k < rows ? W[(size_t)k * cols + c] : 0.f;
+    const __nv_bfloat16 p0 = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(p0);
+    const __nv_bfloat16 p1 = __float2bfloat16_rn(r1);
+    parts[i] = p0;
+    parts[n + i] = p1;
+    parts[2 * n + i] = __float2bfloat16_rn(r1 - __bfloat162float(p1));
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -267,6 +283,13 @@ int make_map(CUtensorMap* map, const void* ptr, int rows, int K, int box_rows) {
 int icrl_split_bf16x3_impl(cudaStream_t st, long long n, const float* x, void* parts) {
   const int blocks = (int)min((long long)148 * 8, (n + 255) / 256);
   split_bf16x3_kernel<<<blocks, 256, 0, st>>>(n, x, (__nv_bfloat16*)parts);
+  ICRL_LAUNCH_CHECK();
+  return ICRL_OK;
+}
+
+int icrl_pack_transposed_bf16x3_impl(cudaStream_t st, int rows, int cols, int Kp, const float* W, void* parts) {
+  ICRL_REQUIRE(rows > 0 && cols > 0 && Kp >= rows, "bad shape");
+  pack_transposed_bf16x3_kernel<<<148 * 4, 256, 0, st>>>(rows, cols, Kp, W, (__nv_bfloat16*)parts);
   ICRL_LAUNCH_CHECK();
   return ICRL_OK;
 }

@@ -99,3 +99,4 @@ int icrl_chain_tc_lstm_bwd_impl(cudaStream_t st, int P, long long seg, int warm,
 size_t icrl_policy_bptt_tc_ws_bytes_impl(int B, int n_cell);
 int icrl_policy_bptt_tc_impl(cudaStream_t st, int B, int n_cell, int p0, const void* packed, const float* Gs,
                              const float* Cs, const float* dHv, float* DG, float* dh0, void* ws, float* err);
+int icrl_pack_transposed_bf16x3_impl(cudaStream_t st, int rows, int cols, int Kp, const float* W, void* parts);

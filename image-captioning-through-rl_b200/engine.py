@@ -186,6 +186,7 @@ class A2CEngine:
             self._stat_err = torch.zeros(28, dtype=torch.float32, device=dev)
         self._tc_err = self._stat_err[4:20]
         self._reward_versions = None
+        self._dz_ld = None
         self._check_params()
         self._bind_flat_grads()
 
@@ -580,9 +581,14 @@ class A2CEngine:
         # (longer warm-up, serial fall-back) runs this backward again with slightly different dL/dlogp, so it works on a
         # copy and the rollout's logits stay intact.
         pl = P.lstm
-        dz = self._buf("p_dlogits", SB * V)
+        tc = self.policy_bptt == "tc"
+        ldz = int(_lib.call("icrl_vocab_pad")) if tc and V <= 1024 else V      # padded rows: vocabulary contractions on tcgen05
+        dz = self._bufs.get("p_dlogits")
+        if dz is None or dz.numel() < SB * ldz or self._dz_ld != ldz:
+            dz = self._bufs["p_dlogits"] = torch.zeros(SB * ldz, dtype=torch.float32, device=self.device)   # padding stays zero
+            self._dz_ld = ldz
         with self._phase("policy_bwd"):
-          dz[:SB * V].copy_(b["p_logits"][:SB * V])
+          dz[:SB * ldz].view(SB, ldz)[:, :V].copy_(b["p_logits"][:SB * V].view(SB, V))
           args = [st, B, V, p0, S, P.caption_embedding.weight.shape[1], _p(f), _p(P.caption_embedding.weight), _p(pl.weight_ih_l0),
                   _p(pl.weight_hh_l0), _p(P.linear2vocab.weight), _p(tokcm), _p(tokens), _p(b["dlogp"]), _p(b["p_Hs"]),
                   _p(b["p_Cs"]), _p(b["p_Gs"]), _p(dz), _p(self._buf("p_dHv", SB * H)),
@@ -592,8 +598,8 @@ class A2CEngine:
                   _p(g(pl.bias_ih_l0)), _p(g(pl.bias_hh_l0)), _p(g(P.linear2vocab.weight)), _p(g(P.linear2vocab.bias))]
           if self.policy_bptt == "tc":
             # the n_cell serial cell-backward steps as ONE launch of the tcgen05 chain-backward kernel (rows = MMA rows)
-            ws = self._buf("p_bptt_ws", (int(_lib.call("icrl_policy_bptt_tc_ws_bytes", B, n_cell)) + 3) // 4)
-            _lib.call("icrl_policy_rollout_bwd_tc", *args, _p(b["p_chain_pk"]), _p(ws), _p(self._stat_err[20:]), L)
+            ws = self._buf("p_bptt_ws", (int(_lib.call("icrl_policy_bwd_tc_ws_bytes", B, S, n_cell)) + 3) // 4)
+            _lib.call("icrl_policy_rollout_bwd_tc", *args, _p(b["p_chain_pk"]), _p(ws), _p(self._stat_err[20:]), ldz, L)
           else:
             _lib.call("icrl_policy_rollout_bwd", *args, L)
 

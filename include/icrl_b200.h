@@ -122,19 +122,21 @@ int icrl_policy_rollout_bwd(void* stream, int B, int V, int p0, int S, int D, co
                             float* dtable, float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE,
                             float* dW_cnn, float* db_cnn, float* dW_ih, float* dW_hh, float* db_ih, float* db_hh,
                             float* dW_v, float* db_v, int* launches);
-/* The same backward with its serial part -- the n_cell cell-backward steps, one [B x 2048] . W_hh contraction each -- as ONE
- * launch of the tcgen05 chain-backward kernel (chain_tc.cu: batch rows in the MMA M dimension, 128 per cluster of 8 CTAs).
- * tc_packed: icrl_pack_chain_tc_weights(kind 0) of the policy's W_hh; tc_ws: icrl_policy_bptt_tc_ws_bytes(B, p0 - 1 + S)
- * bytes; tc_err: 8 floats (tc_err[4] = max |dL/dh| injected, tc_err[5] = 1 when the fp16 exchange overflowed: re-run with
- * icrl_policy_rollout_bwd). */
-size_t icrl_policy_bptt_tc_ws_bytes(int B, int n_cell);
+/* The same backward with its contractions on tcgen05: the n_cell serial cell-backward steps ([B x 2048] . W_hh each) as ONE
+ * launch of the chain-backward kernel (chain_tc.cu: batch rows in the MMA M dimension, 128 per cluster of 8 CTAs), and --
+ * when the logits are handed over with row stride ldz = icrl_vocab_pad() (1024; columns >= V zero) -- dW_v = dZ^T H
+ * (K = S*B, wgrad_tc) and dHv = dZ W_v (3-part bf16 split).  tc_packed: icrl_pack_chain_tc_weights(kind 0) of the policy's
+ * W_hh; tc_ws: icrl_policy_bwd_tc_ws_bytes(B, S, p0 - 1 + S) bytes; tc_err: 8 floats (tc_err[4] = max |dL/dh| injected,
+ * tc_err[5] = 1 when the fp16 exchange overflowed: re-run with icrl_policy_rollout_bwd). */
+size_t icrl_policy_bwd_tc_ws_bytes(int B, int S, int n_cell);
+int icrl_vocab_pad(void);
 int icrl_policy_rollout_bwd_tc(void* stream, int B, int V, int p0, int S, int D, const float* features, const float* E,
                                const float* W_ih, const float* W_hh, const float* W_v, const int* tokcm,
                                const long long* tokens_out, const float* dlogp, const float* Hs, const float* Cs,
                                const float* Gs, float* logits, float* dHv, float* DG, float* dh, float* dc,
                                float* dtable, float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE,
                                float* dW_cnn, float* db_cnn, float* dW_ih, float* dW_hh, float* db_ih, float* db_hh,
-                               float* dW_v, float* db_v, const void* tc_packed, void* tc_ws, float* tc_err,
+                               float* dW_v, float* db_v, const void* tc_packed, void* tc_ws, float* tc_err, int ldz,
                                int* launches);
 size_t icrl_colsum_ws_floats(long long rows, int cols);
 /* ---- teacher-forced LSTM sequence, one direction (bidirectional policy variant, models.py:59-78; for the reverse
