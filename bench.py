@@ -198,16 +198,20 @@ def roofline_of(phases, Bl, lay, peaks, clk):
                 "frac": None, "traffic": None, "note": "chains too short to cut or chain_segments=1: latency-bound serial walk"}
     (Pv, seg_v, warm_v), (Pr, seg_r, warm_r) = lay["v"], lay["r"]
     if bwd_ms >= fwd_ms:
+        Pv, seg_v, warm_v = lay.get("b") or lay["v"]
         kname, kms = "chain_tc_bwd_kernel", bwd_ms
         alg = Tv * 2.0 * 2048 * 512
         executed = 3.0 * Pv * (seg_v + warm_v) * 2.0 * 2048 * 512
         steps = seg_v + warm_v
         hbm_bytes = Tv * (6 * H * 4 + 4 * H * 4 + 4)          # stash read (gates, c_t, c_{t-1}) + dgates write + take
     else:
-        kname, kms = "chain_tc_fwd_kernel<4> + chain_tc_fwd_kernel<3> (value LSTM, reward GRU; two launches)", fwd_ms
+        fused = bool(lay.get("fused"))
+        kname = ("chains_tc_fwd_fused_kernel (value LSTM + reward GRU side by side, one launch)" if fused else
+                 "chain_tc_fwd_kernel<4> + chain_tc_fwd_kernel<3> (value LSTM, reward GRU; two launches)")
+        kms = fwd_ms
         alg = Tv * 2.0 * 512 * 2048 + Tr * 2.0 * 512 * 1536
         executed = 3.0 * (Pv * (seg_v + warm_v) * 2.0 * 512 * 2048 + Pr * (seg_r + warm_r) * 2.0 * 512 * 1536)
-        steps = seg_v + warm_v + seg_r + warm_r
+        steps = max(seg_v + warm_v, seg_r + warm_r) if fused else seg_v + warm_v + seg_r + warm_r
         hbm_bytes = Tv * (4 * H * 4 + 6 * H * 4 + 4) + Tr * (3 * H * 4 + H * 4 + 4)     # table row + stash (+ token)
     ach = alg / (kms * 1e-3) / 1e12 if kms > 0 else 0.0
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
@@ -456,7 +460,8 @@ def main():
     st = eng.segment_stats
     chain_cfg = None
     if lay is not None:
-        chain_cfg = {"engine": "tc", "pieces": {"value": lay["v"][0], "reward": lay["r"][0]},
+        chain_cfg = {"engine": "tc", "forward_launch": "fused (value + reward side by side)" if lay.get("fused") else "two launches",
+                     "pieces": {"value": lay["v"][0], "reward": lay["r"][0], "value_backward": (lay.get("b") or lay["v"])[0]},
                      "positions_per_piece": {"value": lay["v"][1], "reward": lay["r"][1]},
                      "warmup": {"value": lay["v"][2], "reward": lay["r"][2]}, "tolerance": eng.chain_tol,
                      "checked_max": dict(zip(("value_h", "value_c", "value_h_half", "value_c_half", "reward_h", "-", "reward_h_half",

@@ -57,6 +57,7 @@ SIGNATURES = {
     "icrl_chain_tc_cp_floats": [I],
     "icrl_pack_chain_tc_weights": [P, I, P, P, LP],
     "icrl_chain_tc_fwd": [P, I, I, L, I] + [P] * 10 + [LP],
+    "icrl_chains_tc_fwd_fused": [P, I, L, I] + [P] * 9 + [I, L, I] + [P] * 8 + [LP],
     "icrl_chain_tc_lstm_bwd": [P, I, L, I, P, P, P, P, P, L, P, P, P, P, LP],
     "icrl_chain_tc_set_profile": [P],
     "icrl_chain_tc_set_bias": [F, F],

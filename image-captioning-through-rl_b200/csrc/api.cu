@@ -464,6 +464,18 @@ int icrl_chain_tc_fwd(void* stream, int kind, int pieces, long long seg, int war
   return ICRL_OK;
 }
 
+int icrl_chains_tc_fwd_fused(void* stream, int v_pieces, long long v_seg, int v_warm, const int* v_stream,
+                             const float* v_table, const void* v_packed, float* v_stash_h, float* v_stash_c,
+                             float* v_stash_gates, void* v_ws, float* v_cp_state, float* v_err, int r_pieces, long long r_seg,
+                             int r_warm, const int* r_stream, const float* r_table, const void* r_packed, const float* r_b_hn,
+                             float* r_stash_h, void* r_ws, float* r_cp_state, float* r_err, int* launches) {
+  TRY(icrl_chains_tc_fwd_fused_impl(S_(stream), v_pieces, v_seg, v_warm, v_stream, v_table, v_packed, v_stash_h, v_stash_c,
+                                    v_stash_gates, v_ws, v_cp_state, v_err, r_pieces, r_seg, r_warm, r_stream, r_table,
+                                    r_packed, r_b_hn, r_stash_h, r_ws, r_cp_state, r_err));
+  bump(launches, 3);                       // one persistent cluster kernel for both chains + the two joint checks
+  return ICRL_OK;
+}
+
 int icrl_chain_tc_lstm_bwd(void* stream, int pieces, long long seg, int warm, const void* packed,
                            const float* stash_gates, const float* stash_c, const int* take, const float* dh_take,
                            long long take_rows, float* dgates, void* ws, float* cp_state, float* err, int* launches) {

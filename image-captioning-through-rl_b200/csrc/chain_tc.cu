@@ -96,8 +96,8 @@ struct FwdArgs {
 };
 
 template <int NG>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
-chain_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_w, const FwdArgs p) {
+__device__ __forceinline__ void chain_tc_fwd_body(const CUtensorMap& map_h, const CUtensorMap& map_w, const FwdArgs& p,
+                                                  const int cluster) {
   using C = FwdCfg<NG>;
   constexpr int GN = C::GN, B_TILE = C::B_TILE, STAGE = C::STAGE, STAGES = F_STAGES;
   extern __shared__ unsigned char smem_raw[];
@@ -109,7 +109,7 @@ chain_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned rank = cluster_rank();
-  const int m0 = (blockIdx.x / CL) * BM;
+  const int m0 = cluster * BM;
   const int P = p.P, Ppad = p.Ppad, steps = p.steps;
 
   if (threadIdx.x == 0) {
@@ -202,7 +202,7 @@ chain_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
     const long long seg = p.seg;
     int tok = valid ? p.stream[(long long)k_own * seg] : 0;
     const float mg = p.main_gain;
-    const bool prof = p.prof != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0;
+    const bool prof = p.prof != nullptr && cluster == 0 && rank == 0 && ew == 0 && lane == 0;
     long long pr[5] = {0, 0, 0, 0, 0};
 
     for (int j = 0; j < steps; ++j) {
@@ -379,6 +379,26 @@ chain_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
+}
+
+template <int NG>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
+chain_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_w, const FwdArgs p) {
+  chain_tc_fwd_body<NG>(map_h, map_w, p, blockIdx.x / CL);
+}
+
+// Value LSTM and reward GRU forward chains in ONE launch: clusters [0, clusters_v) walk the value chain, the rest the
+// reward chain.  The two recurrences are independent given the tokens; side by side each gets half of the co-resident
+// clusters, i.e. half the pieces of twice the length -- but the discarded warm-up is paid once in wall time instead of
+// twice, which is what bounds the step when a rank holds few rows (512 rows per rank at 8 GPUs: 51 live + 160..256
+// warm-up positions per piece).
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
+chains_tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_h_v, const __grid_constant__ CUtensorMap map_w_v,
+                           const FwdArgs pv, const __grid_constant__ CUtensorMap map_h_r,
+                           const __grid_constant__ CUtensorMap map_w_r, const FwdArgs pr, const int clusters_v) {
+  const int cluster = blockIdx.x / CL;
+  if (cluster < clusters_v) chain_tc_fwd_body<4>(map_h_v, map_w_v, pv, cluster);
+  else chain_tc_fwd_body<3>(map_h_r, map_w_r, pr, cluster - clusters_v);
 }
 
 // ------------------------------------------------------------------------------------------------ backward (LSTM)
@@ -949,9 +969,10 @@ static int pad_pieces(int P) { return icrl_cdiv(P, BM) * BM; }
 size_t icrl_chain_tc_ws_bytes_impl(int pieces) { return (size_t)4 * pad_pieces(pieces) * 4 * H * sizeof(__half); }
 size_t icrl_chain_tc_cp_floats_impl(int pieces) { return (size_t)2 * 2 * pieces * 2 * H; }
 
-int icrl_chain_tc_fwd_impl(cudaStream_t st, int kind, int P, long long seg, int warm, const int* stream,
-                           const float* table, const void* packed, const float* b_hn, float* stash_h, float* stash_c,
-                           float* stash_g, void* ws, float* cp_state, float* err) {
+// argument block, tensor maps and scratch initialisation of one forward chain launch
+static int fwd_setup(cudaStream_t st, int kind, int P, long long seg, int warm, const int* stream, const float* table,
+                     const void* packed, const float* b_hn, float* stash_h, float* stash_c, float* stash_g, void* ws,
+                     float* cp_state, float* err, FwdArgs* a, CUtensorMap* mh, CUtensorMap* mw) {
   ICRL_REQUIRE(kind == 0 || kind == 1, "kind: 0 = LSTM, 1 = GRU");
   ICRL_REQUIRE(P >= 2 && seg >= 1 && warm >= 1, "chain pieces need P >= 2, seg >= 1, warm >= 1");
   ICRL_REQUIRE((long long)P * seg + warm < (1ll << 31), "token stream longer than 2^31");
@@ -963,25 +984,58 @@ int icrl_chain_tc_fwd_impl(cudaStream_t st, int kind, int P, long long seg, int 
   ICRL_CUDA(cudaMemsetAsync(hparts, 0, (size_t)4 * Ppad * H * sizeof(__half) + (size_t)Ppad * H * sizeof(float), st));
   ICRL_CUDA(cudaMemsetAsync(stash_h, 0, H * sizeof(float), st));
   if (stash_c) ICRL_CUDA(cudaMemsetAsync(stash_c, 0, H * sizeof(float), st));
-  FwdArgs a;
-  a.P = P; a.Ppad = Ppad; a.steps = (int)(seg + warm); a.warm = warm; a.cp_half = cp_half_of(warm); a.seg = seg;
-  a.stream = stream; a.table = table; a.b_hn = b_hn; a.stash_h = stash_h; a.stash_c = stash_c; a.stash_g = stash_g;
-  a.state = state; a.hparts = hparts; a.wstate = cp_state; a.prof = g_chain_tc_prof; a.main_gain = 1.f + g_tc_bias[0];
-  CUtensorMap mh, mw;
+  a->P = P; a->Ppad = Ppad; a->steps = (int)(seg + warm); a->warm = warm; a->cp_half = cp_half_of(warm); a->seg = seg;
+  a->stream = stream; a->table = table; a->b_hn = b_hn; a->stash_h = stash_h; a->stash_c = stash_c; a->stash_g = stash_g;
+  a->state = state; a->hparts = hparts; a->wstate = cp_state; a->prof = g_chain_tc_prof; a->main_gain = 1.f + g_tc_bias[0];
   int rc;
-  if ((rc = make_map_2d(&mh, hparts, H, (long long)4 * Ppad, A_SLICE_ROWS))) return rc;
-  const int grid = CL * (Ppad / BM);
+  if ((rc = make_map_2d(mh, hparts, H, (long long)4 * Ppad, A_SLICE_ROWS))) return rc;
+  if (kind == 0) return make_map_3d(mw, packed, H, 4 * H, FwdCfg<4>::GN);
+  return make_map_3d(mw, packed, H, 3 * H, FwdCfg<3>::GN);
+}
+
+int icrl_chain_tc_fwd_impl(cudaStream_t st, int kind, int P, long long seg, int warm, const int* stream,
+                           const float* table, const void* packed, const float* b_hn, float* stash_h, float* stash_c,
+                           float* stash_g, void* ws, float* cp_state, float* err) {
+  FwdArgs a;
+  CUtensorMap mh, mw;
+  int rc = fwd_setup(st, kind, P, seg, warm, stream, table, packed, b_hn, stash_h, stash_c, stash_g, ws, cp_state, err, &a, &mh, &mw);
+  if (rc) return rc;
+  const int grid = CL * (a.Ppad / BM);
   if (kind == 0) {
-    if ((rc = make_map_3d(&mw, packed, H, 4 * H, FwdCfg<4>::GN))) return rc;
     ICRL_CUDA(cudaFuncSetAttribute(chain_tc_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<4>::SMEM));
     chain_tc_fwd_kernel<4><<<dim3(grid), dim3(THREADS), FwdCfg<4>::SMEM, st>>>(mh, mw, a);
   } else {
-    if ((rc = make_map_3d(&mw, packed, H, 3 * H, FwdCfg<3>::GN))) return rc;
     ICRL_CUDA(cudaFuncSetAttribute(chain_tc_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<3>::SMEM));
     chain_tc_fwd_kernel<3><<<dim3(grid), dim3(THREADS), FwdCfg<3>::SMEM, st>>>(mh, mw, a);
   }
   ICRL_LAUNCH_CHECK();
   chain_tc_check_fwd_kernel<<<dim3(P - 1, 2), H, 0, st>>>(P, seg, warm, a.cp_half, cp_state, stash_h, kind == 0 ? stash_c : nullptr, err);
+  ICRL_LAUNCH_CHECK();
+  return ICRL_OK;
+}
+
+// Both forward chains in one launch (chains_tc_fwd_fused_kernel): value LSTM with Pv pieces, reward GRU with Pr pieces.
+int icrl_chains_tc_fwd_fused_impl(cudaStream_t st, int Pv, long long seg_v, int warm_v, const int* v_stream,
+                                  const float* v_table, const void* v_packed, float* v_stash_h, float* v_stash_c,
+                                  float* v_stash_g, void* v_ws, float* v_cp, float* v_err, int Pr, long long seg_r,
+                                  int warm_r, const int* r_stream, const float* r_table, const void* r_packed,
+                                  const float* r_b_hn, float* r_stash_h, void* r_ws, float* r_cp, float* r_err) {
+  FwdArgs av, ar;
+  CUtensorMap mhv, mwv, mhr, mwr;
+  int rc;
+  if ((rc = fwd_setup(st, 0, Pv, seg_v, warm_v, v_stream, v_table, v_packed, nullptr, v_stash_h, v_stash_c, v_stash_g, v_ws,
+                      v_cp, v_err, &av, &mhv, &mwv))) return rc;
+  if ((rc = fwd_setup(st, 1, Pr, seg_r, warm_r, r_stream, r_table, r_packed, r_b_hn, r_stash_h, nullptr, nullptr, r_ws, r_cp,
+                      r_err, &ar, &mhr, &mwr))) return rc;
+  ar.prof = g_chain_tc_prof ? g_chain_tc_prof + 16 : nullptr;          // reward chain: slots [16..21]
+  const int cv = av.Ppad / BM, cr = ar.Ppad / BM;
+  constexpr int SMEM = FwdCfg<4>::SMEM > FwdCfg<3>::SMEM ? FwdCfg<4>::SMEM : FwdCfg<3>::SMEM;
+  ICRL_CUDA(cudaFuncSetAttribute(chains_tc_fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+  chains_tc_fwd_fused_kernel<<<dim3(CL * (cv + cr)), dim3(THREADS), SMEM, st>>>(mhv, mwv, av, mhr, mwr, ar, cv);
+  ICRL_LAUNCH_CHECK();
+  chain_tc_check_fwd_kernel<<<dim3(Pv - 1, 2), H, 0, st>>>(Pv, seg_v, warm_v, av.cp_half, v_cp, v_stash_h, v_stash_c, v_err);
+  ICRL_LAUNCH_CHECK();
+  chain_tc_check_fwd_kernel<<<dim3(Pr - 1, 2), H, 0, st>>>(Pr, seg_r, warm_r, ar.cp_half, r_cp, r_stash_h, nullptr, r_err);
   ICRL_LAUNCH_CHECK();
   return ICRL_OK;
 }

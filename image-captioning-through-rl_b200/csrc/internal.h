@@ -100,3 +100,8 @@ size_t icrl_policy_bptt_tc_ws_bytes_impl(int B, int n_cell);
 int icrl_policy_bptt_tc_impl(cudaStream_t st, int B, int n_cell, int p0, const void* packed, const float* Gs,
                              const float* Cs, const float* dHv, float* DG, float* dh0, void* ws, float* err);
 int icrl_pack_transposed_bf16x3_impl(cudaStream_t st, int rows, int cols, int Kp, const float* W, void* parts);
+int icrl_chains_tc_fwd_fused_impl(cudaStream_t st, int Pv, long long seg_v, int warm_v, const int* v_stream,
+                                  const float* v_table, const void* v_packed, float* v_stash_h, float* v_stash_c,
+                                  float* v_stash_g, void* v_ws, float* v_cp, float* v_err, int Pr, long long seg_r,
+                                  int warm_r, const int* r_stream, const float* r_table, const void* r_packed,
+                                  const float* r_b_hn, float* r_stash_h, void* r_ws, float* r_cp, float* r_err);

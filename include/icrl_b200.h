@@ -272,6 +272,14 @@ int icrl_pack_chain_tc_weights(void* stream, int kind, const float* W_hh, void* 
 int icrl_chain_tc_fwd(void* stream, int kind, int pieces, long long seg, int warm, const int* tok_stream,
                       const float* table, const void* packed, const float* b_hn, float* stash_h, float* stash_c,
                       float* stash_gates, void* ws, float* cp_state, float* err, int* launches);
+/* Value LSTM and reward GRU forward chains in ONE launch: the co-resident clusters are split between the two independent
+ * recurrences (v_pieces + r_pieces <= icrl_chain_tc_max_pieces(), each rounded up to whole clusters of 128), so the discarded
+ * warm-up is paid once in wall time instead of twice.  Arguments as two icrl_chain_tc_fwd calls (kind 0, then kind 1). */
+int icrl_chains_tc_fwd_fused(void* stream, int v_pieces, long long v_seg, int v_warm, const int* v_stream,
+                             const float* v_table, const void* v_packed, float* v_stash_h, float* v_stash_c,
+                             float* v_stash_gates, void* v_ws, float* v_cp_state, float* v_err, int r_pieces, long long r_seg,
+                             int r_warm, const int* r_stream, const float* r_table, const void* r_packed, const float* r_b_hn,
+                             float* r_stash_h, void* r_ws, float* r_cp_state, float* r_err, int* launches);
 int icrl_chain_tc_lstm_bwd(void* stream, int pieces, long long seg, int warm, const void* packed,
                            const float* stash_gates, const float* stash_c, const int* take, const float* dh_take,
                            long long take_rows, float* dgates, void* ws, float* cp_state, float* err, int* launches);
