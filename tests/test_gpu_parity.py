@@ -667,7 +667,7 @@ def test_flat_adam_matches_torch():
         o2.step()
         for (k, p1), (_, p2) in zip(A1.named_parameters(), A2.named_parameters()):
             d = float((p1 - p2).abs().max())
-            assert d <= 2e-7, (it, k, d)
+            assert d <= 5e-7, (it, k, d)            # one float ulp of the largest weights (|w| < 4)
             p2.data.copy_(p1.data)                  # keep both sides on the same trajectory
     assert A2.policy_network.linear2vocab.weight.data_ptr() >= o2.flat_param.data_ptr()      # parameters live in the flat buffer
     # the kernels must run on parameters that live inside the flat buffer (16-byte accesses: every tensor, including
