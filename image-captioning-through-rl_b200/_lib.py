@@ -61,6 +61,7 @@ SIGNATURES = {
     "icrl_chain_tc_lstm_bwd": [P, I, L, I, P, P, P, P, P, L, P, P, P, P, LP],
     "icrl_chain_tc_set_profile": [P],
     "icrl_chain_tc_set_bias": [F, F],
+    "icrl_chain_tc_set_tma_store": [I],
     "icrl_chain_set_profile": [P],
     "icrl_chain_sync_bytes": [],
     "icrl_chain_lstm_fwd": [P, P, I] + [P] * 10 + [LP],

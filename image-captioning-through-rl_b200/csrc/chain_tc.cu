@@ -92,12 +92,22 @@ struct FwdArgs {
   __half* hparts;          // [2 buffers][2 parts][Ppad][512]; buffer 0 zeroed by the launcher
   float* wstate;           // [2 checkpoints][P][2][512]: (h, c) of piece k after step cp_half (0) / warm-1 (1)
   float main_gain;         // 1 + compensation of the tensor core's truncating accumulation (see g_tc_bias)
+  int tma_store;           // the stash of the live positions leaves through TMA tensor stores (maps in FwdMaps)
   long long* prof;         // optional: cycle sums of CTA 0's first epilogue warp {acc wait, gather, cell, store, barrier}, steps
 };
 
+// fp32 stash arrays as 3-D tensors {column, step j of a piece, piece}: row (k * seg + j [+ 1]) of the array, i.e. strides
+// (4 B, row, seg rows).  The epilogue's staging tiles ([32 pieces][32 units] f32, 16-byte chunk c of row r at
+// r*128 + ((c ^ (r & 7)) << 4)) ARE the 128B-swizzled box {32, 1, 32} of these maps, so a tile leaves with one instruction.
+struct FwdMaps {
+  CUtensorMap h, w;        // operands: fp16 split of h (A, multicast slices), packed W_hh (B)
+  CUtensorMap sg, sc, sh;  // stores: stash_g [..][2048], stash_c / stash_h [..][512] (both based at row 1)
+};
+
 template <int NG>
-__device__ __forceinline__ void chain_tc_fwd_body(const CUtensorMap& map_h, const CUtensorMap& map_w, const FwdArgs& p,
-                                                  const int cluster) {
+__device__ __forceinline__ void chain_tc_fwd_body(const FwdMaps& maps, const FwdArgs& p, const int cluster) {
+  const CUtensorMap& map_h = maps.h;
+  const CUtensorMap& map_w = maps.w;
   using C = FwdCfg<NG>;
   constexpr int GN = C::GN, B_TILE = C::B_TILE, STAGE = C::STAGE, STAGES = F_STAGES;
   extern __shared__ unsigned char smem_raw[];
@@ -324,8 +334,27 @@ __device__ __forceinline__ void chain_tc_fwd_body(const CUtensorMap& map_h, cons
           }
         }
       }
-      // (S2) coalesced stores, 8 lanes per row: backward stash (live positions) and checkpoints
-      {
+      // (S2) backward stash of the live positions.  From the end of the warm-up on every piece is live: each staging tile
+      // leaves as ONE TMA tensor store (pieces past P are clipped by the map).  Before that only piece 0 is live, and the
+      // two checkpoint steps need the per-thread path as well.
+      const bool tma_path = p.tma_store && j >= p.warm;
+      if (tma_path) {
+        fence_proxy_async_smem();                // this thread's staging writes -> visible to the async proxy
+        __syncwarp();
+        if (lane == 0) {
+          const int k0 = m0 + 32 * q;
+          if constexpr (NG == 4) {
+            if (p.stash_g) {
+#pragma unroll
+              for (int a = 0; a < 4; ++a) tma_store_3d(&maps.sg, smem_u32(gst + a * 4096), a * H + ucol0, j, k0);
+            }
+            tma_store_3d(&maps.sc, smem_u32(gst + 4 * 4096), ucol0, j, k0);
+          }
+          tma_store_3d(&maps.sh, smem_u32(gst + (C::NARR - 1) * 4096), ucol0, j, k0);
+          tma_store_commit();
+        }
+      }
+      if (!tma_path || j == p.warm - 1 || j == p.cp_half) {
         const int c4 = lane & 7;
         const bool cp_full = j == p.warm - 1, cp_half = j == p.cp_half;
 #pragma unroll
@@ -335,7 +364,7 @@ __device__ __forceinline__ void chain_tc_fwd_body(const CUtensorMap& map_h, cons
           if (kr < P) {
             const unsigned char* e = gst + r * 128 + ((c4 ^ (r & 7)) << 4);
             const size_t pos = (size_t)kr * seg + j;
-            const bool live = kr == 0 || j >= p.warm;
+            const bool live = !tma_path && (kr == 0 || j >= p.warm);
             const int uc = ucol0 + c4 * 4;
             const float4 h4 = *reinterpret_cast<const float4*>(e + (C::NARR - 1) * 4096);
             if constexpr (NG == 4) {
@@ -357,6 +386,7 @@ __device__ __forceinline__ void chain_tc_fwd_body(const CUtensorMap& map_h, cons
           }
         }
       }
+      if (tma_path && lane == 0) tma_store_wait_read();     // the staging tiles have been read: the ring may be refilled
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty);
@@ -383,8 +413,8 @@ __device__ __forceinline__ void chain_tc_fwd_body(const CUtensorMap& map_h, cons
 
 template <int NG>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
-chain_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_w, const FwdArgs p) {
-  chain_tc_fwd_body<NG>(map_h, map_w, p, blockIdx.x / CL);
+chain_tc_fwd_kernel(const __grid_constant__ FwdMaps maps, const FwdArgs p) {
+  chain_tc_fwd_body<NG>(maps, p, blockIdx.x / CL);
 }
 
 // Value LSTM and reward GRU forward chains in ONE launch: clusters [0, clusters_v) walk the value chain, the rest the
@@ -393,12 +423,11 @@ chain_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
 // twice, which is what bounds the step when a rank holds few rows (512 rows per rank at 8 GPUs: 51 live + 160..256
 // warm-up positions per piece).
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
-chains_tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_h_v, const __grid_constant__ CUtensorMap map_w_v,
-                           const FwdArgs pv, const __grid_constant__ CUtensorMap map_h_r,
-                           const __grid_constant__ CUtensorMap map_w_r, const FwdArgs pr, const int clusters_v) {
+chains_tc_fwd_fused_kernel(const __grid_constant__ FwdMaps maps_v, const FwdArgs pv, const __grid_constant__ FwdMaps maps_r,
+                           const FwdArgs pr, const int clusters_v) {
   const int cluster = blockIdx.x / CL;
-  if (cluster < clusters_v) chain_tc_fwd_body<4>(map_h_v, map_w_v, pv, cluster);
-  else chain_tc_fwd_body<3>(map_h_r, map_w_r, pr, cluster - clusters_v);
+  if (cluster < clusters_v) chain_tc_fwd_body<4>(maps_v, pv, cluster);
+  else chain_tc_fwd_body<3>(maps_r, pr, cluster - clusters_v);
 }
 
 // ------------------------------------------------------------------------------------------------ backward (LSTM)
@@ -912,6 +941,23 @@ int make_map_3d(CUtensorMap* map, const void* ptr, long long cols, long long row
   return ICRL_OK;
 }
 
+// fp32 [..][cols] stash array as {column, step of a piece, piece}: strides (4 B, cols * 4 B, seg * cols * 4 B), box
+// {box_cols, 1, 32} with the swizzle whose span equals the box row (32 floats: 128B, 16 floats: 64B).  Returns
+// ICRL_ERR_CUDA when the driver refuses the (overlapping) strides; callers then keep the per-thread stores.
+int make_map_stash(CUtensorMap* map, const float* base, int cols, long long steps, long long seg, int P, int box_cols) {
+  EncodeTiledFn fn;
+  int rc = encode_fn(&fn);
+  if (rc) return rc;
+  const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)steps, (cuuint64_t)P};
+  const cuuint64_t strides[2] = {(cuuint64_t)cols * 4, (cuuint64_t)seg * cols * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)box_cols, 1, 32};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? ICRL_OK : ICRL_ERR_CUDA;
+}
+
 int cp_half_of(int warm) { return warm >= 8 ? warm / 2 - 1 : -1; }
 
 }  // namespace
@@ -927,6 +973,8 @@ int cp_half_of(int warm) { return warm >= 8 ? warm / 2 - 1 : -1; }
 // overrides the two factors (experiments).
 static float g_tc_bias[2] = {32 * 1.8e-8f, 128 * 1.8e-8f};
 void icrl_chain_tc_set_bias_impl(float fwd, float bwd) { g_tc_bias[0] = fwd; g_tc_bias[1] = bwd; }
+static int g_tc_tma_store = 1;                 // icrl_chain_tc_set_tma_store: stash stores through TMA (1) or per thread (0)
+void icrl_chain_tc_set_tma_store_impl(int on) { g_tc_tma_store = on; }
 static long long* g_chain_tc_prof = nullptr;      // icrl_chain_tc_set_profile: 16 device int64 (forward [0..5], backward [8..13])
 void icrl_chain_tc_set_profile_impl(long long* buf) { g_chain_tc_prof = buf; }
 
@@ -972,7 +1020,9 @@ size_t icrl_chain_tc_cp_floats_impl(int pieces) { return (size_t)2 * 2 * pieces 
 // argument block, tensor maps and scratch initialisation of one forward chain launch
 static int fwd_setup(cudaStream_t st, int kind, int P, long long seg, int warm, const int* stream, const float* table,
                      const void* packed, const float* b_hn, float* stash_h, float* stash_c, float* stash_g, void* ws,
-                     float* cp_state, float* err, FwdArgs* a, CUtensorMap* mh, CUtensorMap* mw) {
+                     float* cp_state, float* err, FwdArgs* a, FwdMaps* m) {
+  CUtensorMap* mh = &m->h;
+  CUtensorMap* mw = &m->w;
   ICRL_REQUIRE(kind == 0 || kind == 1, "kind: 0 = LSTM, 1 = GRU");
   ICRL_REQUIRE(P >= 2 && seg >= 1 && warm >= 1, "chain pieces need P >= 2, seg >= 1, warm >= 1");
   ICRL_REQUIRE((long long)P * seg + warm < (1ll << 31), "token stream longer than 2^31");
@@ -989,6 +1039,21 @@ static int fwd_setup(cudaStream_t st, int kind, int P, long long seg, int warm, 
   a->state = state; a->hparts = hparts; a->wstate = cp_state; a->prof = g_chain_tc_prof; a->main_gain = 1.f + g_tc_bias[0];
   int rc;
   if ((rc = make_map_2d(mh, hparts, H, (long long)4 * Ppad, A_SLICE_ROWS))) return rc;
+  // the stash stores as TMA tensor stores (g_tc_tma_store: experiment switch); a refused encode keeps the per-thread stores
+  a->tma_store = 0;
+  if (g_tc_tma_store) {
+    const long long steps = seg + warm;
+    int ok = make_map_stash(&m->sh, stash_h + H, H, steps, seg, P, 32) == ICRL_OK;
+    if (kind == 0) {
+      ok = ok && make_map_stash(&m->sc, stash_c + H, H, steps, seg, P, 32) == ICRL_OK;
+      if (stash_g) ok = ok && make_map_stash(&m->sg, stash_g, 4 * H, steps, seg, P, 32) == ICRL_OK;
+      else m->sg = m->sh;
+    } else {
+      m->sc = m->sh; m->sg = m->sh;
+    }
+    a->tma_store = ok ? 1 : 0;
+  }
+  if (!a->tma_store) { m->sh = *mh; m->sc = *mh; m->sg = *mh; }       // defined contents for the unused maps
   if (kind == 0) return make_map_3d(mw, packed, H, 4 * H, FwdCfg<4>::GN);
   return make_map_3d(mw, packed, H, 3 * H, FwdCfg<3>::GN);
 }
@@ -997,16 +1062,16 @@ int icrl_chain_tc_fwd_impl(cudaStream_t st, int kind, int P, long long seg, int 
                            const float* table, const void* packed, const float* b_hn, float* stash_h, float* stash_c,
                            float* stash_g, void* ws, float* cp_state, float* err) {
   FwdArgs a;
-  CUtensorMap mh, mw;
-  int rc = fwd_setup(st, kind, P, seg, warm, stream, table, packed, b_hn, stash_h, stash_c, stash_g, ws, cp_state, err, &a, &mh, &mw);
+  FwdMaps m;
+  int rc = fwd_setup(st, kind, P, seg, warm, stream, table, packed, b_hn, stash_h, stash_c, stash_g, ws, cp_state, err, &a, &m);
   if (rc) return rc;
   const int grid = CL * (a.Ppad / BM);
   if (kind == 0) {
     ICRL_CUDA(cudaFuncSetAttribute(chain_tc_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<4>::SMEM));
-    chain_tc_fwd_kernel<4><<<dim3(grid), dim3(THREADS), FwdCfg<4>::SMEM, st>>>(mh, mw, a);
+    chain_tc_fwd_kernel<4><<<dim3(grid), dim3(THREADS), FwdCfg<4>::SMEM, st>>>(m, a);
   } else {
     ICRL_CUDA(cudaFuncSetAttribute(chain_tc_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<3>::SMEM));
-    chain_tc_fwd_kernel<3><<<dim3(grid), dim3(THREADS), FwdCfg<3>::SMEM, st>>>(mh, mw, a);
+    chain_tc_fwd_kernel<3><<<dim3(grid), dim3(THREADS), FwdCfg<3>::SMEM, st>>>(m, a);
   }
   ICRL_LAUNCH_CHECK();
   chain_tc_check_fwd_kernel<<<dim3(P - 1, 2), H, 0, st>>>(P, seg, warm, a.cp_half, cp_state, stash_h, kind == 0 ? stash_c : nullptr, err);
@@ -1021,17 +1086,17 @@ int icrl_chains_tc_fwd_fused_impl(cudaStream_t st, int Pv, long long seg_v, int 
                                   int warm_r, const int* r_stream, const float* r_table, const void* r_packed,
                                   const float* r_b_hn, float* r_stash_h, void* r_ws, float* r_cp, float* r_err) {
   FwdArgs av, ar;
-  CUtensorMap mhv, mwv, mhr, mwr;
+  FwdMaps mv, mr;
   int rc;
   if ((rc = fwd_setup(st, 0, Pv, seg_v, warm_v, v_stream, v_table, v_packed, nullptr, v_stash_h, v_stash_c, v_stash_g, v_ws,
-                      v_cp, v_err, &av, &mhv, &mwv))) return rc;
+                      v_cp, v_err, &av, &mv))) return rc;
   if ((rc = fwd_setup(st, 1, Pr, seg_r, warm_r, r_stream, r_table, r_packed, r_b_hn, r_stash_h, nullptr, nullptr, r_ws, r_cp,
-                      r_err, &ar, &mhr, &mwr))) return rc;
+                      r_err, &ar, &mr))) return rc;
   ar.prof = g_chain_tc_prof ? g_chain_tc_prof + 16 : nullptr;          // reward chain: slots [16..21]
   const int cv = av.Ppad / BM, cr = ar.Ppad / BM;
   constexpr int SMEM = FwdCfg<4>::SMEM > FwdCfg<3>::SMEM ? FwdCfg<4>::SMEM : FwdCfg<3>::SMEM;
   ICRL_CUDA(cudaFuncSetAttribute(chains_tc_fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-  chains_tc_fwd_fused_kernel<<<dim3(CL * (cv + cr)), dim3(THREADS), SMEM, st>>>(mhv, mwv, av, mhr, mwr, ar, cv);
+  chains_tc_fwd_fused_kernel<<<dim3(CL * (cv + cr)), dim3(THREADS), SMEM, st>>>(mv, av, mr, ar, cv);
   ICRL_LAUNCH_CHECK();
   chain_tc_check_fwd_kernel<<<dim3(Pv - 1, 2), H, 0, st>>>(Pv, seg_v, warm_v, av.cp_half, v_cp, v_stash_h, v_stash_c, v_err);
   ICRL_LAUNCH_CHECK();
