@@ -973,7 +973,12 @@ int cp_half_of(int warm) { return warm >= 8 ? warm / 2 - 1 : -1; }
 // overrides the two factors (experiments).
 static float g_tc_bias[2] = {32 * 1.8e-8f, 128 * 1.8e-8f};
 void icrl_chain_tc_set_bias_impl(float fwd, float bwd) { g_tc_bias[0] = fwd; g_tc_bias[1] = bwd; }
-static int g_tc_tma_store = 1;                 // icrl_chain_tc_set_tma_store: stash stores through TMA (1) or per thread (0)
+// icrl_chain_tc_set_tma_store: stash stores through TMA tensor stores (1) or per-thread vector stores (0, default).
+// Measured at B = 4096: no gain (forward 18.5 vs 17.7 ms) -- the store phase is not bound by instruction issue but by the
+// L2: every cluster writes its 240 KB of stash per CTA in the same window (29 MB per kernel step chip-wide, on top of
+// 92 MB of operand fill and 20 MB of gathers: 141 MB per step = 22 K cycles at the measured 6.3 KB/clk L2 cap, against
+// a step of 35 K).  Kept as a switch.
+static int g_tc_tma_store = 0;
 void icrl_chain_tc_set_tma_store_impl(int on) { g_tc_tma_store = on; }
 static long long* g_chain_tc_prof = nullptr;      // icrl_chain_tc_set_profile: 16 device int64 (forward [0..5], backward [8..13])
 void icrl_chain_tc_set_profile_impl(long long* buf) { g_chain_tc_prof = buf; }

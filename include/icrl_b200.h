@@ -290,8 +290,8 @@ int icrl_chain_tc_set_profile(void* buf);
  * chain kernels (the tensor core truncates on every accumulate).  Default 5.76e-7, 2.3e-6 = 1.8e-8 per
  * accumulating MMA instruction. */
 int icrl_chain_tc_set_bias(float fwd, float bwd);
-/* Experiment knob: 1 (default) = the forward stash of the live positions leaves through TMA tensor stores, 0 = per-thread
- * vector stores. */
+/* Experiment knob: 1 = the forward stash of the live positions leaves through TMA tensor stores, 0 (default) = per-thread
+ * vector stores (measured equal: the store phase is L2-bound, not issue-bound). */
 int icrl_chain_tc_set_tma_store(int on);
 /* Debug aid: when buf != NULL (16 device int64), CTA 0 / thread 0 of the sharded / segmented chain kernels accumulates its
  * cycles per phase: [0..3] value LSTM forward {exchange wait, GEMV + reduce, pointwise + publish, T}, [4..7] reward GRU
