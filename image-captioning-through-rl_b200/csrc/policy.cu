@@ -138,6 +138,20 @@ __global__ void softmax_bwd_kernel(int B, int S, int V, float* __restrict__ z, i
   }
 }
 
+// The same with 16-byte vector reductions (red.global.add.v4.f32, sm_90+): a quarter of the instructions and of the L2
+// atomic transactions of the scalar form (1.6 G atomics per step at B = 4096: 3.9 ms, 6.5 % of the step).  C % 4 == 0.
+__global__ void scatter_add_rows_v4_kernel(long long R, int C4, const float4* __restrict__ src, const int* __restrict__ idx,
+                                           float* __restrict__ dst) {
+  const long long total = R * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C4;
+    const int c = (int)(i % C4);
+    const float4 v = __ldg(src + i);
+    float* d = dst + ((size_t)idx[r] * C4 + c) * 4;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  }
+}
+
 // dst[idx[r]][c] += src[r][c]   (gate-table gradient: rows that consumed the same token accumulate)
 __global__ void scatter_add_rows_kernel(long long R, int C, const float* __restrict__ src, const int* __restrict__ idx,
                                         float* __restrict__ dst) {
@@ -206,6 +220,11 @@ int icrl_softmax_bwd(cudaStream_t st, int B, int S, int V, float* z, int ldl, co
 int icrl_scatter_add_rows(cudaStream_t st, long long R, int C, const float* src, const int* idx, float* dst) {
   const long long total = R * C;
   const int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
+  if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    scatter_add_rows_v4_kernel<<<blocks, 256, 0, st>>>(R, C / 4, reinterpret_cast<const float4*>(src), idx, dst);
+    ICRL_LAUNCH_CHECK();
+    return ICRL_OK;
+  }
   scatter_add_rows_kernel<<<blocks, 256, 0, st>>>(R, C, src, idx, dst);
   ICRL_LAUNCH_CHECK();
   return ICRL_OK;

@@ -353,6 +353,15 @@ class A2CEngine:
             assert tuple(u.shape) == (S, B), "uniforms must be (S,B) float64"
         return Prepared(f, prefix_cm, u, B, p0, S)
 
+    def gather_rows(self, matrix, rows):
+        """matrix[rows] on the device: `matrix` (M,512) f32 resident in HBM, `rows` host integers (only they cross the
+        bus).  The device-side half of the reference's minibatch generator (utilities.py:172-176)."""
+        idx = torch.as_tensor(np.asarray(rows), dtype=torch.int32).to(self.device, non_blocking=True)
+        out = torch.empty((idx.numel(), H), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.call("icrl_gather_rows", self._stream, idx.numel(), _p(matrix), _p(idx), 0, _p(out), self.launches.ref)
+        return out
+
     def _stage_inputs(self, prep, forced):
         B, p0, S = prep.B, prep.p0, prep.S
         tokcm = self._buf("tokcm", (p0 + S) * B, torch.int32)

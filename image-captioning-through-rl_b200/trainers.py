@@ -382,10 +382,30 @@ def _module_route_step(a2c_network, reward_network, features, captions, level):
     return _ModuleRouteResult(float(loss), float(rewards.mean()), float(advantage.mean()))
 
 
+def get_coco_minibatches_device(data, eng, batch_size=100, split="train"):
+    """get_coco_minibatches (utilities.py:160-178) with the feature matrix resident in HBM: it is uploaded
+    once per (split, device); every minibatch draws the same torch.randperm slice as the reference, sends only the B image
+    indices to the device and gathers the B feature rows there (icrl_gather_rows).  Yields the reference's tuple with the
+    features as a (B,512) CUDA tensor, which A2CEngine.step / prepare take without a host->device copy."""
+    cache = data.setdefault("_icrl_device_features", {})
+    key = (split, str(eng.device))
+    if key not in cache:
+        cache[key] = torch.as_tensor(np.ascontiguousarray(data["%s_features" % split]), dtype=torch.float32).to(eng.device).contiguous()
+    feats = cache[key]
+    n = data["%s_captions" % split].shape[0]
+    perm = torch.randperm(n)
+    for i in range(0, n, batch_size):
+        mask = perm[i:i + batch_size].numpy()
+        idxs = data["%s_image_idxs" % split][mask]
+        yield data["%s_captions" % split][mask], eng.gather_rows(feats, idxs), data["%s_urls" % split][idxs]
+
+
 def _run_minibatches(train_data, a2c_network, reward_network, optimizer, writer, batch_size, epoch, level, tag, best):
     bidir = getattr(a2c_network.policy_network, "bidirectional", False)
     eng = None if bidir else _engine_for(a2c_network, reward_network)
-    for minibatch_id, (captions, features, _) in enumerate(get_coco_minibatches(train_data, batch_size=batch_size)):
+    batches = get_coco_minibatches(train_data, batch_size=batch_size) if bidir else \
+        get_coco_minibatches_device(train_data, eng, batch_size=batch_size)
+    for minibatch_id, (captions, features, _) in enumerate(batches):
         res = (_module_route_step(a2c_network, reward_network, features, captions, level) if bidir
                else eng.step(features, captions, level=level))
         if res is not None:                           # curriculum: prefix shorter than 1 => skipped (trainers.py:550)
