@@ -61,6 +61,8 @@ SIGNATURES = {
     "icrl_chain_tc_lstm_bwd": [P, I, L, I, P, P, P, P, P, L, P, P, P, P, LP],
     "icrl_chain_tc_set_profile": [P],
     "icrl_chain_tc_set_bias": [F, F],
+    "icrl_chain_tc_bwd_max_pieces": [],
+    "icrl_chain_tc_set_bwd2": [I],
     "icrl_chain_tc_set_tma_store": [I],
     "icrl_chain_set_profile": [P],
     "icrl_chain_sync_bytes": [],
@@ -84,7 +86,7 @@ _RESTYPES = {"icrl_last_error": c_char_p, "icrl_wgrad_tc_ws_bytes": c_size_t, "i
              "icrl_chain_sync_bytes": c_size_t, "icrl_chain_segment_len": c_longlong, "icrl_chain_segment_ws_floats": c_size_t,
              "icrl_chain_tc_weight_halves": c_size_t, "icrl_chain_tc_ws_bytes": c_size_t, "icrl_chain_tc_cp_floats": c_size_t,
              "icrl_policy_bwd_tc_ws_bytes": c_size_t}
-_NO_STATUS = set(_RESTYPES) | {"icrl_version", "icrl_chain_tc_max_pieces", "icrl_vocab_pad"}
+_NO_STATUS = set(_RESTYPES) | {"icrl_version", "icrl_chain_tc_max_pieces", "icrl_chain_tc_bwd_max_pieces", "icrl_vocab_pad"}
 
 
 class IcrlError(RuntimeError):

@@ -449,11 +449,11 @@ class A2CEngine:
                 return (K, seg_v, seg_r, warm)
         return None
 
-    def _pieces_for(self, T, warm):
+    def _pieces_for(self, T, warm, pmax=None):
         """(P, seg) for a chain of T positions cut into tcgen05 pieces with a `warm`-position warm-up, or None when it is
         too short.  As many pieces as are co-resident (whole clusters of 128 once there is more than one), each at least
         max(warm / 4, 8) live positions long: the wall time of a launch is seg + warm kernel steps."""
-        pmax = self.chain_pieces or int(_lib.call("icrl_chain_tc_max_pieces"))
+        pmax = self.chain_pieces or pmax or int(_lib.call("icrl_chain_tc_max_pieces"))
         min_seg = max(warm // 4, 8)
         if T <= warm + 2 * min_seg:
             return None
@@ -481,8 +481,9 @@ class A2CEngine:
         # "b": the backward recurrence of the value chain always gets every co-resident cluster (its own launch); it may
         # be cut differently from the forward as long as the arrays cover both layouts (the stash rows past the forward's
         # end are zeroed: padding positions, whose gate gradients are exactly zero)
+        bw = None if v is None else (self._pieces_for(Tv, wv, int(_lib.call("icrl_chain_tc_bwd_max_pieces"))) or v)
         lay = {"v": None if v is None else (v[0], v[1], wv), "r": (r[0], r[1], wr), "fused": False,
-               "b": None if v is None else (v[0], v[1], wv)}
+               "b": None if bw is None else (bw[0], bw[1], wv)}
         if v is None or not self.chain_fuse_fwd or self.chain_pieces is not None:
             return lay
         C = int(_lib.call("icrl_chain_tc_max_pieces")) // 128
