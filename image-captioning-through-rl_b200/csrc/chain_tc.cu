@@ -30,6 +30,7 @@
 // scaled by a power of two derived from max |dL/dh_take| (fp16 keeps 22 bits down to 2^-18 of that maximum; overflow
 // is detected and reported).  The fp32 gate gradients of live positions go to `dgates` for the parameter-gradient
 // contractions exactly as the serial kernel writes them.
+#include <stdlib.h>
 #include "tc_ptx.cuh"
 #include "internal.h"
 
@@ -131,7 +132,7 @@ __device__ __forceinline__ void chain_tc_fwd_body(const FwdMaps& maps, const Fwd
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -407,7 +408,7 @@ __device__ __forceinline__ void chain_tc_fwd_body(const FwdMaps& maps, const Fwd
   cluster_arrive();                          // nobody leaves while a peer may still multicast into its shared memory
   cluster_wait();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
 }
 
@@ -495,7 +496,7 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(B_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(B_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -793,19 +794,20 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
   cluster_arrive();
   cluster_wait();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(B_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(B_TMEM_COLS) : "memory");
   }
 }
 
 // Two co-resident CTAs per SM (chain_tc_bwd2_kernel): the epilogue of one cluster's step runs under the operand fill of the
 // cluster that shares its SMs.  Needs half the shared memory (4-stage ring; staging in four passes of 8 hidden units) and
-// an epilogue inside 96 registers (320 threads per CTA: no idle warps, the carried dL/dc in shared memory instead of
-// registers); tensor memory is 128 columns per CTA either way.
+// an epilogue inside 80 registers (the carried dL/dc in shared memory instead of registers, the cell gradients in groups
+// of four); tensor memory is 128 columns per CTA either way.
 constexpr int B2_STAGES = 3, B2_NPASS = 4;
 constexpr int B2_GST_WARP = B_NARR * 1024;                  // staging arrays of [32 rows][8 units] f32
 constexpr int B2_DC_BYTES = UN * BM * 4;                    // carried dL/dc of the CTA's 64 units x 128 pieces (32 KB)
 constexpr int B2_SMEM = B2_STAGES * B_STAGE + B2_DC_BYTES + 256 + 1024;
-constexpr int THREADS2 = 32 * (2 + EPI_WARPS);              // TMA warp, MMA warp, 8 epilogue warps: 320 threads, <= 102 registers
+constexpr int THREADS2 = THREADS;                           // registers are granted per 4 warps: 10 warps cost as much as 12, so keep the
+                                                            // two idle warps of the one-CTA kernels (12 warps x 80 registers x 2 CTAs)
 static_assert(EPI_WARPS * B2_GST_WARP <= B2_STAGES * B_STAGE, "epilogue staging lives inside the (idle) TMA ring");
 
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS2, 2)
@@ -834,7 +836,7 @@ chain_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(B_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(B_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -844,7 +846,9 @@ chain_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_co
   cluster_arrive();
   cluster_wait();
 
-  if (warp == 0) {
+  if (warp == 2 || warp == 3) {
+    for (int it = 0; it < iters; ++it) { cluster_arrive(); cluster_wait(); }     // idle warps: keep the barrier counts complete
+  } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (no GEMM before the first step)
     unsigned n = 0;
     for (int it = 0; it < iters; ++it) {
@@ -900,7 +904,7 @@ chain_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_co
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int ew = warp - 2;                   // warps 2..9: TMEM lane quarters 2,3,0,1,2,3,0,1
+    const int ew = warp - EPI_WARP0;
     const int q = warp & 3;
     const int ch = ew >> 2;
     const int k_own = m0 + 32 * q + lane;
@@ -957,7 +961,7 @@ chain_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_co
       }
       const bool w_full = it == p.warm - 1, w_half = it == p.cp_half;            // warm-up side records (pieces < P-1)
       const bool r_full = it == steps - 1, r_half = p.cp_half >= 0 && it == half_ref_it;   // reference side (pieces >= 1)
-#pragma unroll
+#pragma unroll 1
       for (int ps = 0; ps < B2_NPASS; ++ps) {
         const int ucolp = (int)rank * UN + 32 * ch + 8 * ps;
         // (L) stash of this position: activated gates (arrays 0..3), c_t (4), c_{t-1} (5), injected dL/dh (6); 2 lanes per
@@ -1086,7 +1090,7 @@ chain_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_co
   cluster_arrive();
   cluster_wait();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(B_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(B_TMEM_COLS) : "memory");
   }
 }
 
@@ -1273,9 +1277,12 @@ void icrl_chain_tc_set_bias_impl(float fwd, float bwd) { g_tc_bias[0] = fwd; g_t
 // a step of 35 K).  Kept as a switch.
 static int g_tc_tma_store = 0;
 void icrl_chain_tc_set_tma_store_impl(int on) { g_tc_tma_store = on; }
-// icrl_chain_tc_set_bwd2: the backward recurrence (value chain and policy BPTT) on chain_tc_bwd2_kernel (two co-resident
-// CTAs per SM, default) or on chain_tc_bwd_kernel (one CTA per SM, 8-stage ring).
-static int g_tc_bwd2 = 1;
+// icrl_chain_tc_set_bwd2: the backward recurrence (value chain and policy BPTT) on chain_tc_bwd_kernel (one CTA per SM,
+// 8-stage ring; default) or on chain_tc_bwd2_kernel, built for two co-resident CTAs per SM.  Measured (B = 4096): the
+// driver grants this tcgen05 kernel ONE CTA per SM whatever its footprint (cudaOccupancyMaxActiveBlocksPerMultiprocessor
+// = 1 at 0 bytes of dynamic shared memory, 384 threads x 80 registers; 15 clusters either way), so the second cluster
+// never shares the SMs and the leaner kernel is simply slower: 23.8 vs 16.4 ms.  Kept as a switch, off.
+static int g_tc_bwd2 = 0;
 void icrl_chain_tc_set_bwd2_impl(int on) { g_tc_bwd2 = on; }
 static long long* g_chain_tc_prof = nullptr;      // icrl_chain_tc_set_profile: 16 device int64 (forward [0..5], backward [8..13])
 void icrl_chain_tc_set_profile_impl(long long* buf) { g_chain_tc_prof = buf; }
@@ -1306,6 +1313,10 @@ int icrl_chain_tc_bwd_max_pieces_impl() {
   static int cached[2] = {0, 0};
   const int which = g_tc_bwd2 ? 1 : 0;
   if (cached[which]) return cached[which];
+  if (const char* ov = getenv("ICRL_BWD_MAX_PIECES")) {         // experiments: override the occupancy query
+    cached[which] = atoi(ov);
+    return cached[which];
+  }
   int n = 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CL * 64);
@@ -1318,7 +1329,27 @@ int icrl_chain_tc_bwd_max_pieces_impl() {
   cfg.numAttrs = 1;
   const void* fn = which ? (const void*)chain_tc_bwd2_kernel : (const void*)chain_tc_bwd_kernel;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+  // two CTAs of 106 KB each only fit with the whole unified L1 / shared memory carved out as shared memory
+  if (e == cudaSuccess && which) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, fn, &cfg);
+  if (getenv("ICRL_DEBUG_OCC")) {
+    int per_sm = -1;
+    cudaError_t e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, (int)cfg.blockDim.x, cfg.dynamicSmemBytes);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, fn);
+    for (size_t sm : {(size_t)0, (size_t)32768, (size_t)65536, (size_t)98304, (size_t)107776}) {
+      int b = -1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fn, (int)cfg.blockDim.x, sm);
+      fprintf(stderr, "[icrl]   dyn smem %zu -> %d CTAs per SM\n", sm, b);
+    }
+    cudaDeviceProp pr;
+    cudaGetDeviceProperties(&pr, 0);
+    fprintf(stderr, "[icrl]   regsPerSM %d regsPerBlock %d smemPerSM %zu smemOptin %zu reserved %zu maxThreadsPerSM %d maxBlocksPerSM %d\n", pr.regsPerMultiprocessor,
+            pr.regsPerBlock, pr.sharedMemPerMultiprocessor, pr.sharedMemPerBlockOptin, pr.reservedSharedMemPerBlock, pr.maxThreadsPerMultiProcessor, pr.maxBlocksPerMultiProcessor);
+    fprintf(stderr, "[icrl] bwd kernel %d: clusters %d (%s), CTAs per SM %d (%s), regs %d, static smem %zu, dyn smem %zu, max dyn %d, carveout %d\n",
+            which, n, cudaGetErrorString(e), per_sm, cudaGetErrorString(e2), fa.numRegs, fa.sharedSizeBytes, cfg.dynamicSmemBytes,
+            fa.maxDynamicSharedSizeBytes, fa.preferredShmemCarveout);
+  }
   if (e != cudaSuccess || n < 1) { cudaGetLastError(); n = which ? 24 : 12; }
   cached[which] = n * BM;
   return cached[which];
@@ -1454,6 +1485,7 @@ int icrl_chain_tc_lstm_bwd_impl(cudaStream_t st, int P, long long seg, int warm,
   if ((rc = make_map_3d(&mw, whhT, 4 * H, H, UN))) return rc;
   if (g_tc_bwd2) {
     ICRL_CUDA(cudaFuncSetAttribute(chain_tc_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM));
+    ICRL_CUDA(cudaFuncSetAttribute(chain_tc_bwd2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     chain_tc_bwd2_kernel<<<dim3(CL * (Ppad / BM)), dim3(THREADS2), B2_SMEM, st>>>(mg, mw, a);
   } else {
     ICRL_CUDA(cudaFuncSetAttribute(chain_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
@@ -1510,6 +1542,7 @@ int icrl_policy_bptt_tc_impl(cudaStream_t st, int B, int n_cell, int p0, const v
   if ((rc = make_map_3d(&mw, whhT, 4 * H, H, UN))) return rc;
   if (g_tc_bwd2) {
     ICRL_CUDA(cudaFuncSetAttribute(chain_tc_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM));
+    ICRL_CUDA(cudaFuncSetAttribute(chain_tc_bwd2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     chain_tc_bwd2_kernel<<<dim3(CL * (Ppad / BM)), dim3(THREADS2), B2_SMEM, st>>>(mg, mw, a);
   } else {
     ICRL_CUDA(cudaFuncSetAttribute(chain_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));

@@ -83,7 +83,7 @@ class A2CEngine:
 
     def __init__(self, a2c_network, reward_network, use_tc=None, decode="fused", chain_shards=1, wgrad="tc",
                  chain_segments=32, chain_warmup=256, chain_tol=1e-5, chain_bwd_segments=None, chain_engine="tc",
-                 chain_pieces=None, chain_adapt=True, chain_warmup_min=32, policy_bptt="tc", chain_fuse_fwd=True):
+                 chain_pieces=None, chain_adapt=True, chain_warmup_min=32, policy_bptt="tc", chain_fuse_fwd=True, overlap_backward=True):
         self.policy = a2c_network.policy_network
         self.value = a2c_network.value_network
         self.reward = reward_network
@@ -166,6 +166,10 @@ class A2CEngine:
         if policy_bptt not in ("tc", "simt"):
             raise ValueError("policy_bptt must be 'tc' or 'simt'")
         self.policy_bptt = policy_bptt
+        # overlap_backward: the policy's backward on a second stream beside the value-chain backward (separate workspaces)
+        self.overlap_backward = bool(overlap_backward)
+        self._side_stream = None
+        self._n_cell_max = 1
         self.chain_fuse_fwd = bool(chain_fuse_fwd)     # value + reward forward chains in one launch when that is faster
         self.chain_adapt = bool(chain_adapt)
         self.chain_warmup_min = int(chain_warmup_min)
@@ -579,27 +583,71 @@ class A2CEngine:
         return values, rewards
 
     def _backward(self, f, tokcm, tokens, B, p0, S, Tv):
-        st, L, b, V = self._stream, self.launches.ref, self._bufs, self.V
-        P, Vn = self.policy, self.value
+        """Backward of the minibatch.  The policy's backward depends only on dL/dlogp; the value network's only on
+        dL/dvalues: with overlap_backward the policy side runs on a second stream (own workspaces) while the main stream
+        walks the value chain backwards -- the chain kernels occupy 120 of the 148 SMs (clusters of 8 cannot span GPCs),
+        the policy's contractions fill the rest and whatever the chain kernel leaves in time."""
+        main = torch.cuda.current_stream(self.device)
+        if self.overlap_backward:
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=self.device)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            self._backward_value(f, B, S, Tv, launch_only_chain=True)
+            self._side_stream.wait_event(fork)
+            with torch.cuda.stream(self._side_stream):
+                self._backward_policy(f, tokcm, tokens, B, p0, S, "_p")
+                join = torch.cuda.Event()
+                join.record(self._side_stream)
+            self._backward_value(f, B, S, Tv, launch_only_chain=False)
+            main.wait_event(join)
+        else:
+            self._backward_value(f, B, S, Tv, launch_only_chain=True)
+            self._backward_value(f, B, S, Tv, launch_only_chain=False)
+            self._backward_policy(f, tokcm, tokens, B, p0, S, "")
+
+    def _bwd_workspaces(self, B, S, Tv, tag):
+        """(colsum_ws, gemm_ws, gemm_ws_floats, dtable) of the value side (tag "") or the policy side on its own stream."""
+        V = self.V
         SB = S * B
-        n_cell = p0 - 1 + S
-        g = self._g
         cs_rows = max(SB, V, B)
-        colsum_ws = self._buf("colsum_ws", int(_lib.call("icrl_colsum_ws_floats", cs_rows, 4 * H)) + 2 * H + 4 * H * 8)
+        colsum_ws = self._buf("colsum_ws" + tag, int(_lib.call("icrl_colsum_ws_floats", cs_rows, 4 * H)) + 2 * H + 4 * H * 8)
         gemm_ws_floats = 24 * 4 * H * H
         if self.wgrad == "tc":
-            T_total = Tv if self.chain_shards == 1 else self.chain_shards * (Tv + 1)
-            gemm_ws_floats = max(gemm_ws_floats, (int(_lib.call("icrl_wgrad_tc_ws_bytes", 4 * H, H, T_total, 2)) + 3) // 4)
-        gemm_ws = self._buf("gemm_ws", gemm_ws_floats)
+            if tag:       # policy side: dW_v (M = 1024) and dW_hh (M = 2048) contractions over S*B resp. n_cell*B rows
+                n = max(int(_lib.call("icrl_wgrad_tc_ws_bytes", 4 * H, H, (self._n_cell_max) * B, 2)),
+                        int(_lib.call("icrl_wgrad_tc_ws_bytes", 1024, H, SB, 2)))
+            else:
+                T_total = Tv if self.chain_shards == 1 else self.chain_shards * (Tv + 1)
+                n = int(_lib.call("icrl_wgrad_tc_ws_bytes", 4 * H, H, T_total, 2))
+                if not self.overlap_backward:
+                    n = max(n, int(_lib.call("icrl_wgrad_tc_ws_bytes", 1024, H, SB, 2)))
+            gemm_ws_floats = max(gemm_ws_floats, (n + 3) // 4)
+        return colsum_ws, self._buf("gemm_ws" + tag, gemm_ws_floats), gemm_ws_floats, self._buf("dtable" + tag, V * 4 * H)
+
+    def _backward_value(self, f, B, S, Tv, launch_only_chain):
+        st, L, b, V = self._stream, self.launches.ref, self._bufs, self.V
+        Vn = self.value
+        SB = S * B
+        g = self._g
+        colsum_ws, gemm_ws, gemm_ws_floats, dtable = self._bwd_workspaces(B, S, Tv, "")
+        K = self.chain_shards
+        dgates = self._buf("v_dgates", K * (self._padded(Tv, 0) + 1) * 4 * H)
+        if not launch_only_chain:
+            lstm = Vn.valrnn.lstm
+            with self._phase("value_param_grads"):
+              _lib.call("icrl_value_chain_param_grads", st, Tv if K == 1 else K * (Tv + 1), V, Vn.valrnn.caption_embedding.weight.shape[1], _p(b["v_stream"]), _p(dgates), _p(b["v_stash_h"]),
+                      _p(Vn.valrnn.caption_embedding.weight), _p(lstm.weight_ih_l0), _p(dtable), _p(colsum_ws), _p(gemm_ws),
+                      gemm_ws_floats * 4, _p(g(Vn.valrnn.caption_embedding.weight, True)), _p(g(lstm.weight_ih_l0)),
+                      _p(g(lstm.weight_hh_l0)), _p(g(lstm.bias_ih_l0)), _p(g(lstm.bias_hh_l0)), L)
+            return
         # value head -> dh at the take positions + head gradients
         dh_take = self._buf("v_dh_take", SB * H)
         _lib.call("icrl_value_head_bwd", st, B, S, _p(f), _p(b["v_take_h"]), _p(b["dv_sb"]), _p(b["sum_dv"]),
                   _p(Vn.linear1.weight), _p(Vn.linear1.bias), _p(Vn.linear2.weight), _p(b["v_weff"]), _p(dh_take),
                   _p(g(Vn.linear1.weight)), _p(g(Vn.linear1.bias)), _p(g(Vn.linear2.weight)), _p(g(Vn.linear2.bias)),
                   _p(colsum_ws), L)
-        # value chain BPTT (serial) and its parameter gradients (contractions over all T steps)
-        K = self.chain_shards
-        dgates = self._buf("v_dgates", K * (self._padded(Tv, 0) + 1) * 4 * H)
+        # value chain BPTT and (second call) its parameter gradients (contractions over all T steps)
         with self._phase("chain_lstm_bwd"):
           if self._tc is not None:
             Pv, seg_v, warm_v = self._tc["b"]
@@ -623,16 +671,18 @@ class A2CEngine:
           else:
             _lib.call("icrl_chain_lstm_bwd", st, Tv, _p(Vn.valrnn.lstm.weight_hh_l0), _p(b["v_stash_g"]), _p(b["v_stash_c"]),
                   _p(b["v_take"]), _p(dh_take), _p(dgates), _p(self.sync_state), None, None, None, None, L)
-        dtable = self._buf("dtable", V * 4 * H)
-        lstm = Vn.valrnn.lstm
-        with self._phase("value_param_grads"):
-          _lib.call("icrl_value_chain_param_grads", st, Tv if K == 1 else K * (Tv + 1), V, Vn.valrnn.caption_embedding.weight.shape[1], _p(b["v_stream"]), _p(dgates), _p(b["v_stash_h"]),
-                  _p(Vn.valrnn.caption_embedding.weight), _p(lstm.weight_ih_l0), _p(dtable), _p(colsum_ws), _p(gemm_ws),
-                  gemm_ws_floats * 4, _p(g(Vn.valrnn.caption_embedding.weight, True)), _p(g(lstm.weight_ih_l0)),
-                  _p(g(lstm.weight_hh_l0)), _p(g(lstm.bias_ih_l0)), _p(g(lstm.bias_hh_l0)), L)
+
+    def _backward_policy(self, f, tokcm, tokens, B, p0, S, tag):
         # policy BPTT.  icrl_policy_rollout_bwd turns the logits into dL/dlogits IN PLACE; a step whose chains are re-run
         # (longer warm-up, serial fall-back) runs this backward again with slightly different dL/dlogp, so it works on a
         # copy and the rollout's logits stay intact.
+        st, L, b, V = self._stream, self.launches.ref, self._bufs, self.V
+        P = self.policy
+        SB = S * B
+        n_cell = p0 - 1 + S
+        self._n_cell_max = max(self._n_cell_max, n_cell)
+        g = self._g
+        colsum_ws, gemm_ws, gemm_ws_floats, dtable = self._bwd_workspaces(B, S, 0, tag)
         pl = P.lstm
         tc = self.policy_bptt == "tc"
         ldz = int(_lib.call("icrl_vocab_pad")) if tc and V <= 1024 else V      # padded rows: vocabulary contractions on tcgen05
