@@ -313,6 +313,34 @@ def main():
         n_warm += 1
     barrier()
 
+    # Both timed legs start from the SAME training state (weights, Adam moments, chain warm-ups): the optimizer keeps
+    # training across the timed steps, and with these synthetic targets the value LSTM forgets more slowly step by step
+    # (its warm-up grows), so a leg that ran 20 steps later would time a different workload.
+    def snapshot():
+        st = {"warm": dict(eng.warm), "clean": dict(eng._clean), "hold": dict(eng._hold)}
+        if args.torch_adam:
+            import copy
+            st["params"] = [p.detach().clone() for p in A.parameters()]
+            st["opt"] = copy.deepcopy(opt.state_dict())
+        else:
+            st["flat"] = (opt.flat_param.clone(), opt.exp_avg.clone(), opt.exp_avg_sq.clone(), opt.t)
+        return st
+
+    def restore(st):
+        eng.warm, eng._clean, eng._hold = dict(st["warm"]), dict(st["clean"]), dict(st["hold"])
+        if args.torch_adam:
+            with torch.no_grad():
+                for p, q in zip(A.parameters(), st["params"]):
+                    p.copy_(q)
+            opt.load_state_dict(st["opt"])
+        else:
+            opt.flat_param.copy_(st["flat"][0])
+            opt.exp_avg.copy_(st["flat"][1])
+            opt.exp_avg_sq.copy_(st["flat"][2])
+            opt.t = st["flat"][3]
+
+    state0 = snapshot()
+
     # ---- leg 1: minibatch resident in HBM.  The steps run unchecked (no host read inside the timed region) and are
     # verified together afterwards (the joint-check words are running maxima); a failure re-times with a check per step.
     c0 = seg_counters()
@@ -348,8 +376,9 @@ def main():
             res = dp.step(fh, cl, uh, global_rows=B, plan=plan)
             sink.append(res.loss)                     # D2H read of the step's result (rides the joint-check read)
 
+        restore(state0)
         c0 = seg_counters()
-        ms_e2e, _ = timed(step_e2e, args.steps, 1)
+        ms_e2e, _ = timed(step_e2e, args.steps, 1)      # one un-timed step: first touch of the pinned buffers
         e2e = {"value": B / (ms_e2e * 1e-3), "unit": "captions/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(fl.nbytes + (hi - lo) * 4 + ul.nbytes), "d2h_bytes_per_step": 80,
                "chain_checks": seg_delta(c0)}
