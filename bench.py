@@ -413,6 +413,7 @@ def main():
     # ---- BASELINE configs 3 and 5 in the same run (side objects, not the headline)
     reward_tp, curriculum = None, None
     if not args.no_extras:
+        restore(state0)
         # config 3: RewardNetwork embedding-cosine reward throughput, 8192 captions x 20 tokens, one GPU (rank 0)
         if rank == 0:
             f3, c3 = synth.make_inputs(103, 8192, L_CAP)
@@ -492,7 +493,8 @@ def main():
         chain_cfg = {"engine": "tc", "forward_launch": "fused (value + reward side by side)" if lay.get("fused") else "two launches",
                      "pieces": {"value": lay["v"][0], "reward": lay["r"][0], "value_backward": (lay.get("b") or lay["v"])[0]},
                      "positions_per_piece": {"value": lay["v"][1], "reward": lay["r"][1]},
-                     "warmup": {"value": lay["v"][2], "reward": lay["r"][2]}, "tolerance": eng.chain_tol,
+                     "warmup": {"value": lay["v"][2], "reward": lay["r"][2], "value_backward": (lay.get("b") or lay["v"])[2]},
+                     "tolerance": eng.chain_tol,
                      "checked_max": dict(zip(("value_h", "value_c", "value_h_half", "value_c_half", "reward_h", "-", "reward_h_half",
                                               "--", "bwd_dh", "bwd_dc", "bwd_dh_half", "bwd_dc_half", "dh_take_max", "fp16_overflow"),
                                              st["tc_max_err"][:14])),

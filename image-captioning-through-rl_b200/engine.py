@@ -173,9 +173,11 @@ class A2CEngine:
         self.chain_fuse_fwd = bool(chain_fuse_fwd)     # value + reward forward chains in one launch when that is faster
         self.chain_adapt = bool(chain_adapt)
         self.chain_warmup_min = int(chain_warmup_min)
-        self.warm = {"v": self.chain_warmup, "r": self.chain_warmup}      # current warm-up per chain (tc engine)
-        self._clean = {"v": 0, "r": 0}
-        self._hold = {"v": 0, "r": 0}
+        # current warm-up per recurrence (tc engine): value forward, reward forward, value backward -- each follows its own
+        # measured contraction (the forward cell state is the slowest to converge; the backward need not pay for it)
+        self.warm = {"v": self.chain_warmup, "r": self.chain_warmup, "b": self.chain_warmup}
+        self._clean = {"v": 0, "r": 0, "b": 0}
+        self._hold = {"v": 0, "r": 0, "b": 0}
         self._tc = None                   # {"v": (P, seg, warm) | None, "r": (P, seg, warm)} of the current step
         self.segment_stats = {"steps": 0, "segmented_steps": 0, "fallbacks": 0, "reruns": 0, "max_err": [0.0] * 5,
                               "tc_max_err": [0.0] * 16, "warm_history": []}
@@ -485,9 +487,12 @@ class A2CEngine:
         # "b": the backward recurrence of the value chain always gets every co-resident cluster (its own launch); it may
         # be cut differently from the forward as long as the arrays cover both layouts (the stash rows past the forward's
         # end are zeroed: padding positions, whose gate gradients are exactly zero)
-        bw = None if v is None else (self._pieces_for(Tv, wv, int(_lib.call("icrl_chain_tc_bwd_max_pieces"))) or v)
+        wb = self.warm["b"]
+        bw = None if v is None else self._pieces_for(Tv, wb, int(_lib.call("icrl_chain_tc_bwd_max_pieces")))
+        if v is not None and bw is None:
+            bw, wb = v, wv
         lay = {"v": None if v is None else (v[0], v[1], wv), "r": (r[0], r[1], wr), "fused": False,
-               "b": None if bw is None else (bw[0], bw[1], wv)}
+               "b": None if bw is None else (bw[0], bw[1], wb)}
         if v is None or not self.chain_fuse_fwd or self.chain_pieces is not None:
             return lay
         C = int(_lib.call("icrl_chain_tc_max_pieces")) // 128
@@ -829,21 +834,23 @@ class A2CEngine:
         e = host[4:]
         st = self.segment_stats
         st["tc_max_err"] = [max(a, b) if b == b else float("nan") for a, b in zip(st["tc_max_err"], e)]
-        v_full, v_half = max(e[0], e[1], e[8], e[9]), max(e[2], e[3], e[10], e[11])
-        if any(x != x for x in e[0:4] + e[8:12]):
-            v_full = float("nan")
+        nanmax = lambda xs: float("nan") if any(x != x for x in xs) else max(xs)
         self._tc_force_serial = e[13] != 0.0          # the fp16 exchange of the backward recurrence overflowed
-        ok_v = self._adapt_warm("v", v_half, v_full) if self._tc["v"] is not None else True
+        ok_v = ok_b = True
+        if self._tc["v"] is not None:
+            ok_v = self._adapt_warm("v", nanmax(e[2:4]), nanmax(e[0:2]))
+            if e[12] != 0.0 or any(x != 0.0 for x in e[8:12]):        # the backward recurrence ran in this step
+                ok_b = self._adapt_warm("b", nanmax(e[10:12]), nanmax(e[8:10]))
         ok_r = self._adapt_warm("r", e[6], e[4])
-        ok = ok_v and ok_r and not self._tc_force_serial
+        ok = ok_v and ok_b and ok_r and not self._tc_force_serial
         if not ok:
             import warnings
             st["reruns"] += 1
             warnings.warn("chain segments did not converge onto the single chain within %g after the warm-up (value chain "
                           "forward |dh| %.3g |dc| %.3g, backward %.3g %.3g; reward chain |dh| %.3g%s): re-running with "
-                          "warm-ups %d / %d" % (self.chain_tol, e[0], e[1], e[8], e[9], e[4],
-                                                "; gate gradients overflowed the fp16 exchange" if self._tc_force_serial else "",
-                                                self.warm["v"], self.warm["r"]))
+                          "warm-ups %d / %d / %d" % (self.chain_tol, e[0], e[1], e[8], e[9], e[4],
+                                                     "; gate gradients overflowed the fp16 exchange" if self._tc_force_serial else "",
+                                                     self.warm["v"], self.warm["r"], self.warm["b"]))
         return ok, host
 
     def _segments_ok(self):

@@ -771,7 +771,7 @@ def test_chain_pieces_short_warmup_is_caught_and_rerun():
     assert float((rk["values"] - v1).abs().max()) <= TOL and float((rk["rewards"] - w1).abs().max()) <= TOL
     assert float((ek.flat_grad - g1).abs().max() / g1.abs().max()) <= GTOL
     # unverified steps (check=False) are reported by segments_verified()
-    ek.warm = {"v": 4, "r": 4}
+    ek.warm = {"v": 4, "r": 4, "b": 4}
     ek.step(f, c, uniforms=u, check=False)
     with pytest.warns(UserWarning):
         assert ek.segments_verified() is False
