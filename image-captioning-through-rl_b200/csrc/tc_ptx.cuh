@@ -112,6 +112,15 @@ __device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
+// raw special-function forms (the same MUFU instructions __expf / __fdividef end in, without their range fix-ups)
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+constexpr float L2E = 1.4426950408889634f;          // log2(e)
+constexpr float SAT = 20.f * L2E;                   // exponent clamp: sigmoid(+-20) and tanh(+-10) are saturated to the last float bit
+__device__ __forceinline__ float clamp_sat(float y) { return fminf(fmaxf(y, -SAT), SAT); }
+// tanh(x) = 1 - 2 / (1 + e^(2x))
+__device__ __forceinline__ float tanh_lean(float x) { return fmaf(-2.f, rcp_ftz(1.f + ex2_ftz(clamp_sat(x * (2.f * L2E)))), 1.f); }
+
 // fp32 -> {hi, lo'} fp16 pair of four values: x = hi + lo'/2048 (22 mantissa bits; the scaling keeps lo' normal)
 __device__ __forceinline__ void split4_f16(const float4 v, uint2& hi, uint2& lo) {
   const __half a0 = __float2half_rn(v.x), a1 = __float2half_rn(v.y), a2 = __float2half_rn(v.z), a3 = __float2half_rn(v.w);
