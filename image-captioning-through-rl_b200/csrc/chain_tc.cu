@@ -441,7 +441,11 @@ chains_tc_fwd_fused_kernel(const __grid_constant__ FwdMaps maps_v, const FwdArgs
 constexpr int B_STAGES = 8, B_KB = 4 * H / BK;              // 64 K blocks per step (K = 2048 gate gradients)
 constexpr int BB_TILE = UN * BK * 2;                        // 4 KB: this CTA's 64 output units x 32 K
 constexpr int B_STAGE = 2 * A_TILE + 2 * BB_TILE;           // 24 KB
-constexpr int B_NARR = 7, B_GST_WARP = B_NARR * 2048;       // staging arrays of [32 rows][16 units] f32 (two unit passes per step)
+constexpr int B_NARR = 7;                                   // chain_tc_bwd2_kernel: 7 staging arrays per pass
+// chain_tc_bwd_kernel: two unit passes per step, each with its own staging buffer of 6 arrays of [32 rows][16 units] f32
+// (gates i,f,g,o, c_t, c_{t-1}), so that both passes' stash gathers are in flight before the first pass is computed; the
+// injected dL/dh rows (one position in ten) travel through registers.
+constexpr int B1_BUF = 6 * 2048, B_GST_WARP = 2 * B1_BUF;
 constexpr int B_SMEM = B_STAGES * B_STAGE + 256 + 1024;
 constexpr int B_TMEM_COLS = 128, B_CORR = 64;
 static_assert(EPI_WARPS * B_GST_WARP <= B_STAGES * B_STAGE, "epilogue staging lives inside the (idle) TMA ring");
@@ -643,34 +647,45 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
       const bool w_full = it == p.warm - 1, w_half = it == p.cp_half;            // warm-up side records (pieces < P-1)
       const bool r_full = it == steps - 1, r_half = p.cp_half >= 0 && it == half_ref_it;   // reference side (pieces >= 1)
       long long tg = 0, tc = 0, ts = 0;
+      // (L) stash of this position for BOTH unit passes: activated gates (arrays 0..3), c_t (4), c_{t-1} (5) into the
+      //     pass's own buffer; 4 lanes per row; element (row, 16-byte chunk c) lives at row*64 + ((c ^ ((row >> 1) & 3)) << 4).
+#pragma unroll
+      for (int ps = 0; ps < 2; ++ps) {
+        const int ucolp = (int)rank * UN + 32 * ch + 16 * ps;
+        const int c4 = lane & 3;
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int r = i4 * 8 + (lane >> 2);
+          const int kr = m0 + 32 * q + r;
+          if (kr < P) {
+            const size_t pos = (size_t)kr * sk + (size_t)t * stt;
+            const unsigned dst = smem_u32(gst + ps * B1_BUF) + (unsigned)(r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4));
+            const float* gsrc = p.stash_g + pos * (4 * H) + ucolp + c4 * 4;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) cp_async16(dst + a * 2048, gsrc + a * H);
+            cp_async16(dst + 4 * 2048, p.stash_c + (pos + stt) * H + ucolp + c4 * 4);
+            cp_async16(dst + 5 * 2048, p.stash_c + pos * H + ucolp + c4 * 4);
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      // injected dL/dh of this thread's own row (pass 0 now, pass 1 while pass 0 is stored)
+      float4 inj[4];
+      auto load_inj = [&](int ps) {
+        const float* src = p.dh_take + (size_t)(tk >= 0 ? tk : 0) * H + (int)rank * UN + 32 * ch + 16 * ps;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          inj[c] = (valid && tk >= 0) ? __ldg(reinterpret_cast<const float4*>(src) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      load_inj(0);
 #pragma unroll
       for (int ps = 0; ps < 2; ++ps) {
         const long long u0 = prof ? clock64() : 0;
         const int ucolp = (int)rank * UN + 32 * ch + 16 * ps;
-        // (L) stash of this position: activated gates (arrays 0..3), c_t (4), c_{t-1} (5), injected dL/dh (6);
-        //     4 lanes per row; element (row, 16-byte chunk c) lives at row*64 + ((c ^ ((row >> 1) & 3)) << 4).
-        {
-          const int c4 = lane & 3;
-#pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            const int r = i4 * 8 + (lane >> 2);
-            const int tkr = __shfl_sync(0xffffffffu, tk, r);
-            const int kr = m0 + 32 * q + r;
-            if (kr < P) {
-              const size_t pos = (size_t)kr * sk + (size_t)t * stt;
-              const unsigned dst = smem_u32(gst) + (unsigned)(r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4));
-              const float* gsrc = p.stash_g + pos * (4 * H) + ucolp + c4 * 4;
-#pragma unroll
-              for (int a = 0; a < 4; ++a) cp_async16(dst + a * 2048, gsrc + a * H);
-              cp_async16(dst + 4 * 2048, p.stash_c + (pos + stt) * H + ucolp + c4 * 4);
-              cp_async16(dst + 5 * 2048, p.stash_c + pos * H + ucolp + c4 * 4);
-              if (tkr >= 0) cp_async16(dst + 6 * 2048, p.dh_take + (size_t)tkr * H + ucolp + c4 * 4);
-              else *reinterpret_cast<float4*>(gst + 6 * 2048 + r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-          cp_async_wait_all();
-          __syncwarp();
-        }
+        unsigned char* gb = gst + ps * B1_BUF;
+        if (ps == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
         const long long u1 = prof ? clock64() : 0;
         // (C) gate gradients, one row per lane, in place on the staging tile
 #pragma unroll
@@ -682,11 +697,13 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
 #pragma unroll
             for (int i = 0; i < 8; ++i) { rec[i] = 0.f; cor[i] = 0.f; }
           }
-          unsigned char* e0 = gst + lane * 64 + (((2 * c8) ^ ((lane >> 1) & 3)) << 4);
-          unsigned char* e1 = gst + lane * 64 + (((2 * c8 + 1) ^ ((lane >> 1) & 3)) << 4);
-          float tin[B_NARR][8];
+          unsigned char* e0 = gb + lane * 64 + (((2 * c8) ^ ((lane >> 1) & 3)) << 4);
+          unsigned char* e1 = gb + lane * 64 + (((2 * c8 + 1) ^ ((lane >> 1) & 3)) << 4);
+          float tin[6][8];
+          const float injv[8] = {inj[2 * c8].x, inj[2 * c8].y, inj[2 * c8].z, inj[2 * c8].w,
+                                 inj[2 * c8 + 1].x, inj[2 * c8 + 1].y, inj[2 * c8 + 1].z, inj[2 * c8 + 1].w};
 #pragma unroll
-          for (int a = 0; a < B_NARR; ++a) {
+          for (int a = 0; a < 6; ++a) {
             const float4 v0 = *reinterpret_cast<const float4*>(e0 + a * 2048);
             const float4 v1 = *reinterpret_cast<const float4*>(e1 + a * 2048);
             tin[a][0] = v0.x; tin[a][1] = v0.y; tin[a][2] = v0.z; tin[a][3] = v0.w;
@@ -696,7 +713,7 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float gi = tin[0][i], gf = tin[1][i], gg = tin[2][i], go = tin[3][i], cc = tin[4][i], cp = tin[5][i];
-            const float dh = fmaf(cor[i], LO_INV, rec[i] * mg) * invS + tin[6][i];
+            const float dh = fmaf(cor[i], LO_INV, rec[i] * mg) * invS + injv[i];
             const float tcv = tanh_lean(cc);
             const float dct = dc[ps][c8][i] + dh * (go * (1.f - tcv * tcv));
             dhv[i] = dh;
@@ -722,6 +739,7 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
           *reinterpret_cast<float4*>(e1 + 5 * 2048) = make_float4(dci[4], dci[5], dci[6], dci[7]);
         }
         __syncwarp();
+        if (ps == 0) load_inj(1);
         const long long u2 = prof ? clock64() : 0;
         // (S1) the scaled fp16 split of the gate gradients: the next step's A operand of every CTA of the cluster
         {
@@ -731,7 +749,7 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
             const int r = i4 * 8 + (lane >> 2);
             const int kr = m0 + 32 * q + r;
             if (kr < P) {
-              const unsigned char* e = gst + r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4);
+              const unsigned char* e = gb + r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4);
               __half* xp = p.dgx + ((size_t)((((it + 1) & 1) * 2) * Ppad + kr)) * (4 * H) + ucolp + c4 * 4;
 #pragma unroll
               for (int a = 0; a < 4; ++a) {
@@ -753,7 +771,7 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
             const int kr = m0 + 32 * q + r;
             if (kr < P) {
               const size_t pos = (size_t)kr * sk + (size_t)t * stt;
-              const unsigned char* e = gst + r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4);
+              const unsigned char* e = gb + r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4);
               const bool live = kr == P - 1 || it >= p.warm;
               const int uc = ucolp + c4 * 4;
               if (live) {
