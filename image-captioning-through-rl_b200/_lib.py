@@ -62,7 +62,6 @@ SIGNATURES = {
     "icrl_chain_tc_set_profile": [P],
     "icrl_chain_tc_set_bias": [F, F],
     "icrl_chain_tc_bwd_max_pieces": [],
-    "icrl_chain_tc_set_bwd2": [I],
     "icrl_chain_tc_set_tma_store": [I],
     "icrl_chain_set_profile": [P],
     "icrl_chain_sync_bytes": [],

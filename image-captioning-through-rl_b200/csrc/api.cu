@@ -447,7 +447,6 @@ size_t icrl_chain_tc_weight_halves(int kind) { return icrl_chain_tc_weight_halve
 size_t icrl_chain_tc_ws_bytes(int pieces) { return icrl_chain_tc_ws_bytes_impl(pieces); }
 size_t icrl_chain_tc_cp_floats(int pieces) { return icrl_chain_tc_cp_floats_impl(pieces); }
 int icrl_chain_tc_set_tma_store(int on) { icrl_chain_tc_set_tma_store_impl(on); return ICRL_OK; }
-int icrl_chain_tc_set_bwd2(int on) { icrl_chain_tc_set_bwd2_impl(on); return ICRL_OK; }
 int icrl_chain_tc_bwd_max_pieces(void) { return icrl_chain_tc_bwd_max_pieces_impl(); }
 int icrl_chain_tc_set_bias(float fwd, float bwd) { icrl_chain_tc_set_bias_impl(fwd, bwd); return ICRL_OK; }
 int icrl_chain_tc_set_profile(void* buf) { icrl_chain_tc_set_profile_impl(reinterpret_cast<long long*>(buf)); return ICRL_OK; }

@@ -30,7 +30,6 @@
 // scaled by a power of two derived from max |dL/dh_take| (fp16 keeps 22 bits down to 2^-18 of that maximum; overflow
 // is detected and reported).  The fp32 gate gradients of live positions go to `dgates` for the parameter-gradient
 // contractions exactly as the serial kernel writes them.
-#include <stdlib.h>
 #include "tc_ptx.cuh"
 #include "internal.h"
 
@@ -441,7 +440,6 @@ chains_tc_fwd_fused_kernel(const __grid_constant__ FwdMaps maps_v, const FwdArgs
 constexpr int B_STAGES = 8, B_KB = 4 * H / BK;              // 64 K blocks per step (K = 2048 gate gradients)
 constexpr int BB_TILE = UN * BK * 2;                        // 4 KB: this CTA's 64 output units x 32 K
 constexpr int B_STAGE = 2 * A_TILE + 2 * BB_TILE;           // 24 KB
-constexpr int B_NARR = 7;                                   // chain_tc_bwd2_kernel: 7 staging arrays per pass
 // chain_tc_bwd_kernel: two unit passes per step, each with its own staging buffer of 6 arrays of [32 rows][16 units] f32
 // (gates i,f,g,o, c_t, c_{t-1}), so that both passes' stash gathers are in flight before the first pass is computed; the
 // injected dL/dh rows (one position in ten) travel through registers.
@@ -822,302 +820,6 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
   }
 }
 
-// Two co-resident CTAs per SM (chain_tc_bwd2_kernel): the epilogue of one cluster's step runs under the operand fill of the
-// cluster that shares its SMs.  Needs half the shared memory (4-stage ring; staging in four passes of 8 hidden units) and
-// an epilogue inside 80 registers (the carried dL/dc in shared memory instead of registers, the cell gradients in groups
-// of four); tensor memory is 128 columns per CTA either way.
-constexpr int B2_STAGES = 3, B2_NPASS = 4;
-constexpr int B2_GST_WARP = B_NARR * 1024;                  // staging arrays of [32 rows][8 units] f32
-constexpr int B2_DC_BYTES = UN * BM * 4;                    // carried dL/dc of the CTA's 64 units x 128 pieces (32 KB)
-constexpr int B2_SMEM = B2_STAGES * B_STAGE + B2_DC_BYTES + 256 + 1024;
-constexpr int THREADS2 = THREADS;                           // registers are granted per 4 warps: 10 warps cost as much as 12, so keep the
-                                                            // two idle warps of the one-CTA kernels (12 warps x 80 registers x 2 CTAs)
-static_assert(EPI_WARPS * B2_GST_WARP <= B2_STAGES * B_STAGE, "epilogue staging lives inside the (idle) TMA ring");
-
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS2, 2)
-chain_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_constant__ CUtensorMap map_w, const BwdArgs p) {
-  constexpr int STAGES = B2_STAGES, STAGE = B_STAGE;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  float* dcs = reinterpret_cast<float*>(smem + STAGES * STAGE);            // carried dL/dc: [64 units][128 pieces]
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + STAGES * STAGE + B2_DC_BYTES);
-  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * STAGES + 2);
-  const unsigned bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[STAGES]);
-  const unsigned bar_acc_full = smem_u32(&bars[2 * STAGES]), bar_acc_empty = smem_u32(&bars[2 * STAGES + 1]);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned rank = cluster_rank();
-  const int m0 = (blockIdx.x / CL) * BM;
-  const int P = p.P, Ppad = p.Ppad, steps = p.steps;
-  const int iters = steps + (p.dh0_out ? 1 : 0);       // one more contraction when dL/dh0 is wanted
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
-    mbar_init(bar_acc_full, 1);
-    mbar_init(bar_acc_empty, EPI_WARPS);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dg) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(B_TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const unsigned tmem_base = *tmem_slot;
-  cluster_arrive();
-  cluster_wait();
-
-  if (warp == 2 || warp == 3) {
-    for (int it = 0; it < iters; ++it) { cluster_arrive(); cluster_wait(); }     // idle warps: keep the barrier counts complete
-  } else if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (no GEMM before the first step)
-    unsigned n = 0;
-    for (int it = 0; it < iters; ++it) {
-      if (it > 0 && lane == 0) {
-        const int arow = ((it & 1) * 2) * Ppad + m0;
-        for (int kb = 0; kb < B_KB; ++kb, ++n) {
-          const int s = n % STAGES;
-          mbar_wait(bar_empty + 8 * s, ((n / STAGES) & 1u) ^ 1u);
-          const unsigned full = bar_full + 8 * s;
-          mbar_expect_tx(full, 2 * A_TILE + 2 * BB_TILE);
-          const unsigned base = smem_u32(smem + s * STAGE);
-          tma_load_2d_mcast(base + rank * A_SLICE, &map_dg, kb * BK, arow + (int)rank * A_SLICE_ROWS, full, 0xFF);
-          tma_load_2d_mcast(base + A_TILE + rank * A_SLICE, &map_dg, kb * BK, arow + Ppad + (int)rank * A_SLICE_ROWS, full, 0xFF);
-          tma_load_3d(base + 2 * A_TILE, &map_w, kb * BK, (int)rank * UN, 0, full);       // hi at +0, lo' at +BB_TILE
-        }
-      }
-      __syncwarp();
-      cluster_arrive();
-      cluster_wait();                    // the gate gradients of this step (all 8 CTAs) are in global memory
-      if (lane == 0) fence_proxy_async();
-      __syncwarp();
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    unsigned n = 0;
-    for (int it = 0; it < iters; ++it) {
-      if (it > 0) {
-        mbar_wait(bar_acc_empty, (unsigned)(it - 1) & 1u);
-        tc_fence_after();
-        for (int kb = 0; kb < B_KB; ++kb, ++n) {
-          const int s = n % STAGES;
-          mbar_wait(bar_full + 8 * s, (n / STAGES) & 1u);
-          tc_fence_after();
-          const unsigned base = smem_u32(smem + s * STAGE);
-          const unsigned long long dA0 = smem_desc_sw64(base), dA1 = smem_desc_sw64(base + A_TILE);
-          const unsigned long long dB0 = smem_desc_sw64(base + 2 * A_TILE), dB1 = smem_desc_sw64(base + 2 * A_TILE + BB_TILE);
-          if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              tc_mma(tmem_base, dA0 + 2 * k, dB0 + 2 * k, idesc_f16_m128(UN), (kb | k) != 0);
-              tc_mma(tmem_base + B_CORR, dA0 + 2 * k, dB1 + 2 * k, idesc_f16_m128(UN), (kb | k) != 0);
-              tc_mma(tmem_base + B_CORR, dA1 + 2 * k, dB0 + 2 * k, idesc_f16_m128(UN), 1u);
-            }
-            tc_commit_mcast(bar_empty + 8 * s, 0xFF);
-          }
-          __syncwarp();
-        }
-        if (elect_one()) tc_commit(bar_acc_full);
-      }
-      __syncwarp();
-      cluster_arrive();
-      cluster_wait();
-    }
-  } else {
-    // ------------------------------------------------------------------ epilogue warps
-    const int ew = warp - EPI_WARP0;
-    const int q = warp & 3;
-    const int ch = ew >> 2;
-    const int k_own = m0 + 32 * q + lane;
-    const bool valid = k_own < P;
-    const unsigned tq = tmem_base + ((unsigned)(32 * q) << 16);
-    unsigned char* gst = smem + ew * B2_GST_WARP;
-    const long long sk = p.stride_k, stt = p.stride_t;
-    const float S = bwd_scale(*p.dh_max), invS = 1.f / S;
-    const float mg = p.main_gain;
-    float* dcr = dcs + 32 * q + lane;          // this thread's piece; unit u of the CTA at dcr[u * BM]
-#pragma unroll
-    for (int u = 0; u < 32; ++u) dcr[(32 * ch + u) * BM] = 0.f;
-    float ovf = 0.f;
-    int tk = valid ? p.take[(long long)k_own * sk + (long long)(steps - 1) * stt] : -1;
-    const int half_ref_it = steps - 1 - (p.warm - 1 - p.cp_half);      // reference side of the half-way checkpoint
-
-    for (int it = 0; it < iters; ++it) {
-      const int t = steps - 1 - it;
-      const int tk_n = (valid && t > 0) ? p.take[(long long)k_own * sk + (long long)(t - 1) * stt] : -1;
-      if (it > 0) {
-        mbar_wait(bar_acc_full, (unsigned)(it - 1) & 1u);
-        tc_fence_after();
-      }
-      if (it == steps) {
-        // the extra iteration: dL/dh entering local time 0 = the contraction of the last step's gate gradients
-#pragma unroll
-        for (int ps = 0; ps < B2_NPASS; ++ps) {
-          const int ucolp = (int)rank * UN + 32 * ch + 8 * ps;
-          float rec[8], cor[8], o[8];
-          tmem_ld8x2(tq + (unsigned)(32 * ch + 8 * ps), tq + (unsigned)(B_CORR + 32 * ch + 8 * ps), rec, cor);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = fmaf(cor[i], LO_INV, rec[i] * mg) * invS;
-          const int sw = (lane >> 2) & 1;
-          *reinterpret_cast<float4*>(gst + lane * 32 + ((0 ^ sw) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<float4*>(gst + lane * 32 + ((1 ^ sw) << 4)) = make_float4(o[4], o[5], o[6], o[7]);
-          __syncwarp();
-          const int c2 = lane & 1;
-#pragma unroll
-          for (int i2 = 0; i2 < 2; ++i2) {
-            const int r = i2 * 16 + (lane >> 1);
-            const int kr = m0 + 32 * q + r;
-            if (kr < P)
-              *reinterpret_cast<float4*>(p.dh0_out + (size_t)kr * H + ucolp + c2 * 4) =
-                  *reinterpret_cast<const float4*>(gst + r * 32 + ((c2 ^ ((r >> 2) & 1)) << 4));
-          }
-          __syncwarp();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_acc_empty);
-        cluster_arrive();
-        cluster_wait();
-        break;
-      }
-      const bool w_full = it == p.warm - 1, w_half = it == p.cp_half;            // warm-up side records (pieces < P-1)
-      const bool r_full = it == steps - 1, r_half = p.cp_half >= 0 && it == half_ref_it;   // reference side (pieces >= 1)
-#pragma unroll 1
-      for (int ps = 0; ps < B2_NPASS; ++ps) {
-        const int ucolp = (int)rank * UN + 32 * ch + 8 * ps;
-        // (L) stash of this position: activated gates (arrays 0..3), c_t (4), c_{t-1} (5), injected dL/dh (6); 2 lanes per
-        //     row; element (row, 16-byte chunk c) lives at row*32 + ((c ^ ((row >> 2) & 1)) << 4).
-        {
-          const int c2 = lane & 1;
-#pragma unroll
-          for (int i2 = 0; i2 < 2; ++i2) {
-            const int r = i2 * 16 + (lane >> 1);
-            const int tkr = __shfl_sync(0xffffffffu, tk, r);
-            const int kr = m0 + 32 * q + r;
-            if (kr < P) {
-              const size_t pos = (size_t)kr * sk + (size_t)t * stt;
-              const unsigned off = (unsigned)(r * 32 + ((c2 ^ ((r >> 2) & 1)) << 4));
-              const unsigned dst = smem_u32(gst) + off;
-              const float* gsrc = p.stash_g + pos * (4 * H) + ucolp + c2 * 4;
-#pragma unroll
-              for (int a = 0; a < 4; ++a) cp_async16(dst + a * 1024, gsrc + a * H);
-              cp_async16(dst + 4 * 1024, p.stash_c + (pos + stt) * H + ucolp + c2 * 4);
-              cp_async16(dst + 5 * 1024, p.stash_c + pos * H + ucolp + c2 * 4);
-              if (tkr >= 0) cp_async16(dst + 6 * 1024, p.dh_take + (size_t)tkr * H + ucolp + c2 * 4);
-              else *reinterpret_cast<float4*>(gst + 6 * 1024 + off) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-          cp_async_wait_all();
-          __syncwarp();
-        }
-        // (C) gate gradients, one row per lane, in place on the staging tile (two halves of 4 units: register budget)
-        {
-          float rec[8], cor[8];
-          if (it > 0) {
-            tmem_ld8x2(tq + (unsigned)(32 * ch + 8 * ps), tq + (unsigned)(B_CORR + 32 * ch + 8 * ps), rec, cor);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { rec[i] = 0.f; cor[i] = 0.f; }
-          }
-          const int sw = (lane >> 2) & 1;
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            unsigned char* e = gst + lane * 32 + ((hf ^ sw) << 4);
-            const float4 gi = *reinterpret_cast<const float4*>(e), gf = *reinterpret_cast<const float4*>(e + 1024);
-            const float4 gg = *reinterpret_cast<const float4*>(e + 2 * 1024), go = *reinterpret_cast<const float4*>(e + 3 * 1024);
-            const float4 cc = *reinterpret_cast<const float4*>(e + 4 * 1024), cp = *reinterpret_cast<const float4*>(e + 5 * 1024);
-            const float4 inj = *reinterpret_cast<const float4*>(e + 6 * 1024);
-            const float a_gi[4] = {gi.x, gi.y, gi.z, gi.w}, a_gf[4] = {gf.x, gf.y, gf.z, gf.w}, a_gg[4] = {gg.x, gg.y, gg.z, gg.w};
-            const float a_go[4] = {go.x, go.y, go.z, go.w}, a_cc[4] = {cc.x, cc.y, cc.z, cc.w}, a_cp[4] = {cp.x, cp.y, cp.z, cp.w};
-            const float a_in[4] = {inj.x, inj.y, inj.z, inj.w};
-            float d_i[4], d_f[4], d_g[4], d_o[4], dhv[4], dci[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float* dcp = dcr + (32 * ch + 8 * ps + 4 * hf + i) * BM;
-              const float dc0 = *dcp;
-              const float dh = fmaf(cor[4 * hf + i], LO_INV, rec[4 * hf + i] * mg) * invS + a_in[i];
-              const float tcv = tanh_lean(a_cc[i]);
-              const float dct = dc0 + dh * (a_go[i] * (1.f - tcv * tcv));
-              dhv[i] = dh;
-              dci[i] = dc0;
-              d_o[i] = dh * (tcv * a_go[i] * (1.f - a_go[i]));
-              d_i[i] = dct * (a_gg[i] * a_gi[i] * (1.f - a_gi[i]));
-              d_f[i] = dct * (a_cp[i] * a_gf[i] * (1.f - a_gf[i]));
-              d_g[i] = dct * (a_gi[i] * (1.f - a_gg[i] * a_gg[i]));
-              *dcp = dct * a_gf[i];
-              ovf = fmaxf(ovf, fmaxf(fmaxf(fabsf(d_i[i]), fabsf(d_f[i])), fmaxf(fabsf(d_g[i]), fabsf(d_o[i]))));
-            }
-            *reinterpret_cast<float4*>(e) = make_float4(d_i[0], d_i[1], d_i[2], d_i[3]);
-            *reinterpret_cast<float4*>(e + 1024) = make_float4(d_f[0], d_f[1], d_f[2], d_f[3]);
-            *reinterpret_cast<float4*>(e + 2 * 1024) = make_float4(d_g[0], d_g[1], d_g[2], d_g[3]);
-            *reinterpret_cast<float4*>(e + 3 * 1024) = make_float4(d_o[0], d_o[1], d_o[2], d_o[3]);
-            *reinterpret_cast<float4*>(e + 4 * 1024) = make_float4(dhv[0], dhv[1], dhv[2], dhv[3]);
-            *reinterpret_cast<float4*>(e + 5 * 1024) = make_float4(dci[0], dci[1], dci[2], dci[3]);
-          }
-        }
-        __syncwarp();
-        // (S1) the scaled fp16 split of the gate gradients: the next step's A operand of every CTA of the cluster
-        {
-          const int c2 = lane & 1;
-#pragma unroll
-          for (int i2 = 0; i2 < 2; ++i2) {
-            const int r = i2 * 16 + (lane >> 1);
-            const int kr = m0 + 32 * q + r;
-            if (kr < P) {
-              const unsigned char* e = gst + r * 32 + ((c2 ^ ((r >> 2) & 1)) << 4);
-              __half* xp = p.dgx + ((size_t)((((it + 1) & 1) * 2) * Ppad + kr)) * (4 * H) + ucolp + c2 * 4;
-              const size_t pos = (size_t)kr * sk + (size_t)t * stt;
-              const bool live = kr == P - 1 || it >= p.warm;
-#pragma unroll
-              for (int a = 0; a < 4; ++a) {
-                const float4 d = *reinterpret_cast<const float4*>(e + a * 1024);
-                uint2 hi, lo;
-                split4_f16(make_float4(d.x * S, d.y * S, d.z * S, d.w * S), hi, lo);
-                *reinterpret_cast<uint2*>(xp + a * H) = hi;
-                *reinterpret_cast<uint2*>(xp + (size_t)Ppad * (4 * H) + a * H) = lo;
-                if (live) *reinterpret_cast<float4*>(p.dgates + pos * (4 * H) + a * H + ucolp + c2 * 4) = d;
-              }
-              if (p.bstate && ((kr < P - 1 && (w_full || w_half)) || (kr >= 1 && (r_full || r_half)))) {
-                const float4 dh4 = *reinterpret_cast<const float4*>(e + 4 * 1024);
-                const float4 dc4 = *reinterpret_cast<const float4*>(e + 5 * 1024);
-                const int uc = ucolp + c2 * 4;
-                if (kr < P - 1 && (w_full || w_half)) {
-                  float* b = p.bstate + ((size_t)(((w_full ? 1 : 0) * 2 + 0) * P + kr) * 2) * H + uc;
-                  *reinterpret_cast<float4*>(b) = dh4;
-                  *reinterpret_cast<float4*>(b + H) = dc4;
-                }
-                if (kr >= 1 && (r_full || r_half)) {
-                  float* b = p.bstate + ((size_t)(((r_full ? 1 : 0) * 2 + 1) * P + kr) * 2) * H + uc;
-                  *reinterpret_cast<float4*>(b) = dh4;
-                  *reinterpret_cast<float4*>(b + H) = dc4;
-                }
-              }
-            }
-          }
-        }
-        __syncwarp();                          // the next pass overwrites the staging tile
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acc_empty);
-      publish_exchange();
-      cluster_wait();
-      tk = tk_n;
-    }
-    if (valid && !(ovf * S < 30000.f)) *p.overflow = 1.f;       // also catches NaN
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_arrive();
-  cluster_wait();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(B_TMEM_COLS) : "memory");
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ packing / checks
 // LSTM / GRU forward operand: [2 parts][NG*512][512], row (r*GN + g*64 + jj) = W_hh row (g*512 + r*64 + jj).
 // LSTM backward operand:      [2 parts][512][2048],   row n (hidden unit), column k (gate row): W_hh[k][n].
@@ -1301,13 +1003,12 @@ void icrl_chain_tc_set_bias_impl(float fwd, float bwd) { g_tc_bias[0] = fwd; g_t
 // a step of 35 K).  Kept as a switch.
 static int g_tc_tma_store = 0;
 void icrl_chain_tc_set_tma_store_impl(int on) { g_tc_tma_store = on; }
-// icrl_chain_tc_set_bwd2: the backward recurrence (value chain and policy BPTT) on chain_tc_bwd_kernel (one CTA per SM,
-// 8-stage ring; default) or on chain_tc_bwd2_kernel, built for two co-resident CTAs per SM.  Measured (B = 4096): the
-// driver grants this tcgen05 kernel ONE CTA per SM whatever its footprint (cudaOccupancyMaxActiveBlocksPerMultiprocessor
-// = 1 at 0 bytes of dynamic shared memory, 384 threads x 80 registers; 15 clusters either way), so the second cluster
-// never shares the SMs and the leaner kernel is simply slower: 23.8 vs 16.4 ms.  Kept as a switch, off.
-static int g_tc_bwd2 = 0;
-void icrl_chain_tc_set_bwd2_impl(int on) { g_tc_bwd2 = on; }
+// (Tried and removed: a second backward kernel sized for two co-resident CTAs per SM -- 3-stage ring, 8-unit staging
+// passes, dL/dc in shared memory, 80 registers, 106 KB -- so that one cluster's epilogue would run under the operand fill of
+// the cluster sharing its SMs.  It was correct, but the driver grants a tcgen05 kernel ONE CTA per SM whatever its
+// footprint (cudaOccupancyMaxActiveBlocksPerMultiprocessor = 1 at 0 bytes of dynamic shared memory, 384 threads x 80
+// registers; registers are granted per 4 warps, setmaxnreg does not raise ptxas' allocation above the launch-bounds cap), so
+// the second cluster never shared the SMs and the leaner kernel was simply slower: 23.8 vs 16.4 ms at B = 4096.)
 static long long* g_chain_tc_prof = nullptr;      // icrl_chain_tc_set_profile: 16 device int64 (forward [0..5], backward [8..13])
 void icrl_chain_tc_set_profile_impl(long long* buf) { g_chain_tc_prof = buf; }
 
@@ -1332,52 +1033,8 @@ int icrl_chain_tc_max_pieces_impl() {
   return cached;
 }
 
-// pieces of the backward recurrence that are co-resident (twice the forward's with chain_tc_bwd2_kernel)
-int icrl_chain_tc_bwd_max_pieces_impl() {
-  static int cached[2] = {0, 0};
-  const int which = g_tc_bwd2 ? 1 : 0;
-  if (cached[which]) return cached[which];
-  if (const char* ov = getenv("ICRL_BWD_MAX_PIECES")) {         // experiments: override the occupancy query
-    cached[which] = atoi(ov);
-    return cached[which];
-  }
-  int n = 0;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(CL * 64);
-  cfg.blockDim = dim3(which ? THREADS2 : THREADS);
-  cfg.dynamicSmemBytes = which ? B2_SMEM : B_SMEM;
-  cudaLaunchAttribute at;
-  at.id = cudaLaunchAttributeClusterDimension;
-  at.val.clusterDim.x = CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
-  cfg.attrs = &at;
-  cfg.numAttrs = 1;
-  const void* fn = which ? (const void*)chain_tc_bwd2_kernel : (const void*)chain_tc_bwd_kernel;
-  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
-  // two CTAs of 106 KB each only fit with the whole unified L1 / shared memory carved out as shared memory
-  if (e == cudaSuccess && which) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, fn, &cfg);
-  if (getenv("ICRL_DEBUG_OCC")) {
-    int per_sm = -1;
-    cudaError_t e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, (int)cfg.blockDim.x, cfg.dynamicSmemBytes);
-    cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, fn);
-    for (size_t sm : {(size_t)0, (size_t)32768, (size_t)65536, (size_t)98304, (size_t)107776}) {
-      int b = -1;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fn, (int)cfg.blockDim.x, sm);
-      fprintf(stderr, "[icrl]   dyn smem %zu -> %d CTAs per SM\n", sm, b);
-    }
-    cudaDeviceProp pr;
-    cudaGetDeviceProperties(&pr, 0);
-    fprintf(stderr, "[icrl]   regsPerSM %d regsPerBlock %d smemPerSM %zu smemOptin %zu reserved %zu maxThreadsPerSM %d maxBlocksPerSM %d\n", pr.regsPerMultiprocessor,
-            pr.regsPerBlock, pr.sharedMemPerMultiprocessor, pr.sharedMemPerBlockOptin, pr.reservedSharedMemPerBlock, pr.maxThreadsPerMultiProcessor, pr.maxBlocksPerMultiProcessor);
-    fprintf(stderr, "[icrl] bwd kernel %d: clusters %d (%s), CTAs per SM %d (%s), regs %d, static smem %zu, dyn smem %zu, max dyn %d, carveout %d\n",
-            which, n, cudaGetErrorString(e), per_sm, cudaGetErrorString(e2), fa.numRegs, fa.sharedSizeBytes, cfg.dynamicSmemBytes,
-            fa.maxDynamicSharedSizeBytes, fa.preferredShmemCarveout);
-  }
-  if (e != cudaSuccess || n < 1) { cudaGetLastError(); n = which ? 24 : 12; }
-  cached[which] = n * BM;
-  return cached[which];
-}
+// pieces of the backward recurrence that are co-resident: the same clusters as the forward kernels (one CTA per SM)
+int icrl_chain_tc_bwd_max_pieces_impl() { return icrl_chain_tc_max_pieces_impl(); }
 
 size_t icrl_chain_tc_weight_halves_impl(int kind) { return kind == 0 ? (size_t)4 * 4 * H * H : (size_t)2 * 3 * H * H; }
 
@@ -1507,14 +1164,8 @@ int icrl_chain_tc_lstm_bwd_impl(cudaStream_t st, int P, long long seg, int warm,
   int rc;
   if ((rc = make_map_2d(&mg, dgx, 4 * H, (long long)4 * Ppad, A_SLICE_ROWS))) return rc;
   if ((rc = make_map_3d(&mw, whhT, 4 * H, H, UN))) return rc;
-  if (g_tc_bwd2) {
-    ICRL_CUDA(cudaFuncSetAttribute(chain_tc_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM));
-    ICRL_CUDA(cudaFuncSetAttribute(chain_tc_bwd2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    chain_tc_bwd2_kernel<<<dim3(CL * (Ppad / BM)), dim3(THREADS2), B2_SMEM, st>>>(mg, mw, a);
-  } else {
-    ICRL_CUDA(cudaFuncSetAttribute(chain_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
-    chain_tc_bwd_kernel<<<dim3(CL * (Ppad / BM)), dim3(THREADS), B_SMEM, st>>>(mg, mw, a);
-  }
+  ICRL_CUDA(cudaFuncSetAttribute(chain_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+  chain_tc_bwd_kernel<<<dim3(CL * (Ppad / BM)), dim3(THREADS), B_SMEM, st>>>(mg, mw, a);
   ICRL_LAUNCH_CHECK();
   chain_tc_check_bwd_kernel<<<dim3(P - 1, 2), H, 0, st>>>(P, a.cp_half, cp_state, err);
   ICRL_LAUNCH_CHECK();
@@ -1564,14 +1215,8 @@ int icrl_policy_bptt_tc_impl(cudaStream_t st, int B, int n_cell, int p0, const v
   int rc;
   if ((rc = make_map_2d(&mg, dgx, 4 * H, (long long)4 * Ppad, A_SLICE_ROWS))) return rc;
   if ((rc = make_map_3d(&mw, whhT, 4 * H, H, UN))) return rc;
-  if (g_tc_bwd2) {
-    ICRL_CUDA(cudaFuncSetAttribute(chain_tc_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM));
-    ICRL_CUDA(cudaFuncSetAttribute(chain_tc_bwd2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    chain_tc_bwd2_kernel<<<dim3(CL * (Ppad / BM)), dim3(THREADS2), B2_SMEM, st>>>(mg, mw, a);
-  } else {
-    ICRL_CUDA(cudaFuncSetAttribute(chain_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
-    chain_tc_bwd_kernel<<<dim3(CL * (Ppad / BM)), dim3(THREADS), B_SMEM, st>>>(mg, mw, a);
-  }
+  ICRL_CUDA(cudaFuncSetAttribute(chain_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+  chain_tc_bwd_kernel<<<dim3(CL * (Ppad / BM)), dim3(THREADS), B_SMEM, st>>>(mg, mw, a);
   ICRL_LAUNCH_CHECK();
   return ICRL_OK;
 }

@@ -106,5 +106,4 @@ int icrl_chains_tc_fwd_fused_impl(cudaStream_t st, int Pv, long long seg_v, int 
                                   int warm_r, const int* r_stream, const float* r_table, const void* r_packed,
                                   const float* r_b_hn, float* r_stash_h, void* r_ws, float* r_cp, float* r_err);
 void icrl_chain_tc_set_tma_store_impl(int on);
-void icrl_chain_tc_set_bwd2_impl(int on);
 int icrl_chain_tc_bwd_max_pieces_impl();

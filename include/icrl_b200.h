@@ -290,11 +290,8 @@ int icrl_chain_tc_set_profile(void* buf);
  * chain kernels (the tensor core truncates on every accumulate).  Default 5.76e-7, 2.3e-6 = 1.8e-8 per
  * accumulating MMA instruction. */
 int icrl_chain_tc_set_bias(float fwd, float bwd);
-/* Pieces of the backward recurrence that are co-resident, and the switch between its two kernels: 0 (default) = one CTA per
- * SM; 1 = a kernel sized for two CTAs per SM (the driver grants only one to a tcgen05 kernel: measured slower, kept as an
- * experiment). */
+/* Pieces of the backward recurrence that are co-resident (same clusters as the forward). */
 int icrl_chain_tc_bwd_max_pieces(void);
-int icrl_chain_tc_set_bwd2(int on);
 /* Experiment knob: 1 = the forward stash of the live positions leaves through TMA tensor stores, 0 (default) = per-thread
  * vector stores (measured equal: the store phase is L2-bound, not issue-bound). */
 int icrl_chain_tc_set_tma_store(int on);

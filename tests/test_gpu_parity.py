@@ -968,3 +968,36 @@ def test_chain_segments_simt_fall_back_to_the_serial_kernels():
     assert ek.segment_stats["fallbacks"] == 1 and ek.chain_warmup == 16
     assert torch.equal(rk["values"], v1) and torch.equal(rk["rewards"], w1)
     assert float((ek.flat_grad - g1).abs().max() / g1.abs().max()) <= 1e-6      # atomics in the table scatter reorder sums
+
+
+@pytest.mark.parametrize("switch", ["tma_store", "separate_forward_launches", "no_backward_overlap", "simt_policy_bptt"])
+def test_chain_engine_switches_agree(switch):
+    """The alternative code paths kept behind switches compute the same step as the default engine: the forward stash
+    through TMA tensor stores, value / reward forward chains as two launches instead of the fused one, the policy
+    backward on the main stream instead of a second one, and the per-step SIMT policy BPTT."""
+    from icrl_b200 import _lib
+    from icrl_b200.engine import A2CEngine
+    seed, B, L = 173, 384, 14
+    A, R, w = make_nets(seed)
+    f, c = synth.make_inputs(seed, B, L)
+    u = synth.make_uniforms(seed, L - 1, B)
+    e0 = A2CEngine(A, R, chain_warmup=160)
+    r0 = e0.step(f, c, uniforms=u)
+    v0, w0, g0 = r0["values"].clone(), r0["rewards"].clone(), e0.flat_grad.clone()
+    assert e0.piece_layout is not None and e0.piece_layout["fused"]
+    kw = {"separate_forward_launches": dict(chain_fuse_fwd=False), "no_backward_overlap": dict(overlap_backward=False),
+          "simt_policy_bptt": dict(policy_bptt="simt")}.get(switch, {})
+    if switch == "tma_store":
+        _lib.call("icrl_chain_tc_set_tma_store", 1)
+    try:
+        e1 = A2CEngine(A, R, chain_warmup=160, **kw)
+        r1 = e1.step(f, c, uniforms=u)
+        torch.cuda.synchronize()
+    finally:
+        _lib.call("icrl_chain_tc_set_tma_store", 0)
+    assert e1.piece_layout is not None and e1.segment_stats["fallbacks"] == 0
+    if switch == "separate_forward_launches":
+        assert not e1.piece_layout["fused"]
+    assert torch.equal(r1["tokens"], r0["tokens"])
+    assert float((r1["values"] - v0).abs().max()) <= TOL and float((r1["rewards"] - w0).abs().max()) <= TOL
+    assert float((e1.flat_grad - g0).abs().max() / g0.abs().max()) <= GTOL
