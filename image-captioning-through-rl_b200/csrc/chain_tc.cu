@@ -24,9 +24,10 @@
 //
 // Backward (LSTM).  Mirrored: piece k walks positions (k+1)*seg + warm - 1 down to k*seg, pieces other than the last
 // start with dh = dc = 0 and discard the gate gradients of their first `warm` steps (injections at take positions inside
-// the window are applied).  Step GEMM: dh_{t-1} [P x 512] = dgates_t [P x 2048] . W_hh [2048 x 512]: CTA r produces the
-// 64 hidden units it owns (N = 64, K = 2048; A = fp16 split of the gate gradients of all 8 CTAs, exchanged through
-// L2 and TMA-multicast; B = W_hh^T slice).  Gate gradients span many orders of magnitude, so the exchanged copy is
+// the window are applied).  Step GEMM: dh_{t-1} [P x 512] = dgates_t [P x 2048] . W_hh [2048 x 512], cut over the
+// cluster as 2 K halves x 4 column quarters (see BwdCfg; A = fp16 split of the gate gradients of all 8 CTAs, exchanged
+// through L2 and TMA-multicast to the 4 CTAs of a K half; B = W_hh^T slice; partial sums swapped through DSMEM); each
+// CTA owns the cell arithmetic of 64 hidden units.  Gate gradients span many orders of magnitude, so the exchanged copy is
 // scaled by a power of two derived from max |dL/dh_take| (fp16 keeps 22 bits down to 2^-18 of that maximum; overflow
 // is detected and reported).  The fp32 gate gradients of live positions go to `dgates` for the parameter-gradient
 // contractions exactly as the serial kernel writes them.
@@ -437,16 +438,34 @@ chains_tc_fwd_fused_kernel(const __grid_constant__ FwdMaps maps_v, const FwdArgs
 }
 
 // ------------------------------------------------------------------------------------------------ backward (LSTM)
-constexpr int B_STAGES = 8, B_KB = 4 * H / BK;              // 64 K blocks per step (K = 2048 gate gradients)
-constexpr int BB_TILE = UN * BK * 2;                        // 4 KB: this CTA's 64 output units x 32 K
-constexpr int B_STAGE = 2 * A_TILE + 2 * BB_TILE;           // 24 KB
+// The step GEMM dh_{t-1} [128 x 512] = dgates_t [128 x 2048] . W_hh [2048 x 512] is cut over the cluster's 8 CTAs two
+// ways.  KS = false: 8 column slices (N = 64, K = 2048 per CTA): every CTA ingests ALL the exchanged gate gradients
+// (1 MB of A + 0.5 MB of W_hh^T per step).  KS = true: 2 K halves x 4 column quarters (N = 128, K = 1024 per CTA): half the
+// A traffic per CTA (0.5 MB + 0.5 MB), the same MMA cycles, and the two CTAs that share a column quarter swap the 64
+// columns of their partial sums the other one owns through DSMEM (32 KB per CTA per step, st.async into the partner's
+// receive buffer, one mbarrier per step).  L2 -> SM operand fill bounds these kernels, so the second form is the one
+// launched (measured at 4,096 rows: 38.8 K instead of 46.8 K cycles per step, 14.8 instead of 17.1 ms per launch); the
+// first is kept as the template's other branch for comparison.
+template <bool KS> struct BwdCfg {
+  static constexpr int STAGES = KS ? 6 : 8;
+  static constexpr int KB = (KS ? 2 : 4) * H / BK;            // 32 / 64 K blocks per step and CTA
+  static constexpr int NCOL = KS ? 2 * UN : UN;               // 128 / 64 output columns per CTA
+  static constexpr int B_TILE = NCOL * BK * 2;                // 8 / 4 KB
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;       // 32 / 24 KB
+  static constexpr int GROUP = KS ? 4 : CL;                   // CTAs that share (and multicast) an A tile
+  static constexpr int SLICE_ROWS = BM / GROUP;               // 32 / 16 rows fetched per CTA
+  static constexpr int SLICE = SLICE_ROWS * BK * 2;
+  static constexpr int XBUF = KS ? BM * UN * 4 : 0;           // 32 KB receive buffer of the partner's partial sums
+  static constexpr int TMEM_COLS = 2 * NCOL, CORR = NCOL;
+  static constexpr int SMEM = STAGES * STAGE + XBUF + 256 + 1024;
+};
 // chain_tc_bwd_kernel: two unit passes per step, each with its own staging buffer of 6 arrays of [32 rows][16 units] f32
 // (gates i,f,g,o, c_t, c_{t-1}), so that both passes' stash gathers are in flight before the first pass is computed; the
 // injected dL/dh rows (one position in ten) travel through registers.
 constexpr int B1_BUF = 6 * 2048, B_GST_WARP = 2 * B1_BUF;
-constexpr int B_SMEM = B_STAGES * B_STAGE + 256 + 1024;
-constexpr int B_TMEM_COLS = 128, B_CORR = 64;
-static_assert(EPI_WARPS * B_GST_WARP <= B_STAGES * B_STAGE, "epilogue staging lives inside the (idle) TMA ring");
+static_assert(EPI_WARPS * B_GST_WARP <= BwdCfg<false>::STAGES * BwdCfg<false>::STAGE &&
+              EPI_WARPS * B_GST_WARP <= BwdCfg<true>::STAGES * BwdCfg<true>::STAGE, "epilogue staging lives inside the (idle) TMA ring");
+static_assert(BwdCfg<true>::SMEM <= 232448, "shared memory budget");
 
 struct BwdArgs {
   int P, Ppad, steps, warm, cp_half;
@@ -479,32 +498,53 @@ __device__ __forceinline__ float bwd_scale(float m) {
   return ldexpf(1.f, ex);
 }
 
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_v4(unsigned raddr, const float* v, unsigned rbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(raddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "r"(rbar) : "memory");
+}
+
+template <bool KS>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
 chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_constant__ CUtensorMap map_w, const BwdArgs p) {
-  constexpr int STAGES = B_STAGES, STAGE = B_STAGE;
+  using Cfg = BwdCfg<KS>;
+  constexpr int STAGES = Cfg::STAGES, STAGE = Cfg::STAGE, B_KB = Cfg::KB, B_CORR = Cfg::CORR, BB_TILE = Cfg::B_TILE;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + STAGES * STAGE);
-  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * STAGES + 2);
+  unsigned char* xbuf = smem + STAGES * STAGE;       // [128 rows][16 chunks of 4 floats], chunk c of row r at c ^ (r & 7)
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(xbuf + Cfg::XBUF);
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * STAGES + 3);
   const unsigned bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[STAGES]);
   const unsigned bar_acc_full = smem_u32(&bars[2 * STAGES]), bar_acc_empty = smem_u32(&bars[2 * STAGES + 1]);
+  const unsigned bar_x = smem_u32(&bars[2 * STAGES + 2]);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned rank = cluster_rank();
+  // KS: rank = 4 * (K half) + (column quarter); the CTA contracts K half kh for the 128 columns of quarter nq and owns
+  // (cell arithmetic, stores) the 64 columns [128 nq + 64 kh, +64) of them
+  const int kh = KS ? (int)(rank >> 2) : 0, nq = KS ? (int)(rank & 3) : (int)rank;
+  const int ub = KS ? 128 * nq + 64 * kh : (int)rank * UN;          // first hidden unit this CTA owns
+  const int own_c = KS ? 64 * kh : 0;                               // its column in this CTA's accumulators
+  const unsigned short grp_mask = KS ? (unsigned short)(0xF << (4 * kh)) : (unsigned short)0xFF;
   const int m0 = (blockIdx.x / CL) * BM;
   const int P = p.P, Ppad = p.Ppad, steps = p.steps;
   const int iters = steps + (p.dh0_out ? 1 : 0);       // one more contraction when dL/dh0 is wanted
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, Cfg::GROUP); }
     mbar_init(bar_acc_full, 1);
     mbar_init(bar_acc_empty, EPI_WARPS);
+    mbar_init(bar_x, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dg) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(B_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -530,9 +570,10 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
           const unsigned full = bar_full + 8 * s;
           mbar_expect_tx(full, 2 * A_TILE + 2 * BB_TILE);
           const unsigned base = smem_u32(smem + s * STAGE);
-          tma_load_2d_mcast(base + rank * A_SLICE, &map_dg, kb * BK, arow + (int)rank * A_SLICE_ROWS, full, 0xFF);
-          tma_load_2d_mcast(base + A_TILE + rank * A_SLICE, &map_dg, kb * BK, arow + Ppad + (int)rank * A_SLICE_ROWS, full, 0xFF);
-          tma_load_3d(base + 2 * A_TILE, &map_w, kb * BK, (int)rank * UN, 0, full);       // hi at +0, lo' at +BB_TILE
+          const int kc = (kh * B_KB + kb) * BK;
+          tma_load_2d_mcast(base + nq * Cfg::SLICE, &map_dg, kc, arow + nq * Cfg::SLICE_ROWS, full, grp_mask);
+          tma_load_2d_mcast(base + A_TILE + nq * Cfg::SLICE, &map_dg, kc, arow + Ppad + nq * Cfg::SLICE_ROWS, full, grp_mask);
+          tma_load_3d(base + 2 * A_TILE, &map_w, kc, nq * Cfg::NCOL, 0, full);            // hi at +0, lo' at +BB_TILE
         }
       }
       __syncwarp();
@@ -559,11 +600,11 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              tc_mma(tmem_base, dA0 + 2 * k, dB0 + 2 * k, idesc_f16_m128(UN), (kb | k) != 0);
-              tc_mma(tmem_base + B_CORR, dA0 + 2 * k, dB1 + 2 * k, idesc_f16_m128(UN), (kb | k) != 0);
-              tc_mma(tmem_base + B_CORR, dA1 + 2 * k, dB0 + 2 * k, idesc_f16_m128(UN), 1u);
+              tc_mma(tmem_base, dA0 + 2 * k, dB0 + 2 * k, idesc_f16_m128(Cfg::NCOL), (kb | k) != 0);
+              tc_mma(tmem_base + B_CORR, dA0 + 2 * k, dB1 + 2 * k, idesc_f16_m128(Cfg::NCOL), (kb | k) != 0);
+              tc_mma(tmem_base + B_CORR, dA1 + 2 * k, dB0 + 2 * k, idesc_f16_m128(Cfg::NCOL), 1u);
             }
-            tc_commit_mcast(bar_empty + 8 * s, 0xFF);
+            tc_commit_mcast(bar_empty + 8 * s, grp_mask);
           }
           __syncwarp();
         }
@@ -598,27 +639,60 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
     const bool prof = p.prof != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0;
     long long pr[5] = {0, 0, 0, 0, 0};
     const int half_ref_it = steps - 1 - (p.warm - 1 - p.cp_half);      // reference side of the half-way checkpoint
+    // K split: receive buffer of the partner CTA (rank ^ 4) and this thread's row in it / in the own one
+    const int xrow = (32 * q + lane) * 256, xsw = lane & 7;
+    const unsigned x_remote = KS ? mapa_u32(smem_u32(xbuf), rank ^ 4u) : 0u, x_rbar = KS ? mapa_u32(bar_x, rank ^ 4u) : 0u;
+    bool x_have = false;                       // whether this iteration has partial sums to add (it > 0)
+    auto load_partner = [&](int ps, int c8, float* xr) {
+      if (KS && x_have) {
+        const float4 a = *reinterpret_cast<const float4*>(xbuf + xrow + (((8 * ch + 4 * ps + 2 * c8) ^ xsw) << 4));
+        const float4 b = *reinterpret_cast<const float4*>(xbuf + xrow + (((8 * ch + 4 * ps + 2 * c8 + 1) ^ xsw) << 4));
+        xr[0] = a.x; xr[1] = a.y; xr[2] = a.z; xr[3] = a.w; xr[4] = b.x; xr[5] = b.y; xr[6] = b.z; xr[7] = b.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xr[i] = 0.f;
+      }
+    };
 
     for (int it = 0; it < iters; ++it) {
       const long long t0 = prof ? clock64() : 0;
       const int t = steps - 1 - it;
+      x_have = it > 0;
       const int tk_n = (valid && t > 0) ? p.take[(long long)k_own * sk + (long long)(t - 1) * stt] : -1;
       if (it > 0) {
         mbar_wait(bar_acc_full, (unsigned)(it - 1) & 1u);
         tc_fence_after();
+        if (KS) {
+          // the 64 columns of this CTA's partial sums that the partner (other K half, same column quarter) owns: this
+          // thread's row, its 32-column half, combined main + correction, straight into the partner's receive buffer
+          if (ew == 0 && lane == 0) mbar_expect_tx(bar_x, Cfg::XBUF);
+          const int pc = 64 * (1 - kh) + 32 * ch;
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            float rec[8], cor[8], v[8];
+            tmem_ld8x2(tq + (unsigned)(pc + 8 * j8), tq + (unsigned)(B_CORR + pc + 8 * j8), rec, cor);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaf(cor[i], LO_INV, rec[i] * mg);
+            st_async_v4(x_remote + (unsigned)(xrow + (((8 * ch + 2 * j8) ^ xsw) << 4)), v, x_rbar);
+            st_async_v4(x_remote + (unsigned)(xrow + (((8 * ch + 2 * j8 + 1) ^ xsw) << 4)), v + 4, x_rbar);
+          }
+        }
       }
+      bool x_ready = !(KS && it > 0);
       if (it == steps) {
+        if (!x_ready) { mbar_wait(bar_x, (unsigned)(it - 1) & 1u); x_ready = true; }
         // the extra iteration: dL/dh entering local time 0 = the contraction of the last step's gate gradients
 #pragma unroll
         for (int ps = 0; ps < 2; ++ps) {
-          const int ucolp = (int)rank * UN + 32 * ch + 16 * ps;
+          const int ucolp = ub + 32 * ch + 16 * ps;
 #pragma unroll
           for (int c8 = 0; c8 < 2; ++c8) {
-            float rec[8], cor[8];
-            tmem_ld8x2(tq + (unsigned)(32 * ch + 16 * ps + 8 * c8), tq + (unsigned)(B_CORR + 32 * ch + 16 * ps + 8 * c8), rec, cor);
+            float rec[8], cor[8], xr[8];
+            tmem_ld8x2(tq + (unsigned)(own_c + 32 * ch + 16 * ps + 8 * c8), tq + (unsigned)(B_CORR + own_c + 32 * ch + 16 * ps + 8 * c8), rec, cor);
+            load_partner(ps, c8, xr);
             float o[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = fmaf(cor[i], LO_INV, rec[i] * mg) * invS;
+            for (int i = 0; i < 8; ++i) o[i] = (fmaf(cor[i], LO_INV, rec[i] * mg) + xr[i]) * invS;
             *reinterpret_cast<float4*>(gst + lane * 64 + (((2 * c8) ^ ((lane >> 1) & 3)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
             *reinterpret_cast<float4*>(gst + lane * 64 + (((2 * c8 + 1) ^ ((lane >> 1) & 3)) << 4)) = make_float4(o[4], o[5], o[6], o[7]);
           }
@@ -649,7 +723,7 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
       //     pass's own buffer; 4 lanes per row; element (row, 16-byte chunk c) lives at row*64 + ((c ^ ((row >> 1) & 3)) << 4).
 #pragma unroll
       for (int ps = 0; ps < 2; ++ps) {
-        const int ucolp = (int)rank * UN + 32 * ch + 16 * ps;
+        const int ucolp = ub + 32 * ch + 16 * ps;
         const int c4 = lane & 3;
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
@@ -670,16 +744,17 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
       // injected dL/dh of this thread's own row (pass 0 now, pass 1 while pass 0 is stored)
       float4 inj[4];
       auto load_inj = [&](int ps) {
-        const float* src = p.dh_take + (size_t)(tk >= 0 ? tk : 0) * H + (int)rank * UN + 32 * ch + 16 * ps;
+        const float* src = p.dh_take + (size_t)(tk >= 0 ? tk : 0) * H + ub + 32 * ch + 16 * ps;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           inj[c] = (valid && tk >= 0) ? __ldg(reinterpret_cast<const float4*>(src) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       };
       load_inj(0);
+      if (!x_ready) mbar_wait(bar_x, (unsigned)(it - 1) & 1u);
 #pragma unroll
       for (int ps = 0; ps < 2; ++ps) {
         const long long u0 = prof ? clock64() : 0;
-        const int ucolp = (int)rank * UN + 32 * ch + 16 * ps;
+        const int ucolp = ub + 32 * ch + 16 * ps;
         unsigned char* gb = gst + ps * B1_BUF;
         if (ps == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -688,9 +763,10 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
         // (C) gate gradients, one row per lane, in place on the staging tile
 #pragma unroll
         for (int c8 = 0; c8 < 2; ++c8) {
-          float rec[8], cor[8];
+          float rec[8], cor[8], xr[8];
+          load_partner(ps, c8, xr);
           if (it > 0) {
-            tmem_ld8x2(tq + (unsigned)(32 * ch + 16 * ps + 8 * c8), tq + (unsigned)(B_CORR + 32 * ch + 16 * ps + 8 * c8), rec, cor);
+            tmem_ld8x2(tq + (unsigned)(own_c + 32 * ch + 16 * ps + 8 * c8), tq + (unsigned)(B_CORR + own_c + 32 * ch + 16 * ps + 8 * c8), rec, cor);
           } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) { rec[i] = 0.f; cor[i] = 0.f; }
@@ -711,7 +787,7 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float gi = tin[0][i], gf = tin[1][i], gg = tin[2][i], go = tin[3][i], cc = tin[4][i], cp = tin[5][i];
-            const float dh = fmaf(cor[i], LO_INV, rec[i] * mg) * invS + injv[i];
+            const float dh = (fmaf(cor[i], LO_INV, rec[i] * mg) + xr[i]) * invS + injv[i];
             const float tcv = tanh_lean(cc);
             const float dct = dc[ps][c8][i] + dh * (go * (1.f - tcv * tcv));
             dhv[i] = dh;
@@ -816,7 +892,7 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
   cluster_arrive();
   cluster_wait();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(B_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
   }
 }
 
@@ -1142,6 +1218,26 @@ int icrl_chains_tc_fwd_fused_impl(cudaStream_t st, int Pv, long long seg_v, int 
   return ICRL_OK;
 }
 
+namespace {
+template <bool KS>
+int launch_bwd_cfg(cudaStream_t st, const __half* dgx, const __half* whhT, int Ppad, BwdArgs* a) {
+  using Cfg = BwdCfg<KS>;
+  // truncation bias of the tensor-core accumulation grows with the MMAs chained into one accumulator: 128 (K = 2048) or 64
+  a->main_gain = 1.f + g_tc_bias[1] * (KS ? 0.5f : 1.f);
+  CUtensorMap mg, mw;
+  int rc;
+  if ((rc = make_map_2d(&mg, dgx, 4 * H, (long long)4 * Ppad, Cfg::SLICE_ROWS))) return rc;
+  if ((rc = make_map_3d(&mw, whhT, 4 * H, H, Cfg::NCOL))) return rc;
+  ICRL_CUDA(cudaFuncSetAttribute(chain_tc_bwd_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  chain_tc_bwd_kernel<KS><<<dim3(CL * (Ppad / BM)), dim3(THREADS), Cfg::SMEM, st>>>(mg, mw, *a);
+  ICRL_LAUNCH_CHECK();
+  return ICRL_OK;
+}
+int launch_bwd(cudaStream_t st, const __half* dgx, const __half* whhT, int Ppad, BwdArgs* a) {
+  return launch_bwd_cfg<true>(st, dgx, whhT, Ppad, a);
+}
+}  // namespace
+
 int icrl_chain_tc_lstm_bwd_impl(cudaStream_t st, int P, long long seg, int warm, const void* packed,
                                 const float* stash_g, const float* stash_c, const int* take, const float* dh_take,
                                 long long take_rows, float* dgates, void* ws, float* cp_state, float* err) {
@@ -1159,14 +1255,8 @@ int icrl_chain_tc_lstm_bwd_impl(cudaStream_t st, int P, long long seg, int warm,
   a.stride_k = seg; a.stride_t = 1; a.dh0_out = nullptr;
   a.stash_g = stash_g; a.stash_c = stash_c; a.take = take; a.dh_take = dh_take; a.dgates = dgates; a.dgx = dgx;
   a.dh_max = err + 4; a.bstate = cp_state; a.overflow = err + 5; a.prof = g_chain_tc_prof ? g_chain_tc_prof + 8 : nullptr;
-  a.main_gain = 1.f + g_tc_bias[1];
-  CUtensorMap mg, mw;
   int rc;
-  if ((rc = make_map_2d(&mg, dgx, 4 * H, (long long)4 * Ppad, A_SLICE_ROWS))) return rc;
-  if ((rc = make_map_3d(&mw, whhT, 4 * H, H, UN))) return rc;
-  ICRL_CUDA(cudaFuncSetAttribute(chain_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
-  chain_tc_bwd_kernel<<<dim3(CL * (Ppad / BM)), dim3(THREADS), B_SMEM, st>>>(mg, mw, a);
-  ICRL_LAUNCH_CHECK();
+  if ((rc = launch_bwd(st, dgx, whhT, Ppad, &a))) return rc;
   chain_tc_check_bwd_kernel<<<dim3(P - 1, 2), H, 0, st>>>(P, a.cp_half, cp_state, err);
   ICRL_LAUNCH_CHECK();
   return ICRL_OK;
@@ -1210,13 +1300,7 @@ int icrl_policy_bptt_tc_impl(cudaStream_t st, int B, int n_cell, int p0, const v
   a.stride_k = 1; a.stride_t = B; a.dh0_out = dh0;
   a.stash_g = Gs; a.stash_c = Cs; a.take = take; a.dh_take = dHv; a.dgates = DG; a.dgx = dgx;
   a.dh_max = err + 4; a.bstate = nullptr; a.overflow = err + 5; a.prof = nullptr;
-  a.main_gain = 1.f + g_tc_bias[1];
-  CUtensorMap mg, mw;
   int rc;
-  if ((rc = make_map_2d(&mg, dgx, 4 * H, (long long)4 * Ppad, A_SLICE_ROWS))) return rc;
-  if ((rc = make_map_3d(&mw, whhT, 4 * H, H, UN))) return rc;
-  ICRL_CUDA(cudaFuncSetAttribute(chain_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
-  chain_tc_bwd_kernel<<<dim3(CL * (Ppad / BM)), dim3(THREADS), B_SMEM, st>>>(mg, mw, a);
-  ICRL_LAUNCH_CHECK();
+  if ((rc = launch_bwd(st, dgx, whhT, Ppad, &a))) return rc;
   return ICRL_OK;
 }
