@@ -438,24 +438,33 @@ chains_tc_fwd_fused_kernel(const __grid_constant__ FwdMaps maps_v, const FwdArgs
 }
 
 // ------------------------------------------------------------------------------------------------ backward (LSTM)
-// The step GEMM dh_{t-1} [128 x 512] = dgates_t [128 x 2048] . W_hh [2048 x 512] is cut over the cluster's 8 CTAs two
-// ways.  KS = false: 8 column slices (N = 64, K = 2048 per CTA): every CTA ingests ALL the exchanged gate gradients
-// (1 MB of A + 0.5 MB of W_hh^T per step).  KS = true: 2 K halves x 4 column quarters (N = 128, K = 1024 per CTA): half the
-// A traffic per CTA (0.5 MB + 0.5 MB), the same MMA cycles, and the two CTAs that share a column quarter swap the 64
-// columns of their partial sums the other one owns through DSMEM (32 KB per CTA per step, st.async into the partner's
-// receive buffer, one mbarrier per step).  L2 -> SM operand fill bounds these kernels, so the second form is the one
-// launched (measured at 4,096 rows: 38.8 K instead of 46.8 K cycles per step, 14.8 instead of 17.1 ms per launch); the
-// first is kept as the template's other branch for comparison.
-template <bool KS> struct BwdCfg {
-  static constexpr int STAGES = KS ? 6 : 8;
-  static constexpr int KB = (KS ? 2 : 4) * H / BK;            // 32 / 64 K blocks per step and CTA
-  static constexpr int NCOL = KS ? 2 * UN : UN;               // 128 / 64 output columns per CTA
-  static constexpr int B_TILE = NCOL * BK * 2;                // 8 / 4 KB
-  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;       // 32 / 24 KB
-  static constexpr int GROUP = KS ? 4 : CL;                   // CTAs that share (and multicast) an A tile
-  static constexpr int SLICE_ROWS = BM / GROUP;               // 32 / 16 rows fetched per CTA
+// The step GEMM dh_{t-1} [128 x 512] = dgates_t [128 x 2048] . W_hh [2048 x 512] is cut over the cluster's 8 CTAs as
+// 2 K halves x 4 column quarters (N = 128, K = 1024 per CTA; rank = 4 * (K half) + quarter): per step a CTA ingests
+// 0.5 MB of exchanged gate gradients (TMA-multicast among the 4 CTAs of its K half) + 0.5 MB of W_hh^T, and the two
+// CTAs that share a column quarter swap the 64 columns of their partial sums the other one owns through DSMEM (32 KB per
+// CTA per step, st.async into the partner's receive buffer, one mbarrier per step).
+//
+// What bounds the GEMM part of a step is the SHARED-MEMORY bandwidth of the SM (128 B/clk): operand reads of the MMAs
+// plus the TMA writes of the fill.  Measured against that model (cycles from the GEMM's first load to its last MMA):
+//   8 column slices (N = 64, K = 2048), 3 MMAs per K step:        2.3 MB read + 1.5 MB fill -> 29.7 K  (28.6 K measured)
+//   2 K halves x 4 quarters (N = 128, K = 1024), 3 MMAs:           1.5 MB      + 1.0 MB      -> 19.5 K  (19.4 K measured)
+//   the same, A_hi x [B_hi | B_lo] as ONE N = 256 MMA (below):     1.25 MB     + 1.0 MB      -> 17.6 K
+// The two parts of W_hh^T of a stage are adjacent in shared memory (rows 0..127 hi, 128..255 lo' of one K-major tile),
+// so main and the first correction term come from one instruction into adjacent accumulator columns; A_lo x B_hi
+// accumulates onto the correction columns.  (Two alternating sets of 128 pieces per cluster -- the GEMM of one under
+// the epilogue of the other -- were built and measured: 35.4 K cycles per set and step against 38.8 K, because the
+// epilogue's staging traffic then competes for the same shared-memory bandwidth; with twice the warm-ups to pay it
+// loses below ~14,000 rows and was removed.)
+struct BwdCfg {
+  static constexpr int STAGES = 6;
+  static constexpr int KB = 2 * H / BK;                       // 32 K blocks per step and CTA
+  static constexpr int NCOL = 2 * UN;                         // 128 output columns per CTA
+  static constexpr int B_TILE = NCOL * BK * 2;                // 8 KB
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;       // 32 KB
+  static constexpr int GROUP = 4;                             // CTAs that share (and multicast) an A tile
+  static constexpr int SLICE_ROWS = BM / GROUP;               // 32 rows fetched per CTA
   static constexpr int SLICE = SLICE_ROWS * BK * 2;
-  static constexpr int XBUF = KS ? BM * UN * 4 : 0;           // 32 KB receive buffer of the partner's partial sums
+  static constexpr int XBUF = BM * UN * 4;                    // 32 KB receive buffer of the partner's partial sums
   static constexpr int TMEM_COLS = 2 * NCOL, CORR = NCOL;
   static constexpr int SMEM = STAGES * STAGE + XBUF + 256 + 1024;
 };
@@ -463,9 +472,8 @@ template <bool KS> struct BwdCfg {
 // (gates i,f,g,o, c_t, c_{t-1}), so that both passes' stash gathers are in flight before the first pass is computed; the
 // injected dL/dh rows (one position in ten) travel through registers.
 constexpr int B1_BUF = 6 * 2048, B_GST_WARP = 2 * B1_BUF;
-static_assert(EPI_WARPS * B_GST_WARP <= BwdCfg<false>::STAGES * BwdCfg<false>::STAGE &&
-              EPI_WARPS * B_GST_WARP <= BwdCfg<true>::STAGES * BwdCfg<true>::STAGE, "epilogue staging lives inside the (idle) TMA ring");
-static_assert(BwdCfg<true>::SMEM <= 232448, "shared memory budget");
+static_assert(EPI_WARPS * B_GST_WARP <= BwdCfg::STAGES * BwdCfg::STAGE, "epilogue staging lives inside the (idle) TMA ring");
+static_assert(BwdCfg::SMEM <= 232448, "shared memory budget");
 
 struct BwdArgs {
   int P, Ppad, steps, warm, cp_half;
@@ -508,10 +516,9 @@ __device__ __forceinline__ void st_async_v4(unsigned raddr, const float* v, unsi
                ::"r"(raddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "r"(rbar) : "memory");
 }
 
-template <bool KS>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
 chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_constant__ CUtensorMap map_w, const BwdArgs p) {
-  using Cfg = BwdCfg<KS>;
+  using Cfg = BwdCfg;
   constexpr int STAGES = Cfg::STAGES, STAGE = Cfg::STAGE, B_KB = Cfg::KB, B_CORR = Cfg::CORR, BB_TILE = Cfg::B_TILE;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -524,12 +531,12 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned rank = cluster_rank();
-  // KS: rank = 4 * (K half) + (column quarter); the CTA contracts K half kh for the 128 columns of quarter nq and owns
+  // rank = 4 * (K half) + (column quarter); the CTA contracts K half kh for the 128 columns of quarter nq and owns
   // (cell arithmetic, stores) the 64 columns [128 nq + 64 kh, +64) of them
-  const int kh = KS ? (int)(rank >> 2) : 0, nq = KS ? (int)(rank & 3) : (int)rank;
-  const int ub = KS ? 128 * nq + 64 * kh : (int)rank * UN;          // first hidden unit this CTA owns
-  const int own_c = KS ? 64 * kh : 0;                               // its column in this CTA's accumulators
-  const unsigned short grp_mask = KS ? (unsigned short)(0xF << (4 * kh)) : (unsigned short)0xFF;
+  const int kh = (int)(rank >> 2), nq = (int)(rank & 3);
+  const int ub = 128 * nq + 64 * kh;                                // first hidden unit this CTA owns
+  const int own_c = 64 * kh;                                        // its column in this CTA's accumulators
+  const unsigned short grp_mask = (unsigned short)(0xF << (4 * kh));
   const int m0 = (blockIdx.x / CL) * BM;
   const int P = p.P, Ppad = p.Ppad, steps = p.steps;
   const int iters = steps + (p.dh0_out ? 1 : 0);       // one more contraction when dL/dh0 is wanted
@@ -596,12 +603,12 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
           tc_fence_after();
           const unsigned base = smem_u32(smem + s * STAGE);
           const unsigned long long dA0 = smem_desc_sw64(base), dA1 = smem_desc_sw64(base + A_TILE);
-          const unsigned long long dB0 = smem_desc_sw64(base + 2 * A_TILE), dB1 = smem_desc_sw64(base + 2 * A_TILE + BB_TILE);
+          const unsigned long long dB0 = smem_desc_sw64(base + 2 * A_TILE);      // 256 rows: hi, then lo' at +BB_TILE
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              tc_mma(tmem_base, dA0 + 2 * k, dB0 + 2 * k, idesc_f16_m128(Cfg::NCOL), (kb | k) != 0);
-              tc_mma(tmem_base + B_CORR, dA0 + 2 * k, dB1 + 2 * k, idesc_f16_m128(Cfg::NCOL), (kb | k) != 0);
+              // [main | correction] = A_hi x [B_hi | B_lo'] in one N = 256 instruction, then correction += A_lo' x B_hi
+              tc_mma(tmem_base, dA0 + 2 * k, dB0 + 2 * k, idesc_f16_m128(2 * Cfg::NCOL), (kb | k) != 0);
               tc_mma(tmem_base + B_CORR, dA1 + 2 * k, dB0 + 2 * k, idesc_f16_m128(Cfg::NCOL), 1u);
             }
             tc_commit_mcast(bar_empty + 8 * s, grp_mask);
@@ -641,10 +648,10 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
     const int half_ref_it = steps - 1 - (p.warm - 1 - p.cp_half);      // reference side of the half-way checkpoint
     // K split: receive buffer of the partner CTA (rank ^ 4) and this thread's row in it / in the own one
     const int xrow = (32 * q + lane) * 256, xsw = lane & 7;
-    const unsigned x_remote = KS ? mapa_u32(smem_u32(xbuf), rank ^ 4u) : 0u, x_rbar = KS ? mapa_u32(bar_x, rank ^ 4u) : 0u;
+    const unsigned x_remote = mapa_u32(smem_u32(xbuf), rank ^ 4u), x_rbar = mapa_u32(bar_x, rank ^ 4u);
     bool x_have = false;                       // whether this iteration has partial sums to add (it > 0)
     auto load_partner = [&](int ps, int c8, float* xr) {
-      if (KS && x_have) {
+      if (x_have) {
         const float4 a = *reinterpret_cast<const float4*>(xbuf + xrow + (((8 * ch + 4 * ps + 2 * c8) ^ xsw) << 4));
         const float4 b = *reinterpret_cast<const float4*>(xbuf + xrow + (((8 * ch + 4 * ps + 2 * c8 + 1) ^ xsw) << 4));
         xr[0] = a.x; xr[1] = a.y; xr[2] = a.z; xr[3] = a.w; xr[4] = b.x; xr[5] = b.y; xr[6] = b.z; xr[7] = b.w;
@@ -662,7 +669,7 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
       if (it > 0) {
         mbar_wait(bar_acc_full, (unsigned)(it - 1) & 1u);
         tc_fence_after();
-        if (KS) {
+        {
           // the 64 columns of this CTA's partial sums that the partner (other K half, same column quarter) owns: this
           // thread's row, its 32-column half, combined main + correction, straight into the partner's receive buffer
           if (ew == 0 && lane == 0) mbar_expect_tx(bar_x, Cfg::XBUF);
@@ -678,7 +685,7 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
           }
         }
       }
-      bool x_ready = !(KS && it > 0);
+      bool x_ready = it == 0;
       if (it == steps) {
         if (!x_ready) { mbar_wait(bar_x, (unsigned)(it - 1) & 1u); x_ready = true; }
         // the extra iteration: dL/dh entering local time 0 = the contraction of the last step's gate gradients
@@ -1219,22 +1226,19 @@ int icrl_chains_tc_fwd_fused_impl(cudaStream_t st, int Pv, long long seg_v, int 
 }
 
 namespace {
-template <bool KS>
-int launch_bwd_cfg(cudaStream_t st, const __half* dgx, const __half* whhT, int Ppad, BwdArgs* a) {
-  using Cfg = BwdCfg<KS>;
-  // truncation bias of the tensor-core accumulation grows with the MMAs chained into one accumulator: 128 (K = 2048) or 64
-  a->main_gain = 1.f + g_tc_bias[1] * (KS ? 0.5f : 1.f);
+int launch_bwd(cudaStream_t st, const __half* dgx, const __half* whhT, int Ppad, BwdArgs* a) {
+  using Cfg = BwdCfg;
+  // truncation bias of the tensor-core accumulation: g_tc_bias[1] is quoted for 128 chained MMAs (K = 2048); each K half
+  // chains 64
+  a->main_gain = 1.f + 0.5f * g_tc_bias[1];
   CUtensorMap mg, mw;
   int rc;
   if ((rc = make_map_2d(&mg, dgx, 4 * H, (long long)4 * Ppad, Cfg::SLICE_ROWS))) return rc;
   if ((rc = make_map_3d(&mw, whhT, 4 * H, H, Cfg::NCOL))) return rc;
-  ICRL_CUDA(cudaFuncSetAttribute(chain_tc_bwd_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-  chain_tc_bwd_kernel<KS><<<dim3(CL * (Ppad / BM)), dim3(THREADS), Cfg::SMEM, st>>>(mg, mw, *a);
+  ICRL_CUDA(cudaFuncSetAttribute(chain_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  chain_tc_bwd_kernel<<<dim3(CL * (Ppad / BM)), dim3(THREADS), Cfg::SMEM, st>>>(mg, mw, *a);
   ICRL_LAUNCH_CHECK();
   return ICRL_OK;
-}
-int launch_bwd(cudaStream_t st, const __half* dgx, const __half* whhT, int Ppad, BwdArgs* a) {
-  return launch_bwd_cfg<true>(st, dgx, whhT, Ppad, a);
 }
 }  // namespace
 
