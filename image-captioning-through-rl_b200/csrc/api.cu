@@ -612,20 +612,30 @@ int icrl_value_head_bwd(void* stream, int B, int S, const float* features, const
 int icrl_value_chain_param_grads(void* stream, int T, int V, int D, const int* tok_stream, const float* dgates,
                                  const float* stash_h, const float* E, const float* W_ih, float* dtable,
                                  float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE, float* dW_ih,
-                                 float* dW_hh, float* db_ih, float* db_hh, int* launches) {
+                                 float* dW_hh, float* db_ih, float* db_hh, int B, int p0, int S, int* launches) {
   cudaStream_t st = S_(stream);
+  // Gate-table gradient: dtable[token] += dgates of every position that consumed the token.  When the caller names the
+  // stream's shape (B > 0: tok_stream = icrl_build_stream(B, p0, S, extra 0)) the positions of one (column, row) are
+  // summed before the reduction and the column maxima of dgates come back for the contraction below.
+  unsigned* colmax = nullptr;
+  ICRL_CUDA(cudaMemsetAsync(dtable, 0, (size_t)V * 4 * H * sizeof(float), st));
+  if (B > 0) {
+    ICRL_REQUIRE(T == icrl_stream_len(B, p0, S, 0), "T is not the length of the (B, p0, S) stream");
+    colmax = reinterpret_cast<unsigned*>(colsum_ws);             // consumed by the transposes below, before colsum_ws is reused
+    TRY(icrl_scatter_add_stream(st, B, p0, S, 0, 4 * H, dgates, tok_stream, dtable, colmax));
+  } else {
+    TRY(icrl_scatter_add_rows(st, T, 4 * H, dgates, tok_stream, dtable));
+  }
+  bump(launches, 1);
   // dW_hh = sum_t dgates_t (x) h_{t-1};  stash_h row t = h_{t-1}.  With a workspace of icrl_wgrad_tc_ws_bytes(2048, 512,
   // T, 2) bytes the contraction runs on tcgen05 (wgrad_tc.cu), otherwise on the fp32 SIMT GEMM.
   if (gemm_ws_bytes >= icrl_wgrad_tc_ws_bytes_impl(4 * H, H, T, 2)) {
-    TRY(icrl_wgrad_tc_impl(st, 4 * H, H, T, dgates, 4 * H, stash_h, H, dW_hh, H, gemm_ws, gemm_ws_bytes, 2));
-    bump(launches, 5);
+    TRY(icrl_wgrad_tc_impl(st, 4 * H, H, T, dgates, 4 * H, stash_h, H, dW_hh, H, gemm_ws, gemm_ws_bytes, 2, colmax));
+    bump(launches, colmax ? 4 : 5);
   } else {
     TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, H, T, dgates, 4 * H, stash_h, H, dW_hh, H, nullptr, 0.f, gemm_ws,
                            gemm_ws_bytes, launches));
   }
-  ICRL_CUDA(cudaMemsetAsync(dtable, 0, (size_t)V * 4 * H * sizeof(float), st));
-  TRY(icrl_scatter_add_rows(st, T, 4 * H, dgates, tok_stream, dtable));
-  bump(launches, 1);
   TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, D, V, dtable, 4 * H, E, D, dW_ih, D, nullptr, 0.f, nullptr, 0, launches));
   if (dE)
     TRY(icrl_gemm_f32_impl(st, 0, 0, V, D, 4 * H, dtable, 4 * H, W_ih, D, dE, D, nullptr, 0.f, nullptr, 0, launches));

@@ -14,6 +14,8 @@ int icrl_softmax_sample(cudaStream_t st, int B, int V, const float* logits, int 
 int icrl_softmax_bwd(cudaStream_t st, int B, int S, int V, float* z, int ldl, const long long* tokens_out,
                      const float* dlogp);
 int icrl_scatter_add_rows(cudaStream_t st, long long R, int C, const float* src, const int* idx, float* dst);
+int icrl_scatter_add_stream(cudaStream_t st, int B, int p0, int S, int extra, int C, const float* src, const int* tok_stream,
+                            float* dst, unsigned* colmax);
 int icrl_wcolsum_chunks(long long R);
 int icrl_wcolsum(cudaStream_t st, long long R, int C, const float* X, const float* w, long long row_mod,
                  float* partial, float* out);
@@ -78,7 +80,7 @@ int icrl_chain_lstm_bwd_batched_impl(cudaStream_t st, int shards, int T, const f
 void icrl_chain_set_profile_impl(long long* buf);
 size_t icrl_wgrad_tc_ws_bytes_impl(int M, int N, long long T, int splits);
 int icrl_wgrad_tc_impl(cudaStream_t st, int M, int N, long long T, const float* A, int lda, const float* B, int ldb,
-                       float* C, int ldc, void* ws, size_t ws_bytes, int splits);
+                       float* C, int ldc, void* ws, size_t ws_bytes, int splits, const unsigned* colmax = nullptr);
 int icrl_adam_flat_impl(cudaStream_t st, long long n, float* p, const float* g, float* m, float* v, float lr, float b1,
                         float b2, float eps, int step);
 

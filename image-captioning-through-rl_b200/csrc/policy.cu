@@ -152,6 +152,48 @@ __global__ void scatter_add_rows_v4_kernel(long long R, int C4, const float4* __
   }
 }
 
+// The same for the rows of a batch-as-time token stream (build_stream_kernel, heads.cu): block s of the stream holds the
+// columns 0 .. p0+s+extra-1 of the [col][B] token matrix, so the token at (col, b) is consumed once in every block that
+// contains column col.  Those positions are summed in registers first -- one vector reduction per (col, b) instead of
+// one per stream position: B * n_col * C/4 of them instead of T * C/4 (10 times fewer at 19 rollout steps), which turns
+// the scatter from atomic-throughput-bound into a streaming read of src.  The kernel also returns the column |max| of
+// src (the weight-gradient GEMM's per-column scale: wgrad_tc.cu) from the values it has in registers anyway.
+// blockDim.x = C/4; thread c owns columns 4c .. 4c+3 of every row.
+__global__ void scatter_add_stream_kernel(int B, int p0, int S, int extra, const float4* __restrict__ src,
+                                          const int* __restrict__ tok_stream, float* __restrict__ dst,
+                                          unsigned* __restrict__ colmax) {
+  const int C4 = blockDim.x, c = threadIdx.x;
+  const int n_col = p0 + S - 1 + extra;
+  const long long rows = (long long)n_col * B;
+  float4 mx = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto take = [&](float4& acc, const float4 v) {
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    mx.x = fmaxf(mx.x, fabsf(v.x)); mx.y = fmaxf(mx.y, fabsf(v.y)); mx.z = fmaxf(mx.z, fabsf(v.z)); mx.w = fmaxf(mx.w, fabsf(v.w));
+  };
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int col = (int)(r / B), b = (int)(r % B);
+    const int s0 = max(0, col - p0 - extra + 1);                       // first block with more than `col` columns
+    // stream position of (col, b) in block s: B * (s * (p0 + extra) + s (s - 1) / 2) + col * B + b
+    auto pos = [&](int s) { return (long long)B * ((long long)s * (p0 + extra) + (long long)s * (s - 1) / 2 + col) + b; };
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = s0;
+    for (; s + 3 < S; s += 4) {
+      const float4 v0 = __ldg(src + pos(s) * C4 + c), v1 = __ldg(src + pos(s + 1) * C4 + c);
+      const float4 v2 = __ldg(src + pos(s + 2) * C4 + c), v3 = __ldg(src + pos(s + 3) * C4 + c);
+      take(acc, v0); take(acc, v1); take(acc, v2); take(acc, v3);
+    }
+    for (; s < S; ++s) take(acc, __ldg(src + pos(s) * C4 + c));
+    float* d = dst + ((size_t)tok_stream[pos(s0)] * C4 + c) * 4;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
+  }
+  if (colmax) {                                                        // non-negative floats order like their bit patterns
+    atomicMax(colmax + 4 * c, __float_as_uint(mx.x));
+    atomicMax(colmax + 4 * c + 1, __float_as_uint(mx.y));
+    atomicMax(colmax + 4 * c + 2, __float_as_uint(mx.z));
+    atomicMax(colmax + 4 * c + 3, __float_as_uint(mx.w));
+  }
+}
+
 // dst[idx[r]][c] += src[r][c]   (gate-table gradient: rows that consumed the same token accumulate)
 __global__ void scatter_add_rows_kernel(long long R, int C, const float* __restrict__ src, const int* __restrict__ idx,
                                         float* __restrict__ dst) {
@@ -226,6 +268,20 @@ int icrl_scatter_add_rows(cudaStream_t st, long long R, int C, const float* src,
     return ICRL_OK;
   }
   scatter_add_rows_kernel<<<blocks, 256, 0, st>>>(R, C, src, idx, dst);
+  ICRL_LAUNCH_CHECK();
+  return ICRL_OK;
+}
+
+// src [T][C] rows of the stream of icrl_build_stream(B, p0, S, extra); colmax (nullable): C words, zeroed here.
+int icrl_scatter_add_stream(cudaStream_t st, int B, int p0, int S, int extra, int C, const float* src, const int* tok_stream,
+                            float* dst, unsigned* colmax) {
+  ICRL_REQUIRE(B >= 1 && p0 >= 1 && S >= 1 && extra >= 0, "bad stream shape");
+  ICRL_REQUIRE(C % 4 == 0 && C / 4 <= 1024 && (C / 4) % 32 == 0, "scatter_add_stream: C must be a multiple of 128, at most 4096");
+  ICRL_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0, "unaligned rows");
+  if (colmax) ICRL_CUDA(cudaMemsetAsync(colmax, 0, (size_t)C * sizeof(unsigned), st));
+  const long long rows = (long long)(p0 + S - 1 + extra) * B;
+  const int blocks = (int)min((long long)148 * 4, rows);
+  scatter_add_stream_kernel<<<blocks, C / 4, 0, st>>>(B, p0, S, extra, reinterpret_cast<const float4*>(src), tok_stream, dst, colmax);
   ICRL_LAUNCH_CHECK();
   return ICRL_OK;
 }

@@ -6,7 +6,7 @@
 //      would fall into fp16 subnormals / underflow; h is in (-1, 1) and needs none)
 //   2. transpose + split: x*s = hi + lo'/2048 (fp16 pair, 22 mantissa bits) -> [2][rows][Tp] with Tp = T rounded to 64
 // GEMM: 128x128 tiles, split-K over gridDim.z, 3-stage TMA ring of 64-wide K blocks (hi and lo' of an operand in ONE
-// 3-D box), 3 MMAs per K step (hi*hi -> main, hi*lo' + lo'*hi -> correction accumulator).  Because the tensor core
+// 3-D box), 2 MMAs per K step (hi * [hi | lo'] -> [main | correction], lo'*hi -> correction accumulator).  Because the tensor core
 // truncates on every accumulate (gemm_tc.cu header), a TMEM accumulator only ever sums 512 K elements: after 8 K blocks
 // the epilogue warps add main + correction/2048 into fp32 REGISTERS (round to nearest) while the MMAs continue in the
 // second accumulator set.  Each split writes its partial tile; a last kernel sums the splits and undoes the row scale.
@@ -73,6 +73,7 @@ __device__ __forceinline__ unsigned long long smem_desc(unsigned addr) {
 }
 // F32 accumulate, fp16 x fp16, K-major, N = 128, M = 128
 constexpr unsigned IDESC = (1u << 4) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+constexpr unsigned IDESC2 = (1u << 4) | ((unsigned)(2 * BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);     // N = 256
 
 __device__ __forceinline__ void tmem_ld32x2(unsigned ta, unsigned tb, float* a, float* b) {
   unsigned r[64];
@@ -254,13 +255,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         tc_fence_after();
         const unsigned base = smem_u32(smem + s * STAGE_BYTES);
         const unsigned long long dA0 = smem_desc(base), dA1 = smem_desc(base + OP_TILE / 2);
-        const unsigned long long dB0 = smem_desc(base + OP_TILE), dB1 = smem_desc(base + OP_TILE + OP_TILE / 2);
+        const unsigned long long dB0 = smem_desc(base + OP_TILE);       // 256 rows: hi, then lo' (adjacent in the stage)
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const unsigned first = (i == i0 && k == 0) ? 0u : 1u;
-            tc_mma(acc_main, dA0 + 2 * k, dB0 + 2 * k, IDESC, first);
-            tc_mma(acc_corr, dA0 + 2 * k, dB1 + 2 * k, IDESC, first);
+            // [main | correction] = A_hi x [B_hi | B_lo'] in ONE N = 256 instruction (A_hi is read from shared memory once
+            // instead of twice: operand reads + TMA fill bound this kernel, chain_tc.cu BwdCfg), then correction += A_lo' x B_hi
+            tc_mma(acc_main, dA0 + 2 * k, dB0 + 2 * k, IDESC2, first);
             tc_mma(acc_corr, dA1 + 2 * k, dB0 + 2 * k, IDESC, 1u);
           }
           tc_commit(bar_empty + 8 * s);
@@ -357,8 +359,10 @@ size_t icrl_wgrad_tc_ws_bytes_impl(int M, int N, long long T, int splits) {
 }
 
 // C [M][ldc] = A^T B with A [T][lda] (M columns used, scaled per column), B [T][ldb] (N columns used).
+// colmax (nullable): M words holding the bit patterns of max_t |A[t][m]| when the caller has them already (the gate-table
+// scatter reads all of A and returns them: icrl_scatter_add_stream); otherwise a pre-pass over A computes them.
 int icrl_wgrad_tc_impl(cudaStream_t st, int M, int N, long long T, const float* A, int lda, const float* B, int ldb,
-                       float* C, int ldc, void* ws, size_t ws_bytes, int splits) {
+                       float* C, int ldc, void* ws, size_t ws_bytes, int splits, const unsigned* colmax) {
   ICRL_REQUIRE(M % BM == 0 && N % BN == 0 && T > 0 && splits >= 1, "wgrad_tc needs M, N multiples of 128");
   ICRL_REQUIRE(ws && ws_bytes >= icrl_wgrad_tc_ws_bytes_impl(M, N, T, splits), "wgrad_tc workspace too small");
   static bool attr_set = false;
@@ -371,9 +375,11 @@ int icrl_wgrad_tc_impl(cudaStream_t st, int M, int N, long long T, const float* 
   __half* b_pk = a_pk + (size_t)2 * M * Tp;                             // [2][N][Tp]
   float* partial = reinterpret_cast<float*>(b_pk + (size_t)2 * N * Tp);  // [splits][M][N]
   unsigned* mx = reinterpret_cast<unsigned*>(partial + (size_t)splits * M * N);
-  float* inv_scale = reinterpret_cast<float*>(mx + M);
-  ICRL_CUDA(cudaMemsetAsync(mx, 0, (size_t)M * sizeof(unsigned), st));
-  {
+  float* inv_scale = reinterpret_cast<float*>(mx + M);      // (before mx may be redirected to the caller's maxima)
+  if (colmax) {
+    mx = const_cast<unsigned*>(colmax);
+  } else {
+    ICRL_CUDA(cudaMemsetAsync(mx, 0, (size_t)M * sizeof(unsigned), st));
     dim3 grid(icrl_cdiv(M, 128), (unsigned)min((long long)592, (T + 255) / 256));
     col_absmax_kernel<<<grid, 128, 0, st>>>(T, M, A, lda, mx);
     ICRL_LAUNCH_CHECK();

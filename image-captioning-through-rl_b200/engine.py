@@ -598,17 +598,17 @@ class A2CEngine:
                 self._side_stream = torch.cuda.Stream(device=self.device)
             fork = torch.cuda.Event()
             fork.record(main)
-            self._backward_value(f, B, S, Tv, launch_only_chain=True)
+            self._backward_value(f, B, p0, S, Tv, launch_only_chain=True)
             self._side_stream.wait_event(fork)
             with torch.cuda.stream(self._side_stream):
                 self._backward_policy(f, tokcm, tokens, B, p0, S, "_p")
                 join = torch.cuda.Event()
                 join.record(self._side_stream)
-            self._backward_value(f, B, S, Tv, launch_only_chain=False)
+            self._backward_value(f, B, p0, S, Tv, launch_only_chain=False)
             main.wait_event(join)
         else:
-            self._backward_value(f, B, S, Tv, launch_only_chain=True)
-            self._backward_value(f, B, S, Tv, launch_only_chain=False)
+            self._backward_value(f, B, p0, S, Tv, launch_only_chain=True)
+            self._backward_value(f, B, p0, S, Tv, launch_only_chain=False)
             self._backward_policy(f, tokcm, tokens, B, p0, S, "")
 
     def _bwd_workspaces(self, B, S, Tv, tag):
@@ -630,7 +630,7 @@ class A2CEngine:
             gemm_ws_floats = max(gemm_ws_floats, (n + 3) // 4)
         return colsum_ws, self._buf("gemm_ws" + tag, gemm_ws_floats), gemm_ws_floats, self._buf("dtable" + tag, V * 4 * H)
 
-    def _backward_value(self, f, B, S, Tv, launch_only_chain):
+    def _backward_value(self, f, B, p0, S, Tv, launch_only_chain):
         st, L, b, V = self._stream, self.launches.ref, self._bufs, self.V
         Vn = self.value
         SB = S * B
@@ -644,7 +644,8 @@ class A2CEngine:
               _lib.call("icrl_value_chain_param_grads", st, Tv if K == 1 else K * (Tv + 1), V, Vn.valrnn.caption_embedding.weight.shape[1], _p(b["v_stream"]), _p(dgates), _p(b["v_stash_h"]),
                       _p(Vn.valrnn.caption_embedding.weight), _p(lstm.weight_ih_l0), _p(dtable), _p(colsum_ws), _p(gemm_ws),
                       gemm_ws_floats * 4, _p(g(Vn.valrnn.caption_embedding.weight, True)), _p(g(lstm.weight_ih_l0)),
-                      _p(g(lstm.weight_hh_l0)), _p(g(lstm.bias_ih_l0)), _p(g(lstm.bias_hh_l0)), L)
+                      _p(g(lstm.weight_hh_l0)), _p(g(lstm.bias_ih_l0)), _p(g(lstm.bias_hh_l0)),
+                      B if K == 1 else 0, p0, S, L)
             return
         # value head -> dh at the take positions + head gradients
         dh_take = self._buf("v_dh_take", SB * H)

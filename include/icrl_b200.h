@@ -316,11 +316,15 @@ int icrl_value_head_bwd(void* stream, int B, int S, const float* features, const
                         const float* sum_dv, const float* W1, const float* b1, const float* W2, const float* w_eff,
                         float* dh_take, float* dW1, float* db1, float* dW2, float* db2, float* ws, int* launches);
 /*      value-chain parameter gradients from the chain backward's dgates (overwritten):
- *      dW_hh = dgates^T h_prev, gate-table scatter, dW_ih = dtable^T E, dE = dtable W_ih, db = colsum. */
+ *      dW_hh = dgates^T h_prev, gate-table scatter, dW_ih = dtable^T E, dE = dtable W_ih, db = colsum.
+ *      B > 0: tok_stream is the stream icrl_build_stream(B, p0, S, extra 0) built (T = icrl_stream_len(B, p0, S, 0)); the
+ *      scatter then sums the positions that consumed the same (column, row) token before one vector reduction each
+ *      (ten times fewer reductions at 19 rollout steps) and hands the column maxima of dgates to the contraction.
+ *      B = 0: any token stream of T positions (one reduction per position). */
 int icrl_value_chain_param_grads(void* stream, int T, int V, int D, const int* tok_stream, const float* dgates,
                                  const float* stash_h, const float* E, const float* W_ih, float* dtable,
                                  float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE, float* dW_ih,
-                                 float* dW_hh, float* db_ih, float* db_hh, int* launches);
+                                 float* dW_hh, float* db_ih, float* db_hh, int B, int p0, int S, int* launches);
 /*      reward (models.py:259-260 + GetRewards trainers.py:117-120): rewards [B][S] = cos(ve[b], se[s][b]). */
 int icrl_reward_cosine_fwd(void* stream, int B, int S, const float* ve, const float* se, float* rewards,
                            int* launches);
