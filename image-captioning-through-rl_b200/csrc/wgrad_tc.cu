@@ -23,6 +23,8 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 constexpr int FLUSH_KB = 8;                                // K blocks per TMEM accumulation (512 K elements)
 constexpr int TMEM_COLS = 512;                             // 2 sets x (main 128 + correction 128)
 constexpr int THREADS = 192;
+constexpr int CLN = 4;                                      // CTAs of a cluster: the 4 N tiles of one (M tile, split) share A
+constexpr int A_SLICE_ROWS = BM / CLN, A_SLICE = A_SLICE_ROWS * BK * 2;    // 32 rows = 4 KB per part fetched per CTA
 constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -49,6 +51,24 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned bar) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mcast(unsigned dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned bar,
+                                                  unsigned short mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mcast(unsigned bar, unsigned short mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ unsigned cluster_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ bool elect_one() {
   unsigned pred;
@@ -195,8 +215,11 @@ __global__ void __launch_bounds__(256) transpose_split64_kernel(long long T, lon
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM
-// map_a / map_b: 3-D {Tp, rows, 2 parts}, box {64, 128, 2}.  partial [gridDim.z][M][N].
-__global__ void __launch_bounds__(THREADS, 1)
+// map_a: 3-D {Tp, rows, 2 parts}, box {64, 32, 1}; map_b: box {64, 128, 2}.  partial [gridDim.z][M][N].
+// The 4 CTAs of a cluster (the N tiles of one M tile and split) consume the same A tile: each fetches a quarter of its
+// rows and TMA-multicasts it to all four, so A crosses L2 -> SM once per cluster instead of once per CTA and the four
+// stay in lockstep (a ring stage is refilled only after all four have consumed it).
+__global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(THREADS, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
              int kb_total, float* __restrict__ partial) {
   extern __shared__ unsigned char smem_raw[];
@@ -215,7 +238,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   const int nchunk = (nkb + FLUSH_KB - 1) / FLUSH_KB;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CLN); }
     for (int s = 0; s < 2; ++s) { mbar_init(bar_acc_full + 8 * s, 1); mbar_init(bar_acc_empty + 8 * s, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -229,16 +252,21 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const unsigned tmem_base = *tmem_slot;
+  const unsigned rank = cluster_rank();
+  cluster_sync_all();                                       // every CTA's barriers exist before a peer multicasts into it
 
   if (warp == 0) {
     if (lane == 0) {
       for (int i = 0; i < nkb; ++i) {
         const int s = i % STAGES;
-        mbar_wait(bar_empty + 8 * s, ((unsigned)(i / STAGES) & 1u) ^ 1u);
+        mbar_wait(bar_empty + 8 * s, ((unsigned)(i / STAGES) & 1u) ^ 1u);      // all 4 CTAs have consumed the stage
         const unsigned full = bar_full + 8 * s;
         mbar_expect_tx(full, STAGE_BYTES);
         const unsigned base = smem_u32(smem + s * STAGE_BYTES);
-        tma_load_3d(base, &map_a, (kb0 + i) * BK, m0, 0, full);
+        const unsigned a_dst = base + rank * A_SLICE;
+        const int a_row = m0 + (int)rank * A_SLICE_ROWS;
+        tma_load_3d_mcast(a_dst, &map_a, (kb0 + i) * BK, a_row, 0, full, (unsigned short)0xF);
+        tma_load_3d_mcast(a_dst + OP_TILE / 2, &map_a, (kb0 + i) * BK, a_row, 1, full, (unsigned short)0xF);
         tma_load_3d(base + OP_TILE, &map_b, (kb0 + i) * BK, n0, 0, full);
       }
     }
@@ -265,7 +293,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             tc_mma(acc_main, dA0 + 2 * k, dB0 + 2 * k, IDESC2, first);
             tc_mma(acc_corr, dA1 + 2 * k, dB0 + 2 * k, IDESC, 1u);
           }
-          tc_commit(bar_empty + 8 * s);
+          tc_commit_mcast(bar_empty + 8 * s, (unsigned short)0xF);
         }
         __syncwarp();
       }
@@ -303,6 +331,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                                       // nobody leaves while a peer may still multicast into it
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
@@ -323,7 +352,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_map(CUtensorMap* map, const void* ptr, long long Tp, int rows) {
+int make_map(CUtensorMap* map, const void* ptr, long long Tp, int rows, int box_rows, int box_parts) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     cudaDriverEntryPointQueryResult qres;
@@ -334,7 +363,7 @@ int make_map(CUtensorMap* map, const void* ptr, long long Tp, int rows) {
   }
   const cuuint64_t dims[3] = {(cuuint64_t)Tp, (cuuint64_t)rows, 2};
   const cuuint64_t strides[2] = {(cuuint64_t)Tp * 2, (cuuint64_t)rows * Tp * 2};
-  const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BM, 2};
+  const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, (cuuint32_t)box_parts};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -363,7 +392,7 @@ size_t icrl_wgrad_tc_ws_bytes_impl(int M, int N, long long T, int splits) {
 // scatter reads all of A and returns them: icrl_scatter_add_stream); otherwise a pre-pass over A computes them.
 int icrl_wgrad_tc_impl(cudaStream_t st, int M, int N, long long T, const float* A, int lda, const float* B, int ldb,
                        float* C, int ldc, void* ws, size_t ws_bytes, int splits, const unsigned* colmax) {
-  ICRL_REQUIRE(M % BM == 0 && N % BN == 0 && T > 0 && splits >= 1, "wgrad_tc needs M, N multiples of 128");
+  ICRL_REQUIRE(M % BM == 0 && N % (BN * CLN) == 0 && T > 0 && splits >= 1, "wgrad_tc needs M a multiple of 128, N of 512");
   ICRL_REQUIRE(ws && ws_bytes >= icrl_wgrad_tc_ws_bytes_impl(M, N, T, splits), "wgrad_tc workspace too small");
   static bool attr_set = false;
   if (!attr_set) {
@@ -401,8 +430,8 @@ int icrl_wgrad_tc_impl(cudaStream_t st, int M, int N, long long T, const float* 
   }
   CUtensorMap ma, mb;
   int rc;
-  if ((rc = make_map(&ma, a_pk, Tp, M))) return rc;
-  if ((rc = make_map(&mb, b_pk, Tp, N))) return rc;
+  if ((rc = make_map(&ma, a_pk, Tp, M, A_SLICE_ROWS, 1))) return rc;
+  if ((rc = make_map(&mb, b_pk, Tp, N, BN, 2))) return rc;
   dim3 grid(N / BN, M / BM, splits);
   wgrad_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma, mb, M, N, (int)(Tp / BK), partial);
   ICRL_LAUNCH_CHECK();

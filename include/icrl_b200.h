@@ -85,7 +85,8 @@ int icrl_policy_rollout_fwd_tc(void* stream, int B, int V, int p0, int S, int gr
                                float* Cs, float* Gs, float* logits, float* gpre, void* h_parts, int* launches);
 
 /* ---- weight-gradient contraction on tcgen05 (wgrad_tc.cu): C [M][ldc] = A^T B for time-major fp32 operands A [T][lda]
- *      (M columns), B [T][ldb] (N columns); M, N multiples of 128.  Operands are transposed, scaled per A column and
+ *      (M columns), B [T][ldb] (N columns); M a multiple of 128, N of 512 (the 4 N tiles of an M tile form a cluster
+ *      that shares the A tile by TMA multicast).  Operands are transposed, scaled per A column and
  *      split into fp16 pairs by two pre-passes; f32 accumulation in TMEM is flushed to registers every 512 K elements.
  *      ws: icrl_wgrad_tc_ws_bytes(M, N, T, splits) device bytes.  icrl_value_chain_param_grads takes this path by
  *      itself when its gemm_ws is at least icrl_wgrad_tc_ws_bytes(2048, 512, T, 2) bytes. */
