@@ -332,7 +332,14 @@ class A2CEngine:
             n = int(_lib.call("icrl_chain_tc_weight_halves", 1))
             _lib.call("icrl_pack_chain_tc_weights", self._stream, 1, _p(R.rewrnn.gru.weight_hh_l0),
                       _p(self._buf("r_chain_pk", n, torch.float16)), self.launches.ref)
+        # 3-part bf16 split of the sentence-embedding weight: the [S*B x 512] x [512 x 512] projection of the reward head
+        # runs on the tensor-core GEMM of the decode step (gemm_tc.cu, fp32-grade) once it is large enough to fill tiles
+        n = R.semantic_embed.weight.numel()
+        _lib.call("icrl_split_bf16x3", self._stream, n, _p(R.semantic_embed.weight),
+                  _p(self._buf("r_se_parts", 3 * n, torch.bfloat16)), self.launches.ref)
         self._reward_versions = tuple(p._version for p in R.parameters()) + tuple(p.data_ptr() for p in R.parameters())
+
+    _TC_LINEAR_MIN_ROWS = 4096
 
     def _gemm(self, ta, tb, M, N, K, A, lda, B, ldb, C, ldc, bias=None, beta=0.0):
         _lib.call("icrl_gemm_f32", self._stream, ta, tb, M, N, K, _p(A), lda, _p(B), ldb, _p(C), ldc, _p(bias),
@@ -582,7 +589,12 @@ class A2CEngine:
         _lib.call("icrl_value_head_fwd", st, B, S, _p(f), _p(v_take_h), _p(b["v_weff"]), _p(b["v_beff"]), _p(values), L)
         se = self._buf("r_se", SB * H)
         ve = self._buf("r_ve", B * H)
-        self._gemm(0, 1, SB, H, H, r_take_h, H, R.semantic_embed.weight, H, se, H, R.semantic_embed.bias)
+        if SB >= self._TC_LINEAR_MIN_ROWS:
+            parts = self._buf("r_take_parts", 3 * SB * H, torch.bfloat16)
+            _lib.call("icrl_split_bf16x3", st, SB * H, _p(r_take_h), _p(parts), L)
+            _lib.call("icrl_gemm_bf16x3", st, SB, H, H, _p(parts), _p(b["r_se_parts"]), _p(se), H, _p(R.semantic_embed.bias), L)
+        else:
+            self._gemm(0, 1, SB, H, H, r_take_h, H, R.semantic_embed.weight, H, se, H, R.semantic_embed.bias)
         self._gemm(0, 1, B, H, H, f, H, R.visual_embed.weight, H, ve, H, R.visual_embed.bias)
         _lib.call("icrl_reward_cosine_fwd", st, B, S, _p(ve), _p(se), _p(rewards), L)
         return values, rewards
