@@ -320,30 +320,10 @@ __device__ __forceinline__ void chain_tc_fwd_body(const FwdMaps& maps, const Fwd
       }
       __syncwarp();
       const long long t3 = prof ? clock64() : 0;
-      // (S1) what the next step needs: fp16 split of h (read by every CTA of the cluster through TMA) and the carried state
-      {
-        const int c4 = lane & 7;
-#pragma unroll
-        for (int i8 = 0; i8 < 8; ++i8) {
-          const int r = i8 * 4 + (lane >> 3);
-          const int kr = m0 + 32 * q + r;
-          if (kr < P) {
-            const unsigned char* e = gst + r * 128 + ((c4 ^ (r & 7)) << 4);
-            const int uc = ucol0 + c4 * 4;
-            const float4 h4 = *reinterpret_cast<const float4*>(e + (C::NARR - 1) * 4096);
-            uint2 hi, lo;
-            split4_f16(h4, hi, lo);
-            __half* hp = p.hparts + ((size_t)(((j + 1) & 1) * 2) * Ppad + kr) * H + uc;
-            *reinterpret_cast<uint2*>(hp) = hi;
-            *reinterpret_cast<uint2*>(hp + (size_t)Ppad * H) = lo;
-            if constexpr (NG == 4) *reinterpret_cast<float4*>(p.state + (size_t)kr * H + uc) = *reinterpret_cast<const float4*>(e + 4 * 4096);
-            else *reinterpret_cast<float4*>(p.state + (size_t)kr * H + uc) = h4;
-          }
-        }
-      }
-      // (S2) backward stash of the live positions.  From the end of the warm-up on every piece is live: each staging tile
-      // leaves as ONE TMA tensor store (pieces past P are clipped by the map).  Before that only piece 0 is live, and the
-      // two checkpoint steps need the per-thread path as well.
+      // (S) one pass over the staged results.  What the next step needs: the fp16 split of h (read by every CTA of the
+      // cluster through TMA) and the carried state.  The backward stash of the live positions: from the end of the warm-up
+      // on every piece is live (before that only piece 0); with the TMA path each staging tile leaves as ONE tensor store
+      // (pieces past P are clipped by the map).  The joint checkpoints at the two checkpoint steps.
       const bool tma_path = p.tma_store && j >= p.warm;
       if (tma_path) {
         fence_proxy_async_smem();                // this thread's staging writes -> visible to the async proxy
@@ -361,7 +341,7 @@ __device__ __forceinline__ void chain_tc_fwd_body(const FwdMaps& maps, const Fwd
           tma_store_commit();
         }
       }
-      if (!tma_path || j == p.warm - 1 || j == p.cp_half) {
+      {
         const int c4 = lane & 7;
         const bool cp_full = j == p.warm - 1, cp_half = j == p.cp_half;
 #pragma unroll
@@ -372,10 +352,17 @@ __device__ __forceinline__ void chain_tc_fwd_body(const FwdMaps& maps, const Fwd
             const unsigned char* e = gst + r * 128 + ((c4 ^ (r & 7)) << 4);
             const size_t pos = (size_t)kr * seg + j;
             const bool live = !tma_path && (kr == 0 || j >= p.warm);
+            const bool cp = kr >= 1 && (cp_full || cp_half);
             const int uc = ucol0 + c4 * 4;
             const float4 h4 = *reinterpret_cast<const float4*>(e + (C::NARR - 1) * 4096);
+            uint2 hi, lo;
+            split4_f16(h4, hi, lo);
+            __half* hp = p.hparts + ((size_t)(((j + 1) & 1) * 2) * Ppad + kr) * H + uc;
+            *reinterpret_cast<uint2*>(hp) = hi;
+            *reinterpret_cast<uint2*>(hp + (size_t)Ppad * H) = lo;
             if constexpr (NG == 4) {
               const float4 cn4 = *reinterpret_cast<const float4*>(e + 4 * 4096);
+              *reinterpret_cast<float4*>(p.state + (size_t)kr * H + uc) = cn4;
               if (live) {
                 if (p.stash_g) {
                   float* gs = p.stash_g + pos * (4 * H) + uc;
@@ -384,12 +371,12 @@ __device__ __forceinline__ void chain_tc_fwd_body(const FwdMaps& maps, const Fwd
                 }
                 *reinterpret_cast<float4*>(p.stash_c + (pos + 1) * H + uc) = cn4;
               }
-              if (kr >= 1 && (cp_full || cp_half))
-                *reinterpret_cast<float4*>(p.wstate + ((size_t)((cp_full ? 1 : 0) * P + kr) * 2 + 1) * H + uc) = cn4;
+              if (cp) *reinterpret_cast<float4*>(p.wstate + ((size_t)((cp_full ? 1 : 0) * P + kr) * 2 + 1) * H + uc) = cn4;
+            } else {
+              *reinterpret_cast<float4*>(p.state + (size_t)kr * H + uc) = h4;
             }
             if (live) *reinterpret_cast<float4*>(p.stash_h + (pos + 1) * H + uc) = h4;
-            if (kr >= 1 && (cp_full || cp_half))
-              *reinterpret_cast<float4*>(p.wstate + ((size_t)((cp_full ? 1 : 0) * P + kr) * 2) * H + uc) = h4;
+            if (cp) *reinterpret_cast<float4*>(p.wstate + ((size_t)((cp_full ? 1 : 0) * P + kr) * 2) * H + uc) = h4;
           }
         }
       }
@@ -725,6 +712,7 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
       const long long t1 = prof ? clock64() : 0;
       const bool w_full = it == p.warm - 1, w_half = it == p.cp_half;            // warm-up side records (pieces < P-1)
       const bool r_full = it == steps - 1, r_half = p.cp_half >= 0 && it == half_ref_it;   // reference side (pieces >= 1)
+      const bool cp_it = p.bstate != nullptr && (w_full || w_half || r_full || r_half);
       long long tg = 0, tc = 0, ts = 0;
       // (L) stash of this position for BOTH unit passes: activated gates (arrays 0..3), c_t (4), c_{t-1} (5) into the
       //     pass's own buffer; 4 lanes per row; element (row, 16-byte chunk c) lives at row*64 + ((c ^ ((row >> 1) & 3)) << 4).
@@ -814,36 +802,18 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
           *reinterpret_cast<float4*>(e1 + 2 * 2048) = make_float4(d_g[4], d_g[5], d_g[6], d_g[7]);
           *reinterpret_cast<float4*>(e0 + 3 * 2048) = make_float4(d_o[0], d_o[1], d_o[2], d_o[3]);
           *reinterpret_cast<float4*>(e1 + 3 * 2048) = make_float4(d_o[4], d_o[5], d_o[6], d_o[7]);
-          *reinterpret_cast<float4*>(e0 + 4 * 2048) = make_float4(dhv[0], dhv[1], dhv[2], dhv[3]);
-          *reinterpret_cast<float4*>(e1 + 4 * 2048) = make_float4(dhv[4], dhv[5], dhv[6], dhv[7]);
-          *reinterpret_cast<float4*>(e0 + 5 * 2048) = make_float4(dci[0], dci[1], dci[2], dci[3]);
-          *reinterpret_cast<float4*>(e1 + 5 * 2048) = make_float4(dci[4], dci[5], dci[6], dci[7]);
+          if (cp_it) {                           // (dh, dc) entering the step: only the joint checkpoints read them
+            *reinterpret_cast<float4*>(e0 + 4 * 2048) = make_float4(dhv[0], dhv[1], dhv[2], dhv[3]);
+            *reinterpret_cast<float4*>(e1 + 4 * 2048) = make_float4(dhv[4], dhv[5], dhv[6], dhv[7]);
+            *reinterpret_cast<float4*>(e0 + 5 * 2048) = make_float4(dci[0], dci[1], dci[2], dci[3]);
+            *reinterpret_cast<float4*>(e1 + 5 * 2048) = make_float4(dci[4], dci[5], dci[6], dci[7]);
+          }
         }
         __syncwarp();
         if (ps == 0) load_inj(1);
         const long long u2 = prof ? clock64() : 0;
-        // (S1) the scaled fp16 split of the gate gradients: the next step's A operand of every CTA of the cluster
-        {
-          const int c4 = lane & 3;
-#pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            const int r = i4 * 8 + (lane >> 2);
-            const int kr = m0 + 32 * q + r;
-            if (kr < P) {
-              const unsigned char* e = gb + r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4);
-              __half* xp = p.dgx + ((size_t)((((it + 1) & 1) * 2) * Ppad + kr)) * (4 * H) + ucolp + c4 * 4;
-#pragma unroll
-              for (int a = 0; a < 4; ++a) {
-                const float4 d = *reinterpret_cast<const float4*>(e + a * 2048);
-                uint2 hi, lo;
-                split4_f16(make_float4(d.x * S, d.y * S, d.z * S, d.w * S), hi, lo);
-                *reinterpret_cast<uint2*>(xp + a * H) = hi;
-                *reinterpret_cast<uint2*>(xp + (size_t)Ppad * (4 * H) + a * H) = lo;
-              }
-            }
-          }
-        }
-        // (S2) fp32 gate gradients of the live positions (parameter-gradient contractions) and the joint checkpoints
+        // (S) one pass over the staged gate gradients: the scaled fp16 split (the next step's A operand of every CTA of
+        //     the cluster), the fp32 values of the live positions (parameter-gradient contractions), the joint checkpoints
         {
           const int c4 = lane & 3;
 #pragma unroll
@@ -855,22 +825,29 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
               const unsigned char* e = gb + r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4);
               const bool live = kr == P - 1 || it >= p.warm;
               const int uc = ucolp + c4 * 4;
-              if (live) {
+              __half* xp = p.dgx + ((size_t)((((it + 1) & 1) * 2) * Ppad + kr)) * (4 * H) + uc;
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
-                  *reinterpret_cast<float4*>(p.dgates + pos * (4 * H) + a * H + uc) = *reinterpret_cast<const float4*>(e + a * 2048);
+              for (int a = 0; a < 4; ++a) {
+                const float4 d = *reinterpret_cast<const float4*>(e + a * 2048);
+                uint2 hi, lo;
+                split4_f16(make_float4(d.x * S, d.y * S, d.z * S, d.w * S), hi, lo);
+                *reinterpret_cast<uint2*>(xp + a * H) = hi;
+                *reinterpret_cast<uint2*>(xp + (size_t)Ppad * (4 * H) + a * H) = lo;
+                if (live) *reinterpret_cast<float4*>(p.dgates + pos * (4 * H) + a * H + uc) = d;
               }
-              const float4 dh4 = *reinterpret_cast<const float4*>(e + 4 * 2048);
-              const float4 dc4 = *reinterpret_cast<const float4*>(e + 5 * 2048);
-              if (p.bstate && kr < P - 1 && (w_full || w_half)) {
-                float* b = p.bstate + ((size_t)(((w_full ? 1 : 0) * 2 + 0) * P + kr) * 2) * H + uc;
-                *reinterpret_cast<float4*>(b) = dh4;
-                *reinterpret_cast<float4*>(b + H) = dc4;
-              }
-              if (p.bstate && kr >= 1 && (r_full || r_half)) {
-                float* b = p.bstate + ((size_t)(((r_full ? 1 : 0) * 2 + 1) * P + kr) * 2) * H + uc;
-                *reinterpret_cast<float4*>(b) = dh4;
-                *reinterpret_cast<float4*>(b + H) = dc4;
+              if (cp_it) {
+                const float4 dh4 = *reinterpret_cast<const float4*>(e + 4 * 2048);
+                const float4 dc4 = *reinterpret_cast<const float4*>(e + 5 * 2048);
+                if (kr < P - 1 && (w_full || w_half)) {
+                  float* bs = p.bstate + ((size_t)(((w_full ? 1 : 0) * 2 + 0) * P + kr) * 2) * H + uc;
+                  *reinterpret_cast<float4*>(bs) = dh4;
+                  *reinterpret_cast<float4*>(bs + H) = dc4;
+                }
+                if (kr >= 1 && (r_full || r_half)) {
+                  float* bs = p.bstate + ((size_t)(((r_full ? 1 : 0) * 2 + 1) * P + kr) * 2) * H + uc;
+                  *reinterpret_cast<float4*>(bs) = dh4;
+                  *reinterpret_cast<float4*>(bs + H) = dc4;
+                }
               }
             }
           }
