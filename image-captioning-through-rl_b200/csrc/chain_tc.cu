@@ -214,6 +214,11 @@ __device__ __forceinline__ void chain_tc_fwd_body(const FwdMaps& maps, const Fwd
     int tok = valid ? p.stream[(long long)k_own * seg] : 0;
     const float mg = p.main_gain;
     const float k0 = -mg * L2E, k1 = -LO_INV * L2E;            // accumulators -> exponent of a sigmoid gate
+    // The stash of a live step already holds the state the next step carries (row pos + 1 of stash_c / stash_h), so live
+    // steps skip the separate state store (32 KB of the ~32 B/clk an SM can push towards L2); not with the TMA store path,
+    // whose writes travel through the async proxy.
+    const bool stash_carry = !p.tma_store;
+    const float* carry_stash = NG == 4 ? p.stash_c : p.stash_h;
     const bool prof = p.prof != nullptr && cluster == 0 && rank == 0 && ew == 0 && lane == 0;
     long long pr[5] = {0, 0, 0, 0, 0};
 
@@ -237,7 +242,11 @@ __device__ __forceinline__ void chain_tc_fwd_body(const FwdMaps& maps, const Fwd
             const float* tsrc = p.table + (size_t)tokr * (NG * H) + ucol0 + c4 * 4;
 #pragma unroll
             for (int a = 0; a < NG; ++a) cp_async16(dst + a * 4096, tsrc + a * H);
-            cp_async16(dst + NG * 4096, p.state + (size_t)kr * H + ucol0 + c4 * 4);
+            // carried state (c of the LSTM, h of the GRU): the stash row the previous step wrote when that step was live
+            // (this very thread wrote these 16 bytes), else the state array
+            const bool prev_live = stash_carry && j >= 1 && (kr == 0 || j - 1 >= p.warm);
+            const float* ssrc = prev_live ? carry_stash + ((size_t)kr * seg + j) * H : p.state + (size_t)kr * H;
+            cp_async16(dst + NG * 4096, ssrc + ucol0 + c4 * 4);
           }
         }
         cp_async_wait_all();
@@ -362,7 +371,7 @@ __device__ __forceinline__ void chain_tc_fwd_body(const FwdMaps& maps, const Fwd
             *reinterpret_cast<uint2*>(hp + (size_t)Ppad * H) = lo;
             if constexpr (NG == 4) {
               const float4 cn4 = *reinterpret_cast<const float4*>(e + 4 * 4096);
-              *reinterpret_cast<float4*>(p.state + (size_t)kr * H + uc) = cn4;
+              if (!(stash_carry && live)) *reinterpret_cast<float4*>(p.state + (size_t)kr * H + uc) = cn4;
               if (live) {
                 if (p.stash_g) {
                   float* gs = p.stash_g + pos * (4 * H) + uc;
@@ -373,7 +382,7 @@ __device__ __forceinline__ void chain_tc_fwd_body(const FwdMaps& maps, const Fwd
               }
               if (cp) *reinterpret_cast<float4*>(p.wstate + ((size_t)((cp_full ? 1 : 0) * P + kr) * 2 + 1) * H + uc) = cn4;
             } else {
-              *reinterpret_cast<float4*>(p.state + (size_t)kr * H + uc) = h4;
+              if (!(stash_carry && live)) *reinterpret_cast<float4*>(p.state + (size_t)kr * H + uc) = h4;
             }
             if (live) *reinterpret_cast<float4*>(p.stash_h + (pos + 1) * H + uc) = h4;
             if (cp) *reinterpret_cast<float4*>(p.wstate + ((size_t)((cp_full ? 1 : 0) * P + kr) * 2) * H + uc) = h4;
