@@ -1001,3 +1001,54 @@ def test_chain_engine_switches_agree(switch):
     assert torch.equal(r1["tokens"], r0["tokens"])
     assert float((r1["values"] - v0).abs().max()) <= TOL and float((r1["rewards"] - w0).abs().max()) <= TOL
     assert float((e1.flat_grad - g0).abs().max() / g0.abs().max()) <= GTOL
+
+
+@pytest.mark.parametrize("B,p0,S", [(96, 1, 7), (64, 5, 4), (130, 1, 19)])
+def test_value_param_grads_stream_scatter_matches_generic(B, p0, S):
+    """icrl_value_chain_param_grads with the stream's shape (positions that consumed the same token summed before one
+    vector reduction, column maxima handed to the contraction) against the same call without it (one reduction per
+    position, maxima from a pre-pass) and against float64 for the gate-table gradient."""
+    import ctypes
+    from icrl_b200 import _lib
+    V, D, G = 211, 512, 2048
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    rs = np.random.RandomState(B + S)
+    T = int(_lib.call("icrl_stream_len", B, p0, S, 0))
+    tokcm = torch.from_numpy(rs.randint(0, V, size=((p0 + S) * B,)).astype(np.int32)).cuda()
+    stream = torch.zeros(T + 1, dtype=torch.int32, device="cuda")
+    take = torch.zeros(T + 1, dtype=torch.int32, device="cuda")
+    pos = torch.zeros(S * B, dtype=torch.int32, device="cuda")
+    _lib.call("icrl_build_stream", st, B, p0, S, 0, p(tokcm), p(stream), p(take), p(pos), None)
+    colscale = 10.0 ** rs.uniform(-9, -3, size=G)
+    dgates = torch.from_numpy((rs.standard_normal((T, G)) * colscale).astype(np.float32)).cuda()
+    stash_h = torch.from_numpy(np.tanh(rs.standard_normal((T + 1, 512))).astype(np.float32)).cuda()
+    E = torch.from_numpy(rs.standard_normal((V, D)).astype(np.float32)).cuda()
+    W_ih = torch.from_numpy((rs.standard_normal((G, D)) * 0.05).astype(np.float32)).cuda()
+    cs = int(_lib.call("icrl_colsum_ws_floats", max(T, V), G))
+    wsb = int(_lib.call("icrl_wgrad_tc_ws_bytes", G, 512, T, 2))
+    out = {}
+    for tag, shape in (("stream", (B, p0, S)), ("generic", (0, 0, 0))):
+        dtable = torch.full((V, G), float("nan"), device="cuda")
+        csws = torch.zeros(cs, device="cuda")
+        ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+        dE, dWih = torch.empty((V, D), device="cuda"), torch.empty((G, D), device="cuda")
+        dWhh, dbi, dbh = torch.empty((G, 512), device="cuda"), torch.empty(G, device="cuda"), torch.empty(G, device="cuda")
+        _lib.call("icrl_value_chain_param_grads", st, T, V, D, p(stream), p(dgates), p(stash_h), p(E), p(W_ih), p(dtable),
+                  p(csws), p(ws), wsb, p(dE), p(dWih), p(dWhh), p(dbi), p(dbh), *shape, None)
+        torch.cuda.synchronize()
+        out[tag] = dict(dtable=dtable, dE=dE, dWih=dWih, dWhh=dWhh, dbi=dbi, dbh=dbh)
+    ref = torch.zeros((V, G), dtype=torch.float64, device="cuda")
+    ref.index_add_(0, stream[:T].long(), dgates.double())
+    rowscale = ref.abs().max(dim=0).values.clamp_min(1e-300)
+    for tag in out:
+        err = ((out[tag]["dtable"].double() - ref).abs() / rowscale).max().item()
+        assert err < 2e-6, (tag, err)
+    worst = 0.0
+    for k in out["stream"]:
+        a, b = out["stream"][k].double(), out["generic"][k].double()
+        assert torch.isfinite(a).all(), k
+        rel = ((a - b).abs().max() / b.abs().max().clamp_min(1e-300)).item()
+        worst = max(worst, rel)
+        assert rel < 2e-6, (k, rel)
+    _record("value_param_grads_stream_b%d_s%d" % (B, S), rel_vs_generic=worst)
