@@ -219,8 +219,8 @@ int icrl_lstm_seq_bwd(void* stream, int B, int n, int V, int D, const int* tokcm
   ICRL_CUDA(cudaMemsetAsync(dtable, 0, (size_t)V * 4 * H * sizeof(float), st));
   TRY(icrl_scatter_add_rows(st, nB, 4 * H, DG, tokcm, dtable));
   bump(launches, 1);
-  TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, D, V, dtable, 4 * H, E, D, dW_ih, D, nullptr, 0.f, nullptr, 0, launches));
-  if (dE) TRY(icrl_gemm_f32_impl(st, 0, 0, V, D, 4 * H, dtable, 4 * H, W_ih, D, dE, D, nullptr, 0.f, nullptr, 0, launches));
+  TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, D, V, dtable, 4 * H, E, D, dW_ih, D, nullptr, 0.f, gemm_ws, gemm_ws_bytes, launches));
+  if (dE) TRY(icrl_gemm_f32_impl(st, 0, 0, V, D, 4 * H, dtable, 4 * H, W_ih, D, dE, D, nullptr, 0.f, gemm_ws, gemm_ws_bytes, launches));
   TRY(icrl_wcolsum(st, V, 4 * H, dtable, nullptr, 0, colsum_ws, db_ih));
   bump(launches, 2);
   ICRL_CUDA(cudaMemcpyAsync(db_hh, db_ih, 4 * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -319,14 +319,14 @@ static int policy_rollout_bwd_common(void* stream, int B, int V, int p0, int S, 
   ICRL_CUDA(cudaMemsetAsync(dtable, 0, (size_t)V * 4 * H * sizeof(float), st));
   TRY(icrl_scatter_add_rows(st, nB, 4 * H, DG, tokcm, dtable));
   bump(launches, 1);
-  TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, D, V, dtable, 4 * H, E, D, dW_ih, D, nullptr, 0.f, nullptr, 0, launches));
+  TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, D, V, dtable, 4 * H, E, D, dW_ih, D, nullptr, 0.f, gemm_ws, gemm_ws_bytes, launches));
   if (dE)                                            // null: frozen pretrained embedding (models.py:61-63)
-    TRY(icrl_gemm_f32_impl(st, 0, 0, V, D, 4 * H, dtable, 4 * H, W_ih, D, dE, D, nullptr, 0.f, nullptr, 0, launches));
+    TRY(icrl_gemm_f32_impl(st, 0, 0, V, D, 4 * H, dtable, 4 * H, W_ih, D, dE, D, nullptr, 0.f, gemm_ws, gemm_ws_bytes, launches));
   TRY(icrl_wcolsum(st, V, 4 * H, dtable, nullptr, 0, colsum_ws, db_ih));
   bump(launches, 2);
   ICRL_CUDA(cudaMemcpyAsync(db_hh, db_ih, 4 * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // 7. cnn2linear
-  TRY(icrl_gemm_f32_impl(st, 1, 0, H, H, B, dh_cur, H, features, H, dW_cnn, H, nullptr, 0.f, nullptr, 0, launches));
+  TRY(icrl_gemm_f32_impl(st, 1, 0, H, H, B, dh_cur, H, features, H, dW_cnn, H, nullptr, 0.f, gemm_ws, gemm_ws_bytes, launches));
   TRY(icrl_wcolsum(st, B, H, dh_cur, nullptr, 0, colsum_ws, db_cnn));
   bump(launches, 2);
   return ICRL_OK;
@@ -636,9 +636,9 @@ int icrl_value_chain_param_grads(void* stream, int T, int V, int D, const int* t
     TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, H, T, dgates, 4 * H, stash_h, H, dW_hh, H, nullptr, 0.f, gemm_ws,
                            gemm_ws_bytes, launches));
   }
-  TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, D, V, dtable, 4 * H, E, D, dW_ih, D, nullptr, 0.f, nullptr, 0, launches));
+  TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, D, V, dtable, 4 * H, E, D, dW_ih, D, nullptr, 0.f, gemm_ws, gemm_ws_bytes, launches));
   if (dE)
-    TRY(icrl_gemm_f32_impl(st, 0, 0, V, D, 4 * H, dtable, 4 * H, W_ih, D, dE, D, nullptr, 0.f, nullptr, 0, launches));
+    TRY(icrl_gemm_f32_impl(st, 0, 0, V, D, 4 * H, dtable, 4 * H, W_ih, D, dE, D, nullptr, 0.f, gemm_ws, gemm_ws_bytes, launches));
   TRY(icrl_wcolsum(st, V, 4 * H, dtable, nullptr, 0, colsum_ws, db_ih));
   bump(launches, 2);
   ICRL_CUDA(cudaMemcpyAsync(db_hh, db_ih, 4 * H * sizeof(float), cudaMemcpyDeviceToDevice, st));

@@ -192,10 +192,11 @@ int icrl_gemm_f32_impl(cudaStream_t st, int transA, int transB, int M, int N, in
                    ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0);
   const int tiles = icrl_cdiv(M, BM) * icrl_cdiv(N, BN);
   int splits = 1;
-  if (ws && tiles < 148 && K >= 1024) {
-    // few output tiles: split K so that ~2 waves of CTAs exist; long K (weight gradients) in chunks >= 1024, the
-    // K = 2048 per-step BPTT products of small local batches in chunks >= 256
-    splits = min(icrl_cdiv(2 * 148, tiles), K >= 4096 ? K / 1024 : K / 256);
+  if (ws && tiles < 148 && K >= 512) {
+    // few output tiles: split K so that ~2 waves of CTAs exist; very long K (weight gradients over the serial steps) in
+    // chunks >= 1024, everything else (gate-table products with K = vocabulary, K = 2048 BPTT products of small local
+    // batches, K = batch rows) in chunks >= 256
+    splits = min(icrl_cdiv(2 * 148, tiles), K >= 65536 ? K / 1024 : K / 256);
     while (splits > 1 && (size_t)splits * M * N * sizeof(float) > ws_bytes) --splits;
     if (splits < 1) splits = 1;
   }

@@ -218,7 +218,9 @@ __global__ void __launch_bounds__(256) transpose_split64_kernel(long long T, lon
 // map_a: 3-D {Tp, rows, 2 parts}, box {64, 32, 1}; map_b: box {64, 128, 2}.  partial [gridDim.z][M][N].
 // The 4 CTAs of a cluster (the N tiles of one M tile and split) consume the same A tile: each fetches a quarter of its
 // rows and TMA-multicasts it to all four, so A crosses L2 -> SM once per cluster instead of once per CTA and the four
-// stay in lockstep (a ring stage is refilled only after all four have consumed it).
+// stay in lockstep (a ring stage is refilled only after all four have consumed it).  (Also sharing the B tile between two
+// M tiles -- clusters of 4 x 2 -- was measured and is slower: the 128 CTAs of the value chain's contraction are 16 clusters
+// of 8, of which a B200 holds 15 at a time, so the last cluster runs as a second wave.)
 __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(THREADS, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
              int kb_total, float* __restrict__ partial) {
