@@ -84,7 +84,7 @@ if "time" in stages or "prof" in stages:
             eng.step(prep)
         torch.cuda.synchronize()
         eng.phase_events = []
-        buf = torch.zeros(16, dtype=torch.int64, device=dev)
+        buf = torch.zeros(24, dtype=torch.int64, device=dev)
         n = 3
         t0 = time.time()
         for i in range(n):
@@ -100,7 +100,9 @@ if "time" in stages or "prof" in stages:
               (B, eng.piece_layout, eng.warm, wall * 1e3, B / wall, {k: round(v, 2) for k, v in ph.items()}), flush=True)
         t = buf.cpu().numpy()
         names = ("acc wait", "gather", "cell", "store", "barrier")
-        for label, o in (("forward (last launch = reward GRU)", 0), ("backward", 8)):
+        for label, o in (("forward, cluster 0 (value LSTM when the launch is fused)", 0), ("backward", 8), ("forward, reward GRU of the fused launch", 16)):
+            if o + 6 > t.size:
+                continue
             T = max(int(t[o + 5]), 1)
             print("  %s: %d steps, cycles per step: %s, total %.0f" % (label, T, ", ".join("%s %.0f" % (nm, t[o + i] / T) for i, nm in enumerate(names)),
                   float(sum(t[o:o + 5])) / T), flush=True)
