@@ -1078,7 +1078,7 @@ void icrl_chain_tc_set_tma_store_impl(int on) { g_tc_tma_store = on; }
 // footprint (cudaOccupancyMaxActiveBlocksPerMultiprocessor = 1 at 0 bytes of dynamic shared memory, 384 threads x 80
 // registers; registers are granted per 4 warps, setmaxnreg does not raise ptxas' allocation above the launch-bounds cap), so
 // the second cluster never shared the SMs and the leaner kernel was simply slower: 23.8 vs 16.4 ms at B = 4096.)
-static long long* g_chain_tc_prof = nullptr;      // icrl_chain_tc_set_profile: 16 device int64 (forward [0..5], backward [8..13])
+static long long* g_chain_tc_prof = nullptr;      // icrl_chain_tc_set_profile: 24 device int64 (forward [0..5], backward [8..13], fused reward chain [16..21])
 void icrl_chain_tc_set_profile_impl(long long* buf) { g_chain_tc_prof = buf; }
 
 // Co-resident clusters of 8 CTAs x 128 pieces (a cluster cannot span GPCs: 15-16 clusters on a B200).

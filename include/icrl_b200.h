@@ -284,8 +284,9 @@ int icrl_chains_tc_fwd_fused(void* stream, int v_pieces, long long v_seg, int v_
 int icrl_chain_tc_lstm_bwd(void* stream, int pieces, long long seg, int warm, const void* packed,
                            const float* stash_gates, const float* stash_c, const int* take, const float* dh_take,
                            long long take_rows, float* dgates, void* ws, float* cp_state, float* err, int* launches);
-/* Debug aid: buf != NULL (16 device int64): cycle sums of cluster 0 / CTA 0's first epilogue warp, forward [0..5] =
- * {accumulator wait, gather, cell update, stores, cluster barrier, steps}, backward [8..13] likewise. */
+/* Debug aid: buf != NULL (24 device int64): cycle sums of cluster 0 / CTA 0's first epilogue warp, forward [0..5] =
+ * {accumulator wait, gather, cell update, stores, cluster barrier, steps}, backward [8..13] likewise, [16..21] the reward
+ * chain's first cluster when the forward launch is fused. */
 int icrl_chain_tc_set_profile(void* buf);
 /* Experiment knob: relative compensation (1 + x) applied to the main tensor-memory accumulator of the forward / backward
  * chain kernels (the tensor core truncates on every accumulate).  Default 5.76e-7, 2.3e-6 = 1.8e-8 per
