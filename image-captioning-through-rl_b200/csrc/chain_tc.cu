@@ -464,10 +464,12 @@ struct BwdCfg {
   static constexpr int TMEM_COLS = 2 * NCOL, CORR = NCOL;
   static constexpr int SMEM = STAGES * STAGE + XBUF + 256 + 1024;
 };
-// chain_tc_bwd_kernel: two unit passes per step, each with its own staging buffer of 6 arrays of [32 rows][16 units] f32
-// (gates i,f,g,o, c_t, c_{t-1}), so that both passes' stash gathers are in flight before the first pass is computed; the
-// injected dL/dh rows (one position in ten) travel through registers.
-constexpr int B1_BUF = 6 * 2048, B_GST_WARP = 2 * B1_BUF;
+// chain_tc_bwd_kernel: per epilogue warp one staging buffer of 6 arrays of [32 rows][32 units] f32 (gates i,f,g,o, c_t,
+// c_{t-1}): 128-byte row segments in both directions.  What a gather or a store pass costs is the NUMBER of row segments it
+// touches (~2-3 cycles each, LSU and TMA engine alike: 3,072 segments of 64 bytes per step took 8.9 K cycles to request with
+// cp.async and 11.3 K as TMA boxes -- both measured -- against 2.4 K for the forward's 1,280 segments of 128 bytes), so the
+// tile is as wide as the 32 units a warp owns.  The injected dL/dh rows (one position in ten) travel through registers.
+constexpr int B_GST_WARP = 6 * 4096;
 static_assert(EPI_WARPS * B_GST_WARP <= BwdCfg::STAGES * BwdCfg::STAGE, "epilogue staging lives inside the (idle) TMA ring");
 static_assert(BwdCfg::SMEM <= 232448, "shared memory budget");
 
@@ -630,26 +632,24 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
     const long long sk = p.stride_k, stt = p.stride_t;
     const float S = bwd_scale(*p.dh_max), invS = 1.f / S;
     const float mg = p.main_gain;
-    float dc[2][2][8];                         // carried dL/dc of this thread's piece: [unit pass][8-unit group][unit]
+    float dc[4][8];                            // carried dL/dc of this thread's piece: [8-unit group][unit]
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 2; ++b)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dc[a][b][i] = 0.f;
+      for (int i = 0; i < 8; ++i) dc[a][i] = 0.f;
     float ovf = 0.f;
     int tk = valid ? p.take[(long long)k_own * sk + (long long)(steps - 1) * stt] : -1;
     const bool prof = p.prof != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0;
-    long long pr[5] = {0, 0, 0, 0, 0};
+    long long pr[5] = {0, 0, 0, 0, 0}, pr_issue = 0, pr_xwait = 0;
     const int half_ref_it = steps - 1 - (p.warm - 1 - p.cp_half);      // reference side of the half-way checkpoint
     // K split: receive buffer of the partner CTA (rank ^ 4) and this thread's row in it / in the own one
     const int xrow = (32 * q + lane) * 256, xsw = lane & 7;
     const unsigned x_remote = mapa_u32(smem_u32(xbuf), rank ^ 4u), x_rbar = mapa_u32(bar_x, rank ^ 4u);
     bool x_have = false;                       // whether this iteration has partial sums to add (it > 0)
-    auto load_partner = [&](int ps, int c8, float* xr) {
+    auto load_partner = [&](int c8, float* xr) {       // c8: 8-unit group 0..3 of this warp's 32 units
       if (x_have) {
-        const float4 a = *reinterpret_cast<const float4*>(xbuf + xrow + (((8 * ch + 4 * ps + 2 * c8) ^ xsw) << 4));
-        const float4 b = *reinterpret_cast<const float4*>(xbuf + xrow + (((8 * ch + 4 * ps + 2 * c8 + 1) ^ xsw) << 4));
+        const float4 a = *reinterpret_cast<const float4*>(xbuf + xrow + (((8 * ch + 2 * c8) ^ xsw) << 4));
+        const float4 b = *reinterpret_cast<const float4*>(xbuf + xrow + (((8 * ch + 2 * c8 + 1) ^ xsw) << 4));
         xr[0] = a.x; xr[1] = a.y; xr[2] = a.z; xr[3] = a.w; xr[4] = b.x; xr[5] = b.y; xr[6] = b.z; xr[7] = b.w;
       } else {
 #pragma unroll
@@ -692,7 +692,7 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
           for (int c8 = 0; c8 < 2; ++c8) {
             float rec[8], cor[8], xr[8];
             tmem_ld8x2(tq + (unsigned)(own_c + 32 * ch + 16 * ps + 8 * c8), tq + (unsigned)(B_CORR + own_c + 32 * ch + 16 * ps + 8 * c8), rec, cor);
-            load_partner(ps, c8, xr);
+            load_partner(2 * ps + c8, xr);
             float o[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = (fmaf(cor[i], LO_INV, rec[i] * mg) + xr[i]) * invS;
@@ -723,147 +723,138 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
       const bool r_full = it == steps - 1, r_half = p.cp_half >= 0 && it == half_ref_it;   // reference side (pieces >= 1)
       const bool cp_it = p.bstate != nullptr && (w_full || w_half || r_full || r_half);
       long long tg = 0, tc = 0, ts = 0;
-      // (L) stash of this position for BOTH unit passes: activated gates (arrays 0..3), c_t (4), c_{t-1} (5) into the
-      //     pass's own buffer; 4 lanes per row; element (row, 16-byte chunk c) lives at row*64 + ((c ^ ((row >> 1) & 3)) << 4).
+      // (L) stash of this position: activated gates (arrays 0..3), c_t (4), c_{t-1} (5), 8 lanes per row (128 bytes);
+      //     element (row, 16-byte chunk c) lives at row*128 + ((c ^ (row & 7)) << 4).
+      const int ucolw = ub + 32 * ch;            // first of this warp's 32 units
+      {
+        const int c4 = lane & 7;
 #pragma unroll
-      for (int ps = 0; ps < 2; ++ps) {
-        const int ucolp = ub + 32 * ch + 16 * ps;
-        const int c4 = lane & 3;
-#pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-          const int r = i4 * 8 + (lane >> 2);
+        for (int i8 = 0; i8 < 8; ++i8) {
+          const int r = i8 * 4 + (lane >> 3);
           const int kr = m0 + 32 * q + r;
           if (kr < P) {
             const size_t pos = (size_t)kr * sk + (size_t)t * stt;
-            const unsigned dst = smem_u32(gst + ps * B1_BUF) + (unsigned)(r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4));
-            const float* gsrc = p.stash_g + pos * (4 * H) + ucolp + c4 * 4;
+            const unsigned dst = smem_u32(gst) + (unsigned)(r * 128 + ((c4 ^ (r & 7)) << 4));
+            const float* gsrc = p.stash_g + pos * (4 * H) + ucolw + c4 * 4;
 #pragma unroll
-            for (int a = 0; a < 4; ++a) cp_async16(dst + a * 2048, gsrc + a * H);
-            cp_async16(dst + 4 * 2048, p.stash_c + (pos + stt) * H + ucolp + c4 * 4);
-            cp_async16(dst + 5 * 2048, p.stash_c + pos * H + ucolp + c4 * 4);
+            for (int a = 0; a < 4; ++a) cp_async16(dst + a * 4096, gsrc + a * H);
+            cp_async16(dst + 4 * 4096, p.stash_c + (pos + stt) * H + ucolw + c4 * 4);
+            cp_async16(dst + 5 * 4096, p.stash_c + pos * H + ucolw + c4 * 4);
           }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
       }
-      // injected dL/dh of this thread's own row (pass 0 now, pass 1 while pass 0 is stored)
-      float4 inj[4];
-      auto load_inj = [&](int ps) {
-        const float* src = p.dh_take + (size_t)(tk >= 0 ? tk : 0) * H + ub + 32 * ch + 16 * ps;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          inj[c] = (valid && tk >= 0) ? __ldg(reinterpret_cast<const float4*>(src) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      };
-      load_inj(0);
+      const long long t2 = prof ? clock64() : 0;
       if (!x_ready) mbar_wait(bar_x, (unsigned)(it - 1) & 1u);
+      const long long u0 = prof ? clock64() : 0;
+      cp_async_wait_all();
+      __syncwarp();
+      const long long u1 = prof ? clock64() : 0;
+      if (prof) { pr_issue += t2 - t1; pr_xwait += u0 - t2; tg += u1 - u0; }
+      // (C) gate gradients, one row per lane, in place on the staging tile
 #pragma unroll
-      for (int ps = 0; ps < 2; ++ps) {
-        const long long u0 = prof ? clock64() : 0;
-        const int ucolp = ub + 32 * ch + 16 * ps;
-        unsigned char* gb = gst + ps * B1_BUF;
-        if (ps == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
-        const long long u1 = prof ? clock64() : 0;
-        // (C) gate gradients, one row per lane, in place on the staging tile
-#pragma unroll
-        for (int c8 = 0; c8 < 2; ++c8) {
-          float rec[8], cor[8], xr[8];
-          load_partner(ps, c8, xr);
-          if (it > 0) {
-            tmem_ld8x2(tq + (unsigned)(own_c + 32 * ch + 16 * ps + 8 * c8), tq + (unsigned)(B_CORR + own_c + 32 * ch + 16 * ps + 8 * c8), rec, cor);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { rec[i] = 0.f; cor[i] = 0.f; }
-          }
-          unsigned char* e0 = gb + lane * 64 + (((2 * c8) ^ ((lane >> 1) & 3)) << 4);
-          unsigned char* e1 = gb + lane * 64 + (((2 * c8 + 1) ^ ((lane >> 1) & 3)) << 4);
-          float tin[6][8];
-          const float injv[8] = {inj[2 * c8].x, inj[2 * c8].y, inj[2 * c8].z, inj[2 * c8].w,
-                                 inj[2 * c8 + 1].x, inj[2 * c8 + 1].y, inj[2 * c8 + 1].z, inj[2 * c8 + 1].w};
-#pragma unroll
-          for (int a = 0; a < 6; ++a) {
-            const float4 v0 = *reinterpret_cast<const float4*>(e0 + a * 2048);
-            const float4 v1 = *reinterpret_cast<const float4*>(e1 + a * 2048);
-            tin[a][0] = v0.x; tin[a][1] = v0.y; tin[a][2] = v0.z; tin[a][3] = v0.w;
-            tin[a][4] = v1.x; tin[a][5] = v1.y; tin[a][6] = v1.z; tin[a][7] = v1.w;
-          }
-          float d_i[8], d_f[8], d_g[8], d_o[8], dhv[8], dci[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float gi = tin[0][i], gf = tin[1][i], gg = tin[2][i], go = tin[3][i], cc = tin[4][i], cp = tin[5][i];
-            const float dh = (fmaf(cor[i], LO_INV, rec[i] * mg) + xr[i]) * invS + injv[i];
-            const float tcv = tanh_lean(cc);
-            const float dct = dc[ps][c8][i] + dh * (go * (1.f - tcv * tcv));
-            dhv[i] = dh;
-            dci[i] = dc[ps][c8][i];
-            d_o[i] = dh * (tcv * go * (1.f - go));
-            d_i[i] = dct * (gg * gi * (1.f - gi));
-            d_f[i] = dct * (cp * gf * (1.f - gf));
-            d_g[i] = dct * (gi * (1.f - gg * gg));
-            dc[ps][c8][i] = dct * gf;
-            ovf = fmaxf(ovf, fmaxf(fmaxf(fabsf(d_i[i]), fabsf(d_f[i])), fmaxf(fabsf(d_g[i]), fabsf(d_o[i]))));
-          }
-          *reinterpret_cast<float4*>(e0) = make_float4(d_i[0], d_i[1], d_i[2], d_i[3]);
-          *reinterpret_cast<float4*>(e1) = make_float4(d_i[4], d_i[5], d_i[6], d_i[7]);
-          *reinterpret_cast<float4*>(e0 + 2048) = make_float4(d_f[0], d_f[1], d_f[2], d_f[3]);
-          *reinterpret_cast<float4*>(e1 + 2048) = make_float4(d_f[4], d_f[5], d_f[6], d_f[7]);
-          *reinterpret_cast<float4*>(e0 + 2 * 2048) = make_float4(d_g[0], d_g[1], d_g[2], d_g[3]);
-          *reinterpret_cast<float4*>(e1 + 2 * 2048) = make_float4(d_g[4], d_g[5], d_g[6], d_g[7]);
-          *reinterpret_cast<float4*>(e0 + 3 * 2048) = make_float4(d_o[0], d_o[1], d_o[2], d_o[3]);
-          *reinterpret_cast<float4*>(e1 + 3 * 2048) = make_float4(d_o[4], d_o[5], d_o[6], d_o[7]);
-          if (cp_it) {                           // (dh, dc) entering the step: only the joint checkpoints read them
-            *reinterpret_cast<float4*>(e0 + 4 * 2048) = make_float4(dhv[0], dhv[1], dhv[2], dhv[3]);
-            *reinterpret_cast<float4*>(e1 + 4 * 2048) = make_float4(dhv[4], dhv[5], dhv[6], dhv[7]);
-            *reinterpret_cast<float4*>(e0 + 5 * 2048) = make_float4(dci[0], dci[1], dci[2], dci[3]);
-            *reinterpret_cast<float4*>(e1 + 5 * 2048) = make_float4(dci[4], dci[5], dci[6], dci[7]);
-          }
+      for (int c8 = 0; c8 < 4; ++c8) {
+        float rec[8], cor[8], xr[8];
+        // injected dL/dh of this thread's own row (one position in ten)
+        float4 inj0 = make_float4(0.f, 0.f, 0.f, 0.f), inj1 = inj0;
+        if (valid && tk >= 0) {
+          const float4* src = reinterpret_cast<const float4*>(p.dh_take + (size_t)tk * H + ucolw + 8 * c8);
+          inj0 = __ldg(src);
+          inj1 = __ldg(src + 1);
         }
-        __syncwarp();
-        if (ps == 0) load_inj(1);
-        const long long u2 = prof ? clock64() : 0;
-        // (S) one pass over the staged gate gradients: the scaled fp16 split (the next step's A operand of every CTA of
-        //     the cluster), the fp32 values of the live positions (parameter-gradient contractions), the joint checkpoints
-        {
-          const int c4 = lane & 3;
+        load_partner(c8, xr);
+        if (it > 0) {
+          tmem_ld8x2(tq + (unsigned)(own_c + 32 * ch + 8 * c8), tq + (unsigned)(B_CORR + own_c + 32 * ch + 8 * c8), rec, cor);
+        } else {
 #pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            const int r = i4 * 8 + (lane >> 2);
-            const int kr = m0 + 32 * q + r;
-            if (kr < P) {
-              const size_t pos = (size_t)kr * sk + (size_t)t * stt;
-              const unsigned char* e = gb + r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4);
-              const bool live = kr == P - 1 || it >= p.warm;
-              const int uc = ucolp + c4 * 4;
-              __half* xp = p.dgx + ((size_t)((((it + 1) & 1) * 2) * Ppad + kr)) * (4 * H) + uc;
+          for (int i = 0; i < 8; ++i) { rec[i] = 0.f; cor[i] = 0.f; }
+        }
+        unsigned char* e0 = gst + lane * 128 + (((2 * c8) ^ (lane & 7)) << 4);
+        unsigned char* e1 = gst + lane * 128 + (((2 * c8 + 1) ^ (lane & 7)) << 4);
+        float tin[6][8];
+        const float injv[8] = {inj0.x, inj0.y, inj0.z, inj0.w, inj1.x, inj1.y, inj1.z, inj1.w};
 #pragma unroll
-              for (int a = 0; a < 4; ++a) {
-                const float4 d = *reinterpret_cast<const float4*>(e + a * 2048);
-                uint2 hi, lo;
-                split4_f16(make_float4(d.x * S, d.y * S, d.z * S, d.w * S), hi, lo);
-                *reinterpret_cast<uint2*>(xp + a * H) = hi;
-                *reinterpret_cast<uint2*>(xp + (size_t)Ppad * (4 * H) + a * H) = lo;
-                if (live) *reinterpret_cast<float4*>(p.dgates + pos * (4 * H) + a * H + uc) = d;
+        for (int a = 0; a < 6; ++a) {
+          const float4 v0 = *reinterpret_cast<const float4*>(e0 + a * 4096);
+          const float4 v1 = *reinterpret_cast<const float4*>(e1 + a * 4096);
+          tin[a][0] = v0.x; tin[a][1] = v0.y; tin[a][2] = v0.z; tin[a][3] = v0.w;
+          tin[a][4] = v1.x; tin[a][5] = v1.y; tin[a][6] = v1.z; tin[a][7] = v1.w;
+        }
+        float d_i[8], d_f[8], d_g[8], d_o[8], dhv[8], dci[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float gi = tin[0][i], gf = tin[1][i], gg = tin[2][i], go = tin[3][i], cc = tin[4][i], cp = tin[5][i];
+          const float dh = (fmaf(cor[i], LO_INV, rec[i] * mg) + xr[i]) * invS + injv[i];
+          const float tcv = tanh_lean(cc);
+          const float dct = dc[c8][i] + dh * (go * (1.f - tcv * tcv));
+          dhv[i] = dh;
+          dci[i] = dc[c8][i];
+          d_o[i] = dh * (tcv * go * (1.f - go));
+          d_i[i] = dct * (gg * gi * (1.f - gi));
+          d_f[i] = dct * (cp * gf * (1.f - gf));
+          d_g[i] = dct * (gi * (1.f - gg * gg));
+          dc[c8][i] = dct * gf;
+          ovf = fmaxf(ovf, fmaxf(fmaxf(fabsf(d_i[i]), fabsf(d_f[i])), fmaxf(fabsf(d_g[i]), fabsf(d_o[i]))));
+        }
+        *reinterpret_cast<float4*>(e0) = make_float4(d_i[0], d_i[1], d_i[2], d_i[3]);
+        *reinterpret_cast<float4*>(e1) = make_float4(d_i[4], d_i[5], d_i[6], d_i[7]);
+        *reinterpret_cast<float4*>(e0 + 4096) = make_float4(d_f[0], d_f[1], d_f[2], d_f[3]);
+        *reinterpret_cast<float4*>(e1 + 4096) = make_float4(d_f[4], d_f[5], d_f[6], d_f[7]);
+        *reinterpret_cast<float4*>(e0 + 2 * 4096) = make_float4(d_g[0], d_g[1], d_g[2], d_g[3]);
+        *reinterpret_cast<float4*>(e1 + 2 * 4096) = make_float4(d_g[4], d_g[5], d_g[6], d_g[7]);
+        *reinterpret_cast<float4*>(e0 + 3 * 4096) = make_float4(d_o[0], d_o[1], d_o[2], d_o[3]);
+        *reinterpret_cast<float4*>(e1 + 3 * 4096) = make_float4(d_o[4], d_o[5], d_o[6], d_o[7]);
+        if (cp_it) {                             // (dh, dc) entering the step: only the joint checkpoints read them
+          *reinterpret_cast<float4*>(e0 + 4 * 4096) = make_float4(dhv[0], dhv[1], dhv[2], dhv[3]);
+          *reinterpret_cast<float4*>(e1 + 4 * 4096) = make_float4(dhv[4], dhv[5], dhv[6], dhv[7]);
+          *reinterpret_cast<float4*>(e0 + 5 * 4096) = make_float4(dci[0], dci[1], dci[2], dci[3]);
+          *reinterpret_cast<float4*>(e1 + 5 * 4096) = make_float4(dci[4], dci[5], dci[6], dci[7]);
+        }
+      }
+      __syncwarp();
+      const long long u2 = prof ? clock64() : 0;
+      // (S) one pass over the staged gate gradients, 8 lanes per row: the scaled fp16 split (the next step's A operand of
+      //     every CTA of the cluster), the fp32 values of the live positions (parameter-gradient contractions), the joint
+      //     checkpoints
+      {
+        const int c4 = lane & 7;
+#pragma unroll
+        for (int i8 = 0; i8 < 8; ++i8) {
+          const int r = i8 * 4 + (lane >> 3);
+          const int kr = m0 + 32 * q + r;
+          if (kr < P) {
+            const size_t pos = (size_t)kr * sk + (size_t)t * stt;
+            const unsigned char* e = gst + r * 128 + ((c4 ^ (r & 7)) << 4);
+            const bool live = kr == P - 1 || it >= p.warm;
+            const int uc = ucolw + c4 * 4;
+            __half* xp = p.dgx + ((size_t)((((it + 1) & 1) * 2) * Ppad + kr)) * (4 * H) + uc;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              const float4 d = *reinterpret_cast<const float4*>(e + a * 4096);
+              uint2 hi, lo;
+              split4_f16(make_float4(d.x * S, d.y * S, d.z * S, d.w * S), hi, lo);
+              *reinterpret_cast<uint2*>(xp + a * H) = hi;
+              *reinterpret_cast<uint2*>(xp + (size_t)Ppad * (4 * H) + a * H) = lo;
+              if (live) *reinterpret_cast<float4*>(p.dgates + pos * (4 * H) + a * H + uc) = d;
+            }
+            if (cp_it) {
+              const float4 dh4 = *reinterpret_cast<const float4*>(e + 4 * 4096);
+              const float4 dc4 = *reinterpret_cast<const float4*>(e + 5 * 4096);
+              if (kr < P - 1 && (w_full || w_half)) {
+                float* bs = p.bstate + ((size_t)(((w_full ? 1 : 0) * 2 + 0) * P + kr) * 2) * H + uc;
+                *reinterpret_cast<float4*>(bs) = dh4;
+                *reinterpret_cast<float4*>(bs + H) = dc4;
               }
-              if (cp_it) {
-                const float4 dh4 = *reinterpret_cast<const float4*>(e + 4 * 2048);
-                const float4 dc4 = *reinterpret_cast<const float4*>(e + 5 * 2048);
-                if (kr < P - 1 && (w_full || w_half)) {
-                  float* bs = p.bstate + ((size_t)(((w_full ? 1 : 0) * 2 + 0) * P + kr) * 2) * H + uc;
-                  *reinterpret_cast<float4*>(bs) = dh4;
-                  *reinterpret_cast<float4*>(bs + H) = dc4;
-                }
-                if (kr >= 1 && (r_full || r_half)) {
-                  float* bs = p.bstate + ((size_t)(((r_full ? 1 : 0) * 2 + 1) * P + kr) * 2) * H + uc;
-                  *reinterpret_cast<float4*>(bs) = dh4;
-                  *reinterpret_cast<float4*>(bs + H) = dc4;
-                }
+              if (kr >= 1 && (r_full || r_half)) {
+                float* bs = p.bstate + ((size_t)(((r_full ? 1 : 0) * 2 + 1) * P + kr) * 2) * H + uc;
+                *reinterpret_cast<float4*>(bs) = dh4;
+                *reinterpret_cast<float4*>(bs + H) = dc4;
               }
             }
           }
         }
-        __syncwarp();                          // the next pass overwrites the staging tile
-        if (prof) { const long long u3 = clock64(); tg += u1 - u0; tc += u2 - u1; ts += u3 - u2; }
       }
+      __syncwarp();                            // the next step's gather overwrites the staging tile
+      if (prof) { const long long u3 = clock64(); tc += u2 - u1; ts += u3 - u2; }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty);
@@ -878,6 +869,8 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
 #pragma unroll
       for (int i = 0; i < 5; ++i) p.prof[i] = pr[i];
       p.prof[5] = steps;
+      p.prof[6] = pr_issue;                    // gather requests
+      p.prof[7] = pr_xwait;                    // wait for the partner's partial sums
     }
   }
   tc_fence_before();

@@ -104,7 +104,8 @@ if "time" in stages or "prof" in stages:
             if o + 6 > t.size:
                 continue
             T = max(int(t[o + 5]), 1)
-            print("  %s: %d steps, cycles per step: %s, total %.0f" % (label, T, ", ".join("%s %.0f" % (nm, t[o + i] / T) for i, nm in enumerate(names)),
-                  float(sum(t[o:o + 5])) / T), flush=True)
+            extra = ", gather issue %.0f, partner wait %.0f" % (t[o + 6] / T, t[o + 7] / T) if o == 8 else ""
+            print("  %s: %d steps, cycles per step: %s%s, total %.0f" % (label, T, ", ".join("%s %.0f" % (nm, t[o + i] / T) for i, nm in enumerate(names)),
+                  extra, float(sum(t[o:o + 5]) + (t[o + 6] + t[o + 7] if o == 8 else 0)) / T), flush=True)
         print("  reruns %d fallbacks %d tc_max_err %s" % (eng.segment_stats["reruns"], eng.segment_stats["fallbacks"],
               ["%.1e" % x for x in eng.segment_stats["tc_max_err"][:14]]), flush=True)
