@@ -657,14 +657,43 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
       }
     };
 
+    const int ucolw = ub + 32 * ch;              // first of this warp's 32 units
+    // (L) stash of position t: activated gates (arrays 0..3), c_t (4), c_{t-1} (5), 8 lanes per row (128 bytes); element
+    //     (row, 16-byte chunk c) lives at row*128 + ((c ^ (row & 7)) << 4).  Requested as soon as the ring is idle (the
+    //     step's MMAs have completed), before the partial-sum swap, so that the rows travel while that is under way.
+    auto issue_gather = [&](int t) {
+      const int c4 = lane & 7;
+#pragma unroll
+      for (int i8 = 0; i8 < 8; ++i8) {
+        const int r = i8 * 4 + (lane >> 3);
+        const int kr = m0 + 32 * q + r;
+        if (kr < P) {
+          const size_t pos = (size_t)kr * sk + (size_t)t * stt;
+          const unsigned dst = smem_u32(gst) + (unsigned)(r * 128 + ((c4 ^ (r & 7)) << 4));
+          const float* gsrc = p.stash_g + pos * (4 * H) + ucolw + c4 * 4;
+#pragma unroll
+          for (int a = 0; a < 4; ++a) cp_async16(dst + a * 4096, gsrc + a * H);
+          cp_async16(dst + 4 * 4096, p.stash_c + (pos + stt) * H + ucolw + c4 * 4);
+          cp_async16(dst + 5 * 4096, p.stash_c + pos * H + ucolw + c4 * 4);
+        }
+      }
+    };
+
     for (int it = 0; it < iters; ++it) {
       const long long t0 = prof ? clock64() : 0;
       const int t = steps - 1 - it;
       x_have = it > 0;
       const int tk_n = (valid && t > 0) ? p.take[(long long)k_own * sk + (long long)(t - 1) * stt] : -1;
+      long long tgi = 0;
+      if (it == 0) issue_gather(t);
       if (it > 0) {
         mbar_wait(bar_acc_full, (unsigned)(it - 1) & 1u);
         tc_fence_after();
+        if (it < steps) {
+          const long long g0 = prof ? clock64() : 0;
+          issue_gather(t);
+          if (prof) tgi = clock64() - g0;
+        }
         {
           // the 64 columns of this CTA's partial sums that the partner (other K half, same column quarter) owns: this
           // thread's row, its 32-column half, combined main + correction, straight into the partner's receive buffer
@@ -723,33 +752,13 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
       const bool r_full = it == steps - 1, r_half = p.cp_half >= 0 && it == half_ref_it;   // reference side (pieces >= 1)
       const bool cp_it = p.bstate != nullptr && (w_full || w_half || r_full || r_half);
       long long tg = 0, tc = 0, ts = 0;
-      // (L) stash of this position: activated gates (arrays 0..3), c_t (4), c_{t-1} (5), 8 lanes per row (128 bytes);
-      //     element (row, 16-byte chunk c) lives at row*128 + ((c ^ (row & 7)) << 4).
-      const int ucolw = ub + 32 * ch;            // first of this warp's 32 units
-      {
-        const int c4 = lane & 7;
-#pragma unroll
-        for (int i8 = 0; i8 < 8; ++i8) {
-          const int r = i8 * 4 + (lane >> 3);
-          const int kr = m0 + 32 * q + r;
-          if (kr < P) {
-            const size_t pos = (size_t)kr * sk + (size_t)t * stt;
-            const unsigned dst = smem_u32(gst) + (unsigned)(r * 128 + ((c4 ^ (r & 7)) << 4));
-            const float* gsrc = p.stash_g + pos * (4 * H) + ucolw + c4 * 4;
-#pragma unroll
-            for (int a = 0; a < 4; ++a) cp_async16(dst + a * 4096, gsrc + a * H);
-            cp_async16(dst + 4 * 4096, p.stash_c + (pos + stt) * H + ucolw + c4 * 4);
-            cp_async16(dst + 5 * 4096, p.stash_c + pos * H + ucolw + c4 * 4);
-          }
-        }
-      }
       const long long t2 = prof ? clock64() : 0;
       if (!x_ready) mbar_wait(bar_x, (unsigned)(it - 1) & 1u);
       const long long u0 = prof ? clock64() : 0;
       cp_async_wait_all();
       __syncwarp();
       const long long u1 = prof ? clock64() : 0;
-      if (prof) { pr_issue += t2 - t1; pr_xwait += u0 - t2; tg += u1 - u0; }
+      if (prof) { pr_issue += tgi; pr_xwait += u0 - t2; tg += u1 - u0; }
       // (C) gate gradients, one row per lane, in place on the staging tile
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
@@ -862,7 +871,7 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
       publish_exchange();
       cluster_wait();
       tk = tk_n;
-      if (prof) { const long long t5 = clock64(); pr[0] += t1 - t0; pr[1] += tg; pr[2] += tc; pr[3] += ts; pr[4] += t5 - t4; }
+      if (prof) { const long long t5 = clock64(); pr[0] += t1 - t0 - tgi; pr[1] += tg; pr[2] += tc; pr[3] += ts; pr[4] += t5 - t4; }
     }
     if (valid && !(ovf * S < 30000.f)) *p.overflow = 1.f;       // also catches NaN
     if (prof) {
