@@ -752,6 +752,11 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
       const bool r_full = it == steps - 1, r_half = p.cp_half >= 0 && it == half_ref_it;   // reference side (pieces >= 1)
       const bool cp_it = p.bstate != nullptr && (w_full || w_half || r_full || r_half);
       long long tg = 0, tc = 0, ts = 0;
+      // injected dL/dh of this thread's own row (one position in ten): 8 units at a time, one group ahead of its use
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool has_inj = valid && tk >= 0;
+      const float4* inj_src = reinterpret_cast<const float4*>(p.dh_take + (size_t)(has_inj ? tk : 0) * H + ucolw);
+      float4 nx0 = has_inj ? __ldg(inj_src) : zero4, nx1 = has_inj ? __ldg(inj_src + 1) : zero4;
       const long long t2 = prof ? clock64() : 0;
       if (!x_ready) mbar_wait(bar_x, (unsigned)(it - 1) & 1u);
       const long long u0 = prof ? clock64() : 0;
@@ -763,13 +768,8 @@ chain_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_con
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
         float rec[8], cor[8], xr[8];
-        // injected dL/dh of this thread's own row (one position in ten)
-        float4 inj0 = make_float4(0.f, 0.f, 0.f, 0.f), inj1 = inj0;
-        if (valid && tk >= 0) {
-          const float4* src = reinterpret_cast<const float4*>(p.dh_take + (size_t)tk * H + ucolw + 8 * c8);
-          inj0 = __ldg(src);
-          inj1 = __ldg(src + 1);
-        }
+        const float4 inj0 = nx0, inj1 = nx1;
+        if (c8 < 3 && has_inj) { nx0 = __ldg(inj_src + 2 * (c8 + 1)); nx1 = __ldg(inj_src + 2 * (c8 + 1) + 1); }
         load_partner(c8, xr);
         if (it > 0) {
           tmem_ld8x2(tq + (unsigned)(own_c + 32 * ch + 8 * c8), tq + (unsigned)(B_CORR + own_c + 32 * ch + 8 * c8), rec, cor);
