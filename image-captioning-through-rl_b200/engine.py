@@ -809,10 +809,12 @@ class A2CEngine:
         """Size the next warm-up of chain `key` from the joint errors half-way through / at the end of this one.
         The two errors give the contraction rate of the recurrence under the current weights: the warm-up GROWS as soon
         as the end-of-warm-up error passes chain_tol / 4 (before the check can fail; by the measured rate, at least
-        x1.25, at most x4), and SHRINKS after _SHRINK_AFTER consecutive steps that allow it: to 5/8 once the half-way
-        error alone is below that target (the new end point then lies beyond a point already measured clean), else by
-        the positions the measured rate says can be given back with the predicted end error still a factor 2 below the
-        growth threshold (never below 5/8 in one move); after a growth it is held for _HOLD_AFTER_GROWTH steps.  Returns False when the step failed its check (end-of-warm-up
+        x1.25, at most x4), and SHRINKS to 5/8 once the half-way error alone has been below that target on
+        _SHRINK_AFTER consecutive steps (the new end point then lies beyond a point already measured clean); after a
+        growth it is held for _HOLD_AFTER_GROWTH steps.  (A finer shrink by the positions the measured rate predicts can be
+        given back was tried: 2 % faster on one GPU, but with 512 rows per rank the value chain then needed growth inside
+        the next ten optimizer steps and paid for it with re-runs -- the half-way rule is the one with a measured point
+        behind it.)  Returns False when the step failed its check (end-of-warm-up
         error above chain_tol, or not a number)."""
         tol = self.chain_tol
         target = tol / 4.0
@@ -828,23 +830,10 @@ class A2CEngine:
             self.warm[key] = int(-(-int(np.ceil(new)) // 32) * 32)
             self._clean[key] = 0
             self._hold[key] = self._HOLD_AFTER_GROWTH
-        elif self.chain_adapt and warm >= 8 and self._hold[key] == 0:
-            ceil32 = lambda x: int(-(-int(np.ceil(x)) // 32) * 32)
-            floor_w = max(self.chain_warmup_min, ceil32(0.625 * warm))
-            cand = warm
-            if e_half <= target:
-                cand = floor_w                       # the half-way point is clean by itself
-            elif e_half > e_full > 0.0 and np.isfinite(e_half) and e_full < target / 2.0:
-                # positions that can be given back while the PREDICTED end-of-warm-up error (measured rate) stays a factor
-                # 2 below the growth threshold; an end error at the rounding floor makes the rate, and so the step, smaller
-                rate = np.log(e_half / e_full) / float(warm - warm // 2)
-                cand = max(floor_w, ceil32(warm - np.log((target / 2.0) / e_full) / rate))
-            if cand < warm:
-                self._clean[key] += 1
-                if self._clean[key] >= self._SHRINK_AFTER:
-                    self.warm[key] = cand
-                    self._clean[key] = 0
-            else:
+        elif self.chain_adapt and warm >= 8 and e_half <= target and self._hold[key] == 0:
+            self._clean[key] += 1
+            if self._clean[key] >= self._SHRINK_AFTER and warm > self.chain_warmup_min:
+                self.warm[key] = max(self.chain_warmup_min, int(-(-int(0.625 * warm) // 32) * 32))
                 self._clean[key] = 0
         else:
             self._clean[key] = 0
