@@ -181,7 +181,7 @@ def main_reference(args, rank):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the chain kernels from `ncu --set full` captures of THIS command
 # (profiles/r02b_ncu.md); keyed by (kernel, local batch).  A configuration that was not captured reports null.
-NCU_TRAFFIC = {("chains_tc_fwd_fused_kernel", 4096): 12.56e9, ("chain_tc_bwd_kernel", 4096): 23.15e9}
+NCU_TRAFFIC = {("chains_tc_fwd_fused_kernel", 4096): 12.61e9, ("chain_tc_bwd_kernel", 4096): 23.96e9}
 
 
 def roofline_of(phases, Bl, lay, peaks, clk):
