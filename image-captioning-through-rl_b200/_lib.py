@@ -77,7 +77,8 @@ SIGNATURES = {
     "icrl_gather_rows": [P, L, P, P, L, P, LP],
     "icrl_value_head_fwd": [P, I, I, P, P, P, P, P, LP],
     "icrl_value_head_bwd": [P, I, I] + [P] * 14 + [LP],
-    "icrl_value_chain_param_grads": [P, I, I, I] + [P] * 8 + [Z] + [P] * 5 + [I, I, I, LP],
+    "icrl_value_chain_param_grads": [P, I, I, I] + [P] * 8 + [Z] + [P] * 5 + [I, I, I, I, LP],
+    "icrl_wgrad_tc_pack_b": [P, I, I, L, P, I, P, Z, I, LP],
     "icrl_reward_cosine_fwd": [P, I, I, P, P, P, LP],
     "icrl_a2c_loss_fwd_bwd": [P, I, I, P, P, P, F, P, P, P, P, LP],
 }

@@ -151,6 +151,13 @@ int icrl_wgrad_tc(void* stream, int M, int N, long long T, const float* A, int l
   return ICRL_OK;
 }
 
+int icrl_wgrad_tc_pack_b(void* stream, int M, int N, long long T, const float* B, int ldb, void* ws, size_t ws_bytes,
+                         int splits, int* launches) {
+  TRY(icrl_wgrad_tc_pack_b_impl(S_(stream), M, N, T, B, ldb, ws, ws_bytes, splits));
+  bump(launches, 1);
+  return ICRL_OK;
+}
+
 size_t icrl_decode_weight_halves(void) { return icrl_decode_weight_halves_impl(); }
 
 int icrl_pack_decode_weights(void* stream, int V, const float* W_hh, const float* W_v, void* packed, int* launches) {
@@ -612,7 +619,8 @@ int icrl_value_head_bwd(void* stream, int B, int S, const float* features, const
 int icrl_value_chain_param_grads(void* stream, int T, int V, int D, const int* tok_stream, const float* dgates,
                                  const float* stash_h, const float* E, const float* W_ih, float* dtable,
                                  float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE, float* dW_ih,
-                                 float* dW_hh, float* db_ih, float* db_hh, int B, int p0, int S, int* launches) {
+                                 float* dW_hh, float* db_ih, float* db_hh, int B, int p0, int S, int h_packed,
+                                 int* launches) {
   cudaStream_t st = S_(stream);
   // Gate-table gradient: dtable[token] += dgates of every position that consumed the token.  When the caller names the
   // stream's shape (B > 0: tok_stream = icrl_build_stream(B, p0, S, extra 0)) the positions of one (column, row) are
@@ -629,9 +637,10 @@ int icrl_value_chain_param_grads(void* stream, int T, int V, int D, const int* t
   bump(launches, 1);
   // dW_hh = sum_t dgates_t (x) h_{t-1};  stash_h row t = h_{t-1}.  With a workspace of icrl_wgrad_tc_ws_bytes(2048, 512,
   // T, 2) bytes the contraction runs on tcgen05 (wgrad_tc.cu), otherwise on the fp32 SIMT GEMM.
+  ICRL_REQUIRE(!h_packed || gemm_ws_bytes >= icrl_wgrad_tc_ws_bytes_impl(4 * H, H, T, 2), "h_packed needs the wgrad_tc workspace");
   if (gemm_ws_bytes >= icrl_wgrad_tc_ws_bytes_impl(4 * H, H, T, 2)) {
-    TRY(icrl_wgrad_tc_impl(st, 4 * H, H, T, dgates, 4 * H, stash_h, H, dW_hh, H, gemm_ws, gemm_ws_bytes, 2, colmax));
-    bump(launches, colmax ? 4 : 5);
+    TRY(icrl_wgrad_tc_impl(st, 4 * H, H, T, dgates, 4 * H, stash_h, H, dW_hh, H, gemm_ws, gemm_ws_bytes, 2, colmax, h_packed));
+    bump(launches, (colmax ? 4 : 5) - (h_packed ? 1 : 0));
   } else {
     TRY(icrl_gemm_f32_impl(st, 1, 0, 4 * H, H, T, dgates, 4 * H, stash_h, H, dW_hh, H, nullptr, 0.f, gemm_ws,
                            gemm_ws_bytes, launches));

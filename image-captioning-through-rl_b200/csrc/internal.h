@@ -80,7 +80,10 @@ int icrl_chain_lstm_bwd_batched_impl(cudaStream_t st, int shards, int T, const f
 void icrl_chain_set_profile_impl(long long* buf);
 size_t icrl_wgrad_tc_ws_bytes_impl(int M, int N, long long T, int splits);
 int icrl_wgrad_tc_impl(cudaStream_t st, int M, int N, long long T, const float* A, int lda, const float* B, int ldb,
-                       float* C, int ldc, void* ws, size_t ws_bytes, int splits, const unsigned* colmax = nullptr);
+                       float* C, int ldc, void* ws, size_t ws_bytes, int splits, const unsigned* colmax = nullptr,
+                       int b_packed = 0);
+int icrl_wgrad_tc_pack_b_impl(cudaStream_t st, int M, int N, long long T, const float* B, int ldb, void* ws, size_t ws_bytes,
+                              int splits);
 int icrl_adam_flat_impl(cudaStream_t st, long long n, float* p, const float* g, float* m, float* v, float lr, float b1,
                         float b2, float eps, int step);
 

@@ -390,10 +390,27 @@ size_t icrl_wgrad_tc_ws_bytes_impl(int M, int N, long long T, int splits) {
 }
 
 // C [M][ldc] = A^T B with A [T][lda] (M columns used, scaled per column), B [T][ldb] (N columns used).
+// The B operand's pre-pass alone (transpose + split into the workspace of the same M, N, T, splits): B is often final long
+// before A (the value chain's h stash exists after the forward), so a caller can run this on another stream beside
+// whatever produces A and then pass b_packed = 1 to the contraction.
+int icrl_wgrad_tc_pack_b_impl(cudaStream_t st, int M, int N, long long T, const float* B, int ldb, void* ws, size_t ws_bytes,
+                              int splits) {
+  ICRL_REQUIRE(M % BM == 0 && N % (BN * CLN) == 0 && T > 0 && splits >= 1, "wgrad_tc needs M a multiple of 128, N of 512");
+  ICRL_REQUIRE(ws && ws_bytes >= icrl_wgrad_tc_ws_bytes_impl(M, N, T, splits), "wgrad_tc workspace too small");
+  ICRL_REQUIRE(ldb % 4 == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0, "wgrad_tc_pack_b needs 16-byte aligned rows");
+  const long long Tp = round_up(T, 64);
+  __half* b_pk = reinterpret_cast<__half*>(ws) + (size_t)2 * M * Tp;
+  dim3 gb((unsigned)(Tp / 64), N / 64);
+  transpose_split64_kernel<<<gb, 256, 0, st>>>(T, Tp, N, B, ldb, nullptr, b_pk, b_pk + (size_t)N * Tp, nullptr);
+  ICRL_LAUNCH_CHECK();
+  return ICRL_OK;
+}
+
 // colmax (nullable): M words holding the bit patterns of max_t |A[t][m]| when the caller has them already (the gate-table
 // scatter reads all of A and returns them: icrl_scatter_add_stream); otherwise a pre-pass over A computes them.
+// b_packed: the B operand already lies in the workspace (icrl_wgrad_tc_pack_b_impl).
 int icrl_wgrad_tc_impl(cudaStream_t st, int M, int N, long long T, const float* A, int lda, const float* B, int ldb,
-                       float* C, int ldc, void* ws, size_t ws_bytes, int splits, const unsigned* colmax) {
+                       float* C, int ldc, void* ws, size_t ws_bytes, int splits, const unsigned* colmax, int b_packed) {
   ICRL_REQUIRE(M % BM == 0 && N % (BN * CLN) == 0 && T > 0 && splits >= 1, "wgrad_tc needs M a multiple of 128, N of 512");
   ICRL_REQUIRE(ws && ws_bytes >= icrl_wgrad_tc_ws_bytes_impl(M, N, T, splits), "wgrad_tc workspace too small");
   static bool attr_set = false;
@@ -420,15 +437,19 @@ int icrl_wgrad_tc_impl(cudaStream_t st, int M, int N, long long T, const float* 
     dim3 ga((unsigned)(Tp / 64), M / 64), gb((unsigned)(Tp / 64), N / 64);
     transpose_split64_kernel<<<ga, 256, 0, st>>>(T, Tp, M, A, lda, mx, a_pk, a_pk + (size_t)M * Tp, inv_scale);
     ICRL_LAUNCH_CHECK();
-    transpose_split64_kernel<<<gb, 256, 0, st>>>(T, Tp, N, B, ldb, nullptr, b_pk, b_pk + (size_t)N * Tp, nullptr);
-    ICRL_LAUNCH_CHECK();
+    if (!b_packed) {
+      transpose_split64_kernel<<<gb, 256, 0, st>>>(T, Tp, N, B, ldb, nullptr, b_pk, b_pk + (size_t)N * Tp, nullptr);
+      ICRL_LAUNCH_CHECK();
+    }
   } else {
     dim3 blk(32, 8);
     dim3 ga(icrl_cdiv(M, 32), (unsigned)(Tp / 32)), gb(icrl_cdiv(N, 32), (unsigned)(Tp / 32));
     transpose_split_kernel<<<ga, blk, 0, st>>>(T, Tp, M, A, lda, mx, a_pk, a_pk + (size_t)M * Tp, inv_scale);
     ICRL_LAUNCH_CHECK();
-    transpose_split_kernel<<<gb, blk, 0, st>>>(T, Tp, N, B, ldb, nullptr, b_pk, b_pk + (size_t)N * Tp, nullptr);
-    ICRL_LAUNCH_CHECK();
+    if (!b_packed) {
+      transpose_split_kernel<<<gb, blk, 0, st>>>(T, Tp, N, B, ldb, nullptr, b_pk, b_pk + (size_t)N * Tp, nullptr);
+      ICRL_LAUNCH_CHECK();
+    }
   }
   CUtensorMap ma, mb;
   int rc;

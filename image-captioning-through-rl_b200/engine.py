@@ -612,11 +612,22 @@ class A2CEngine:
             fork.record(main)
             self._backward_value(f, B, p0, S, Tv, launch_only_chain=True)
             self._side_stream.wait_event(fork)
+            h_packed = None
             with torch.cuda.stream(self._side_stream):
+                if self.wgrad == "tc" and self.chain_shards == 1:
+                    # the h stash is final since the forward: its transpose + split (B operand of dW_hh = dgates^T h) leaves
+                    # the critical path and runs beside the chain backward
+                    _, gemm_ws, gemm_ws_floats, _ = self._bwd_workspaces(B, S, Tv, "")
+                    _lib.call("icrl_wgrad_tc_pack_b", self._stream, 4 * H, H, Tv, _p(self._bufs["v_stash_h"]), H, _p(gemm_ws),
+                              gemm_ws_floats * 4, 2, self.launches.ref)
+                    h_packed = torch.cuda.Event()
+                    h_packed.record(self._side_stream)
                 self._backward_policy(f, tokcm, tokens, B, p0, S, "_p")
                 join = torch.cuda.Event()
                 join.record(self._side_stream)
-            self._backward_value(f, B, p0, S, Tv, launch_only_chain=False)
+            if h_packed is not None:
+                main.wait_event(h_packed)
+            self._backward_value(f, B, p0, S, Tv, launch_only_chain=False, h_packed=h_packed is not None)
             main.wait_event(join)
         else:
             self._backward_value(f, B, p0, S, Tv, launch_only_chain=True)
@@ -642,7 +653,7 @@ class A2CEngine:
             gemm_ws_floats = max(gemm_ws_floats, (n + 3) // 4)
         return colsum_ws, self._buf("gemm_ws" + tag, gemm_ws_floats), gemm_ws_floats, self._buf("dtable" + tag, V * 4 * H)
 
-    def _backward_value(self, f, B, p0, S, Tv, launch_only_chain):
+    def _backward_value(self, f, B, p0, S, Tv, launch_only_chain, h_packed=False):
         st, L, b, V = self._stream, self.launches.ref, self._bufs, self.V
         Vn = self.value
         SB = S * B
@@ -657,7 +668,7 @@ class A2CEngine:
                       _p(Vn.valrnn.caption_embedding.weight), _p(lstm.weight_ih_l0), _p(dtable), _p(colsum_ws), _p(gemm_ws),
                       gemm_ws_floats * 4, _p(g(Vn.valrnn.caption_embedding.weight, True)), _p(g(lstm.weight_ih_l0)),
                       _p(g(lstm.weight_hh_l0)), _p(g(lstm.bias_ih_l0)), _p(g(lstm.bias_hh_l0)),
-                      B if K == 1 else 0, p0, S, L)
+                      B if K == 1 else 0, p0, S, int(bool(h_packed)), L)
             return
         # value head -> dh at the take positions + head gradients
         dh_take = self._buf("v_dh_take", SB * H)

@@ -245,7 +245,7 @@ class _ChainLSTMFn(torch.autograd.Function):
             dtable, csws = new(V, 4 * HID), new(cs)
             _lib.call("icrl_value_chain_param_grads", st, T, V, D, _p(stream), _p(dgates), _p(stash_h), _p(E), _p(W_ih),
                       _p(dtable), _p(csws), _p(ws), ws.numel() * 4, _p(dE), _p(dWih), _p(dWhh), _p(dbih),
-                      _p(dbhh), 0, 0, 0, None)
+                      _p(dbhh), 0, 0, 0, 0, None)
         return None, dh0.view(ctx.state_shapes[0]), dc0.view(ctx.state_shapes[1]), dE, dWih, dWhh, dbih, dbhh
 
 

@@ -93,6 +93,11 @@ int icrl_policy_rollout_fwd_tc(void* stream, int B, int V, int p0, int S, int gr
 size_t icrl_wgrad_tc_ws_bytes(int M, int N, long long T, int splits);
 int icrl_wgrad_tc(void* stream, int M, int N, long long T, const float* A, int lda, const float* B, int ldb, float* C,
                   int ldc, void* ws, size_t ws_bytes, int splits, int* launches);
+/*      The B operand's pre-pass alone, into the workspace of the same (M, N, T, splits): for callers whose B is final before
+ *      A (the value chain's h stash exists after the forward) and who want it off the critical path, on another stream;
+ *      icrl_value_chain_param_grads(..., h_packed = 1) then skips it. */
+int icrl_wgrad_tc_pack_b(void* stream, int M, int N, long long T, const float* B, int ldb, void* ws, size_t ws_bytes,
+                         int splits, int* launches);
 
 /*      The same rollout as ONE persistent kernel (decode.cu): clusters of 8 CTAs own 128 rows each for all
  *      timesteps; gate and vocab GEMMs on tcgen05 (2-part fp16 split, 3 MMAs, f32 accumulation in TMEM) with the
@@ -322,11 +327,13 @@ int icrl_value_head_bwd(void* stream, int B, int S, const float* features, const
  *      B > 0: tok_stream is the stream icrl_build_stream(B, p0, S, extra 0) built (T = icrl_stream_len(B, p0, S, 0)); the
  *      scatter then sums the positions that consumed the same (column, row) token before one vector reduction each
  *      (ten times fewer reductions at 19 rollout steps) and hands the column maxima of dgates to the contraction.
- *      B = 0: any token stream of T positions (one reduction per position). */
+ *      B = 0: any token stream of T positions (one reduction per position).
+ *      h_packed = 1: gemm_ws already holds the transposed fp16 split of stash_h (icrl_wgrad_tc_pack_b(2048, 512, T, ...)). */
 int icrl_value_chain_param_grads(void* stream, int T, int V, int D, const int* tok_stream, const float* dgates,
                                  const float* stash_h, const float* E, const float* W_ih, float* dtable,
                                  float* colsum_ws, float* gemm_ws, size_t gemm_ws_bytes, float* dE, float* dW_ih,
-                                 float* dW_hh, float* db_ih, float* db_hh, int B, int p0, int S, int* launches);
+                                 float* dW_hh, float* db_ih, float* db_hh, int B, int p0, int S, int h_packed,
+                                 int* launches);
 /*      reward (models.py:259-260 + GetRewards trainers.py:117-120): rewards [B][S] = cos(ve[b], se[s][b]). */
 int icrl_reward_cosine_fwd(void* stream, int B, int S, const float* ve, const float* se, float* rewards,
                            int* launches);

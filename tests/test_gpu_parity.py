@@ -1035,7 +1035,7 @@ def test_value_param_grads_stream_scatter_matches_generic(B, p0, S):
         dE, dWih = torch.empty((V, D), device="cuda"), torch.empty((G, D), device="cuda")
         dWhh, dbi, dbh = torch.empty((G, 512), device="cuda"), torch.empty(G, device="cuda"), torch.empty(G, device="cuda")
         _lib.call("icrl_value_chain_param_grads", st, T, V, D, p(stream), p(dgates), p(stash_h), p(E), p(W_ih), p(dtable),
-                  p(csws), p(ws), wsb, p(dE), p(dWih), p(dWhh), p(dbi), p(dbh), *shape, None)
+                  p(csws), p(ws), wsb, p(dE), p(dWih), p(dWhh), p(dbi), p(dbh), *shape, 0, None)
         torch.cuda.synchronize()
         out[tag] = dict(dtable=dtable, dE=dE, dWih=dWih, dWhh=dWhh, dbi=dbi, dbh=dbh)
     ref = torch.zeros((V, G), dtype=torch.float64, device="cuda")
