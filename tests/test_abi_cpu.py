@@ -224,3 +224,31 @@ def test_stream_length_and_take_positions_match_the_oracle(lib):
             assert np.array_equal(blk, tokens[:, :p0 + s + extra].T)
 
     check()
+
+
+def test_stream_positions_of_a_token_closed_form():
+    """The gate-table scatter (scatter_add_stream_kernel, policy.cu) sums, for every (column, row) of the token matrix, the
+    stream positions B * (s (p0 + extra) + s (s - 1) / 2 + col) + b of the blocks s >= max(0, col - p0 - extra + 1) and
+    reduces once into the row of the token at the first of them.  Checked against the oracle's stream builder: those
+    positions are exactly the positions that consumed that token, every position is covered once."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import single_pass
+
+    @settings(max_examples=60, deadline=None)
+    @given(B=st.integers(1, 9), p0=st.integers(1, 6), S=st.integers(1, 8), extra=st.integers(0, 1))
+    def check(B, p0, S, extra):
+        n_col = p0 + S - 1 + extra
+        tokens = np.arange(B * (n_col + 1), dtype=np.int64).reshape(B, n_col + 1)       # every (row, column) its own token
+        stream, _ = single_pass.stream_tokens(tokens, p0, S, extra)
+        seen = np.zeros(len(stream), dtype=np.int64)
+        for col in range(n_col):
+            for b in range(B):
+                s0 = max(0, col - p0 - extra + 1)
+                pos = [B * (s * (p0 + extra) + s * (s - 1) // 2 + col) + b for s in range(s0, S)]
+                assert pos and all(0 <= q < len(stream) for q in pos)
+                assert all(stream[q] == tokens[b, col] for q in pos)
+                assert sorted(np.nonzero(stream == tokens[b, col])[0].tolist()) == pos
+                seen[pos] += 1
+        assert (seen == 1).all()
+
+    check()
