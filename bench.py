@@ -222,6 +222,10 @@ def roofline_of(phases, Bl, lay, peaks, clk):
             "frac_executed": executed / (kms * 1e-3) / 1e12 / peak if kms > 0 else 0.0,
             "kernel_steps_per_launch": steps, "us_per_kernel_step": kms * 1e3 / steps if steps else None,
             "pieces": {"value": Pv, "reward": Pr}, "warmup": {"value": warm_v, "reward": warm_r},
+            "limited_by": "shared-memory bandwidth of the SM during the step GEMM (MMA operand reads + TMA fill at 128 B/clk: model "
+                          "within 1 % of the measured cycles) and the number of global row segments gathered / stored in the "
+                          "epilogue; the tensor pipe itself needs 12.3 K of a step's 31 K (forward) / 38 K (backward) cycles "
+                          "(DESIGN.md 4.0)",
             "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                     "note": "algorithmic stash / table bytes of the same launch against the measured copy bandwidth"},
             "note": "one kernel step = [pieces x 512] . W_hh^T on tcgen05 (M = 128 pieces per cluster of 8 CTAs) + cell "
